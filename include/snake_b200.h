@@ -1,0 +1,169 @@
+/*
+ * snake_b200.h — C ABI of libsnake_b200.so, the B200-native batched Snake environment
+ * and Laplace D-matrix kernels.
+ *
+ * This is the drop-in boundary for the environment hot path of
+ * lucagiorgetti/Laplace-DQN-Snake-game (Julia).  The reference has no FFI of its own; each
+ * entry point below names the Julia function (file:line in the reference repository) it
+ * replaces.  A Julia host binds these with `ccall` (see INTEGRATION.md and
+ * laplace-dqn-snake-game_b200/julia/SnakeB200.jl); the tests and bench bind the identical
+ * symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns int: 0 = SNK_OK, < 0 = error (snk_last_error() has the text);
+ *     no C++ exception crosses this boundary;
+ *   - pointers are DEVICE pointers unless the function name ends in `_host`;
+ *   - N = number of envs of the handle; per-env arrays are length N, `(3,N)` arrays are
+ *     3*N elements with the 3 contiguous (Julia column-major), observations are
+ *     `(10,10,2,N)` column-major exactly as `stack_exp` builds them (utils.jl:348-362):
+ *     element (r,c,f,n), 1-based, lives at (r-1) + 10(c-1) + 100(f-1) + 200(n-1);
+ *     frame f=1 is the older board, f=2 the newer one;
+ *   - calls enqueue work on the handle's CUDA stream and return; snk_sync() waits;
+ *   - one handle per host thread; there is no hidden global state besides the
+ *     thread-local error string;
+ *   - there is no CPU fallback: without a CUDA device snk_create fails.
+ *
+ * Codes
+ *   direction: 0=U(-1,0) 1=D(+1,0) 2=L(0,-1) 3=R(0,+1)             (utils.jl:8)
+ *   action index 0..2: position in available_actions(game)          (utils.jl:7-10)
+ *   board cell: -1 wall, 0 empty, 1 snake, 2 food                   (structs.jl:34-51)
+ *   rewards: +1f0 eat, -1f0 loss, -0.01f0 otherwise                 (structs.jl:89-91)
+ */
+#ifndef SNAKE_B200_H
+#define SNAKE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNK_VERSION 100
+
+#if defined(__GNUC__)
+#define SNK_API __attribute__((visibility("default")))
+#else
+#define SNK_API
+#endif
+
+/* return codes */
+#define SNK_OK 0
+#define SNK_ERR_INVALID (-1)   /* bad argument */
+#define SNK_ERR_CUDA (-2)      /* a CUDA runtime call failed */
+#define SNK_ERR_NODEVICE (-3)  /* no CUDA device / not a Blackwell part */
+#define SNK_ERR_UNSUPPORTED (-4)
+#define SNK_ERR_NCCL (-5)
+
+/* snk_create flags */
+#define SNK_AUTO_RESET 1u      /* a lost env is re-initialised (a fresh SnakeGame(), utils.jl:199) after its terminal outputs */
+
+/* per-env sticky error bits (snk_get_error_flags) */
+#define SNK_ENV_ERR_FOOD 1u    /* sample_food! had empty cells but no usable list entry: BoundsError in the reference (utils.jl:23,37) */
+#define SNK_ENV_ERR_ACTION 2u  /* action index > 2 or direction > 3 was passed; treated as 0 */
+
+/* observation formats */
+#define SNK_OBS_NONE 0
+#define SNK_OBS_F32 1          /* Float32.(state), utils.jl:361-362: 800 B/env */
+#define SNK_OBS_I8 2           /* same values as int8: 200 B/env */
+#define SNK_OBS_I64 3          /* game.state::Array{Int,4}, structs.jl:17: 1600 B/env */
+#define SNK_OBS_PACKED2 4      /* 2 bits/cell, 4 cells/byte (cell j of a byte in bits 2j..2j+1), codes 0,1,2 and 3 = wall: 50 B/env */
+
+typedef struct snk_env *snk_handle;
+
+/* ---- lifecycle: SnakeGame(board_size=10, n_frames=2)  structs.jl:33-99 ------------------- */
+SNK_API int snk_create(snk_handle *out, int64_t n_envs, int device, uint32_t flags);
+SNK_API int snk_destroy(snk_handle h);
+/* every env back to the constructor state (R1): walls, food (4,5), snake [(8,2),(9,2)], prev_dir U */
+SNK_API int snk_reset(snk_handle h);
+/* food_list injection (structs.jl:70).  cells_rc_host: n pairs (row, col), 1-based, 2..9; n <= 64.
+ * Default = the 50 cells Xoshiro(42) yields (snk_default_food_list).  Takes effect at the next reset
+ * of each env; call snk_reset to apply it everywhere. */
+SNK_API int snk_set_food_list_host(snk_handle h, const uint8_t *cells_rc_host, int n);
+SNK_API int snk_default_food_list_host(uint8_t *cells_rc_host /* 100 bytes */, int *n);
+/* adopt an external CUDA stream (cudaStream_t / CUstream, e.g. torch's); NULL restores the handle's own */
+SNK_API int snk_set_stream(snk_handle h, void *cuda_stream);
+SNK_API int snk_get_stream(snk_handle h, void **cuda_stream);
+/* seed of the internal counter-based generator used when draws are not injected */
+SNK_API int snk_set_seed(snk_handle h, uint64_t seed);
+SNK_API int snk_sync(snk_handle h);
+SNK_API int64_t snk_num_envs(snk_handle h);
+SNK_API const char *snk_last_error(void);
+SNK_API int snk_version(void);
+
+/* ---- available_actions(game)  utils.jl:7-10 ---------------------------------------------- */
+SNK_API int snk_available_actions(snk_handle h, uint8_t *dirs_3xN);
+
+/* ---- step!(game, action)  utils.jl:100-109 (+ grow_maybe!, sample_food!, check_collision,
+ *      update_board!, move_wrapper!: utils.jl:13-96) ---------------------------------------
+ * act_idx: 0..2 into available_actions (what the Q-net's argmax means, utils.jl:165-167).
+ * reward: game.reward (exact Float32 bit patterns), done: game.lost.  Either may be NULL.
+ * A lost env without SNK_AUTO_RESET is left untouched and reports reward 0, done 1. */
+SNK_API int snk_step(snk_handle h, const uint8_t *act_idx, float *reward, uint8_t *done);
+/* absolute directions as play_snake.jl:96-111 sends them; a reverse move loses (utils.jl:57) */
+SNK_API int snk_step_abs(snk_handle h, const uint8_t *dir, float *reward, uint8_t *done);
+
+/* ---- the fused hot path: one kernel per rollout step -------------------------------------
+ * = epsilon_greedy (optional) + step! + virtual_step + assemble_states_vector's next_state +
+ *   Float32.() of stack_exp, for all N envs  (utils.jl:153-172, 100-109, 112-132, 141-149, 361-362).
+ * Inputs:  q != NULL  -> actions are chosen here by epsilon_greedy from q (3,N) f32 with
+ *                        eps; u (N) f32 and ridx (N) u8 in 0..2 are the injected draws
+ *                        `Float32(rand())` and the index `rand(av_actions)` picks; if u / ridx
+ *                        are NULL they come from the internal generator.  act_idx then is an
+ *                        optional OUTPUT (N) u8.
+ *          q == NULL  -> act_idx (N) u8 is the INPUT action index.
+ * Outputs (any may be NULL): reward (N) f32, done (N) u8,
+ *          obs: next_state (board_{t-1}, board_t) in obs_fmt, the terminal pair when done;
+ *          mask (3,N) u8: next_is_suicidal (trues(3) when done);
+ *          ep_return (N) f32: running Float32 episode reward (utils.jl:200,207) incl. this step;
+ *          ep_score (N) i32: game.score after this step. */
+SNK_API int snk_step_fused(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx,
+                   uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt,
+                   uint8_t *mask, float *ep_return, int32_t *ep_score);
+/* same call with HOST buffers (pinned memory recommended: snk_host_alloc): copies the inputs up,
+ * runs the fused kernel in env chunks and streams the outputs back, overlapped. */
+SNK_API int snk_step_fused_host(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx,
+                        uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt,
+                        uint8_t *mask, float *ep_return, int32_t *ep_score);
+SNK_API int snk_host_alloc(void **p, size_t bytes);   /* pinned host memory */
+SNK_API int snk_host_free(void *p);
+
+/* ---- assemble_state! / assemble_states_vector  utils.jl:135-149 --------------------------- */
+/* current two-frame state (board_{t-1}, board_t) of every env, in obs_fmt */
+SNK_API int snk_state(snk_handle h, void *obs, int obs_fmt);
+
+/* ---- virtual_step(game, model)  utils.jl:112-132 ------------------------------------------ */
+/* next_is_suicidal for the CURRENT state: for each available action, would step! lose?
+ * trues(3) for a lost env.  Includes the history-length rule (all true after 499 steps). */
+SNK_API int snk_losing_mask(snk_handle h, uint8_t *mask_3xN);
+
+/* ---- epsilon_greedy(game, model, eps)  utils.jl:153-172 ----------------------------------- */
+/* out[i] = ridx[i] if u[i] < eps else argmax(q[:,i]) (Julia argmax: first maximum, NaN wins). */
+SNK_API int snk_select_action(snk_handle h, const float *q_3xN, float eps, const float *u, const uint8_t *ridx,
+                      uint8_t *act_idx_out);
+
+/* ---- masked max-Q target  utils.jl:448-451 ------------------------------------------------ */
+/* q_next[mask] .= fill; y = r + gamma * max_a q_next * (1 - done), evaluated in Float64 as the
+ * reference's broadcast does (0.97 is a Float64 literal).  y_f64 and/or y_f32 (= Float32(y)) may be
+ * NULL.  Stateless; runs on `cuda_stream` (NULL = default stream) of the current device. */
+SNK_API int snk_masked_target(const float *q_next_3xB, const uint8_t *mask_3xB, const float *r, const uint8_t *done,
+                      double gamma, float fill, double *y_f64, float *y_f32, int64_t B, void *cuda_stream);
+
+/* ---- per-env scalars ---------------------------------------------------------------------- */
+SNK_API int snk_get_score(snk_handle h, int32_t *score);          /* game.score  structs.jl:21 */
+SNK_API int snk_get_done(snk_handle h, uint8_t *done);            /* game.lost   structs.jl:28 */
+SNK_API int snk_get_error_flags(snk_handle h, uint8_t *flags);    /* SNK_ENV_ERR_* */
+SNK_API int snk_get_steps(snk_handle h, int32_t *steps);          /* steps taken in the current episode */
+/* number of envs with any error bit set (synchronises) */
+SNK_API int snk_count_errors_host(snk_handle h, int64_t *count);
+
+/* ---- Laplace deviation matrix  compute_D.jl:9-31, 66-81; la_utils.jl:14-36, 154-169 -------- */
+/* D is P x K Float64, column-major (column k = snapshot k).  Welford mean / M2 over the columns in
+ * column order, var = M2 / max(K-1,1), then D .-= mean, all in Float64 without FMA contraction so
+ * the result is bit-identical to the Julia loop.  mean/var (P) may be NULL. */
+SNK_API int snk_center_columns(double *D, int64_t P, int64_t K, double *mean, double *var, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAKE_B200_H */

@@ -1,0 +1,319 @@
+"""snake_b200 — host-side mirror of the reference's environment API over libsnake_b200.so.
+
+The directory is called ``laplace-dqn-snake-game_b200`` (not an importable name); load it with
+``__graft_entry__.load_package()`` which registers it as the module ``snake_b200``.
+
+Julia is not available in this image, so this ctypes layer plays the role the shipped
+``julia/SnakeB200.jl`` wrapper plays for a Julia host: the same function names and argument
+meaning as the reference (`structs.jl`, `utils.jl`), batched over N envs, calling the identical
+C symbols declared in ``include/snake_b200.h``.  torch is used only to own device memory and
+streams.  There is NO CPU fallback: if the CUDA library is missing or no B200 is present every
+entry point raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnake_b200.so")
+
+OBS_NONE, OBS_F32, OBS_I8, OBS_I64, OBS_PACKED2 = 0, 1, 2, 3, 4
+AUTO_RESET = 1
+ENV_ERR_FOOD, ENV_ERR_ACTION = 1, 2
+_OBS = {
+    "f32": (OBS_F32, torch.float32, 200), "i8": (OBS_I8, torch.int8, 200),
+    "i64": (OBS_I64, torch.int64, 200), "packed2": (OBS_PACKED2, torch.uint8, 50),
+}
+
+# direction codes in the order of utils.jl:8
+U, D, L, R = 0, 1, 2, 3
+DIRS = ((-1, 0), (1, 0), (0, -1), (0, 1))
+
+
+class SnakeB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libsnake_b200.so (built by __graft_entry__.build()); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SnakeB200Error(
+            "%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+            "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, u32, i32, f32, f64 = C.c_void_p, C.c_int64, C.c_uint32, C.c_int, C.c_float, C.c_double
+    sig = {
+        "snk_create": [C.POINTER(vp), i64, i32, u32],
+        "snk_destroy": [vp], "snk_reset": [vp], "snk_sync": [vp],
+        "snk_set_food_list_host": [vp, vp, i32],
+        "snk_default_food_list_host": [vp, C.POINTER(i32)],
+        "snk_set_stream": [vp, vp], "snk_get_stream": [vp, C.POINTER(vp)],
+        "snk_set_seed": [vp, C.c_uint64],
+        "snk_available_actions": [vp, vp],
+        "snk_step": [vp, vp, vp, vp], "snk_step_abs": [vp, vp, vp, vp],
+        "snk_step_fused": [vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
+        "snk_step_fused_host": [vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
+        "snk_host_alloc": [C.POINTER(vp), C.c_size_t], "snk_host_free": [vp],
+        "snk_state": [vp, vp, i32], "snk_losing_mask": [vp, vp],
+        "snk_select_action": [vp, vp, f32, vp, vp, vp],
+        "snk_masked_target": [vp, vp, vp, vp, f64, f32, vp, vp, i64, vp],
+        "snk_get_score": [vp, vp], "snk_get_done": [vp, vp], "snk_get_error_flags": [vp, vp],
+        "snk_get_steps": [vp, vp], "snk_count_errors_host": [vp, C.POINTER(i64)],
+        "snk_center_columns": [vp, i64, i64, vp, vp, vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = i32
+    L.snk_num_envs.argtypes = [vp]
+    L.snk_num_envs.restype = i64
+    L.snk_last_error.restype = C.c_char_p
+    L.snk_version.restype = i32
+    for name in ("snk_gram_workspace_bytes", "snk_gram_pack", "snk_gram"):
+        if hasattr(L, name):
+            getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise SnakeB200Error("libsnake_b200 error %d: %s" % (rc, lib().snk_last_error().decode()))
+
+
+def _ptr(t, dtype=None, numel=None, device=None):
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("expected %s, got %s" % (dtype, t.dtype))
+    if numel is not None and t.numel() != numel:
+        raise ValueError("expected %d elements, got %d" % (numel, t.numel()))
+    if device is not None and t.device != device:
+        raise ValueError("tensor on %s, env on %s" % (t.device, device))
+    return C.c_void_p(t.data_ptr())
+
+
+def default_food_list():
+    """The 50 cells a fresh Xoshiro(42) yields (structs.jl:70), 1-based (row, col)."""
+    buf = (C.c_uint8 * 100)()
+    n = C.c_int(0)
+    _check(lib().snk_default_food_list_host(buf, C.byref(n)))
+    return [(buf[2 * i], buf[2 * i + 1]) for i in range(n.value)]
+
+
+class SnakeGame:
+    """N batched reference games (structs.jl:6-100) living in the HBM of one B200.
+
+    Method names follow utils.jl; every array is batched with N as the LAST Julia dimension,
+    i.e. the leading torch dimension: obs (N, 2, 10, 10) torch-contiguous is byte-identical to
+    Julia's (10, 10, 2, N) column-major array.
+    """
+
+    def __init__(self, n_envs, device=0, auto_reset=True, board_size=10, n_frames=2, food_list=None, seed=42):
+        if board_size != 10 or n_frames != 2:
+            raise ValueError("only board_size=10, n_frames=2 (the reference defaults, structs.jl:33) are supported")
+        self.n = int(n_envs)
+        self.device = torch.device("cuda", device)
+        self._h = C.c_void_p()
+        _check(lib().snk_create(C.byref(self._h), self.n, int(device), AUTO_RESET if auto_reset else 0))
+        self.auto_reset = bool(auto_reset)
+        self.use_stream(torch.cuda.current_stream(self.device))
+        if food_list is not None:
+            self.set_food_list(food_list)
+            self.reset()
+        if seed != 42:
+            _check(lib().snk_set_seed(self._h, int(seed)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().snk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def use_stream(self, stream):
+        """Run on a torch stream (so torch ops and env kernels are ordered)."""
+        _check(lib().snk_set_stream(self._h, C.c_void_p(stream.cuda_stream)))
+
+    def sync(self):
+        _check(lib().snk_sync(self._h))
+
+    def _new(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # -- structs.jl:33-99 -----------------------------------------------------------------------
+    def reset(self):
+        _check(lib().snk_reset(self._h))
+
+    def set_food_list(self, cells_rc):
+        """Inject the food_list (structs.jl:70): 1-based (row, col) pairs in 2..9, at most 64."""
+        flat = bytes(int(v) for rc in cells_rc for v in rc)
+        buf = (C.c_uint8 * max(len(flat), 1)).from_buffer_copy(flat or b"\0")
+        _check(lib().snk_set_food_list_host(self._h, buf, len(flat) // 2))
+
+    # -- utils.jl:7-10 --------------------------------------------------------------------------
+    def available_actions(self):
+        out = self._new((self.n, 3), torch.uint8)
+        _check(lib().snk_available_actions(self._h, _ptr(out)))
+        return out
+
+    # -- utils.jl:100-109 -----------------------------------------------------------------------
+    def step(self, act_idx):
+        """step!(game, available_actions(game)[act_idx]) -> (reward f32, done u8)"""
+        r, d = self._new((self.n,), torch.float32), self._new((self.n,), torch.uint8)
+        _check(lib().snk_step(self._h, _ptr(act_idx, torch.uint8, self.n, self.device), _ptr(r), _ptr(d)))
+        return r, d
+
+    def step_abs(self, dirs):
+        """step!(game, DIRS[dir]) with absolute directions (play_snake.jl:96-111)"""
+        r, d = self._new((self.n,), torch.float32), self._new((self.n,), torch.uint8)
+        _check(lib().snk_step_abs(self._h, _ptr(dirs, torch.uint8, self.n, self.device), _ptr(r), _ptr(d)))
+        return r, d
+
+    # -- the fused rollout step -----------------------------------------------------------------
+    def alloc_outputs(self, obs="f32", mask=True, ep_stats=False, act=False):
+        out = {"reward": self._new((self.n,), torch.float32), "done": self._new((self.n,), torch.uint8)}
+        if obs:
+            _, dt, per = _OBS[obs]
+            out["obs"] = self._new((self.n, 2, 10, 10) if per == 200 else (self.n, per), dt)
+            out["obs_fmt"] = obs
+        if mask:
+            out["mask"] = self._new((self.n, 3), torch.uint8)
+        if ep_stats:
+            out["ep_return"] = self._new((self.n,), torch.float32)
+            out["ep_score"] = self._new((self.n,), torch.int32)
+        if act:
+            out["act_idx"] = self._new((self.n,), torch.uint8)
+        return out
+
+    def step_fused(self, act_idx=None, q=None, eps=0.0, u=None, ridx=None, out=None, obs="f32"):
+        """One kernel: [epsilon_greedy] + step! + virtual_step + next_state (+ Float32 cast).
+
+        Either act_idx (N) u8 or q (N,3) f32 must be given.  Returns the `out` dict
+        (reward, done, obs, mask, ...); pass a dict from alloc_outputs() to reuse buffers.
+        """
+        if out is None:
+            out = self.alloc_outputs(obs=obs, act=q is not None)
+        fmt = _OBS[out["obs_fmt"]][0] if out.get("obs") is not None else OBS_NONE
+        dev = self.device
+        if q is not None:
+            act_p = _ptr(out.get("act_idx"), torch.uint8, self.n, dev)
+        else:
+            if act_idx is None:
+                raise ValueError("need act_idx or q")
+            act_p = _ptr(act_idx, torch.uint8, self.n, dev)
+        _check(lib().snk_step_fused(
+            self._h, _ptr(q, torch.float32, 3 * self.n, dev) if q is not None else None, float(eps),
+            _ptr(u, torch.float32, self.n, dev), _ptr(ridx, torch.uint8, self.n, dev), act_p,
+            _ptr(out.get("reward")), _ptr(out.get("done")), _ptr(out.get("obs")), fmt, _ptr(out.get("mask")),
+            _ptr(out.get("ep_return")), _ptr(out.get("ep_score"))))
+        return out
+
+    def step_fused_host(self, host, q=False, eps=0.0):
+        """Same through HOST (pinned) tensors: `host` is a dict of CPU tensors with the keys of
+        alloc_outputs() plus the inputs ('act_idx', or 'q' [+ 'u', 'ridx'])."""
+        fmt = _OBS[host["obs_fmt"]][0] if host.get("obs") is not None else OBS_NONE
+        g = lambda k: _ptr(host.get(k))
+        _check(lib().snk_step_fused_host(
+            self._h, g("q") if q else None, float(eps), g("u") if q else None, g("ridx") if q else None,
+            g("act_idx"), g("reward"), g("done"), g("obs"), fmt, g("mask"), g("ep_return"), g("ep_score")))
+        return host
+
+    # -- utils.jl:135-149 -----------------------------------------------------------------------
+    def assemble_state(self, fmt="f32"):
+        """(board_{t-1}, board_t) of every env: (N,2,10,10) [= Julia (10,10,2,N)]"""
+        code, dt, per = _OBS[fmt]
+        out = self._new((self.n, 2, 10, 10) if per == 200 else (self.n, per), dt)
+        _check(lib().snk_state(self._h, _ptr(out), code))
+        return out
+
+    # -- utils.jl:112-132 -----------------------------------------------------------------------
+    def virtual_step(self):
+        """next_is_suicidal (N,3) u8 for the current state"""
+        out = self._new((self.n, 3), torch.uint8)
+        _check(lib().snk_losing_mask(self._h, _ptr(out)))
+        return out
+
+    # -- utils.jl:153-172 -----------------------------------------------------------------------
+    def epsilon_greedy(self, q, eps, u=None, ridx=None):
+        """action index (N) u8: ridx where u < eps else argmax(q).  u/ridx None -> internal draws."""
+        out = self._new((self.n,), torch.uint8)
+        _check(lib().snk_select_action(self._h, _ptr(q, torch.float32, 3 * self.n, self.device), float(eps),
+                                       _ptr(u, torch.float32, self.n, self.device),
+                                       _ptr(ridx, torch.uint8, self.n, self.device), _ptr(out)))
+        return out
+
+    # -- fields ---------------------------------------------------------------------------------
+    def _scalar(self, fn, dtype):
+        out = self._new((self.n,), dtype)
+        _check(fn(self._h, _ptr(out)))
+        return out
+
+    @property
+    def score(self):
+        return self._scalar(lib().snk_get_score, torch.int32)
+
+    @property
+    def lost(self):
+        return self._scalar(lib().snk_get_done, torch.uint8)
+
+    @property
+    def error_flags(self):
+        return self._scalar(lib().snk_get_error_flags, torch.uint8)
+
+    @property
+    def steps(self):
+        return self._scalar(lib().snk_get_steps, torch.int32)
+
+    def count_errors(self):
+        c = C.c_int64(0)
+        _check(lib().snk_count_errors_host(self._h, C.byref(c)))
+        return c.value
+
+
+def masked_target(q_next, mask, rewards, dones, gamma=0.97, fill=-100.0, out_dtype=torch.float64):
+    """utils.jl:448-451: q_next[mask] .= -100; y = r + 0.97 * max_a q_next * (1 - done).
+
+    q_next (B,3) f32, mask (B,3) u8, rewards (B) f32, dones (B) u8 on one CUDA device.
+    Float64 result like the reference's broadcast (out_dtype=torch.float32 rounds it once).
+    """
+    B = rewards.numel()
+    dev = rewards.device
+    y = torch.empty(B, dtype=out_dtype, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _check(lib().snk_masked_target(
+            _ptr(q_next, torch.float32, 3 * B, dev), _ptr(mask, torch.uint8, 3 * B, dev),
+            _ptr(rewards, torch.float32, B, dev), _ptr(dones, torch.uint8, B, dev), float(gamma), float(fill),
+            _ptr(y) if out_dtype == torch.float64 else None, _ptr(y) if out_dtype == torch.float32 else None, B, st))
+    return y
+
+
+def center_columns(Dt):
+    """compute_D.jl:76-81 / la_utils.jl:163-169 on device.
+
+    Dt: (K, P) float64 torch-contiguous CUDA tensor = Julia's P x K column-major deviation_matrix
+    (row k of Dt is snapshot k).  Centred in place; returns (mean (P), var (P)).
+    """
+    K, P = Dt.shape
+    dev = Dt.device
+    mean = torch.empty(P, dtype=torch.float64, device=dev)
+    var = torch.empty(P, dtype=torch.float64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _check(lib().snk_center_columns(_ptr(Dt, torch.float64), P, K, _ptr(mean), _ptr(var), st))
+    return mean, var
+
+
+def pinned_empty(shape, dtype):
+    return torch.empty(shape, dtype=dtype, pin_memory=True)

@@ -1,0 +1,29 @@
+// common.h — error plumbing shared by the C-ABI translation units of libsnake_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "snake_b200.h"
+
+namespace snk {
+
+char *err_buf();                       // thread-local, 512 bytes
+int fail(int code, const char *fmt, ...);
+
+#define SNK_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return snk::fail(SNK_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,       \
+                             cudaGetErrorString(e__));                                         \
+    } while (0)
+
+#define SNK_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) return snk::fail(SNK_ERR_INVALID, "%s: %s", __func__, msg);               \
+    } while (0)
+
+typedef unsigned long long u64;
+
+}  // namespace snk

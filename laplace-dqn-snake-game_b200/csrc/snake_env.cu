@@ -1,0 +1,934 @@
+// snake_env.cu — batched Snake environment for B200 (sm_100a): kernels + C ABI.
+//
+// Replaces, for N independent envs at once, the reference's per-game Julia methods
+// (lucagiorgetti/Laplace-DQN-Snake-game):
+//   structs.jl:33-99   SnakeGame()            -> k_reset / auto-reset in k_step
+//   utils.jl:7-10      available_actions      -> av_dir(), k_available_actions
+//   utils.jl:13-40     sample_food!           -> food_search()
+//   utils.jl:43-109    update_board!/check_collision/grow_maybe!/move_wrapper!/step! -> env_step()
+//   utils.jl:112-132   virtual_step           -> losing_mask3()
+//   utils.jl:135-149   assemble_state(s)      -> board planes + expand_obs()
+//   utils.jl:153-172   epsilon_greedy         -> select_idx()
+//   utils.jl:448-451   masked max-Q target    -> k_masked_target
+//
+// Design: the game state is struct-of-arrays, 52 B/env:
+//   occ   u64  snake occupancy of the 8x8 interior, bit = (r-1) + 8(c-1)   (r,c 0-based board coords)
+//   pocc  u64  the same for the previous board (frame 1 of the two-frame state)
+//   clo/chi    128-bit chain of 2-bit directions, entry j = move that took segment j+1 to segment j
+//   cons  u64  which food_list entries have been used ("deleteat!") this episode
+//   misc  u64  head, tail, food, previous food (4-bit r,c each), prev_dir, length, step count, done, error bits
+//   ret   f32  running episode reward
+// One thread steps one env with bit-board arithmetic (phase A, coalesced 8-byte loads/stores), drops two
+// 100-cell boards as 2 bit-planes into shared memory, and then the whole CTA streams the (10,10,2,N)
+// observation out as fully coalesced 16-byte stores through a 256-entry nibble->float4 table (phase B).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.h"
+
+namespace snk {
+
+static thread_local char g_err[512];
+char *err_buf() { return g_err; }
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int TPB = 128;          // envs (= threads) per CTA
+constexpr int MAX_FOOD = 64;
+constexpr int PLANE_WORDS = 16;   // per env in smem: [frame 0/1][plane 0/1][4 x u32]
+
+// misc field layout
+constexpr int M_HR = 0, M_HC = 4, M_TR = 8, M_TC = 12, M_FR = 16, M_FC = 20, M_PFR = 24, M_PFC = 28;
+constexpr int M_PD = 32, M_LEN = 34, M_T = 41, M_DONE = 51, M_ERR = 52;
+
+// walls of the 10x10 board in full-board bit space k = r + 10 c
+constexpr u64 wall_bits(int lo_hi) {
+    u64 lo = 0, hi = 0;
+    for (int c = 0; c < 10; c++)
+        for (int r = 0; r < 10; r++)
+            if (r == 0 || r == 9 || c == 0 || c == 9) {
+                int k = r + 10 * c;
+                if (k < 64) lo |= 1ull << k; else hi |= 1ull << (k - 64);
+            }
+    return lo_hi ? hi : lo;
+}
+constexpr u64 WALL_LO = wall_bits(0), WALL_HI = wall_bits(1);
+
+// R1 initial state (structs.jl:37-66): snake [(8,2),(9,2)] 1-based = head (7,1), tail (8,1) 0-based, food (4,5) -> (3,4)
+constexpr u64 INIT_OCC = (1ull << (6 + 0)) | (1ull << (7 + 0));
+constexpr u64 INIT_MISC = (7ull << M_HR) | (1ull << M_HC) | (8ull << M_TR) | (1ull << M_TC) | (3ull << M_FR) |
+                          (4ull << M_FC) | (3ull << M_PFR) | (4ull << M_PFC) | (0ull << M_PD) | (2ull << M_LEN);
+
+struct FoodTable {
+    uint8_t bit[MAX_FOOD];   // interior bit index of list entry i
+    int n;
+};
+
+struct EnvState {
+    u64 *occ, *pocc, *clo, *chi, *cons, *misc;
+    float *ret;
+};
+
+struct StepArgs {
+    EnvState s;
+    const uint8_t *act;      // input action (idx or abs dir) when !SELECT
+    const float *q;          // (3,N) when SELECT
+    const float *u;          // (N) or NULL
+    const uint8_t *ridx;     // (N) or NULL
+    float eps;
+    uint8_t *act_out;
+    float *reward;
+    uint8_t *done;
+    void *obs;
+    uint8_t *mask;
+    float *ep_return;
+    int32_t *ep_score;
+    long long env_begin, env_end;
+    u64 seed, step_counter;
+    int auto_reset, is_abs;
+    FoodTable food;
+};
+
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ void dir_delta(int d, int &dr, int &dc) {   // utils.jl:8 order U D L R
+    int s = (d & 1) ? 1 : -1;
+    dr = (d & 2) ? 0 : s;
+    dc = (d & 2) ? s : 0;
+}
+// available_actions (utils.jl:7-10): [U,D,L,R] minus the reverse of prev_dir, order kept
+__device__ __forceinline__ int av_dir(int prev_dir, int idx) { return idx + (idx >= (prev_dir ^ 1) ? 1 : 0); }
+
+__device__ __forceinline__ int chain_get(u64 lo, u64 hi, int i) {
+    int pos = 2 * i;
+    return (int)(((pos < 64) ? (lo >> pos) : (hi >> (pos - 64))) & 3ull);
+}
+
+// sample_food! (utils.jl:13-40): first not-yet-used list entry whose cell is empty on the pre-update board.
+// blocked = cells that are not 0 there (old snake incl. tail, and the eaten food cell).  Returns the list
+// index or -1 (BoundsError in the reference), -2 when no cell is empty at all (utils.jl:18-21).
+__device__ __forceinline__ int food_search(u64 blocked, u64 cons, u64 list_mask, const uint8_t *s_food_bit) {
+    if (~blocked == 0ull) return -2;
+    u64 cand = ~cons & list_mask;
+    while (cand) {
+        int i = __ffsll((long long)cand) - 1;
+        if (!((blocked >> s_food_bit[i]) & 1ull)) return i;
+        cand &= cand - 1;
+    }
+    return -1;
+}
+
+// Julia argmax over 3 Float32 (findmax with isless: first maximum, NaN largest, -0.0 < 0.0)
+__device__ __forceinline__ bool jl_isless(float a, float b) {
+    if (a != a) return false;
+    if (b != b) return true;
+    if (a < b) return true;
+    if (a == b) return (__float_as_uint(a) >> 31) && !(__float_as_uint(b) >> 31);
+    return false;
+}
+__device__ __forceinline__ int select_idx(float q0, float q1, float q2, float eps, float u, int ridx) {
+    if (u < eps) return ridx;
+    int best = 0;
+    float qb = q0;
+    if (jl_isless(qb, q1)) { best = 1; qb = q1; }
+    if (jl_isless(qb, q2)) { best = 2; }
+    return best;
+}
+__device__ __forceinline__ void internal_draw(u64 seed, u64 step, long long env, float &u, int &ridx) {
+    u64 x = splitmix64(seed ^ splitmix64((u64)env * 0x100000001B3ull + step));
+    u = (float)(x >> 40) * 5.9604644775390625e-08f;   // 24 bits -> [0,1)
+    ridx = (int)((x & 0xFFFFFFull) % 3ull);
+}
+
+// 8x8 interior bitmap -> 10x10 full-board bit space (k = r + 10c = b + 2(c-1) + 11)
+__device__ __forceinline__ void to_full(u64 occ, u64 &lo, u64 &hi) {
+    u64 b0 = occ & 0xFF, b1 = (occ >> 8) & 0xFF, b2 = (occ >> 16) & 0xFF, b3 = (occ >> 24) & 0xFF;
+    u64 b4 = (occ >> 32) & 0xFF, b5 = (occ >> 40) & 0xFF, b6 = (occ >> 48) & 0xFF, b7 = occ >> 56;
+    lo = (b0 << 11) | (b1 << 21) | (b2 << 31) | (b3 << 41) | (b4 << 51) | (b5 << 61);
+    hi = (b5 >> 3) | (b6 << 7) | (b7 << 17);
+}
+__device__ __forceinline__ void set_k(int r, int c, u64 &lo, u64 &hi) {
+    int k = r + 10 * c;
+    u64 b = 1ull << (k & 63);
+    if (k < 64) lo |= b; else hi |= b;
+}
+// Two bit-planes of one board, code = 2*p1 + p0: 0 empty, 1 snake, 2 food, 3 wall.  The head is drawn last
+// as snake, which reproduces update_board! overwriting the wall cell on a wall death (utils.jl:48-50).
+__device__ __forceinline__ void board_planes(u64 occ, int fr, int fc, bool has_head, int hr, int hc, uint32_t *dst) {
+    u64 slo, shi;
+    to_full(occ, slo, shi);
+    if (has_head) set_k(hr, hc, slo, shi);
+    u64 flo = WALL_LO, fhi = WALL_HI;
+    if (fr != 0) set_k(fr, fc, flo, fhi);
+    u64 p0lo = slo | WALL_LO, p0hi = shi | WALL_HI;
+    u64 p1lo = flo & ~slo, p1hi = fhi & ~shi;
+    uint4 a = make_uint4((uint32_t)p0lo, (uint32_t)(p0lo >> 32), (uint32_t)p0hi, (uint32_t)(p0hi >> 32));
+    uint4 b = make_uint4((uint32_t)p1lo, (uint32_t)(p1lo >> 32), (uint32_t)p1hi, (uint32_t)(p1hi >> 32));
+    reinterpret_cast<uint4 *>(dst)[0] = a;
+    reinterpret_cast<uint4 *>(dst)[1] = b;
+}
+
+__device__ __forceinline__ int cell_code(const uint32_t *pl, int k) {
+    return (int)(((pl[k >> 5] >> (k & 31)) & 1u) | (((pl[4 + (k >> 5)] >> (k & 31)) & 1u) << 1));
+}
+__device__ __forceinline__ int code_value(int code) { return code == 3 ? -1 : code; }
+
+// ------------------------------------------------------------------------------------------------
+// Phase B: the CTA streams n_local envs' two boards out of shared memory in the requested format.
+// The CTA's output region is contiguous (envs env0 .. env0+n_local-1), so unit j of the region is
+// stored by thread j % TPB: every warp-wide store covers one contiguous 512-byte (f32) span.
+struct ObsTables {
+    float4 f32[256];         // (n1<<4 | n0) -> 4 cells as Float32
+};
+template <int OBS>
+__device__ __forceinline__ void fill_tables(ObsTables &tb, int tid) {
+    if (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I8 || OBS == SNK_OBS_PACKED2) {
+        for (int i = tid; i < 256; i += TPB) {
+            int n0 = i & 15, n1 = i >> 4;
+            float v[4];
+            uint32_t bytes = 0, packed = 0;
+            for (int j = 0; j < 4; j++) {
+                int code = ((n0 >> j) & 1) | (((n1 >> j) & 1) << 1);
+                v[j] = (float)code_value(code);
+                bytes |= (uint32_t)(uint8_t)(int8_t)code_value(code) << (8 * j);
+                packed |= (uint32_t)code << (2 * j);
+            }
+            if (OBS == SNK_OBS_F32) tb.f32[i] = make_float4(v[0], v[1], v[2], v[3]);
+            else if (OBS == SNK_OBS_I8) reinterpret_cast<uint32_t *>(tb.f32)[i] = bytes;
+            else reinterpret_cast<uint8_t *>(tb.f32)[i] = (uint8_t)packed;
+        }
+    }
+}
+
+template <int OBS>
+__device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_local, const uint32_t *s_planes,
+                                           const ObsTables &tb, int tid) {
+    if (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I8 || OBS == SNK_OBS_PACKED2) {
+        // unit = 4 consecutive cells = one nibble of each plane; 50 units per env
+        const int total = n_local * 50;
+        float4 *o32 = reinterpret_cast<float4 *>(obs) + env0 * 50;
+        uint32_t *o8 = reinterpret_cast<uint32_t *>(obs) + env0 * 50;
+        uint8_t *op = reinterpret_cast<uint8_t *>(obs) + env0 * 50;
+#pragma unroll 5
+        for (int j = tid; j < total; j += TPB) {
+            int e = (int)(((unsigned)j * 5243u) >> 18);     // j / 50 for j < 2^15
+            int qq = j - e * 50;
+            int f = qq >= 25;
+            int q = qq - 25 * f;
+            const uint32_t *pl = s_planes + e * PLANE_WORDS + f * 8;
+            int w = q >> 3, sh = (q & 7) * 4;
+            uint32_t idx = ((pl[w] >> sh) & 15u) | (((pl[4 + w] >> sh) & 15u) << 4);
+            if (OBS == SNK_OBS_F32) __stcs(o32 + j, tb.f32[idx]);
+            else if (OBS == SNK_OBS_I8) __stcs(o8 + j, reinterpret_cast<const uint32_t *>(tb.f32)[idx]);
+            else op[j] = reinterpret_cast<const uint8_t *>(tb.f32)[idx];
+        }
+    } else if (OBS == SNK_OBS_I64) {
+        // unit = 2 consecutive cells (16 bytes); 100 units per env
+        const int total = n_local * 100;
+        longlong2 *o = reinterpret_cast<longlong2 *>(obs) + env0 * 100;
+        for (int j = tid; j < total; j += TPB) {
+            int e = j / 100;
+            int p = j - e * 100;
+            int f = p >= 50;
+            int k = 2 * (p - 50 * f);
+            const uint32_t *pl = s_planes + e * PLANE_WORDS + f * 8;
+            longlong2 v;
+            v.x = code_value(cell_code(pl, k));
+            v.y = code_value(cell_code(pl, k + 1));
+            __stcs(o + j, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losing mask of a live state (virtual_step, utils.jl:112-132), closed form:
+// action k loses iff it hits a wall, or hits the body after the conditional tail pop, or the
+// history-length rule fires (t >= 499 steps already taken).  A virtual eat runs sample_food! on the
+// copy, which can raise the reference's BoundsError -> error bit.
+__device__ __forceinline__ uint32_t losing_mask3(u64 occ, u64 cons, int hr, int hc, int tr, int tc, int fr, int fc,
+                                                 int pd, int t, u64 list_mask, const uint8_t *s_food_bit, int &err) {
+    const bool cap = t >= 499;
+    const u64 occ_nt = occ & ~(1ull << ((tr - 1) + 8 * (tc - 1)));
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int d = av_dir(pd, k), dr, dc;
+        dir_delta(d, dr, dc);
+        int nr = hr + dr, nc = hc + dc;
+        bool lose;
+        if (nr == 0 || nr == 9 || nc == 0 || nc == 9) {
+            lose = true;
+        } else {
+            int b = (nr - 1) + 8 * (nc - 1);
+            if (fr != 0 && nr == fr && nc == fc) {
+                lose = cap;
+                if (food_search(occ | (1ull << b), cons, list_mask, s_food_bit) == -1) err |= SNK_ENV_ERR_FOOD;
+            } else {
+                lose = cap || ((occ_nt >> b) & 1ull);
+            }
+        }
+        m |= (lose ? 1u : 0u) << k;
+    }
+    return m;
+}
+
+template <int OBS, bool SELECT>
+__global__ void __launch_bounds__(TPB) k_step(const __grid_constant__ StepArgs a) {
+    __shared__ __align__(16) uint32_t s_planes[TPB * PLANE_WORDS];
+    __shared__ ObsTables s_tb;
+    __shared__ uint8_t s_food_bit[MAX_FOOD];
+
+    const int tid = threadIdx.x;
+    const long long env0 = a.env_begin + (long long)blockIdx.x * TPB;
+    const long long rem = a.env_end - env0;
+    const int n_local = rem < TPB ? (int)rem : TPB;
+    const long long env = env0 + tid;
+
+    if (tid < MAX_FOOD) s_food_bit[tid] = a.food.bit[tid];
+    if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid);
+    __syncthreads();
+
+    if (tid < n_local) {
+        // ---- phase A: one thread, one env ------------------------------------------------------
+        u64 occ = a.s.occ[env], pocc = a.s.pocc[env], clo = a.s.clo[env], chi = a.s.chi[env];
+        u64 cons = a.s.cons[env], misc = a.s.misc[env];
+        float ret = a.s.ret[env];
+        int hr = (int)(misc >> M_HR) & 15, hc = (int)(misc >> M_HC) & 15;
+        int tr = (int)(misc >> M_TR) & 15, tc = (int)(misc >> M_TC) & 15;
+        int fr = (int)(misc >> M_FR) & 15, fc = (int)(misc >> M_FC) & 15;
+        int pfr = (int)(misc >> M_PFR) & 15, pfc = (int)(misc >> M_PFC) & 15;
+        int pd = (int)(misc >> M_PD) & 3, len = (int)(misc >> M_LEN) & 127, t = (int)(misc >> M_T) & 1023;
+        int dn = (int)(misc >> M_DONE) & 1, err = (int)(misc >> M_ERR) & 15;
+        const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
+
+        int aidx;
+        if (SELECT) {
+            float q0 = a.q[3 * env], q1 = a.q[3 * env + 1], q2 = a.q[3 * env + 2];
+            float u;
+            int ri;
+            if (a.u != nullptr && a.ridx != nullptr) {
+                u = a.u[env];
+                ri = a.ridx[env];
+            } else {
+                internal_draw(a.seed, a.step_counter, env, u, ri);
+                if (a.u != nullptr) u = a.u[env];
+                if (a.ridx != nullptr) ri = a.ridx[env];
+            }
+            aidx = select_idx(q0, q1, q2, a.eps, u, ri);
+            if (a.act_out != nullptr) a.act_out[env] = (uint8_t)aidx;
+        } else {
+            aidx = a.act[env];
+        }
+
+        float reward = 0.0f;
+        uint32_t m3 = 7u;
+        if (!dn) {
+            int d;
+            if (a.is_abs) {
+                d = aidx;
+                if (d > 3) { err |= SNK_ENV_ERR_ACTION; d = 0; }
+            } else {
+                if (aidx > 2) { err |= SNK_ENV_ERR_ACTION; aidx = 0; }
+                d = av_dir(pd, aidx);
+            }
+            // grow_maybe! (utils.jl:66-81) on the board of the previous step
+            int dr, dc;
+            dir_delta(d, dr, dc);
+            const int nr = hr + dr, nc = hc + dc;
+            const bool wall = (nr == 0) | (nr == 9) | (nc == 0) | (nc == 9);
+            const u64 nbit = wall ? 0ull : (1ull << ((nr - 1) + 8 * (nc - 1)));
+            const bool eat = (fr != 0) & (nr == fr) & (nc == fc);
+            const bool reverse = d == (pd ^ 1);                     // utils.jl:57, third clause
+            pocc = occ; pfr = fr; pfc = fc;                        // this board becomes frame 1
+            chi = (chi << 2) | (clo >> 62);                         // pushfirst!(snake, new_head)
+            clo = (clo << 2) | (u64)d;
+            len++;
+            bool self = false;
+            if (eat) {
+                reward = 1.0f;                                      // eating_reward
+                fr = 0; fc = 0;
+                int i = food_search(occ | nbit, cons, list_mask, s_food_bit);
+                if (i >= 0) {
+                    cons |= 1ull << i;                              // deleteat!(food_list, idx)
+                    int b = s_food_bit[i];
+                    fr = (b & 7) + 1; fc = (b >> 3) + 1;
+                } else if (i == -1) {
+                    err |= SNK_ENV_ERR_FOOD;
+                }
+                occ |= nbit;
+            } else {
+                occ &= ~(1ull << ((tr - 1) + 8 * (tc - 1)));        // remove_tail!
+                int e = chain_get(clo, chi, len - 2), er, ec;
+                dir_delta(e, er, ec);
+                tr += er; tc += ec;
+                len--;
+                reward = -0.01f;                                    // male_di_vivere
+                self = (occ & nbit) != 0ull;                        // count(==(head), snake) > 1
+                occ |= nbit;
+            }
+            t++;
+            const bool lost = wall | self | reverse | (t >= 500);   // utils.jl:88 (history length > 500)
+            if (lost) reward = -1.0f;                               // suicide_penalty
+            hr = nr; hc = nc; pd = d; dn = lost;
+            ret += reward;
+            if (!lost) m3 = losing_mask3(occ, cons, hr, hc, tr, tc, fr, fc, pd, t, list_mask, s_food_bit, err);
+        }
+
+        if (a.reward != nullptr) a.reward[env] = reward;
+        if (a.done != nullptr) a.done[env] = (uint8_t)dn;
+        if (a.mask != nullptr) {
+            a.mask[3 * env + 0] = (uint8_t)(m3 & 1u);
+            a.mask[3 * env + 1] = (uint8_t)((m3 >> 1) & 1u);
+            a.mask[3 * env + 2] = (uint8_t)((m3 >> 2) & 1u);
+        }
+        if (a.ep_return != nullptr) a.ep_return[env] = ret;
+        if (a.ep_score != nullptr) a.ep_score[env] = len - 2;
+
+        if (OBS != SNK_OBS_NONE) {
+            board_planes(pocc, pfr, pfc, false, 0, 0, s_planes + tid * PLANE_WORDS);
+            board_planes(occ, fr, fc, true, hr, hc, s_planes + tid * PLANE_WORDS + 8);
+        }
+
+        if (dn && a.auto_reset) {                                   // a fresh SnakeGame() (utils.jl:199)
+            occ = INIT_OCC; pocc = INIT_OCC; clo = 0; chi = 0; cons = 0; ret = 0.0f;
+            misc = INIT_MISC | ((u64)err << M_ERR);
+        } else {
+            misc = ((u64)hr << M_HR) | ((u64)hc << M_HC) | ((u64)tr << M_TR) | ((u64)tc << M_TC) | ((u64)fr << M_FR) |
+                   ((u64)fc << M_FC) | ((u64)pfr << M_PFR) | ((u64)pfc << M_PFC) | ((u64)pd << M_PD) |
+                   ((u64)len << M_LEN) | ((u64)t << M_T) | ((u64)dn << M_DONE) | ((u64)err << M_ERR);
+        }
+        a.s.occ[env] = occ; a.s.pocc[env] = pocc; a.s.clo[env] = clo; a.s.chi[env] = chi;
+        a.s.cons[env] = cons; a.s.misc[env] = misc; a.s.ret[env] = ret;
+    }
+
+    if (OBS != SNK_OBS_NONE) {
+        __syncthreads();
+        expand_obs<OBS>(a.obs, env0, n_local, s_planes, s_tb, tid);
+    }
+}
+
+// ---- stand-alone views of the state ------------------------------------------------------------
+template <int OBS>
+__global__ void __launch_bounds__(TPB) k_state(EnvState s, long long n, void *obs) {
+    __shared__ __align__(16) uint32_t s_planes[TPB * PLANE_WORDS];
+    __shared__ ObsTables s_tb;
+    const int tid = threadIdx.x;
+    const long long env0 = (long long)blockIdx.x * TPB;
+    const int n_local = (n - env0) < TPB ? (int)(n - env0) : TPB;
+    fill_tables<OBS>(s_tb, tid);
+    if (tid < n_local) {
+        long long env = env0 + tid;
+        u64 misc = s.misc[env];
+        board_planes(s.pocc[env], (int)(misc >> M_PFR) & 15, (int)(misc >> M_PFC) & 15, false, 0, 0,
+                     s_planes + tid * PLANE_WORDS);
+        board_planes(s.occ[env], (int)(misc >> M_FR) & 15, (int)(misc >> M_FC) & 15, true, (int)(misc >> M_HR) & 15,
+                     (int)(misc >> M_HC) & 15, s_planes + tid * PLANE_WORDS + 8);
+    }
+    __syncthreads();
+    expand_obs<OBS>(obs, env0, n_local, s_planes, s_tb, tid);
+}
+
+__global__ void k_reset(EnvState s, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    s.occ[i] = INIT_OCC; s.pocc[i] = INIT_OCC; s.clo[i] = 0; s.chi[i] = 0; s.cons[i] = 0;
+    s.misc[i] = INIT_MISC; s.ret[i] = 0.0f;
+}
+
+__global__ void k_available_actions(EnvState s, long long n, uint8_t *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int pd = (int)(s.misc[i] >> M_PD) & 3;
+    for (int k = 0; k < 3; k++) out[3 * i + k] = (uint8_t)av_dir(pd, k);
+}
+
+__global__ void k_losing_mask(EnvState s, long long n, uint8_t *out, FoodTable food) {
+    __shared__ uint8_t s_food_bit[MAX_FOOD];
+    if (threadIdx.x < MAX_FOOD) s_food_bit[threadIdx.x] = food.bit[threadIdx.x];
+    __syncthreads();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 misc = s.misc[i];
+    uint32_t m3 = 7u;
+    if (!((misc >> M_DONE) & 1ull)) {
+        int err = (int)(misc >> M_ERR) & 15, err0 = err;
+        const u64 list_mask = food.n >= 64 ? ~0ull : ((1ull << food.n) - 1ull);
+        m3 = losing_mask3(s.occ[i], s.cons[i], (int)(misc >> M_HR) & 15, (int)(misc >> M_HC) & 15,
+                          (int)(misc >> M_TR) & 15, (int)(misc >> M_TC) & 15, (int)(misc >> M_FR) & 15,
+                          (int)(misc >> M_FC) & 15, (int)(misc >> M_PD) & 3, (int)(misc >> M_T) & 1023, list_mask,
+                          s_food_bit, err);
+        if (err != err0) s.misc[i] = (misc & ~(15ull << M_ERR)) | ((u64)err << M_ERR);
+    }
+    out[3 * i + 0] = m3 & 1u; out[3 * i + 1] = (m3 >> 1) & 1u; out[3 * i + 2] = (m3 >> 2) & 1u;
+}
+
+__global__ void k_select(long long n, const float *q, float eps, const float *u, const uint8_t *ridx, u64 seed,
+                         u64 step, uint8_t *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float uu;
+    int ri;
+    internal_draw(seed, step, i, uu, ri);
+    if (u != nullptr) uu = u[i];
+    if (ridx != nullptr) ri = ridx[i];
+    out[i] = (uint8_t)select_idx(q[3 * i], q[3 * i + 1], q[3 * i + 2], eps, uu, ri);
+}
+
+// which: 0 score (i32), 1 done (u8), 2 error flags (u8), 3 steps (i32)
+__global__ void k_scalars(EnvState s, long long n, int which, void *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 misc = s.misc[i];
+    if (which == 0) ((int32_t *)out)[i] = ((int)(misc >> M_LEN) & 127) - 2;
+    else if (which == 1) ((uint8_t *)out)[i] = (uint8_t)((misc >> M_DONE) & 1ull);
+    else if (which == 2) ((uint8_t *)out)[i] = (uint8_t)((misc >> M_ERR) & 15ull);
+    else ((int32_t *)out)[i] = (int)(misc >> M_T) & 1023;
+}
+
+__global__ void k_count_errors(EnvState s, long long n, unsigned long long *count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool e = i < n && ((s.misc[i] >> M_ERR) & 15ull) != 0ull;
+    unsigned b = __ballot_sync(0xffffffffu, e);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
+}
+
+// masked max-Q target (utils.jl:448-451).  Base.max: NaN-propagating, +0.0 > -0.0.
+__device__ __forceinline__ float jl_max(float a, float b) {
+    if (a != a || b != b) return a + b;
+    if (a > b) return a;
+    if (b > a) return b;
+    return (__float_as_uint(a) >> 31) ? b : a;
+}
+__global__ void k_masked_target(const float *q, const uint8_t *mask, const float *r, const uint8_t *done, double gamma,
+                                float fill, double *y64, float *y32, long long B) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    float q0 = mask[3 * i] ? fill : q[3 * i];
+    float q1 = mask[3 * i + 1] ? fill : q[3 * i + 1];
+    float q2 = mask[3 * i + 2] ? fill : q[3 * i + 2];
+    float m = jl_max(jl_max(q0, q1), q2);
+    // @. rewards + 0.97 * max_next_q * (1 - dones): Float64 per element, left to right, no FMA
+    double tt = __dmul_rn(gamma, (double)m);
+    tt = __dmul_rn(tt, (double)(1 - (int)(done[i] != 0)));
+    double y = __dadd_rn((double)r[i], tt);
+    if (y64 != nullptr) y64[i] = y;
+    if (y32 != nullptr) y32[i] = (float)y;
+}
+
+}  // namespace snk
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace snk;
+
+struct snk_env {
+    long long n;
+    int device;
+    uint32_t flags;
+    EnvState s;
+    FoodTable food;            // active list
+    cudaStream_t own_stream, stream;
+    cudaStream_t copy_stream[2];
+    cudaEvent_t ev_in, ev_chunk[64], ev_done;
+    u64 seed, step_counter;
+    unsigned long long *d_count;
+    // staging for the _host entry points (allocated on first use)
+    float *d_q, *d_u, *d_reward, *d_ep_return;
+    uint8_t *d_ridx, *d_act, *d_done, *d_mask;
+    int32_t *d_ep_score;
+    void *d_obs;
+    size_t d_obs_bytes;
+};
+
+static const uint8_t kDefaultFoodRC[100] = {  // Xoshiro(42) list, structs.jl:70 (pinned by tests/test_oracle_golden.py)
+    7, 5, 5, 7, 7, 3, 6, 7, 5, 4, 7, 7, 4, 4, 6, 2, 4, 3, 5, 5, 2, 6, 3, 6, 5, 4, 5, 8, 4, 6, 4, 3, 7, 4,
+    2, 2, 7, 5, 7, 3, 6, 5, 8, 3, 4, 9, 4, 7, 8, 6, 4, 4, 6, 6, 4, 2, 2, 8, 9, 3, 7, 4, 4, 8, 7, 7, 4, 2,
+    3, 9, 4, 8, 7, 8, 2, 7, 2, 6, 9, 5, 9, 9, 7, 5, 8, 6, 4, 2, 7, 6, 4, 6, 8, 5, 2, 5, 2, 8, 9, 4};
+
+static int set_food(FoodTable &ft, const uint8_t *rc, int n) {
+    if (n < 0 || n > MAX_FOOD) return fail(SNK_ERR_INVALID, "food list length %d not in 0..64", n);
+    memset(&ft, 0, sizeof(ft));
+    for (int i = 0; i < n; i++) {
+        int r = rc[2 * i], c = rc[2 * i + 1];
+        if (r < 2 || r > 9 || c < 2 || c > 9) return fail(SNK_ERR_INVALID, "food cell %d = (%d,%d) outside 2..9", i, r, c);
+        ft.bit[i] = (uint8_t)((r - 2) + 8 * (c - 2));
+    }
+    ft.n = n;
+    return SNK_OK;
+}
+
+static inline unsigned nblocks(long long n, int tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+#define SNK_CHECK_HANDLE(h)                                                  \
+    do {                                                                     \
+        if ((h) == nullptr) return fail(SNK_ERR_INVALID, "%s: null handle", __func__); \
+        SNK_CUDA(cudaSetDevice((h)->device));                                \
+    } while (0)
+
+template <typename T>
+static cudaError_t ensure(T **p, size_t bytes) {
+    if (*p != nullptr) return cudaSuccess;
+    return cudaMalloc((void **)p, bytes);
+}
+
+extern "C" {
+
+int snk_version(void) { return SNK_VERSION; }
+const char *snk_last_error(void) { return err_buf(); }
+
+int snk_default_food_list_host(uint8_t *cells_rc_host, int *n) {
+    SNK_REQUIRE(cells_rc_host != nullptr && n != nullptr, "null argument");
+    memcpy(cells_rc_host, kDefaultFoodRC, 100);
+    *n = 50;
+    return SNK_OK;
+}
+
+int snk_create(snk_handle *out, int64_t n_envs, int device, uint32_t flags) {
+    SNK_REQUIRE(out != nullptr, "null out");
+    SNK_REQUIRE(n_envs > 0 && n_envs <= (1ll << 31), "n_envs must be in 1..2^31");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SNK_ERR_NODEVICE, "no CUDA device (%s); libsnake_b200 has no CPU fallback", cudaGetErrorString(e));
+    SNK_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    cudaDeviceProp prop;
+    SNK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(SNK_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    SNK_CUDA(cudaSetDevice(device));
+    snk_env *h = new (std::nothrow) snk_env();
+    if (h == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->n = n_envs; h->device = device; h->flags = flags; h->seed = 42;
+    set_food(h->food, kDefaultFoodRC, 50);
+    size_t n = (size_t)n_envs;
+    cudaError_t ce = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(p, bytes); };
+    A((void **)&h->s.occ, 8 * n); A((void **)&h->s.pocc, 8 * n); A((void **)&h->s.clo, 8 * n);
+    A((void **)&h->s.chi, 8 * n); A((void **)&h->s.cons, 8 * n); A((void **)&h->s.misc, 8 * n);
+    A((void **)&h->s.ret, 4 * n); A((void **)&h->d_count, 8);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && ce == cudaSuccess; i++) ce = cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+    for (int i = 0; i < 64 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming);
+    if (ce != cudaSuccess) {
+        int rc = fail(SNK_ERR_CUDA, "snk_create: %s", cudaGetErrorString(ce));
+        snk_destroy(h);
+        return rc;
+    }
+    h->stream = h->own_stream;
+    k_reset<<<nblocks(h->n, 256), 256, 0, h->stream>>>(h->s, h->n);
+    SNK_CUDA(cudaGetLastError());
+    *out = h;
+    return SNK_OK;
+}
+
+int snk_destroy(snk_handle h) {
+    if (h == nullptr) return SNK_OK;
+    cudaSetDevice(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    void *ptrs[] = {h->s.occ, h->s.pocc, h->s.clo, h->s.chi, h->s.cons, h->s.misc, h->s.ret, h->d_count, h->d_q, h->d_u,
+                    h->d_reward, h->d_ep_return, h->d_ridx, h->d_act, h->d_done, h->d_mask, h->d_ep_score, h->d_obs};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 2; i++) if (h->copy_stream[i]) cudaStreamDestroy(h->copy_stream[i]);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (int i = 0; i < 64; i++) if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return SNK_OK;
+}
+
+int snk_reset(snk_handle h) {
+    SNK_CHECK_HANDLE(h);
+    k_reset<<<nblocks(h->n, 256), 256, 0, h->stream>>>(h->s, h->n);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_set_food_list_host(snk_handle h, const uint8_t *cells_rc_host, int n) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(cells_rc_host != nullptr || n == 0, "null list");
+    FoodTable ft;
+    int rc = set_food(ft, cells_rc_host, n);
+    if (rc != SNK_OK) return rc;
+    SNK_CUDA(cudaStreamSynchronize(h->stream));   // kernels in flight carry the old table by value; just order the change
+    h->food = ft;
+    return SNK_OK;
+}
+
+int snk_set_stream(snk_handle h, void *cuda_stream) {
+    SNK_CHECK_HANDLE(h);
+    SNK_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return SNK_OK;
+}
+int snk_get_stream(snk_handle h, void **cuda_stream) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(cuda_stream != nullptr, "null out");
+    *cuda_stream = (void *)h->stream;
+    return SNK_OK;
+}
+int snk_set_seed(snk_handle h, uint64_t seed) {
+    SNK_CHECK_HANDLE(h);
+    h->seed = seed; h->step_counter = 0;
+    return SNK_OK;
+}
+int snk_sync(snk_handle h) {
+    SNK_CHECK_HANDLE(h);
+    SNK_CUDA(cudaStreamSynchronize(h->stream));
+    return SNK_OK;
+}
+int64_t snk_num_envs(snk_handle h) { return h ? h->n : 0; }
+
+int snk_available_actions(snk_handle h, uint8_t *dirs_3xN) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(dirs_3xN != nullptr, "null out");
+    k_available_actions<<<nblocks(h->n, 256), 256, 0, h->stream>>>(h->s, h->n, dirs_3xN);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+// launches the fused kernel for envs [begin, end) on `st`
+static int launch_step(snk_handle h, StepArgs &a, int obs_fmt, bool select, long long begin, long long end, cudaStream_t st) {
+    a.env_begin = begin; a.env_end = end;
+    unsigned grid = nblocks(end - begin, TPB);
+    if (grid == 0) return SNK_OK;
+#define SNK_LAUNCH(FMT)                                                        \
+    do {                                                                       \
+        if (select) k_step<FMT, true><<<grid, TPB, 0, st>>>(a);                \
+        else k_step<FMT, false><<<grid, TPB, 0, st>>>(a);                      \
+    } while (0)
+    switch (obs_fmt) {
+        case SNK_OBS_NONE: SNK_LAUNCH(SNK_OBS_NONE); break;
+        case SNK_OBS_F32: SNK_LAUNCH(SNK_OBS_F32); break;
+        case SNK_OBS_I8: SNK_LAUNCH(SNK_OBS_I8); break;
+        case SNK_OBS_I64: SNK_LAUNCH(SNK_OBS_I64); break;
+        case SNK_OBS_PACKED2: SNK_LAUNCH(SNK_OBS_PACKED2); break;
+        default: return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
+    }
+#undef SNK_LAUNCH
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+static void base_args(snk_handle h, StepArgs &a) {
+    memset(&a, 0, sizeof(a));
+    a.s = h->s; a.food = h->food; a.seed = h->seed; a.step_counter = h->step_counter;
+    a.auto_reset = (h->flags & SNK_AUTO_RESET) ? 1 : 0;
+}
+
+int snk_step(snk_handle h, const uint8_t *act_idx, float *reward, uint8_t *done) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(act_idx != nullptr, "null actions");
+    StepArgs a;
+    base_args(h, a);
+    a.act = act_idx; a.reward = reward; a.done = done;
+    int rc = launch_step(h, a, SNK_OBS_NONE, false, 0, h->n, h->stream);
+    h->step_counter++;
+    return rc;
+}
+
+int snk_step_abs(snk_handle h, const uint8_t *dir, float *reward, uint8_t *done) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(dir != nullptr, "null directions");
+    StepArgs a;
+    base_args(h, a);
+    a.act = dir; a.reward = reward; a.done = done; a.is_abs = 1;
+    int rc = launch_step(h, a, SNK_OBS_NONE, false, 0, h->n, h->stream);
+    h->step_counter++;
+    return rc;
+}
+
+int snk_step_fused(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx, uint8_t *act_idx,
+                   float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask, float *ep_return,
+                   int32_t *ep_score) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(q != nullptr || act_idx != nullptr, "need q (select) or act_idx (input)");
+    SNK_REQUIRE(obs_fmt == SNK_OBS_NONE || obs != nullptr, "obs_fmt given without an obs buffer");
+    SNK_REQUIRE(obs_fmt == SNK_OBS_NONE || ((uintptr_t)obs & 15u) == 0, "obs must be 16-byte aligned");
+    StepArgs a;
+    base_args(h, a);
+    a.q = q; a.eps = eps; a.u = u; a.ridx = ridx;
+    if (q != nullptr) a.act_out = act_idx; else a.act = act_idx;
+    a.reward = reward; a.done = done; a.obs = obs; a.mask = mask; a.ep_return = ep_return; a.ep_score = ep_score;
+    int rc = launch_step(h, a, obs ? obs_fmt : SNK_OBS_NONE, q != nullptr, 0, h->n, h->stream);
+    h->step_counter++;
+    return rc;
+}
+
+static size_t obs_bytes_per_env(int fmt) {
+    switch (fmt) {
+        case SNK_OBS_F32: return 800;
+        case SNK_OBS_I8: return 200;
+        case SNK_OBS_I64: return 1600;
+        case SNK_OBS_PACKED2: return 50;
+        default: return 0;
+    }
+}
+
+int snk_host_alloc(void **p, size_t bytes) {
+    SNK_REQUIRE(p != nullptr, "null out");
+    SNK_CUDA(cudaMallocHost(p, bytes));
+    return SNK_OK;
+}
+int snk_host_free(void *p) {
+    if (p) SNK_CUDA(cudaFreeHost(p));
+    return SNK_OK;
+}
+
+int snk_step_fused_host(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx, uint8_t *act_idx,
+                        float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask, float *ep_return,
+                        int32_t *ep_score) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(q != nullptr || act_idx != nullptr, "need q (select) or act_idx (input)");
+    SNK_REQUIRE(obs_fmt == SNK_OBS_NONE || obs != nullptr, "obs_fmt given without an obs buffer");
+    const size_t n = (size_t)h->n;
+    const size_t opb = obs ? obs_bytes_per_env(obs_fmt) : 0;
+    if (obs && opb == 0) return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
+    // device staging
+    SNK_CUDA(ensure(&h->d_act, n));
+    if (q) { SNK_CUDA(ensure(&h->d_q, 12 * n)); }
+    if (u) { SNK_CUDA(ensure(&h->d_u, 4 * n)); }
+    if (ridx) { SNK_CUDA(ensure(&h->d_ridx, n)); }
+    if (reward) { SNK_CUDA(ensure(&h->d_reward, 4 * n)); }
+    if (done) { SNK_CUDA(ensure(&h->d_done, n)); }
+    if (mask) { SNK_CUDA(ensure(&h->d_mask, 3 * n)); }
+    if (ep_return) { SNK_CUDA(ensure(&h->d_ep_return, 4 * n)); }
+    if (ep_score) { SNK_CUDA(ensure(&h->d_ep_score, 4 * n)); }
+    if (opb && h->d_obs_bytes < opb * n) {
+        if (h->d_obs) { SNK_CUDA(cudaStreamSynchronize(h->stream)); SNK_CUDA(cudaFree(h->d_obs)); h->d_obs = nullptr; }
+        SNK_CUDA(cudaMalloc(&h->d_obs, opb * n));
+        h->d_obs_bytes = opb * n;
+    }
+    cudaStream_t st = h->stream, c0 = h->copy_stream[0];
+    // inputs up (small: <= 17 B/env) on the compute stream
+    if (q) SNK_CUDA(cudaMemcpyAsync(h->d_q, q, 12 * n, cudaMemcpyHostToDevice, st));
+    if (u) SNK_CUDA(cudaMemcpyAsync(h->d_u, u, 4 * n, cudaMemcpyHostToDevice, st));
+    if (ridx) SNK_CUDA(cudaMemcpyAsync(h->d_ridx, ridx, n, cudaMemcpyHostToDevice, st));
+    if (!q) SNK_CUDA(cudaMemcpyAsync(h->d_act, act_idx, n, cudaMemcpyHostToDevice, st));
+    StepArgs a;
+    base_args(h, a);
+    a.q = q ? h->d_q : nullptr; a.eps = eps; a.u = u ? h->d_u : nullptr; a.ridx = ridx ? h->d_ridx : nullptr;
+    if (q) a.act_out = act_idx ? h->d_act : nullptr; else a.act = h->d_act;
+    a.reward = reward ? h->d_reward : nullptr; a.done = done ? h->d_done : nullptr; a.obs = opb ? h->d_obs : nullptr;
+    a.mask = mask ? h->d_mask : nullptr; a.ep_return = ep_return ? h->d_ep_return : nullptr;
+    a.ep_score = ep_score ? h->d_ep_score : nullptr;
+    // env chunks: kernel of chunk c+1 overlaps the device->host copy of chunk c
+    const long long align = TPB * 8;
+    int n_chunks = (int)((h->n + (1 << 16) - 1) >> 16);
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 16) n_chunks = 16;
+    long long per = ((h->n + n_chunks - 1) / n_chunks + align - 1) / align * align;
+    int ci = 0;
+    for (long long b = 0; b < h->n; b += per, ci++) {
+        long long e = b + per < h->n ? b + per : h->n;
+        int rc = launch_step(h, a, opb ? obs_fmt : SNK_OBS_NONE, q != nullptr, b, e, st);
+        if (rc != SNK_OK) return rc;
+        SNK_CUDA(cudaEventRecord(h->ev_chunk[ci], st));
+        SNK_CUDA(cudaStreamWaitEvent(c0, h->ev_chunk[ci], 0));
+        size_t nb = (size_t)(e - b);
+        if (opb) SNK_CUDA(cudaMemcpyAsync((char *)obs + opb * b, (char *)h->d_obs + opb * b, opb * nb, cudaMemcpyDeviceToHost, c0));
+        if (mask) SNK_CUDA(cudaMemcpyAsync(mask + 3 * b, h->d_mask + 3 * b, 3 * nb, cudaMemcpyDeviceToHost, c0));
+        if (reward) SNK_CUDA(cudaMemcpyAsync(reward + b, h->d_reward + b, 4 * nb, cudaMemcpyDeviceToHost, c0));
+        if (done) SNK_CUDA(cudaMemcpyAsync(done + b, h->d_done + b, nb, cudaMemcpyDeviceToHost, c0));
+        if (ep_return) SNK_CUDA(cudaMemcpyAsync(ep_return + b, h->d_ep_return + b, 4 * nb, cudaMemcpyDeviceToHost, c0));
+        if (ep_score) SNK_CUDA(cudaMemcpyAsync(ep_score + b, h->d_ep_score + b, 4 * nb, cudaMemcpyDeviceToHost, c0));
+        if (q && act_idx) SNK_CUDA(cudaMemcpyAsync(act_idx + b, h->d_act + b, nb, cudaMemcpyDeviceToHost, c0));
+    }
+    h->step_counter++;
+    // make the handle's stream wait for the copies, so snk_sync() covers the whole call
+    SNK_CUDA(cudaEventRecord(h->ev_done, c0));
+    SNK_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+    return SNK_OK;
+}
+
+int snk_state(snk_handle h, void *obs, int obs_fmt) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(obs != nullptr, "null out");
+    SNK_REQUIRE(((uintptr_t)obs & 15u) == 0, "obs must be 16-byte aligned");
+    unsigned grid = nblocks(h->n, TPB);
+    switch (obs_fmt) {
+        case SNK_OBS_F32: k_state<SNK_OBS_F32><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
+        case SNK_OBS_I8: k_state<SNK_OBS_I8><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
+        case SNK_OBS_I64: k_state<SNK_OBS_I64><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
+        case SNK_OBS_PACKED2: k_state<SNK_OBS_PACKED2><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
+        default: return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
+    }
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_losing_mask(snk_handle h, uint8_t *mask_3xN) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(mask_3xN != nullptr, "null out");
+    k_losing_mask<<<nblocks(h->n, 256), 256, 0, h->stream>>>(h->s, h->n, mask_3xN, h->food);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_select_action(snk_handle h, const float *q_3xN, float eps, const float *u, const uint8_t *ridx,
+                      uint8_t *act_idx_out) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(q_3xN != nullptr && act_idx_out != nullptr, "null argument");
+    k_select<<<nblocks(h->n, 256), 256, 0, h->stream>>>(h->n, q_3xN, eps, u, ridx, h->seed, h->step_counter, act_idx_out);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_masked_target(const float *q_next_3xB, const uint8_t *mask_3xB, const float *r, const uint8_t *done, double gamma,
+                      float fill, double *y_f64, float *y_f32, int64_t B, void *cuda_stream) {
+    SNK_REQUIRE(q_next_3xB && mask_3xB && r && done, "null input");
+    SNK_REQUIRE(y_f64 || y_f32, "no output requested");
+    SNK_REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return SNK_OK;
+    k_masked_target<<<nblocks(B, 256), 256, 0, (cudaStream_t)cuda_stream>>>(q_next_3xB, mask_3xB, r, done, gamma, fill,
+                                                                          y_f64, y_f32, B);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+static int scalars(snk_handle h, int which, void *out) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(out != nullptr, "null out");
+    k_scalars<<<nblocks(h->n, 256), 256, 0, h->stream>>>(h->s, h->n, which, out);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+int snk_get_score(snk_handle h, int32_t *score) { return scalars(h, 0, score); }
+int snk_get_done(snk_handle h, uint8_t *done) { return scalars(h, 1, done); }
+int snk_get_error_flags(snk_handle h, uint8_t *flags) { return scalars(h, 2, flags); }
+int snk_get_steps(snk_handle h, int32_t *steps) { return scalars(h, 3, steps); }
+
+int snk_count_errors_host(snk_handle h, int64_t *count) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(count != nullptr, "null out");
+    SNK_CUDA(cudaMemsetAsync(h->d_count, 0, 8, h->stream));
+    k_count_errors<<<nblocks(h->n, 256), 256, 0, h->stream>>>(h->s, h->n, h->d_count);
+    SNK_CUDA(cudaGetLastError());
+    unsigned long long c = 0;
+    SNK_CUDA(cudaMemcpyAsync(&c, h->d_count, 8, cudaMemcpyDeviceToHost, h->stream));
+    SNK_CUDA(cudaStreamSynchronize(h->stream));
+    *count = (int64_t)c;
+    return SNK_OK;
+}
+
+}  // extern "C"

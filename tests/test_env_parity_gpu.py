@@ -1,0 +1,397 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle — bit-exact.
+
+Every call goes ctypes -> libsnake_b200.so; the oracle is only the checker.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_lib as O
+from tests.util import bits, pkg, synth_actions, unpack2
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp_step(out, ref, n, t, obs_key="obs_f32"):
+    assert np.array_equal(bits(out["reward"].cpu().numpy()), bits(ref["reward"])), ("reward", t)
+    assert np.array_equal(out["done"].cpu().numpy(), ref["done"]), ("done", t)
+    if "mask" in out:
+        assert np.array_equal(out["mask"].cpu().numpy(), ref["mask"]), ("mask", t)
+    if "ep_return" in out:
+        assert np.array_equal(bits(out["ep_return"].cpu().numpy()), bits(ref["ep_return"])), ("ep_return", t)
+        assert np.array_equal(out["ep_score"].cpu().numpy(), ref["ep_score"]), ("ep_score", t)
+    if obs_key and out.get("obs") is not None:
+        got = out["obs"].cpu().numpy().reshape(n, -1)
+        assert np.array_equal(got, ref[obs_key]), ("obs", t)
+
+
+def test_config2_4096_envs_fused_step_bit_exact():
+    """BASELINE config 2: 4,096 envs, uniform random actions, f32 two-frame obs + mask, auto-reset."""
+    S = pkg()
+    n, steps = 4096, 2000
+    env = S.SnakeGame(n, auto_reset=True)
+    ora = O.OracleBatch(n, auto_reset=True)
+    out = env.alloc_outputs(obs="f32", mask=True, ep_stats=True)
+    n_done = n_eat = 0
+    for t in range(steps):
+        act = synth_actions(n, t)
+        env.step_fused(act_idx=torch.from_numpy(act).cuda(), out=out)
+        ref = ora.step(act)
+        _cmp_step(out, ref, n, t)
+        n_done += int(ref["done"].sum())
+        n_eat += int((ref["reward"] == 1.0).sum())
+    assert n_done > 1000 and n_eat > 1000            # the trace really exercises deaths and eats
+    sc = ora.scalars()
+    assert np.array_equal(env.score.cpu().numpy(), sc["score"])
+    assert np.array_equal(env.lost.cpu().numpy(), sc["lost"])
+    assert np.array_equal(env.steps.cpu().numpy(), sc["n_hist"] - 2)
+    assert env.count_errors() == 0 and not sc["error"].any()
+    assert np.array_equal(env.assemble_state("f32").cpu().numpy().reshape(n, 200), ora.state("f32"))
+    assert np.array_equal(env.virtual_step().cpu().numpy(), ora.losing_mask()[0])
+    assert np.array_equal(env.available_actions().cpu().numpy(), ora.available_actions())
+
+
+def test_config1_single_env_10k_steps_trace():
+    """BASELINE config 1: one env, 10,000 random-action steps, new game on loss; full per-step trace."""
+    S = pkg()
+    env = S.SnakeGame(1, auto_reset=True)
+    ora = O.OracleBatch(1, auto_reset=True)
+    out = env.alloc_outputs(obs="i8", mask=True, ep_stats=True)
+    rng = np.random.default_rng(1)
+    acts = rng.integers(0, 3, 10000).astype(np.uint8)
+    got = {k: [] for k in ("reward", "done", "mask", "obs", "ep_score")}
+    for t in range(10000):
+        env.step_fused(act_idx=torch.from_numpy(acts[t:t + 1]).cuda(), out=out)
+        for k in got:
+            got[k].append(out[k].clone())
+    torch.cuda.synchronize()
+    for t in range(10000):
+        ref = ora.step(acts[t:t + 1], obs=("i8",))
+        assert bits(got["reward"][t].cpu().numpy())[0] == bits(ref["reward"])[0], t
+        assert got["done"][t].item() == ref["done"][0], t
+        assert np.array_equal(got["mask"][t].cpu().numpy(), ref["mask"]), t
+        assert np.array_equal(got["obs"][t].cpu().numpy().reshape(1, 200), ref["obs_i8"]), t
+        assert got["ep_score"][t].item() == ref["ep_score"][0], t
+
+
+@pytest.mark.parametrize("fmt", ["i8", "i64", "packed2", "f32"])
+@pytest.mark.parametrize("n", [1, 127, 129, 1000])
+def test_obs_formats_and_ragged_sizes(fmt, n):
+    S = pkg()
+    env = S.SnakeGame(n, auto_reset=True)
+    ora = O.OracleBatch(n, auto_reset=True)
+    out = env.alloc_outputs(obs=fmt, mask=True)
+    for t in range(150):
+        act = synth_actions(n, t, seed=7)
+        env.step_fused(act_idx=torch.from_numpy(act).cuda(), out=out)
+        ref = ora.step(act, obs=("i8", "i64", "f32"))
+        got = out["obs"].cpu().numpy().reshape(n, -1)
+        if fmt == "packed2":
+            assert np.array_equal(unpack2(got), ref["obs_i8"]), t
+        else:
+            assert np.array_equal(got, ref["obs_" + fmt]), t
+        _cmp_step(out, ref, n, t, obs_key=None)
+    st = env.assemble_state(fmt).cpu().numpy().reshape(n, -1)
+    want = ora.state("i8") if fmt == "packed2" else ora.state(fmt)
+    assert np.array_equal(unpack2(st) if fmt == "packed2" else st, want)
+
+
+def test_plain_step_and_no_auto_reset():
+    """step! without auto-reset: a lost env is frozen (reward 0, done 1, mask trues(3), terminal boards)."""
+    S = pkg()
+    n = 513
+    env = S.SnakeGame(n, auto_reset=False)
+    ora = O.OracleBatch(n, auto_reset=False)
+    for t in range(120):
+        act = synth_actions(n, t, seed=3)
+        r, d = env.step(torch.from_numpy(act).cuda())
+        ref = ora.step(act)
+        assert np.array_equal(bits(r.cpu().numpy()), bits(ref["reward"])), t
+        assert np.array_equal(d.cpu().numpy(), ref["done"]), t
+        if t % 10 == 0:
+            assert np.array_equal(env.assemble_state("i8").cpu().numpy().reshape(n, 200), ora.state("i8")), t
+            assert np.array_equal(env.virtual_step().cpu().numpy(), ora.losing_mask()[0]), t
+    assert ref["done"].all()          # random play never survives 120 steps in all envs... all are lost by now
+    assert np.array_equal(env.score.cpu().numpy(), ora.scalars()["score"])
+    env.reset(); ora.reset()
+    assert np.array_equal(env.assemble_state("i8").cpu().numpy().reshape(n, 200), ora.state("i8"))
+    assert not env.lost.any()
+
+
+def test_step_abs_reverse_move_loses():
+    """play_snake.jl:96-111 sends absolute directions; the reverse of prev_dir loses (utils.jl:57)."""
+    S = pkg()
+    n = 256
+    env = S.SnakeGame(n, auto_reset=True)
+    ora = O.OracleBatch(n, auto_reset=True)
+    rng = np.random.default_rng(5)
+    n_rev = 0
+    for t in range(300):
+        d = rng.integers(0, 4, n).astype(np.uint8)
+        av = ora.available_actions()
+        n_rev += int((~(av == d[:, None]).any(1)).sum())
+        r, dn = env.step_abs(torch.from_numpy(d).cuda())
+        ref = ora.step(d, is_abs=True)
+        assert np.array_equal(bits(r.cpu().numpy()), bits(ref["reward"])), t
+        assert np.array_equal(dn.cpu().numpy(), ref["done"]), t
+        assert np.array_equal(env.assemble_state("i8").cpu().numpy().reshape(n, 200), ref["obs_i8"] if False else ora.state("i8")), t
+    assert n_rev > 100
+    # first move D from the initial state (prev_dir U) is a reverse: lost with reward -1
+    e1 = S.SnakeGame(1, auto_reset=False)
+    r, dn = e1.step_abs(torch.tensor([S.D], dtype=torch.uint8, device="cuda"))
+    assert r.item() == -1.0 and dn.item() == 1
+
+
+def _cycle_dirs(t):
+    # 2x2 loop R, D, L, U around (8,2),(8,3),(9,3),(9,2): never eats, never dies
+    return [3, 1, 2, 0][t % 4]
+
+
+def test_r7_history_length_cap():
+    """utils.jl:88: step 500 is always lost; virtual_step's copies see one more board, so the mask is
+    all-true after 499 real steps."""
+    S = pkg()
+    env = S.SnakeGame(2, auto_reset=False)
+    ora = O.OracleBatch(2, auto_reset=False)
+    for t in range(500):
+        d = np.full(2, _cycle_dirs(t), np.uint8)
+        r, dn = env.step_abs(torch.from_numpy(d).cuda())
+        ref = ora.step(d, is_abs=True)
+        m = env.virtual_step().cpu().numpy()
+        assert np.array_equal(m, ora.losing_mask()[0]), t
+        assert np.array_equal(bits(r.cpu().numpy()), bits(ref["reward"])), t
+        assert np.array_equal(dn.cpu().numpy(), ref["done"]), t
+        if t < 498:
+            assert dn.sum() == 0 and not m.all(), t
+        elif t == 498:                     # 499 real steps taken
+            assert dn.sum() == 0 and m.all()
+        else:                              # step 500
+            assert dn.all() and r[0].item() == -1.0
+    assert env.steps.cpu().tolist() == [500, 500]
+
+
+def test_r9_food_list_exhaustion_sets_error_flag():
+    """utils.jl:23,37: when no remaining list entry is empty the reference throws BoundsError; the
+    replacement sets SNK_ENV_ERR_FOOD and plays on without food.  Differential on short lists."""
+    S = pkg()
+    n = 2048
+    for food in ([(4, 4)], [(5, 5), (4, 5)], [], [(3, 5), (3, 5), (2, 5)]):
+        env = S.SnakeGame(n, auto_reset=True, food_list=food)
+        ora = O.OracleBatch(n, food_rc=food if food else np.zeros((0, 2), np.uint8), auto_reset=True)
+        out = env.alloc_outputs(obs="i8", mask=True, ep_stats=True)
+        for t in range(400):
+            act = synth_actions(n, t, seed=11)
+            env.step_fused(act_idx=torch.from_numpy(act).cuda(), out=out)
+            ref = ora.step(act, obs=("i8",))
+            _cmp_step(out, ref, n, t, obs_key="obs_i8")
+        flags = env.error_flags.cpu().numpy()
+        want = ora.scalars()["error"]
+        assert np.array_equal(flags.astype(np.uint32), want)
+        assert (flags & S.ENV_ERR_FOOD).any(), food     # the condition really occurred
+        assert env.count_errors() == int((want != 0).sum())
+
+
+def test_invalid_actions_are_flagged_not_ub():
+    S = pkg()
+    n = 64
+    env = S.SnakeGame(n, auto_reset=True)
+    ora = O.OracleBatch(n, auto_reset=True)
+    act = np.arange(n, dtype=np.uint8) % 7
+    r, d = env.step(torch.from_numpy(act).cuda())
+    ref = ora.step(act)
+    assert np.array_equal(bits(r.cpu().numpy()), bits(ref["reward"]))
+    assert np.array_equal(env.error_flags.cpu().numpy().astype(np.uint32), ora.scalars()["error"])
+    assert ((env.error_flags.cpu().numpy() & S.ENV_ERR_ACTION) != 0).sum() == int((act > 2).sum())
+
+
+def test_epsilon_greedy_injected_draws():
+    """utils.jl:153-172 with u = Float32(rand()) and the rand(av_actions) index injected."""
+    S = pkg()
+    n = 100_000
+    rng = np.random.default_rng(2)
+    q = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    # ties, signed zeros, NaN, infinities
+    q[:1000, 1] = q[:1000, 0]
+    q[1000:2000, 2] = q[1000:2000, 1]
+    q[2000:2100] = 0.0
+    q[2100:2200] = np.array([-0.0, 0.0, -0.0], np.float32)
+    q[2200:2300] = np.array([0.0, -0.0, 0.0], np.float32)
+    q[2300:2400, 1] = np.nan
+    q[2400:2500] = np.nan
+    q[2500:2600, 2] = np.inf
+    q[2600:2700] = -np.inf
+    u = rng.random(n).astype(np.float32)
+    ridx = rng.integers(0, 3, n).astype(np.uint8)
+    env = S.SnakeGame(n)
+    ora = O.OracleBatch(n)
+    for eps in (0.0, 0.05, 0.5, 1.0):
+        got = env.epsilon_greedy(torch.from_numpy(q).cuda(), eps, torch.from_numpy(u).cuda(),
+                                 torch.from_numpy(ridx).cuda()).cpu().numpy()
+        assert np.array_equal(got, ora.select(q, eps, u, ridx)), eps
+    # numpy cross-check of the plain case
+    plain = slice(3000, None)
+    assert np.array_equal(env.epsilon_greedy(torch.from_numpy(q).cuda(), 0.0, torch.from_numpy(u).cuda(),
+                                             torch.from_numpy(ridx).cuda()).cpu().numpy()[plain],
+                          np.argmax(q[plain], axis=1).astype(np.uint8))
+
+
+def test_config3_fused_select_step():
+    """BASELINE config 3 shape at test size: injected Q, eps=0.05 (structs.jl:165), fused select+step."""
+    S = pkg()
+    n = 8192
+    env = S.SnakeGame(n, auto_reset=True)
+    ora = O.OracleBatch(n, auto_reset=True)
+    out = env.alloc_outputs(obs="f32", mask=True, ep_stats=True, act=True)
+    rng = np.random.default_rng(9)
+    for t in range(300):
+        q = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        u = rng.random(n).astype(np.float32)
+        ridx = rng.integers(0, 3, n).astype(np.uint8)
+        env.step_fused(q=torch.from_numpy(q).cuda(), eps=0.05, u=torch.from_numpy(u).cuda(),
+                       ridx=torch.from_numpy(ridx).cuda(), out=out)
+        act = ora.select(q, 0.05, u, ridx)
+        assert np.array_equal(out["act_idx"].cpu().numpy(), act), t
+        ref = ora.step(act)
+        _cmp_step(out, ref, n, t)
+
+
+def test_internal_draws_are_counter_based_and_reproducible():
+    S = pkg()
+    n = 4096
+    q = torch.rand(n, 3, device="cuda") * 2 - 1
+    a = S.SnakeGame(n, seed=123)
+    b = S.SnakeGame(n, seed=123)
+    c = S.SnakeGame(n, seed=124)
+    ga, gb, gc = (e.epsilon_greedy(q, 0.5) for e in (a, b, c))
+    assert torch.equal(ga, gb) and not torch.equal(ga, gc)
+    greedy = a.epsilon_greedy(q, 0.0)
+    frac_random = (ga != greedy).float().mean().item()       # eps/2 * 2/3 of the picks differ from greedy
+    assert 0.25 < frac_random < 0.42
+
+
+def test_masked_target_matches_reference_broadcast():
+    """utils.jl:448-451 incl. Float64 promotion by the literal 0.97, -100 fill, all-masked rows."""
+    S = pkg()
+    B = 70_000
+    rng = np.random.default_rng(4)
+    q = rng.normal(0, 3, (B, 3)).astype(np.float32)
+    mask = (rng.random((B, 3)) < 0.4).astype(np.uint8)
+    mask[:100] = 1                                    # R7 case: all true on a non-terminal row -> r - 97
+    r = rng.choice(np.array([1.0, -1.0, -0.01], np.float32), B)
+    done = (rng.random(B) < 0.1).astype(np.uint8)
+    done[:100] = 0
+    q[200:300, 0] = np.nan
+    q[300:400] = np.array([-0.0, 0.0, -0.0], np.float32); mask[300:400] = 0
+    q[400:500] = np.inf
+    want = O.masked_target(q, mask, r, done)
+    got = S.masked_target(torch.from_numpy(q).cuda(), torch.from_numpy(mask).cuda(), torch.from_numpy(r).cuda(),
+                          torch.from_numpy(done).cuda())
+    assert got.dtype == torch.float64
+    assert np.array_equal(bits(got.cpu().numpy()), bits(want))
+    assert np.allclose(got[:100].cpu().numpy(), r[:100].astype(np.float64) + 0.97 * -100.0)
+    got32 = S.masked_target(torch.from_numpy(q).cuda(), torch.from_numpy(mask).cuda(), torch.from_numpy(r).cuda(),
+                            torch.from_numpy(done).cuda(), out_dtype=torch.float32)
+    assert np.array_equal(bits(got32.cpu().numpy()), bits(want.astype(np.float32)))
+
+
+def test_host_buffer_entry_point_matches_device_entry_point():
+    S = pkg()
+    n = 70_000          # > one chunk, ragged
+    env_d = S.SnakeGame(n, auto_reset=True)
+    env_h = S.SnakeGame(n, auto_reset=True)
+    out = env_d.alloc_outputs(obs="f32", mask=True, ep_stats=True)
+    host = {"obs_fmt": "f32", "act_idx": S.pinned_empty((n,), torch.uint8),
+            "reward": S.pinned_empty((n,), torch.float32), "done": S.pinned_empty((n,), torch.uint8),
+            "obs": S.pinned_empty((n, 2, 10, 10), torch.float32), "mask": S.pinned_empty((n, 3), torch.uint8),
+            "ep_return": S.pinned_empty((n,), torch.float32), "ep_score": S.pinned_empty((n,), torch.int32)}
+    for t in range(40):
+        act = synth_actions(n, t, seed=21)
+        env_d.step_fused(act_idx=torch.from_numpy(act).cuda(), out=out)
+        host["act_idx"].copy_(torch.from_numpy(act))
+        env_h.step_fused_host(host)
+        env_h.sync()
+        for k in ("reward", "done", "obs", "mask", "ep_return", "ep_score"):
+            assert torch.equal(out[k].cpu(), host[k]), (k, t)
+    # select through host buffers
+    hq = {"obs_fmt": "i8", "q": S.pinned_empty((n, 3), torch.float32), "u": S.pinned_empty((n,), torch.float32),
+          "ridx": S.pinned_empty((n,), torch.uint8), "act_idx": S.pinned_empty((n,), torch.uint8),
+          "reward": S.pinned_empty((n,), torch.float32), "done": S.pinned_empty((n,), torch.uint8),
+          "obs": S.pinned_empty((n, 2, 10, 10), torch.int8), "mask": S.pinned_empty((n, 3), torch.uint8)}
+    hq["q"].uniform_(-1, 1); hq["u"].uniform_(0, 1); hq["ridx"].copy_(torch.randint(0, 3, (n,), dtype=torch.uint8))
+    out2 = env_d.alloc_outputs(obs="i8", mask=True, act=True)
+    env_d.step_fused(q=hq["q"].cuda(), eps=0.3, u=hq["u"].cuda(), ridx=hq["ridx"].cuda(), out=out2)
+    env_h.step_fused_host(hq, q=True, eps=0.3)
+    env_h.sync()
+    for k in ("act_idx", "reward", "done", "obs", "mask"):
+        assert torch.equal(out2[k].cpu(), hq[k]), k
+
+
+def test_full_size_1m_envs_replicates_checked_small_run():
+    """Size-independent property at BASELINE config-3 size: env i driven with the action stream of env
+    (i mod 4096) must reproduce, bit for bit, the 4,096-env run that is checked against the oracle."""
+    S = pkg()
+    n_small, n_big, steps = 4096, 1 << 20, 300
+    small = S.SnakeGame(n_small, auto_reset=True)
+    big = S.SnakeGame(n_big, auto_reset=True)
+    ora = O.OracleBatch(n_small, auto_reset=True)
+    so = small.alloc_outputs(obs="f32", mask=True, ep_stats=True)
+    bo = big.alloc_outputs(obs="f32", mask=True, ep_stats=True)
+    rep = n_big // n_small
+    for t in range(steps):
+        act = synth_actions(n_small, t, seed=77)
+        a = torch.from_numpy(act).cuda()
+        small.step_fused(act_idx=a, out=so)
+        big.step_fused(act_idx=a.repeat(rep), out=bo)
+        if t % 25 == 0 or t == steps - 1:
+            _cmp_step(so, ora.step(act), n_small, t)
+        else:
+            ora.step(act, obs=())
+        for k in ("reward", "done", "mask", "ep_return", "ep_score"):
+            assert torch.equal(bo[k].view(rep, *so[k].shape), so[k].unsqueeze(0).expand(rep, *so[k].shape)), (k, t)
+        assert torch.equal(bo["obs"].view(rep, n_small, 200), so["obs"].view(1, n_small, 200).expand(rep, -1, -1)), t
+    assert big.count_errors() == 0
+
+
+def test_two_frame_chaining_and_board_invariants_at_scale():
+    """Properties that need no oracle: frame 2 of step t is frame 1 of step t+1 for envs that did not
+    reset; walls are intact except the one wall cell a wall death overwrites (R6); one food at most;
+    snake cells = score + 2 on live boards."""
+    S = pkg()
+    n = 1 << 18
+    env = S.SnakeGame(n, auto_reset=True)
+    out = env.alloc_outputs(obs="i8", mask=True, ep_stats=True)
+    prev = env.assemble_state("i8")
+    for t in range(60):
+        act = torch.from_numpy(synth_actions(n, t, seed=5)).cuda()
+        env.step_fused(act_idx=act, out=out)
+        obs = out["obs"]
+        assert torch.equal(obs[:, 0], prev[:, 1])
+        new = obs[:, 1]
+        live = out["done"] == 0
+        border = torch.ones(10, 10, dtype=torch.bool, device="cuda"); border[1:9, 1:9] = False
+        assert (new[live][:, border] == -1).all()
+        assert ((new[~live][:, border] != -1).sum((1,)) <= 1).all()
+        assert ((new == 2).sum((1, 2)) <= 1).all()
+        assert torch.equal((new[live] == 1).sum((1, 2)).int(), out["ep_score"][live] + 2)
+        nxt = env.assemble_state("i8")
+        assert torch.equal(nxt[live], obs[live])
+        init = nxt[~live]
+        if init.numel():
+            assert torch.equal(init[:, 0], init[:, 1]) and (init[:, 1, 3, 4] == 2).all()
+        prev = nxt
+
+
+def test_center_columns_bit_exact():
+    """compute_D.jl:76-81 Welford + centring in Float64, bit-identical to the sequential loop."""
+    S = pkg()
+    rng = np.random.default_rng(8)
+    for (K, P) in ((58, 5000), (1000, 1531), (3, 129), (1, 10)):
+        walk = np.cumsum(rng.normal(0, 1e-3, (K, P)), axis=0) + rng.normal(0, 0.1, (1, P))
+        Dt = np.ascontiguousarray(walk.astype(np.float32).astype(np.float64))   # Float64.(theta::Float32)
+        want = Dt.copy().reshape(-1)
+        mean, var = O.center_columns(want, P, K)
+        dev = torch.from_numpy(Dt).cuda()
+        gm, gv = S.center_columns(dev)
+        assert np.array_equal(bits(gm.cpu().numpy()), bits(mean)), (K, P)
+        assert np.array_equal(bits(gv.cpu().numpy()), bits(var)), (K, P)
+        assert np.array_equal(bits(dev.cpu().numpy().reshape(-1)), bits(want)), (K, P)
