@@ -81,8 +81,10 @@ SNK_API int snk_reset(snk_handle h);
  * of each env; call snk_reset to apply it everywhere. */
 SNK_API int snk_set_food_list_host(snk_handle h, const uint8_t *cells_rc_host, int n);
 SNK_API int snk_default_food_list_host(uint8_t *cells_rc_host /* 100 bytes */, int *n);
-/* adopt an external CUDA stream (cudaStream_t / CUstream, e.g. torch's); NULL restores the handle's own */
+/* A handle starts on its own non-blocking stream.  snk_set_stream adopts an external one (cudaStream_t /
+ * CUstream, e.g. torch's current stream; NULL = the legacy default stream); snk_use_own_stream goes back. */
 SNK_API int snk_set_stream(snk_handle h, void *cuda_stream);
+SNK_API int snk_use_own_stream(snk_handle h);
 SNK_API int snk_get_stream(snk_handle h, void **cuda_stream);
 /* seed of the internal counter-based generator used when draws are not injected */
 SNK_API int snk_set_seed(snk_handle h, uint64_t seed);

@@ -54,7 +54,7 @@ def lib():
         "snk_destroy": [vp], "snk_reset": [vp], "snk_sync": [vp],
         "snk_set_food_list_host": [vp, vp, i32],
         "snk_default_food_list_host": [vp, C.POINTER(i32)],
-        "snk_set_stream": [vp, vp], "snk_get_stream": [vp, C.POINTER(vp)],
+        "snk_set_stream": [vp, vp], "snk_use_own_stream": [vp], "snk_get_stream": [vp, C.POINTER(vp)],
         "snk_set_seed": [vp, C.c_uint64],
         "snk_available_actions": [vp, vp],
         "snk_step": [vp, vp, vp, vp], "snk_step_abs": [vp, vp, vp, vp],

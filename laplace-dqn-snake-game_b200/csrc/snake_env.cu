@@ -678,7 +678,13 @@ int snk_set_food_list_host(snk_handle h, const uint8_t *cells_rc_host, int n) {
 int snk_set_stream(snk_handle h, void *cuda_stream) {
     SNK_CHECK_HANDLE(h);
     SNK_CUDA(cudaStreamSynchronize(h->stream));
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = (cudaStream_t)cuda_stream;
+    return SNK_OK;
+}
+int snk_use_own_stream(snk_handle h) {
+    SNK_CHECK_HANDLE(h);
+    SNK_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = h->own_stream;
     return SNK_OK;
 }
 int snk_get_stream(snk_handle h, void **cuda_stream) {

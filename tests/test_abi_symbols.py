@@ -1,0 +1,93 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/snake_b200.h declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from tests.util import ROOT, graft, pkg
+
+HEADER = os.path.join(ROOT, "include", "snake_b200.h")
+
+
+@pytest.fixture(scope="module")
+def built():
+    graft.build()
+    return pkg()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"SNK_API[^;(]*?\b(snk_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_whole_boundary():
+    names = declared_symbols()
+    for must in ("snk_create", "snk_destroy", "snk_reset", "snk_set_food_list_host", "snk_available_actions",
+                 "snk_step", "snk_step_abs", "snk_step_fused", "snk_step_fused_host", "snk_state",
+                 "snk_losing_mask", "snk_select_action", "snk_masked_target", "snk_get_score", "snk_sync",
+                 "snk_last_error", "snk_center_columns"):
+        assert must in names
+    # every declaration cites the reference interface it replaces
+    src = open(HEADER).read()
+    for cite in ("structs.jl:33-99", "utils.jl:7-10", "utils.jl:100-109", "utils.jl:112-132", "utils.jl:135-149",
+                 "utils.jl:153-172", "utils.jl:448-451", "compute_D.jl"):
+        assert cite in src, cite
+
+
+def test_library_exports_every_declared_symbol(built):
+    S = built
+    out = subprocess.check_output(["nm", "-D", "--defined-only", S.LIB_PATH], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    missing = [n for n in declared_symbols() if n not in exported]
+    assert not missing, missing
+    # nothing but the ABI is exported
+    assert all(n.startswith("snk_") for n in exported), sorted(n for n in exported if not n.startswith("snk_"))
+    L = S.lib()
+    for n in declared_symbols():
+        assert hasattr(L, n)
+    assert L.snk_version() == 100
+
+
+def test_library_is_sm100a_native_and_has_no_oracle_dependency(built):
+    S = built
+    sass = subprocess.run(["cuobjdump", "-lelf", S.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    needed = subprocess.check_output(["readelf", "-d", S.LIB_PATH], text=True)
+    assert "oracle" not in needed
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_gpu_means_loud_failure_not_fallback(built):
+    S = built
+    h = C.c_void_p()
+    rc = S.lib().snk_create(C.byref(h), 16, 0, 0)
+    assert rc == -3 and not h.value                       # SNK_ERR_NODEVICE
+    assert b"no CPU fallback" in S.lib().snk_last_error()
+    with pytest.raises(S.SnakeB200Error):
+        S.SnakeGame(16)
+
+
+def test_argument_validation_without_touching_the_gpu(built):
+    S = built
+    L = S.lib()
+    assert L.snk_masked_target(None, None, None, None, 0.97, -100.0, None, None, 4, None) == -1
+    assert b"null input" in L.snk_last_error()
+    assert L.snk_center_columns(None, 10, 10, None, None, None) == -1
+    h = C.c_void_p()
+    assert L.snk_create(C.byref(h), 0, 0, 0) == -1
+    assert L.snk_create(None, 8, 0, 0) == -1
+    assert L.snk_step(None, None, None, None) == -1
+    assert L.snk_destroy(None) == 0
+    with pytest.raises(ValueError):
+        S.SnakeGame(4, board_size=12)
+    with pytest.raises(ValueError):
+        S.SnakeGame(4, n_frames=1)
+
+
+def test_default_food_list_is_the_pinned_xoshiro42_list(built):
+    from oracle import oracle_lib as O
+    assert built.default_food_list() == O.DEFAULT_FOOD_RC
