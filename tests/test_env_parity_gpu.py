@@ -289,7 +289,7 @@ def test_masked_target_matches_reference_broadcast():
     assert got.dtype == torch.float64
     g = got.cpu().numpy()
     nan = np.isnan(want)                              # NaN payloads are not part of the contract
-    assert nan.sum() >= 100 and np.array_equal(np.isnan(g), nan)
+    assert nan.sum() >= 50 and np.array_equal(np.isnan(g), nan)
     assert np.array_equal(bits(g)[~nan], bits(want)[~nan])
     assert np.allclose(got[:100].cpu().numpy(), r[:100].astype(np.float64) + 0.97 * -100.0)
     got32 = S.masked_target(torch.from_numpy(q).cuda(), torch.from_numpy(mask).cuda(), torch.from_numpy(r).cuda(),
