@@ -165,6 +165,22 @@ SNK_API int snk_count_errors_host(snk_handle h, int64_t *count);
  * the result is bit-identical to the Julia loop.  mean/var (P) may be NULL. */
 SNK_API int snk_center_columns(double *D, int64_t P, int64_t K, double *mean, double *var, void *cuda_stream);
 
+/* ---- Gram of the deviation matrix  plot_traj.jl:10-16 (svd(D), S.^2/(K-1) = eig(D'D)/(K-1)) ------------
+ * G = A A^T with A = D^T: A is K x P row-major (row k = snapshot k) — byte-identical to Julia's P x K
+ * column-major deviation_matrix.  G is K x K Float32 row-major (symmetric).
+ *   snk_gram_pack  splits A (Float64 or Float32) into bf16 hi and 2*lo planes inside the workspace;
+ *   snk_gram       runs the tcgen05 kernel (TMA loads, TMEM accumulators) + the deterministic split-K
+ *                  reduction.  terms = 1: hi hi^T (bf16 inputs, ~3 digits); terms = 3: hi hi^T + hi lo^T + lo hi^T
+ *                  (~2^-17 relative per product), computed as Y = hi hi^T + hi (2 lo)^T, G = (Y + Y^T)/2.
+ *   block_k: 32 or 64 (0 = default); splits: split-K factor (0 = fill the SMs); the same `splits` must be
+ *   given to snk_gram_workspace_bytes. */
+#define SNK_DTYPE_F32 1
+#define SNK_DTYPE_F64 2
+SNK_API int snk_gram_workspace_bytes(int64_t K, int64_t P, int splits, size_t *bytes);
+SNK_API int snk_gram_pack(const void *A, int a_dtype, int64_t P, int64_t K, void *workspace, void *cuda_stream);
+SNK_API int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k, int splits, float *G,
+                     void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

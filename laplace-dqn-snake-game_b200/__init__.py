@@ -67,6 +67,9 @@ def lib():
         "snk_get_score": [vp, vp], "snk_get_done": [vp, vp], "snk_get_error_flags": [vp, vp],
         "snk_get_steps": [vp, vp], "snk_count_errors_host": [vp, C.POINTER(i64)],
         "snk_center_columns": [vp, i64, i64, vp, vp, vp],
+        "snk_gram_workspace_bytes": [i64, i64, i32, C.POINTER(C.c_size_t)],
+        "snk_gram_pack": [vp, i32, i64, i64, vp, vp],
+        "snk_gram": [vp, i64, i64, i32, i32, i32, vp, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -76,9 +79,6 @@ def lib():
     L.snk_num_envs.restype = i64
     L.snk_last_error.restype = C.c_char_p
     L.snk_version.restype = i32
-    for name in ("snk_gram_workspace_bytes", "snk_gram_pack", "snk_gram"):
-        if hasattr(L, name):
-            getattr(L, name).restype = i32
     _lib = L
     return L
 
@@ -317,3 +317,45 @@ def center_columns(Dt):
 
 def pinned_empty(shape, dtype):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+DTYPE_F32, DTYPE_F64 = 1, 2
+
+
+class GramPlan:
+    """Gram G = A A^T of the snapshot matrix on tcgen05 tensor cores (plot_traj.jl:10-16: the K x K matrix
+    whose eigenvalues / (K-1) are S.^2/(K-1) of svd(D)).
+
+    A: (K, P) float64 or float32 CUDA tensor, torch-contiguous = Julia's P x K column-major D.
+    pack() splits it into bf16 planes once; gram() can then be run for terms = 1 or 3.
+    """
+
+    def __init__(self, K, P, device, splits=0):
+        self.K, self.P, self.splits = int(K), int(P), int(splits)
+        self.device = torch.device(device)
+        nbytes = C.c_size_t(0)
+        _check(lib().snk_gram_workspace_bytes(self.K, self.P, self.splits, C.byref(nbytes)))
+        self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def pack(self, A):
+        if tuple(A.shape) != (self.K, self.P):
+            raise ValueError("A must be (K, P) = (%d, %d)" % (self.K, self.P))
+        dt = {torch.float64: DTYPE_F64, torch.float32: DTYPE_F32}[A.dtype]
+        with torch.cuda.device(self.device):
+            _check(lib().snk_gram_pack(_ptr(A, device=self.device), dt, self.P, self.K, _ptr(self.ws), self._stream()))
+        return self
+
+    def gram(self, terms=3, block_k=0, out=None):
+        G = out if out is not None else torch.empty(self.K, self.K, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(lib().snk_gram(_ptr(self.ws), self.P, self.K, int(terms), int(block_k), self.splits,
+                                  _ptr(G, torch.float32, self.K * self.K, self.device), self._stream()))
+        return G
+
+
+def gram(A, terms=3, block_k=0, splits=0):
+    """One-shot G = A A^T (see GramPlan)."""
+    return GramPlan(A.shape[0], A.shape[1], A.device, splits).pack(A).gram(terms, block_k)

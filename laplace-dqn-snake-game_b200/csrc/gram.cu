@@ -1,0 +1,470 @@
+// gram.cu — Gram matrix of the Laplace deviation matrix on the 5th-gen tensor cores (sm_100a).
+//
+// Reference: the only dense contraction in lucagiorgetti/Laplace-DQN-Snake-game is on the deviation matrix D
+// (P x K Float64, compute_D.jl:53,67-81): plot_traj.jl:10-16 takes svd(D) and uses S.^2/(K-1), which is the
+// spectrum of the K x K Gram  G = D' * D  (rows of A = D' are the weight snapshots).  This file computes G.
+//
+//   G = A A^T,  A = D^T  (K x P, row k = snapshot k, contraction over the P = 181,395 weights)
+//
+// Precision: tcgen05 has no FP64 kind.  A is split a = hi + lo (+ eps), hi = bf16(a), lo = bf16(a - hi)
+// (|eps| <= 2^-18 |a|), and
+//      a b ~= hi_a hi_b + hi_a lo_b + lo_a hi_b            (the dropped lo_a lo_b is <= 2^-18 |a b|)
+// Because G is symmetric the two cross terms are transposes of each other, so the kernel computes only
+//      Y = hi hi^T + hi (2 lo)^T          (2 MMAs per k-step instead of 3; 2 lo is exact in bf16)
+// with FP32 accumulation in TMEM, and the reduction pass forms  G = (Y + Y^T) / 2.
+// terms = 1 skips the second MMA (plain bf16 inputs, G = Y).
+//
+// Kernel: persistent, warp-specialised (canonical sm_100 shape):
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B / 64B boxes) -> smem ring, mbarrier expect_tx
+//   warp 1   MMA issuer     one thread issues tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, D in TMEM;
+//                           tcgen05.commit releases smem stages and publishes the accumulator
+//   warps 2-5 epilogue      tcgen05.ld 32x32b.x32 -> registers -> partial tile in the workspace
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of work item i overlap the main loop of i+1.
+// Work item = (128 x 256 output tile, split of the contraction); partial tiles are reduced (deterministically)
+// by k_gram_reduce, which also symmetrises.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace snk {
+namespace gram {
+
+constexpr int BM = 128;           // UMMA M (rows of the A-side operand per tile)
+constexpr int BN = 256;           // UMMA N (rows of the B-side operand per tile)
+constexpr int UMMA_K = 16;        // bf16
+constexpr int NUM_THREADS = 192;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int TMEM_COLS = 512;    // 2 accumulator stages x BN fp32 columns
+
+template <int BK, int TERMS>
+struct Cfg {
+    static constexpr int ROW_BYTES = BK * 2;                                   // 64 (SW64) or 128 (SW128)
+    static constexpr int A_BYTES = BM * ROW_BYTES;
+    static constexpr int B_BYTES = BN * ROW_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (TERMS > 1 ? 2 : 1);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint64_t LAYOUT = (BK == 64) ? 2ull /*SWIZZLE_128B*/ : 4ull /*SWIZZLE_64B*/;
+    static constexpr uint64_t SBO = (8 * ROW_BYTES) >> 4;                      // 8-row swizzle atom pitch
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must fault (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s
+            printf("snk gram: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c_inner, int c_row) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory operand descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1: unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (pitch between 8-row swizzle atoms) | [46,48) version = 1 | [61,64) swizzle mode
+template <int BK, int TERMS>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (Cfg<BK, TERMS>::SBO << 32) | (1ull << 46) |
+           (Cfg<BK, TERMS>::LAYOUT << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, bf16 x bf16, both K-major, M=128, N=256
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct GramArgs {
+    float *partials;        // [splits][Mt][Nt] fp32, Mt = tiles_m*BM, Nt = tiles_n*BN
+    int tiles_m, tiles_n, splits;
+    int kblocks;            // ceil(P / BK)
+    int kb_per_split;
+    long long ld_part;      // Nt
+    long long split_stride; // Mt*Nt
+};
+
+template <int BK, int TERMS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
+       const __grid_constant__ CUtensorMap map_b_hi,   // hi, box BN rows x BK
+       const __grid_constant__ CUtensorMap map_b_lo,   // 2*lo, box BN rows x BK
+       const GramArgs g) {
+    using C = Cfg<BK, TERMS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms need 1024-B alignment
+    uint64_t *bars = (uint64_t *)(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + C::STAGES, *acc_full = bars + 2 * C::STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_work = g.tiles_m * g.tiles_n * g.splits;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b_hi);
+        if (TERMS > 1) tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int n_tiles = g.tiles_m * g.tiles_n;
+                const int split = w / n_tiles, tile = w % n_tiles;      // split-major: concurrent CTAs share a k-range
+                const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * C::STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    tma_load_2d(&map_a, &full[stage], st, kb * BK, tm * BM);
+                    tma_load_2d(&map_b_hi, &full[stage], st + C::A_BYTES, kb * BK, tn * BN);
+                    if (TERMS > 1) tma_load_2d(&map_b_lo, &full[stage], st + C::A_BYTES + C::B_BYTES, kb * BK, tn * BN);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w / (g.tiles_m * g.tiles_n);
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);           // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&full[stage], phase);                   // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t a_desc = make_desc<BK, TERMS>(a_addr);
+                    const uint64_t bh_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES);
+                    const uint64_t bl_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES + C::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B along K inside the swizzled row
+                        umma_bf16(d_tmem, a_desc + adv, bh_desc + adv, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (TERMS > 1) umma_bf16(d_tmem, a_desc + adv, bl_desc + adv, IDESC, 1u);
+                    }
+                    umma_commit(&empty[stage]);                       // frees the smem stage when the MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[acc]);                          // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> partial tile =================
+        const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int n_tiles = g.tiles_m * g.tiles_n;
+            const int split = w / n_tiles, tile = w % n_tiles;
+            const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = tm * BM + q * 32 + lane;
+            float *dst = g.partials + (long long)split * g.split_stride + (long long)row * g.ld_part + (long long)tn * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 2
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// G[i][j] = sum_s Y_s[i][j]                         (terms = 1)
+//         = 0.5 * sum_s (Y_s[i][j] + Y_s[j][i])     (terms = 3: adds the transposed cross term)
+// Y_s tiles are fp32 in the workspace with leading dimension ld (>= K, both index orders in range).
+__global__ void k_gram_reduce(const float *__restrict__ part, int splits, long long split_stride, long long ld, int K,
+                              int symmetrise, float *__restrict__ G) {
+    __shared__ float tile[32][33];
+    const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
+    // transposed block first (coalesced read of Y[bj + ty.., bi + tx]), through smem
+    if (symmetrise) {
+        for (int r = ty; r < 32; r += 8) {
+            int i = bj + r, j = bi + tx;
+            float acc = 0.f;
+            if (i < K && j < K)
+                for (int s = 0; s < splits; s++) acc += part[s * split_stride + (long long)i * ld + j];
+            tile[r][tx] = acc;
+        }
+        __syncthreads();
+    }
+    for (int r = ty; r < 32; r += 8) {
+        int i = bi + r, j = bj + tx;
+        if (i < K && j < K) {
+            float acc = 0.f;
+            for (int s = 0; s < splits; s++) acc += part[s * split_stride + (long long)i * ld + j];
+            G[(long long)i * K + j] = symmetrise ? 0.5f * (acc + tile[tx][r]) : acc;
+        }
+    }
+}
+
+// D (P x K column-major, i.e. row k of A contiguous) -> hi[k][p], lo2[k][p] bf16 with row pitch Ppad
+template <typename T>
+__global__ void k_gram_pack(const T *__restrict__ A, long long P, long long K, long long Ppad,
+                            __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo2) {
+    const long long k = blockIdx.y;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < Ppad; p += (long long)gridDim.x * blockDim.x) {
+        __nv_bfloat16 h = __float2bfloat16_rn(0.f), l = h;
+        if (p < P) {
+            const double a = (double)A[k * P + p];
+            h = __double2bfloat16(a);
+            const double rem = a - (double)__bfloat162float(h);
+            l = __double2bfloat16(2.0 * rem);                 // 2*lo: exact scaling, folds the 1/2 of (Y + Y^T)/2
+        }
+        hi[k * Ppad + p] = h;
+        lo2[k * Ppad + p] = l;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode(EncodeTiledFn *fn) {
+    static EncodeTiledFn cached = nullptr;
+    if (cached == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SNK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || p == nullptr)
+            return fail(SNK_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        cached = (EncodeTiledFn)p;
+    }
+    *fn = cached;
+    return SNK_OK;
+}
+
+static int make_map(CUtensorMap *m, const void *base, long long rows, long long cols, long long pitch_elems, int box_rows,
+                    int bk) {
+    EncodeTiledFn enc;
+    int rc = get_encode(&enc);
+    if (rc != SNK_OK) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};          // innermost first
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SNK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SNK_OK;
+}
+
+struct Plan {
+    long long K, P, Ppad, Mt, Nt;
+    int tiles_m, tiles_n, splits, kblocks, kb_per_split, bk;
+    size_t off_hi, off_lo, off_part, total;
+};
+
+static int make_plan(long long K, long long P, int bk, int splits_req, Plan *pl) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    pl->K = K; pl->P = P; pl->bk = bk;
+    pl->Ppad = (P + 63) / 64 * 64;
+    pl->tiles_m = (int)((K + BM - 1) / BM);
+    pl->tiles_n = (int)((K + BN - 1) / BN);
+    pl->Mt = (long long)pl->tiles_m * BM;
+    pl->Nt = (long long)pl->tiles_n * BN;
+    pl->kblocks = (int)((P + bk - 1) / bk);
+    int tiles = pl->tiles_m * pl->tiles_n;
+    int splits = splits_req > 0 ? splits_req : (tiles >= sms ? 1 : (sms + tiles - 1) / tiles);
+    if (splits > pl->kblocks) splits = pl->kblocks;
+    if (splits > 64) splits = 64;
+    pl->kb_per_split = (pl->kblocks + splits - 1) / splits;
+    pl->splits = (pl->kblocks + pl->kb_per_split - 1) / pl->kb_per_split;   // no empty split
+    long long sq = pl->Mt > pl->Nt ? pl->Mt : pl->Nt;                       // the reduce reads Y[j][i] too
+    pl->Mt = sq; pl->Nt = (sq + BN - 1) / BN * BN;
+    auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+    pl->off_hi = 0;
+    pl->off_lo = al((size_t)K * pl->Ppad * 2);
+    pl->off_part = pl->off_lo + al((size_t)K * pl->Ppad * 2);
+    pl->total = pl->off_part + (size_t)pl->splits * pl->Mt * pl->Nt * 4;
+    return SNK_OK;
+}
+
+template <int BK, int TERMS>
+static int launch(const Plan &pl, const uint8_t *ws, float *G, cudaStream_t st) {
+    using C = Cfg<BK, TERMS>;
+    CUtensorMap ma, mbh, mbl;
+    int rc;
+    if ((rc = make_map(&ma, ws + pl.off_hi, pl.K, pl.P, pl.Ppad, BM, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&mbh, ws + pl.off_hi, pl.K, pl.P, pl.Ppad, BN, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&mbl, ws + pl.off_lo, pl.K, pl.P, pl.Ppad, BN, BK)) != SNK_OK) return rc;
+    GramArgs g;
+    g.partials = (float *)(ws + pl.off_part);
+    g.tiles_m = pl.tiles_m; g.tiles_n = pl.tiles_n; g.splits = pl.splits; g.kblocks = pl.kblocks;
+    g.kb_per_split = pl.kb_per_split; g.ld_part = pl.Nt; g.split_stride = pl.Mt * pl.Nt;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int n_work = pl.tiles_m * pl.tiles_n * pl.splits;
+    int grid = n_work < sms ? n_work : sms;
+    SNK_CUDA(cudaFuncSetAttribute(k_gram<BK, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    k_gram<BK, TERMS><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mbh, mbl, g);
+    SNK_CUDA(cudaGetLastError());
+    dim3 rb(32, 8), rg((unsigned)((pl.K + 31) / 32), (unsigned)((pl.K + 31) / 32));
+    k_gram_reduce<<<rg, rb, 0, st>>>(g.partials, pl.splits, g.split_stride, g.ld_part, (int)pl.K, TERMS > 1 ? 1 : 0, G);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+}  // namespace gram
+}  // namespace snk
+
+using namespace snk;
+using namespace snk::gram;
+
+extern "C" {
+
+int snk_gram_workspace_bytes(int64_t K, int64_t P, int splits, size_t *bytes) {
+    SNK_REQUIRE(bytes != nullptr && K > 0 && P > 0 && splits >= 0, "bad argument");
+    Plan pl;
+    make_plan(K, P, 64, splits, &pl);
+    size_t a = pl.total;
+    make_plan(K, P, 32, splits, &pl);
+    *bytes = a > pl.total ? a : pl.total;
+    return SNK_OK;
+}
+
+int snk_gram_pack(const void *A, int a_dtype, int64_t P, int64_t K, void *workspace, void *cuda_stream) {
+    SNK_REQUIRE(A != nullptr && workspace != nullptr && K > 0 && P > 0, "bad argument");
+    SNK_REQUIRE(a_dtype == SNK_DTYPE_F64 || a_dtype == SNK_DTYPE_F32, "a_dtype must be SNK_DTYPE_F64 or SNK_DTYPE_F32");
+    Plan pl;
+    make_plan(K, P, 64, 0, &pl);
+    uint8_t *ws = (uint8_t *)workspace;
+    dim3 grid((unsigned)((pl.Ppad + 1023) / 1024 < 64 ? (pl.Ppad + 1023) / 1024 : 64), (unsigned)K);
+    if (a_dtype == SNK_DTYPE_F64)
+        k_gram_pack<double><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const double *)A, P, K, pl.Ppad,
+                                                                         (__nv_bfloat16 *)(ws + pl.off_hi),
+                                                                         (__nv_bfloat16 *)(ws + pl.off_lo));
+    else
+        k_gram_pack<float><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const float *)A, P, K, pl.Ppad,
+                                                                        (__nv_bfloat16 *)(ws + pl.off_hi),
+                                                                        (__nv_bfloat16 *)(ws + pl.off_lo));
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k, int splits, float *G, void *cuda_stream) {
+    SNK_REQUIRE(workspace != nullptr && G != nullptr && K > 0 && P > 0, "bad argument");
+    SNK_REQUIRE(terms == 1 || terms == 3, "terms must be 1 (bf16) or 3 (bf16 hi/lo split)");
+    if (block_k == 0) block_k = 32;
+    SNK_REQUIRE(block_k == 32 || block_k == 64, "block_k must be 32 or 64");
+    Plan pl;
+    make_plan(K, P, block_k, splits, &pl);
+    const uint8_t *ws = (const uint8_t *)workspace;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (block_k == 64) return terms == 1 ? launch<64, 1>(pl, ws, G, st) : launch<64, 3>(pl, ws, G, st);
+    return terms == 1 ? launch<32, 1>(pl, ws, G, st) : launch<32, 3>(pl, ws, G, st);
+}
+
+}  // extern "C"

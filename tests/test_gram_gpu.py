@@ -1,0 +1,66 @@
+"""Gram of the deviation matrix on tcgen05 vs the Float64 numpy oracle (tolerances stated per test)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gram_oracle as GO
+from oracle import oracle_lib as O
+from tests.util import pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_fro(G, ref):
+    return float(np.linalg.norm(G.astype(np.float64) - ref) / np.linalg.norm(ref))
+
+
+@pytest.mark.parametrize("block_k", [32, 64])
+@pytest.mark.parametrize("K,P", [(128, 256), (256, 4096), (200, 1000), (1000, 5003), (58, 181395), (384, 77)])
+def test_gram_matches_fp64_oracle(K, P, block_k):
+    S = pkg()
+    rng = np.random.default_rng(K * 7 + P)
+    A = rng.normal(0, 1, (K, P)) * np.exp(rng.normal(0, 1, (K, 1)))         # rows of very different scale
+    ref = GO.gram(A)
+    dA = torch.from_numpy(A).cuda()
+    plan = S.GramPlan(K, P, dA.device).pack(dA)
+    G3 = plan.gram(terms=3, block_k=block_k).cpu().numpy()
+    G1 = plan.gram(terms=1, block_k=block_k).cpu().numpy()
+    scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))                   # |g_ij| <= sqrt(g_ii g_jj)
+    # bf16 hi/lo split: inputs good to 2^-17, products to ~2^-16, fp32 accumulation over P terms
+    assert np.max(np.abs(G3 - ref) / scale) < 2e-5, np.max(np.abs(G3 - ref) / scale)
+    assert _rel_fro(G3, ref) < 5e-6
+    assert np.array_equal(G3, G3.T)                                         # symmetrised exactly
+    # plain bf16 inputs: 2^-9 per operand
+    assert np.max(np.abs(G1 - ref) / scale) < 8e-3
+    assert _rel_fro(G1, ref) < 4e-3
+
+
+def test_gram_of_centred_snapshots_spectrum():
+    """compute_D-shaped input at test size: K snapshots of a drifting random walk, centred by
+    snk_center_columns (bit-exact vs the oracle), Gram by tcgen05; spectrum vs eig of the Float64 Gram."""
+    S = pkg()
+    K, P = 256, 20011
+    A = GO.synthetic_snapshots(K, P, seed=3)
+    want = A.copy().reshape(-1)
+    O.center_columns(want, P, K)
+    dA = torch.from_numpy(A).cuda()
+    S.center_columns(dA)
+    assert np.array_equal(dA.cpu().numpy().reshape(-1), want)
+    ref = GO.gram(want.reshape(K, P))
+    G = S.gram(dA, terms=3).cpu().numpy().astype(np.float64)
+    lam, lam_ref = GO.spectrum(G, K), GO.spectrum(ref, K)
+    top = lam_ref > 1e-4 * lam_ref[0]
+    assert top.sum() >= 5
+    assert np.max(np.abs(lam[top] - lam_ref[top]) / lam_ref[top]) < 1e-3
+    assert abs(lam.sum() - lam_ref.sum()) / lam_ref.sum() < 1e-5           # trace = total variance
+
+
+def test_gram_float32_input_and_explicit_splits():
+    S = pkg()
+    K, P = 300, 9000
+    A = np.random.default_rng(1).normal(0, 1, (K, P)).astype(np.float32)
+    ref = GO.gram(A)
+    dA = torch.from_numpy(A).cuda()
+    for splits in (1, 3, 7):
+        G = S.gram(dA, terms=3, splits=splits).cpu().numpy()
+        assert _rel_fro(G, ref) < 5e-6, splits
