@@ -18,8 +18,10 @@
 //   warp 0   TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B / 64B boxes) -> smem ring, mbarrier expect_tx
 //   warp 1   MMA issuer     one thread issues tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, D in TMEM;
 //                           tcgen05.commit releases smem stages and publishes the accumulator
-//   warps 2-5 epilogue      tcgen05.ld 32x32b.x32 -> registers -> partial tile in the workspace
-// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of work item i overlap the main loop of i+1.
+//   warps 2-9 accumulate    every CHUNK_K contraction elements: tcgen05.ld 32x32b.x32 -> += FP32 registers
+//                           (bounds the tensor core's truncating accumulation chain); at the end of the work
+//                           item the registers go to the partial tile in the workspace
+// Two TMEM accumulator stages (2 x 256 columns): the tensor core fills one while the other is drained.
 // Work item = (128 x 256 output tile, split of the contraction); partial tiles are reduced (deterministically)
 // by k_gram_reduce, which also symmetrises.
 #include <cuda.h>
@@ -33,8 +35,14 @@ namespace gram {
 constexpr int BM = 128;           // UMMA M (rows of the A-side operand per tile)
 constexpr int BN = 256;           // UMMA N (rows of the B-side operand per tile)
 constexpr int UMMA_K = 16;        // bf16
-constexpr int NUM_THREADS = 192;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..9 accumulate/epilogue
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;    // 2 accumulator stages x BN fp32 columns
+// The tensor core adds into its FP32 accumulator with truncation: a long chain of positive products (the
+// diagonal of a Gram) drifts low by ~5e-8 per MMA step.  So the TMEM accumulator only ever holds CHUNK_K
+// contraction elements (32 MMA steps per operand pair); the 8 accumulate warps drain it (tcgen05.ld) and add
+// it, round-to-nearest, into FP32 registers while the tensor core fills the other TMEM stage.
+constexpr int CHUNK_K = 512;
 
 template <int BK, int TERMS>
 struct Cfg {
@@ -173,7 +181,7 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
         tma_prefetch_desc(&map_b_hi);
         if (TERMS > 1) tma_prefetch_desc(&map_b_lo);
         for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NUM_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -207,16 +215,20 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
+            constexpr int CH = CHUNK_K / BK;                          // k-blocks per TMEM accumulation chunk
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
                 const int split = w / (g.tiles_m * g.tiles_n);
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
-                mbar_wait(&acc_empty[acc], acc_phase ^ 1);           // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = kb0; kb < kb1; kb++) {
+                    const int in_chunk = (kb - kb0) % CH;
+                    if (in_chunk == 0) {
+                        mbar_wait(&acc_empty[acc], acc_phase ^ 1);    // accumulate warps have drained this stage
+                        tc_fence_after();
+                    }
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                     mbar_wait(&full[stage], phase);                   // TMA bytes have landed
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -226,45 +238,57 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B along K inside the swizzled row
-                        umma_bf16(d_tmem, a_desc + adv, bh_desc + adv, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+                        umma_bf16(d_tmem, a_desc + adv, bh_desc + adv, IDESC, (in_chunk > 0 || k > 0) ? 1u : 0u);
                         if (TERMS > 1) umma_bf16(d_tmem, a_desc + adv, bl_desc + adv, IDESC, 1u);
                     }
                     umma_commit(&empty[stage]);                       // frees the smem stage when the MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (in_chunk == CH - 1 || kb == kb1 - 1) {
+                        umma_commit(&acc_full[acc]);                  // chunk complete -> accumulate warps
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    }
                 }
-                umma_commit(&acc_full[acc]);                          // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> partial tile =================
+        // ================= accumulate warps: TMEM chunk -> += registers; then -> partial tile =================
+        constexpr int CH = CHUNK_K / BK;
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                             // which 128 columns of the 256-wide tile
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int n_tiles = g.tiles_m * g.tiles_n;
             const int split = w / n_tiles, tile = w % n_tiles;
             const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
-            mbar_wait(&acc_full[acc], acc_phase);
-            tc_fence_after();
-            const int row = tm * BM + q * 32 + lane;
-            float *dst = g.partials + (long long)split * g.split_stride + (long long)row * g.ld_part + (long long)tn * BN;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 2
-            for (int c = 0; c < BN / 32; c++) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-                tmem_ld_wait();
-                float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
+            const int kb0 = split * g.kb_per_split;
+            const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
+            const int n_chunks = (kb1 - kb0 + CH - 1) / CH;
+            float r[128];
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            for (int j = 0; j < 128; j++) r[j] = 0.f;
+            for (int ch = 0; ch < n_chunks; ch++) {
+                mbar_wait(&acc_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) r[c * 32 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            const int row = tm * BM + q * 32 + lane;
+            float4 *d4 = reinterpret_cast<float4 *>(g.partials + (long long)split * g.split_stride +
+                                                    (long long)row * g.ld_part + (long long)tn * BN + half * 128);
+#pragma unroll
+            for (int j = 0; j < 32; j++) d4[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
     }
 
@@ -344,7 +368,7 @@ static int get_encode(EncodeTiledFn *fn) {
 
 static int make_map(CUtensorMap *m, const void *base, long long rows, long long cols, long long pitch_elems, int box_rows,
                     int bk) {
-    EncodeTiledFn enc;
+    EncodeTiledFn enc = nullptr;
     int rc = get_encode(&enc);
     if (rc != SNK_OK) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};          // innermost first
@@ -376,7 +400,7 @@ static int make_plan(long long K, long long P, int bk, int splits_req, Plan *pl)
     pl->Nt = (long long)pl->tiles_n * BN;
     pl->kblocks = (int)((P + bk - 1) / bk);
     int tiles = pl->tiles_m * pl->tiles_n;
-    int splits = splits_req > 0 ? splits_req : (tiles >= sms ? 1 : (sms + tiles - 1) / tiles);
+    int splits = splits_req > 0 ? splits_req : (tiles >= sms ? 1 : sms / tiles);   // one work item per CTA, no second wave
     if (splits > pl->kblocks) splits = pl->kblocks;
     if (splits > 64) splits = 64;
     pl->kb_per_split = (pl->kblocks + splits - 1) / splits;
@@ -457,7 +481,7 @@ int snk_gram_pack(const void *A, int a_dtype, int64_t P, int64_t K, void *worksp
 int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k, int splits, float *G, void *cuda_stream) {
     SNK_REQUIRE(workspace != nullptr && G != nullptr && K > 0 && P > 0, "bad argument");
     SNK_REQUIRE(terms == 1 || terms == 3, "terms must be 1 (bf16) or 3 (bf16 hi/lo split)");
-    if (block_k == 0) block_k = 32;
+    if (block_k == 0) block_k = 64;
     SNK_REQUIRE(block_k == 32 || block_k == 64, "block_k must be 32 or 64");
     Plan pl;
     make_plan(K, P, block_k, splits, &pl);

@@ -28,7 +28,7 @@ def test_gram_matches_fp64_oracle(K, P, block_k):
     scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))                   # |g_ij| <= sqrt(g_ii g_jj)
     # bf16 hi/lo split: inputs good to 2^-17, products to ~2^-16, fp32 accumulation over P terms
     assert np.max(np.abs(G3 - ref) / scale) < 2e-5, np.max(np.abs(G3 - ref) / scale)
-    assert _rel_fro(G3, ref) < 5e-6
+    assert _rel_fro(G3, ref) < 1e-5
     assert np.array_equal(G3, G3.T)                                         # symmetrised exactly
     # plain bf16 inputs: 2^-9 per operand
     assert np.max(np.abs(G1 - ref) / scale) < 8e-3
@@ -63,4 +63,4 @@ def test_gram_float32_input_and_explicit_splits():
     dA = torch.from_numpy(A).cuda()
     for splits in (1, 3, 7):
         G = S.gram(dA, terms=3, splits=splits).cpu().numpy()
-        assert _rel_fro(G, ref) < 5e-6, splits
+        assert _rel_fro(G, ref) < 1e-5, splits
