@@ -260,6 +260,11 @@ def run_ours(args):
                 "note": "3.5 MB per step: launch-latency bound and L2-resident by construction"}
         env2.close()
 
+    # ---- BASELINE config 5a: Gram of the deviation matrix (K=1000 snapshots x P=181,395 weights), tcgen05
+    gram = None
+    if rank == 0 and not args.skip_gram:
+        gram = bench_gram(S, dev)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -297,11 +302,55 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if cfg2 is not None:
             line["config2_4096_envs"] = cfg2
+        if gram is not None:
+            line["gram_5a"] = gram
         print(json.dumps(line))
     env.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bench_gram(S, dev, K=1000, P=181395, iters=10):
+    """G = A A^T for A = D^T (K x P), synthetic N(0,1) snapshots cast through Float32 (the reference stores
+    Float64.(theta::Float32)); L2 flushed between timed iterations; accuracy against torch Float64."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    A = torch.randn(K, P, device=dev, dtype=torch.float32, generator=g).double()
+    ref = A @ A.T
+    plan = S.GramPlan(K, P, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+    out = {"workload": "config5a: Gram G = D'D of K=%d snapshots x P=%d weights (compute_D.jl D, plot_traj.jl spectrum)" % (K, P),
+           "flop_useful": 2.0 * K * K * P, "peak_bf16_tflops_burst": peak}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    out["pack_ms"] = timed(lambda: plan.pack(A))
+    G = torch.empty(K, K, dtype=torch.float32, device=dev)
+    for terms in (3, 1):
+        ms = timed(lambda: plan.gram(terms, 0, out=G))
+        err = float((G.double() - ref).norm() / ref.norm())
+        mma = (2 if terms == 3 else 1) * 2.0 * K * K * P / (ms * 1e-3) / 1e12
+        out["terms%d" % terms] = {"ms": ms, "useful_tflops": 2.0 * K * K * P / (ms * 1e-3) / 1e12, "mma_tflops": mma,
+                                  "frac_of_measured_bf16_peak": mma / peak, "rel_fro_err_vs_fp64": err}
+    Ab = A.to(torch.bfloat16)
+    ms = timed(lambda: torch.matmul(Ab, Ab.T))
+    out["cublas_bf16_same_shape_ms"] = ms
+    return out
 
 
 def main():
@@ -314,6 +363,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-config2", action="store_true")
+    ap.add_argument("--skip-gram", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
