@@ -380,7 +380,7 @@ def test_two_frame_chaining_and_board_invariants_at_scale():
         assert torch.equal(nxt[live], obs[live])
         init = nxt[~live]
         if init.numel():
-            assert torch.equal(init[:, 0], init[:, 1]) and (init[:, 1, 3, 4] == 2).all()
+            assert torch.equal(init[:, 0], init[:, 1]) and (init[:, 1, 4, 3] == 2).all()   # torch dims are (N, frame, col, row): food (4,5) 1-based = row 3, col 4
         prev = nxt
 
 
