@@ -152,6 +152,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SNK_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -295,7 +296,7 @@ def run_ours(args):
                          "bytes_per_env_step": BYTES_PER_STEP_CONFIG3, "kernel_ms": kern_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step": e2e_ms / Ke, "api": "snk_step_fused_host (pinned host buffers)"},
-            "gpu_launches": K,
+            "gpu_launches": K * world,
             "clocks": clocks,
         }
         if cpu is not None:

@@ -181,6 +181,28 @@ SNK_API int snk_gram_pack(const void *A, int a_dtype, int64_t P, int64_t K, void
 SNK_API int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k, int splits, float *G,
                      void *cuda_stream);
 
+/* ---- block-wise pieces, for the row-sharded multi-GPU Gram (rank g owns rows_g of A) -----------
+ * planes: bf16 [rows][pitch] arrays hi and 2*lo (snk_gram_planes_layout gives bytes per plane and the pitch).
+ * snk_gram_block:  Y (rows_a x rows_b, ld ldY) = hi_a hi_b^T [+ hi_a (2 lo_b)^T]; b planes may be a local copy of a
+ *                  peer's planes.  scratch: snk_gram_block_scratch_bytes.
+ * snk_gram_symmetrize_block: G_block = (Y + YT^T)/2 where YT is the (rows_b x rows_a) block the OTHER rank
+ *                  computed; YT may be a peer-memory pointer (the kernel reads it with plain loads over NVLink). */
+SNK_API int snk_gram_planes_layout(int64_t rows, int64_t P, size_t *plane_bytes, int64_t *pitch_elems);
+SNK_API int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, void *hi, void *lo2, void *cuda_stream);
+SNK_API int snk_gram_block_scratch_bytes(int64_t rows_a, int64_t rows_b, int64_t P, int splits, size_t *bytes);
+SNK_API int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, const void *b_lo2, int64_t rows_b, int64_t P,
+                           int terms, int block_k, int splits, void *scratch, float *Y, int64_t ldY, void *cuda_stream);
+SNK_API int snk_gram_symmetrize_block(const float *Y, int64_t ldY, const float *YT, int64_t ldYT, int64_t rows_a,
+                                      int64_t rows_b, float *G, int64_t ldG, void *cuda_stream);
+/* device memory that other ranks of the box can map (cudaIpc*): allocate, export a 64-byte handle, import a
+ * peer's handle, copy (works on peer-mapped pointers: the planes ring of the sharded Gram) */
+SNK_API int snk_ipc_alloc(void **p, size_t bytes);
+SNK_API int snk_ipc_free(void *p);
+SNK_API int snk_ipc_export(void *p, uint8_t *handle64);
+SNK_API int snk_ipc_import(const uint8_t *handle64, void **p);
+SNK_API int snk_ipc_close(void *p);
+SNK_API int snk_copy_async(void *dst, const void *src, size_t bytes, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,14 @@ def lib():
         "snk_gram_workspace_bytes": [i64, i64, i32, C.POINTER(C.c_size_t)],
         "snk_gram_pack": [vp, i32, i64, i64, vp, vp],
         "snk_gram": [vp, i64, i64, i32, i32, i32, vp, vp],
+        "snk_gram_planes_layout": [i64, i64, C.POINTER(C.c_size_t), C.POINTER(i64)],
+        "snk_gram_pack_planes": [vp, i32, i64, i64, vp, vp, vp],
+        "snk_gram_block_scratch_bytes": [i64, i64, i64, i32, C.POINTER(C.c_size_t)],
+        "snk_gram_block": [vp, i64, vp, vp, i64, i64, i32, i32, i32, vp, vp, i64, vp],
+        "snk_gram_symmetrize_block": [vp, i64, vp, i64, i64, i64, vp, i64, vp],
+        "snk_ipc_alloc": [C.POINTER(vp), C.c_size_t], "snk_ipc_free": [vp],
+        "snk_ipc_export": [vp, vp], "snk_ipc_import": [vp, C.POINTER(vp)], "snk_ipc_close": [vp],
+        "snk_copy_async": [vp, vp, C.c_size_t, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)

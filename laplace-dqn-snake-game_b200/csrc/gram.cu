@@ -26,6 +26,7 @@
 // by k_gram_reduce, which also symmetrises.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.h"
 
@@ -383,19 +384,21 @@ static int make_map(CUtensorMap *m, const void *base, long long rows, long long 
 }
 
 struct Plan {
-    long long K, P, Ppad, Mt, Nt;
+    long long rows_a, rows_b, P, Ppad, Mt, Nt;
     int tiles_m, tiles_n, splits, kblocks, kb_per_split, bk;
-    size_t off_hi, off_lo, off_part, total;
+    size_t scratch_bytes;
 };
 
-static int make_plan(long long K, long long P, int bk, int splits_req, Plan *pl) {
+static long long pitch_of(long long P) { return (P + 63) / 64 * 64; }
+
+static void make_plan(long long rows_a, long long rows_b, long long P, int bk, int splits_req, Plan *pl) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    pl->K = K; pl->P = P; pl->bk = bk;
-    pl->Ppad = (P + 63) / 64 * 64;
-    pl->tiles_m = (int)((K + BM - 1) / BM);
-    pl->tiles_n = (int)((K + BN - 1) / BN);
+    pl->rows_a = rows_a; pl->rows_b = rows_b; pl->P = P; pl->bk = bk;
+    pl->Ppad = pitch_of(P);
+    pl->tiles_m = (int)((rows_a + BM - 1) / BM);
+    pl->tiles_n = (int)((rows_b + BN - 1) / BN);
     pl->Mt = (long long)pl->tiles_m * BM;
     pl->Nt = (long long)pl->tiles_n * BN;
     pl->kblocks = (int)((P + bk - 1) / bk);
@@ -404,27 +407,20 @@ static int make_plan(long long K, long long P, int bk, int splits_req, Plan *pl)
     if (splits > pl->kblocks) splits = pl->kblocks;
     if (splits > 64) splits = 64;
     pl->kb_per_split = (pl->kblocks + splits - 1) / splits;
-    pl->splits = (pl->kblocks + pl->kb_per_split - 1) / pl->kb_per_split;   // no empty split
-    long long sq = pl->Mt > pl->Nt ? pl->Mt : pl->Nt;                       // the reduce reads Y[j][i] too
-    pl->Mt = sq; pl->Nt = (sq + BN - 1) / BN * BN;
-    auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
-    pl->off_hi = 0;
-    pl->off_lo = al((size_t)K * pl->Ppad * 2);
-    pl->off_part = pl->off_lo + al((size_t)K * pl->Ppad * 2);
-    pl->total = pl->off_part + (size_t)pl->splits * pl->Mt * pl->Nt * 4;
-    return SNK_OK;
+    pl->splits = (pl->kblocks + pl->kb_per_split - 1) / pl->kb_per_split;          // no empty split
+    pl->scratch_bytes = (size_t)pl->splits * pl->Mt * pl->Nt * 4;
 }
 
 template <int BK, int TERMS>
-static int launch(const Plan &pl, const uint8_t *ws, float *G, cudaStream_t st) {
+static int launch(const Plan &pl, const void *a_hi, const void *b_hi, const void *b_lo, float *scratch, cudaStream_t st) {
     using C = Cfg<BK, TERMS>;
     CUtensorMap ma, mbh, mbl;
     int rc;
-    if ((rc = make_map(&ma, ws + pl.off_hi, pl.K, pl.P, pl.Ppad, BM, BK)) != SNK_OK) return rc;
-    if ((rc = make_map(&mbh, ws + pl.off_hi, pl.K, pl.P, pl.Ppad, BN, BK)) != SNK_OK) return rc;
-    if ((rc = make_map(&mbl, ws + pl.off_lo, pl.K, pl.P, pl.Ppad, BN, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&ma, a_hi, pl.rows_a, pl.P, pl.Ppad, BM, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&mbh, b_hi, pl.rows_b, pl.P, pl.Ppad, BN, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&mbl, TERMS > 1 ? b_lo : b_hi, pl.rows_b, pl.P, pl.Ppad, BN, BK)) != SNK_OK) return rc;
     GramArgs g;
-    g.partials = (float *)(ws + pl.off_part);
+    g.partials = scratch;
     g.tiles_m = pl.tiles_m; g.tiles_n = pl.tiles_n; g.splits = pl.splits; g.kblocks = pl.kblocks;
     g.kb_per_split = pl.kb_per_split; g.ld_part = pl.Nt; g.split_stride = pl.Mt * pl.Nt;
     int dev = 0, sms = 148;
@@ -435,10 +431,37 @@ static int launch(const Plan &pl, const uint8_t *ws, float *G, cudaStream_t st) 
     SNK_CUDA(cudaFuncSetAttribute(k_gram<BK, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     k_gram<BK, TERMS><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mbh, mbl, g);
     SNK_CUDA(cudaGetLastError());
-    dim3 rb(32, 8), rg((unsigned)((pl.K + 31) / 32), (unsigned)((pl.K + 31) / 32));
-    k_gram_reduce<<<rg, rb, 0, st>>>(g.partials, pl.splits, g.split_stride, g.ld_part, (int)pl.K, TERMS > 1 ? 1 : 0, G);
-    SNK_CUDA(cudaGetLastError());
     return SNK_OK;
+}
+
+static int run_block(const Plan &pl, int terms, const void *a_hi, const void *b_hi, const void *b_lo, float *scratch,
+                     cudaStream_t st) {
+    if (pl.bk == 64) return terms == 1 ? launch<64, 1>(pl, a_hi, b_hi, b_lo, scratch, st) : launch<64, 3>(pl, a_hi, b_hi, b_lo, scratch, st);
+    return terms == 1 ? launch<32, 1>(pl, a_hi, b_hi, b_lo, scratch, st) : launch<32, 3>(pl, a_hi, b_hi, b_lo, scratch, st);
+}
+
+// out[i][j] = sum_s part[s][i][j]   (+ optionally 0.5*(. + yt[j][i]) with yt another row-major block, maybe in peer memory)
+__global__ void k_gram_finish(const float *__restrict__ part, int splits, long long split_stride, long long ld_part,
+                              const float *__restrict__ yt, long long ld_yt, int rows_a, int rows_b,
+                              float *__restrict__ out, long long ld_out) {
+    __shared__ float tile[32][33];
+    const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
+    if (yt != nullptr) {
+        for (int r = ty; r < 32; r += 8) {                 // coalesced read of yt[bj + r][bi + tx]
+            int i = bj + r, j = bi + tx;
+            tile[r][tx] = (i < rows_b && j < rows_a) ? yt[(long long)i * ld_yt + j] : 0.f;
+        }
+        __syncthreads();
+    }
+    for (int r = ty; r < 32; r += 8) {
+        int i = bi + r, j = bj + tx;
+        if (i < rows_a && j < rows_b) {
+            float acc = 0.f;
+            for (int s = 0; s < splits; s++) acc += part[s * split_stride + (long long)i * ld_part + j];
+            out[(long long)i * ld_out + j] = (yt != nullptr) ? 0.5f * (acc + tile[tx][r]) : acc;
+        }
+    }
 }
 
 }  // namespace gram
@@ -449,33 +472,80 @@ using namespace snk::gram;
 
 extern "C" {
 
+int snk_gram_planes_layout(int64_t rows, int64_t P, size_t *plane_bytes, int64_t *pitch_elems) {
+    SNK_REQUIRE(rows > 0 && P > 0, "bad argument");
+    if (pitch_elems) *pitch_elems = pitch_of(P);
+    if (plane_bytes) *plane_bytes = ((size_t)rows * pitch_of(P) * 2 + 1023) & ~(size_t)1023;
+    return SNK_OK;
+}
+
+int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, void *hi, void *lo2, void *cuda_stream) {
+    SNK_REQUIRE(A != nullptr && hi != nullptr && lo2 != nullptr && rows > 0 && P > 0, "bad argument");
+    SNK_REQUIRE(a_dtype == SNK_DTYPE_F64 || a_dtype == SNK_DTYPE_F32, "a_dtype must be SNK_DTYPE_F64 or SNK_DTYPE_F32");
+    const long long Ppad = pitch_of(P);
+    dim3 grid((unsigned)((Ppad + 1023) / 1024 < 64 ? (Ppad + 1023) / 1024 : 64), (unsigned)rows);
+    if (a_dtype == SNK_DTYPE_F64)
+        k_gram_pack<double><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const double *)A, P, rows, Ppad, (__nv_bfloat16 *)hi,
+                                                                         (__nv_bfloat16 *)lo2);
+    else
+        k_gram_pack<float><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const float *)A, P, rows, Ppad, (__nv_bfloat16 *)hi,
+                                                                        (__nv_bfloat16 *)lo2);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_gram_block_scratch_bytes(int64_t rows_a, int64_t rows_b, int64_t P, int splits, size_t *bytes) {
+    SNK_REQUIRE(bytes != nullptr && rows_a > 0 && rows_b > 0 && P > 0 && splits >= 0, "bad argument");
+    Plan p64, p32;
+    make_plan(rows_a, rows_b, P, 64, splits, &p64);
+    make_plan(rows_a, rows_b, P, 32, splits, &p32);
+    *bytes = p64.scratch_bytes > p32.scratch_bytes ? p64.scratch_bytes : p32.scratch_bytes;
+    return SNK_OK;
+}
+
+int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, const void *b_lo2, int64_t rows_b, int64_t P,
+                   int terms, int block_k, int splits, void *scratch, float *Y, int64_t ldY, void *cuda_stream) {
+    SNK_REQUIRE(a_hi && b_hi && scratch && Y && rows_a > 0 && rows_b > 0 && P > 0, "bad argument");
+    SNK_REQUIRE(terms == 1 || (terms == 3 && b_lo2 != nullptr), "terms must be 1 (bf16) or 3 (hi/lo split, needs b_lo2)");
+    if (block_k == 0) block_k = 64;
+    SNK_REQUIRE(block_k == 32 || block_k == 64, "block_k must be 32 or 64");
+    SNK_REQUIRE(ldY >= rows_b, "ldY too small");
+    Plan pl;
+    make_plan(rows_a, rows_b, P, block_k, splits, &pl);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = run_block(pl, terms, a_hi, b_hi, b_lo2, (float *)scratch, st);
+    if (rc != SNK_OK) return rc;
+    dim3 rb(32, 8), rg((unsigned)((rows_b + 31) / 32), (unsigned)((rows_a + 31) / 32));
+    k_gram_finish<<<rg, rb, 0, st>>>((const float *)scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, nullptr, 0, (int)rows_a,
+                                     (int)rows_b, Y, ldY);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_gram_symmetrize_block(const float *Y, int64_t ldY, const float *YT, int64_t ldYT, int64_t rows_a, int64_t rows_b,
+                              float *G, int64_t ldG, void *cuda_stream) {
+    SNK_REQUIRE(Y && YT && G && rows_a > 0 && rows_b > 0, "bad argument");
+    dim3 rb(32, 8), rg((unsigned)((rows_b + 31) / 32), (unsigned)((rows_a + 31) / 32));
+    k_gram_finish<<<rg, rb, 0, (cudaStream_t)cuda_stream>>>(Y, 1, 0, ldY, YT, ldYT, (int)rows_a, (int)rows_b, G, ldG);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+// ---- single-GPU convenience: workspace = [hi | lo2 | scratch] ---------------------------------------
 int snk_gram_workspace_bytes(int64_t K, int64_t P, int splits, size_t *bytes) {
     SNK_REQUIRE(bytes != nullptr && K > 0 && P > 0 && splits >= 0, "bad argument");
-    Plan pl;
-    make_plan(K, P, 64, splits, &pl);
-    size_t a = pl.total;
-    make_plan(K, P, 32, splits, &pl);
-    *bytes = a > pl.total ? a : pl.total;
+    size_t plane = 0, scratch = 0;
+    snk_gram_planes_layout(K, P, &plane, nullptr);
+    snk_gram_block_scratch_bytes(K, K, P, splits, &scratch);
+    *bytes = 2 * plane + scratch;
     return SNK_OK;
 }
 
 int snk_gram_pack(const void *A, int a_dtype, int64_t P, int64_t K, void *workspace, void *cuda_stream) {
-    SNK_REQUIRE(A != nullptr && workspace != nullptr && K > 0 && P > 0, "bad argument");
-    SNK_REQUIRE(a_dtype == SNK_DTYPE_F64 || a_dtype == SNK_DTYPE_F32, "a_dtype must be SNK_DTYPE_F64 or SNK_DTYPE_F32");
-    Plan pl;
-    make_plan(K, P, 64, 0, &pl);
-    uint8_t *ws = (uint8_t *)workspace;
-    dim3 grid((unsigned)((pl.Ppad + 1023) / 1024 < 64 ? (pl.Ppad + 1023) / 1024 : 64), (unsigned)K);
-    if (a_dtype == SNK_DTYPE_F64)
-        k_gram_pack<double><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const double *)A, P, K, pl.Ppad,
-                                                                         (__nv_bfloat16 *)(ws + pl.off_hi),
-                                                                         (__nv_bfloat16 *)(ws + pl.off_lo));
-    else
-        k_gram_pack<float><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const float *)A, P, K, pl.Ppad,
-                                                                        (__nv_bfloat16 *)(ws + pl.off_hi),
-                                                                        (__nv_bfloat16 *)(ws + pl.off_lo));
-    SNK_CUDA(cudaGetLastError());
-    return SNK_OK;
+    SNK_REQUIRE(workspace != nullptr && K > 0 && P > 0, "bad argument");
+    size_t plane = 0;
+    snk_gram_planes_layout(K, P, &plane, nullptr);
+    return snk_gram_pack_planes(A, a_dtype, P, K, workspace, (uint8_t *)workspace + plane, cuda_stream);
 }
 
 int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k, int splits, float *G, void *cuda_stream) {
@@ -483,12 +553,55 @@ int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k
     SNK_REQUIRE(terms == 1 || terms == 3, "terms must be 1 (bf16) or 3 (bf16 hi/lo split)");
     if (block_k == 0) block_k = 64;
     SNK_REQUIRE(block_k == 32 || block_k == 64, "block_k must be 32 or 64");
-    Plan pl;
-    make_plan(K, P, block_k, splits, &pl);
+    size_t plane = 0;
+    snk_gram_planes_layout(K, P, &plane, nullptr);
     const uint8_t *ws = (const uint8_t *)workspace;
+    float *scratch = (float *)(ws + 2 * plane);
+    Plan pl;
+    make_plan(K, K, P, block_k, splits, &pl);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (block_k == 64) return terms == 1 ? launch<64, 1>(pl, ws, G, st) : launch<64, 3>(pl, ws, G, st);
-    return terms == 1 ? launch<32, 1>(pl, ws, G, st) : launch<32, 3>(pl, ws, G, st);
+    int rc = run_block(pl, terms, ws, ws, ws + plane, scratch, st);
+    if (rc != SNK_OK) return rc;
+    // G = sum of the split partials; for the hi/lo split also G = (Y + Y^T)/2, Y^T read from the same partials
+    dim3 rb(32, 8), rg((unsigned)((K + 31) / 32), (unsigned)((K + 31) / 32));
+    k_gram_reduce<<<rg, rb, 0, st>>>(scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, (int)K, terms > 1 ? 1 : 0, G);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+// ---- peer-memory plumbing for the row-sharded Gram (one process per GPU) ---------------------------
+int snk_ipc_alloc(void **p, size_t bytes) {
+    SNK_REQUIRE(p != nullptr && bytes > 0, "bad argument");
+    SNK_CUDA(cudaMalloc(p, bytes));
+    return SNK_OK;
+}
+int snk_ipc_free(void *p) {
+    if (p) SNK_CUDA(cudaFree(p));
+    return SNK_OK;
+}
+int snk_ipc_export(void *p, uint8_t *handle64) {
+    SNK_REQUIRE(p != nullptr && handle64 != nullptr, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    SNK_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    return SNK_OK;
+}
+int snk_ipc_import(const uint8_t *handle64, void **p) {
+    SNK_REQUIRE(p != nullptr && handle64 != nullptr, "bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SNK_CUDA(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+    return SNK_OK;
+}
+int snk_ipc_close(void *p) {
+    if (p) SNK_CUDA(cudaIpcCloseMemHandle(p));
+    return SNK_OK;
+}
+int snk_copy_async(void *dst, const void *src, size_t bytes, void *cuda_stream) {
+    SNK_REQUIRE(dst != nullptr && src != nullptr, "bad argument");
+    SNK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+    return SNK_OK;
 }
 
 }  // extern "C"

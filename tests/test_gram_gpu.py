@@ -64,3 +64,22 @@ def test_gram_float32_input_and_explicit_splits():
     for splits in (1, 3, 7):
         G = S.gram(dA, terms=3, splits=splits).cpu().numpy()
         assert _rel_fro(G, ref) < 1e-5, splits
+
+
+@pytest.mark.parametrize("world,K,P,terms", [(2, 512, 3000, 3), (3, 700, 5003, 3), (4, 1000, 2048, 1), (8, 1000, 9999, 3)])
+def test_row_sharded_gram_with_virtual_ranks(world, K, P, terms):
+    """The multi-GPU algorithm (planes ring -> block Grams -> transposed-peer symmetrise) with R virtual ranks
+    in one process on one GPU: same kernels and pointer arithmetic, local 'peer' memory."""
+    S = pkg()
+    from snake_b200 import gram_sharded as GS
+    rng = np.random.default_rng(world * 100 + K)
+    A = rng.normal(0, 1, (K, P)) * np.exp(rng.normal(0, 0.5, (K, 1)))
+    ref = GO.gram(A)
+    peers = GS.LocalPeers(K, P, world, torch.device("cuda", 0))
+    G = peers.gram(torch.from_numpy(A).cuda(), terms=terms).cpu().numpy()
+    peers.free()
+    assert G.shape == (K, K)
+    tol = 1e-5 if terms == 3 else 4e-3
+    assert _rel_fro(G, ref) < tol
+    single = S.gram(torch.from_numpy(A).cuda(), terms=terms).cpu().numpy()
+    assert _rel_fro(G, single.astype(np.float64)) < 2e-6       # same arithmetic up to split-K summation order

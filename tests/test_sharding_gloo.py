@@ -63,3 +63,55 @@ def test_shard_range_properties():
             assert rs[0][0] == 0 and rs[-1][1] == n
             assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
     assert shard.max_over_ranks(3.5) == 3.5
+
+
+def _gram_worker(rank, world, port, K, P, q):
+    """The sharded-Gram schedule (ring order, column offsets, transposed-peer symmetrise) under gloo, with
+    numpy standing in for the device kernels: planes are exchanged with all_gather, block products follow
+    ring_schedule, and the result must be the full Gram's row block."""
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg()
+    from snake_b200 import shard
+    from snake_b200.gram_sharded import ring_schedule
+    rng = np.random.default_rng(0)
+    A = rng.normal(0, 1, (K, P))
+    rows_all = [shard.shard_range(K, r, world)[1] - shard.shard_range(K, r, world)[0] for r in range(world)]
+    col0 = [sum(rows_all[:r]) for r in range(world)]
+    mine = A[col0[rank]:col0[rank] + rows_all[rank]]
+    hi = mine.astype(np.float32).astype(np.float64)            # stand-in split: hi + lo == mine
+    lo2 = 2 * (mine - hi)
+    planes = [None] * world
+    dist.all_gather_object(planes, (hi, lo2))
+    Y = np.zeros((rows_all[rank], K))
+    order = ring_schedule(rank, world)
+    assert order[0] == rank and sorted(order) == list(range(world))
+    for p in order:
+        ph, pl = planes[p]
+        Y[:, col0[p]:col0[p] + rows_all[p]] = hi @ ph.T + hi @ pl.T
+    Ys = [None] * world
+    dist.all_gather_object(Ys, Y)
+    G = np.zeros_like(Y)
+    for p in range(world):
+        yt = Ys[p][:, col0[rank]:col0[rank] + rows_all[rank]]
+        G[:, col0[p]:col0[p] + rows_all[p]] = 0.5 * (Y[:, col0[p]:col0[p] + rows_all[p]] + yt.T)
+    ref = (A @ A.T)[col0[rank]:col0[rank] + rows_all[rank]]
+    q.put((rank, float(np.abs(G - ref).max() / np.abs(ref).max())))
+    dist.destroy_process_group()
+
+
+def test_sharded_gram_schedule_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_gram_worker, args=(r, world, port, 37, 50, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # only lo*lo^T is dropped: relative error ~ (2^-24)^2
+    assert all(err < 1e-12 for _, err in res), res
