@@ -266,6 +266,11 @@ def run_ours(args):
     if rank == 0 and not args.skip_gram:
         gram = bench_gram(S, dev)
 
+    # ---- BASELINE config 5b shape: row-sharded Gram across the ranks (6,250 rows of J per GPU, P = 181,395)
+    gram_sh = None
+    if world > 1 and not args.skip_gram:
+        gram_sh = bench_gram_sharded(S, dev, rank, world, local, max_over_ranks)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -305,11 +310,65 @@ def run_ours(args):
             line["config2_4096_envs"] = cfg2
         if gram is not None:
             line["gram_5a"] = gram
+        if gram_sh is not None:
+            line["gram_5b_sharded"] = gram_sh
+        line["roofline"]["traffic"] = ncu_traffic_bytes()
         print(json.dumps(line))
     env.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_step launch, from the committed ncu --set full capture
+    of this same workload (profiles/r01_ncu_k_step_full.csv); None if the file is absent."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_ncu_k_step_full.csv")
+    if not os.path.exists(p):
+        return None
+    rows = list(csv.reader(open(p)))
+    hdr = rows[0]
+    r, w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    vals = [(float(x[r]) + float(x[w])) * 1e6 for x in rows[2:] if len(x) > w and x[0].startswith("void k_step")]
+    return sum(vals) / len(vals) if vals else None
+
+
+def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181395, iters=3):
+    """Every rank owns R rows of a synthetic J (N(0,1) Float32); G[rows_rank, :] over all ranks through the
+    planes ring (NVLink peer copies under the tcgen05 main loop) and the peer-read symmetrise kernel."""
+    import torch
+    import torch.distributed as dist
+    from snake_b200 import gram_sharded as GS
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)
+    J = torch.randn(R, P, device=dev, dtype=torch.float32, generator=g)
+    dg = GS.DistributedGram([R] * world, P, dev)
+    times = []
+    for it in range(iters + 1):
+        torch.cuda.synchronize()
+        dist.barrier(device_ids=[local])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        G = dg.run(J, terms=3)
+        e1.record()
+        torch.cuda.synchronize()
+        t = max_over_ranks(e0.elapsed_time(e1))
+        if it > 0:
+            times.append(t)
+    want = float((J[0].double() ** 2).sum().item())
+    got = float(G[0, rank * R].item())
+    dg.close()
+    ms = sorted(times)[len(times) // 2]
+    Kt = R * world
+    useful = 2.0 * Kt * Kt * P
+    return {"workload": "config5b shape: Gram of J (%d rows per GPU x %d), row-sharded over %d GPUs, hi/lo bf16 split" % (R, P, world),
+            "K_total": Kt, "ms": ms, "useful_tflops_total": useful / (ms * 1e-3) / 1e12,
+            "mma_tflops_per_gpu": 2 * useful / world / (ms * 1e-3) / 1e12,
+            "diag_rel_err_sample": abs(got - want) / want,
+            "exchange": "planes ring: cudaMemcpyAsync from peer-mapped (cudaIpc) memory on a copy stream under the MMA main loop; "
+                        "transpose exchange: peer loads inside the symmetrise kernel; torch.distributed only for handles/barriers",
+            "timed": "pack + barriers + ring + block Grams + symmetrise; buffers and IPC mappings set up once"}
 
 
 def bench_gram(S, dev, K=1000, P=181395, iters=10):

@@ -323,6 +323,9 @@ def center_columns(Dt):
     return mean, var
 
 
+from . import shard  # noqa: E402,F401
+
+
 def pinned_empty(shape, dtype):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
 

@@ -166,38 +166,57 @@ class LocalPeers:
             s.free()
 
 
-def gram_distributed(A_rows, rows_all, terms=3, block_k=0, splits=0, group=None):
-    """G[rows_rank, :] for this rank (one process per GPU).  A_rows: this rank's (rows, P) CUDA tensor."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    dev = A_rows.device
-    shard = GramShard(rows_all, rank, A_rows.shape[1], dev, splits)
-    try:
-        shard.pack(A_rows)
-        handles = [None] * world
-        dist.all_gather_object(handles, (shard.planes.handle(), shard.Y.handle()), group=group)
-        planes, Ys, opened = [], [], []
+class DistributedGram:
+    """Persistent multi-process sharded Gram (one process per GPU): buffers and peer mappings are set up once
+    (cudaMalloc + cudaIpc handle exchange through torch.distributed), run() can then be called repeatedly."""
+
+    def __init__(self, rows_all, P, device, splits=0, group=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
+        self.shard = GramShard(rows_all, self.rank, P, self.device, splits)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.shard.planes.handle(), self.shard.Y.handle()), group=group)
+        self.planes, self.Ys, self._opened = [], [], []
         for r, (hp, hy) in enumerate(handles):
-            if r == rank:
-                planes.append(shard.planes.ptr.value)
-                Ys.append(shard.Y.ptr.value)
+            if r == self.rank:
+                self.planes.append(self.shard.planes.ptr.value)
+                self.Ys.append(self.shard.Y.ptr.value)
                 continue
             pp, py = C.c_void_p(), C.c_void_p()
-            with torch.cuda.device(dev):
+            with torch.cuda.device(self.device):
                 _check(lib().snk_ipc_import((C.c_uint8 * 64).from_buffer_copy(hp), C.byref(pp)))
                 _check(lib().snk_ipc_import((C.c_uint8 * 64).from_buffer_copy(hy), C.byref(py)))
-            opened += [pp, py]
-            planes.append(pp.value)
-            Ys.append(py.value)
-        torch.cuda.synchronize(dev)
-        dist.barrier(group=group)                 # every rank's planes are packed
-        run_ring(shard, planes, terms, block_k)
-        torch.cuda.synchronize(dev)
-        dist.barrier(group=group)                 # every rank's Y row block is complete
-        G = run_symmetrize(shard, Ys, terms).clone()
-        torch.cuda.synchronize(dev)
-        dist.barrier(group=group)                 # nobody still reads my Y
-        for p in opened:
-            lib().snk_ipc_close(p)
+            self._opened += [pp, py]
+            self.planes.append(pp.value)
+            self.Ys.append(py.value)
+
+    def _barrier(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+    def run(self, A_rows, terms=3, block_k=0):
+        """G[rows_rank, :] (a view of an internal buffer, valid until the next run)."""
+        self.shard.pack(A_rows)
+        self._barrier()                           # every rank's planes are packed
+        run_ring(self.shard, self.planes, terms, block_k)
+        self._barrier()                           # every rank's Y row block is complete
+        G = run_symmetrize(self.shard, self.Ys, terms)
+        self._barrier()                           # nobody still reads my Y / planes
         return G
+
+    def close(self):
+        self._barrier()
+        for p in self._opened:
+            lib().snk_ipc_close(p)
+        self._opened = []
+        self.shard.free()
+
+
+def gram_distributed(A_rows, rows_all, terms=3, block_k=0, splits=0, group=None):
+    """One-shot G[rows_rank, :] for this rank.  A_rows: this rank's (rows, P) CUDA tensor."""
+    dg = DistributedGram(rows_all, A_rows.shape[1], A_rows.device, splits, group)
+    try:
+        return dg.run(A_rows, terms, block_k).clone()
     finally:
-        shard.free()
+        dg.close()
