@@ -152,7 +152,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SNK_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")                 # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
