@@ -159,6 +159,29 @@ SNK_API int snk_get_steps(snk_handle h, int32_t *steps);          /* steps taken
 /* number of envs with any error bit set (synchronises) */
 SNK_API int snk_count_errors_host(snk_handle h, int64_t *count);
 
+/* ---- replay buffer  ReplayBuffer (structs.jl:104-116), store! / sample / stack_exp (utils.jl:265-383) -------
+ * The ring lives on the device as one 128-byte record per transition (three 2-bit-plane boards + scalars);
+ * snk_step_fused_store is snk_step_fused that additionally store!s every env's Experience in env order — the
+ * same slots N sequential store! calls would use (push until full, then overwrite from position 1).
+ * snk_replay_gather is stack_exp for the records at idx[0..B) (0-based slots): states / next_states
+ * (10,10,2,B) Float32, actions (B) u8 0-based index into available_actions (utils.jl:363 stores it 1-based),
+ * rewards (B) f32, dones (B) u8, suicidal_mask (3,B) u8.  Any output may be NULL.
+ * snk_replay_sample_indices draws B distinct slots of the filled part (sample(rpb), utils.jl:280-287; the
+ * reference's StatsBase draw stream is not reproduced — pass your own idx to snk_replay_gather for parity). */
+typedef struct snk_replay_s *snk_replay;
+SNK_API int snk_replay_create(snk_replay *out, int64_t capacity, int device);
+SNK_API int snk_replay_destroy(snk_replay r);
+SNK_API int snk_replay_clear(snk_replay r);                                     /* empty_buffer!  utils.jl:311-314 */
+SNK_API int snk_replay_length(snk_replay r, int64_t *length, int64_t *position);  /* length(rpb), rpb.position (1-based) */
+SNK_API int snk_step_fused_store(snk_handle h, snk_replay r, const float *q, float eps, const float *u, const uint8_t *ridx,
+                                 uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask,
+                                 float *ep_return, int32_t *ep_score);
+SNK_API int snk_replay_gather(snk_replay r, const int64_t *idx, int64_t B, float *states, float *next_states,
+                              uint8_t *actions, float *rewards, uint8_t *dones, uint8_t *mask, float *ep_return,
+                              int32_t *score, void *cuda_stream);
+SNK_API int snk_replay_sample_indices(snk_replay r, uint64_t seed, int64_t B, int64_t *idx_out, void *cuda_stream);
+SNK_API int snk_replay_bad_index_host(snk_replay r, int *flag);
+
 /* ---- Laplace deviation matrix  compute_D.jl:9-31, 66-81; la_utils.jl:14-36, 154-169 -------- */
 /* D is P x K Float64, column-major (column k = snapshot k).  Welford mean / M2 over the columns in
  * column order, var = M2 / max(K-1,1), then D .-= mean, all in Float64 without FMA contraction so

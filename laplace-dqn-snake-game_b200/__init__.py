@@ -67,6 +67,12 @@ def lib():
         "snk_get_score": [vp, vp], "snk_get_done": [vp, vp], "snk_get_error_flags": [vp, vp],
         "snk_get_steps": [vp, vp], "snk_count_errors_host": [vp, C.POINTER(i64)],
         "snk_center_columns": [vp, i64, i64, vp, vp, vp],
+        "snk_replay_create": [C.POINTER(vp), i64, i32], "snk_replay_destroy": [vp], "snk_replay_clear": [vp],
+        "snk_replay_length": [vp, C.POINTER(i64), C.POINTER(i64)],
+        "snk_step_fused_store": [vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
+        "snk_replay_gather": [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "snk_replay_sample_indices": [vp, C.c_uint64, i64, vp, vp],
+        "snk_replay_bad_index_host": [vp, C.POINTER(i32)],
         "snk_gram_workspace_bytes": [i64, i64, i32, C.POINTER(C.c_size_t)],
         "snk_gram_pack": [vp, i32, i64, i64, vp, vp],
         "snk_gram": [vp, i64, i64, i32, i32, i32, vp, vp],
@@ -204,11 +210,12 @@ class SnakeGame:
             out["act_idx"] = self._new((self.n,), torch.uint8)
         return out
 
-    def step_fused(self, act_idx=None, q=None, eps=0.0, u=None, ridx=None, out=None, obs="f32"):
+    def step_fused(self, act_idx=None, q=None, eps=0.0, u=None, ridx=None, out=None, obs="f32", replay=None):
         """One kernel: [epsilon_greedy] + step! + virtual_step + next_state (+ Float32 cast).
 
         Either act_idx (N) u8 or q (N,3) f32 must be given.  Returns the `out` dict
         (reward, done, obs, mask, ...); pass a dict from alloc_outputs() to reuse buffers.
+        replay: a ReplayBuffer — every env's transition is store!d (utils.jl:267-277) by the same kernel.
         """
         if out is None:
             out = self.alloc_outputs(obs=obs, act=q is not None)
@@ -220,11 +227,14 @@ class SnakeGame:
             if act_idx is None:
                 raise ValueError("need act_idx or q")
             act_p = _ptr(act_idx, torch.uint8, self.n, dev)
-        _check(lib().snk_step_fused(
-            self._h, _ptr(q, torch.float32, 3 * self.n, dev) if q is not None else None, float(eps),
-            _ptr(u, torch.float32, self.n, dev), _ptr(ridx, torch.uint8, self.n, dev), act_p,
-            _ptr(out.get("reward")), _ptr(out.get("done")), _ptr(out.get("obs")), fmt, _ptr(out.get("mask")),
-            _ptr(out.get("ep_return")), _ptr(out.get("ep_score"))))
+        args = (_ptr(q, torch.float32, 3 * self.n, dev) if q is not None else None, float(eps),
+                _ptr(u, torch.float32, self.n, dev), _ptr(ridx, torch.uint8, self.n, dev), act_p,
+                _ptr(out.get("reward")), _ptr(out.get("done")), _ptr(out.get("obs")), fmt, _ptr(out.get("mask")),
+                _ptr(out.get("ep_return")), _ptr(out.get("ep_score")))
+        if replay is None:
+            _check(lib().snk_step_fused(self._h, *args))
+        else:                      # also store! every env's Experience into the device replay ring
+            _check(lib().snk_step_fused_store(self._h, replay._r, *args))
         return out
 
     def step_fused_host(self, host, q=False, eps=0.0):
@@ -370,3 +380,82 @@ class GramPlan:
 def gram(A, terms=3, block_k=0, splits=0):
     """One-shot G = A A^T (see GramPlan)."""
     return GramPlan(A.shape[0], A.shape[1], A.device, splits).pack(A).gram(terms, block_k)
+
+
+class ReplayBuffer:
+    """ReplayBuffer (structs.jl:104-116) on the device: capacity 50,000, batch_size 64 by default.
+
+    store! happens inside SnakeGame.step_fused(..., replay=rb); sample()/stack_exp() mirror utils.jl:280-287 and
+    utils.jl:343-383.  Indices are 0-based slots."""
+
+    def __init__(self, capacity=50000, device=0, batch_size=64, seed=0):
+        if batch_size > capacity:
+            raise ValueError("batch_size cannot be greater than the capacity of the buffer.")     # structs.jl:113
+        self.capacity, self.batch_size, self.seed = int(capacity), int(batch_size), int(seed)
+        self.device = torch.device("cuda", device)
+        self._r = C.c_void_p()
+        _check(lib().snk_replay_create(C.byref(self._r), self.capacity, int(device)))
+
+    def close(self):
+        if getattr(self, "_r", None) and self._r.value:
+            lib().snk_replay_destroy(self._r)
+            self._r = C.c_void_p()
+
+    __del__ = close
+
+    def _len_pos(self):
+        n, p = C.c_int64(0), C.c_int64(0)
+        _check(lib().snk_replay_length(self._r, C.byref(n), C.byref(p)))
+        return n.value, p.value
+
+    def __len__(self):
+        return self._len_pos()[0]
+
+    @property
+    def position(self):                 # 1-based like the Julia field
+        return self._len_pos()[1]
+
+    def isfull(self):                   # utils.jl:289-291 (sic: position == capacity)
+        return self.position == self.capacity
+
+    def isready(self):                  # utils.jl:293-296
+        return len(self) >= self.batch_size
+
+    def empty_buffer(self):             # utils.jl:311-314
+        _check(lib().snk_replay_clear(self._r))
+
+    def sample_indices(self, B=None):
+        """min(batch_size, length) distinct slots (utils.jl:280-287), (B,) int64 on the device"""
+        B = min(self.batch_size, len(self)) if B is None else int(B)
+        idx = torch.empty(B, dtype=torch.int64, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _check(lib().snk_replay_sample_indices(self._r, self.seed, B, _ptr(idx), st))
+        return idx
+
+    def stack_exp(self, idx, ep_stats=False):
+        """utils.jl:343-383 for the transitions at idx: dict(states, actions, rewards, next_states, dones, mask)"""
+        B = idx.numel()
+        dev = self.device
+        out = {"states": torch.empty(B, 2, 10, 10, dtype=torch.float32, device=dev),
+               "next_states": torch.empty(B, 2, 10, 10, dtype=torch.float32, device=dev),
+               "actions": torch.empty(B, dtype=torch.uint8, device=dev),
+               "rewards": torch.empty(B, dtype=torch.float32, device=dev),
+               "dones": torch.empty(B, dtype=torch.uint8, device=dev),
+               "mask": torch.empty(B, 3, dtype=torch.uint8, device=dev)}
+        if ep_stats:
+            out["ep_return"] = torch.empty(B, dtype=torch.float32, device=dev)
+            out["score"] = torch.empty(B, dtype=torch.int32, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _check(lib().snk_replay_gather(self._r, _ptr(idx, torch.int64, B, dev), B, _ptr(out["states"]),
+                                       _ptr(out["next_states"]), _ptr(out["actions"]), _ptr(out["rewards"]),
+                                       _ptr(out["dones"]), _ptr(out["mask"]), _ptr(out.get("ep_return")),
+                                       _ptr(out.get("score")), st))
+        return out
+
+    def sample(self):
+        return self.stack_exp(self.sample_indices())
+
+    def bad_index(self):
+        f = C.c_int(0)
+        _check(lib().snk_replay_bad_index_host(self._r, C.byref(f)))
+        return bool(f.value)

@@ -94,8 +94,17 @@ struct StepArgs {
     long long env_begin, env_end;
     u64 seed, step_counter;
     int auto_reset, is_abs;
+    // transition sink = replay ring (store!, utils.jl:267-277): one 128-byte record per env per step
+    uint4 *sink;
+    long long sink_base, sink_cap, sink_n;   // transitions stored before this step; ring capacity; envs in this step
     FoodTable food;
 };
+
+// 128-byte transition record (one cache line): three boards as 2 x 128-bit planes each, then the scalars
+//   [0,32) board_{t-2}  [32,64) board_{t-1}  [64,96) board_t      state = (b_{t-2}, b_{t-1}), next_state = (b_{t-1}, b_t)
+//   [96] reward f32 | [100] action idx u8 | [101] done u8 | [102] next_is_suicidal bits u8 | [103] prev_dir at action time u8
+//   [104] episode return f32 | [108] score i32 | [112] env id u32 | [116] step-in-episode u16
+constexpr int REC_U4 = 8;
 
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
@@ -180,6 +189,18 @@ __device__ __forceinline__ void board_planes(u64 occ, int fr, int fc, bool has_h
     uint4 b = make_uint4((uint32_t)p1lo, (uint32_t)(p1lo >> 32), (uint32_t)p1hi, (uint32_t)(p1hi >> 32));
     reinterpret_cast<uint4 *>(dst)[0] = a;
     reinterpret_cast<uint4 *>(dst)[1] = b;
+}
+
+__device__ __forceinline__ void board_planes_reg(u64 occ, int fr, int fc, bool has_head, int hr, int hc, uint4 &a, uint4 &b) {
+    u64 slo, shi;
+    to_full(occ, slo, shi);
+    if (has_head) set_k(hr, hc, slo, shi);
+    u64 flo = WALL_LO, fhi = WALL_HI;
+    if (fr != 0) set_k(fr, fc, flo, fhi);
+    u64 p0lo = slo | WALL_LO, p0hi = shi | WALL_HI;
+    u64 p1lo = flo & ~slo, p1hi = fhi & ~shi;
+    a = make_uint4((uint32_t)p0lo, (uint32_t)(p0lo >> 32), (uint32_t)p0hi, (uint32_t)(p0hi >> 32));
+    b = make_uint4((uint32_t)p1lo, (uint32_t)(p1lo >> 32), (uint32_t)p1hi, (uint32_t)(p1hi >> 32));
 }
 
 __device__ __forceinline__ int cell_code(const uint32_t *pl, int k) {
@@ -286,7 +307,7 @@ __device__ __forceinline__ uint32_t losing_mask3(u64 occ, u64 cons, int hr, int 
     return m;
 }
 
-template <int OBS, bool SELECT>
+template <int OBS, bool SELECT, bool SINK>
 __global__ void __launch_bounds__(TPB) k_step(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) uint32_t s_planes[TPB * PLANE_WORDS];
     __shared__ ObsTables s_tb;
@@ -314,6 +335,8 @@ __global__ void __launch_bounds__(TPB) k_step(const __grid_constant__ StepArgs a
         int pd = (int)(misc >> M_PD) & 3, len = (int)(misc >> M_LEN) & 127, t = (int)(misc >> M_T) & 1023;
         int dn = (int)(misc >> M_DONE) & 1, err = (int)(misc >> M_ERR) & 15;
         const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
+        const u64 occ_tm2 = pocc;                                   // board_{t-2}, for the transition record
+        const int fr_tm2 = pfr, fc_tm2 = pfc, pd_before = pd;
 
         int aidx;
         if (SELECT) {
@@ -401,6 +424,26 @@ __global__ void __launch_bounds__(TPB) k_step(const __grid_constant__ StepArgs a
         if (OBS != SNK_OBS_NONE) {
             board_planes(pocc, pfr, pfc, false, 0, 0, s_planes + tid * PLANE_WORDS);
             board_planes(occ, fr, fc, true, hr, hc, s_planes + tid * PLANE_WORDS + 8);
+        }
+
+        if (SINK) {
+            // store!(rpb, exp) for envs in index order == ring slot (stored_so_far + env) mod capacity; when the
+            // step holds more envs than the ring, the later env wins exactly as sequential store! calls would
+            const long long e = env - a.env_begin;
+            if (e + a.sink_cap >= a.sink_n) {
+                uint4 *rec = a.sink + ((a.sink_base + e) % a.sink_cap) * REC_U4;
+                uint4 p0, p1;
+                board_planes_reg(occ_tm2, fr_tm2, fc_tm2, false, 0, 0, p0, p1);
+                rec[0] = p0; rec[1] = p1;
+                board_planes_reg(pocc, pfr, pfc, false, 0, 0, p0, p1);
+                rec[2] = p0; rec[3] = p1;
+                board_planes_reg(occ, fr, fc, true, hr, hc, p0, p1);
+                rec[4] = p0; rec[5] = p1;
+                rec[6] = make_uint4(__float_as_uint(reward),
+                                    (uint32_t)aidx | ((uint32_t)dn << 8) | (m3 << 16) | ((uint32_t)pd_before << 24),
+                                    __float_as_uint(ret), (uint32_t)(len - 2));
+                rec[7] = make_uint4((uint32_t)env, (uint32_t)t, 0u, 0u);
+            }
         }
 
         if (dn && a.auto_reset) {                                   // a fresh SnakeGame() (utils.jl:199)
@@ -527,6 +570,85 @@ __global__ void k_masked_target(const float *q, const uint8_t *mask, const float
     double y = __dadd_rn((double)r[i], tt);
     if (y64 != nullptr) y64[i] = y;
     if (y32 != nullptr) y32[i] = (float)y;
+}
+
+
+// ---- replay ring: stack_exp (utils.jl:343-383) of the records at idx[0..B) ------------------------------
+// One CTA per 32 samples; the records' planes go to shared memory, then states (10,10,2,B) and next_states are
+// streamed out with the same nibble->float4 table as the step kernel.
+constexpr int GATHER_S = 32;
+__global__ void __launch_bounds__(TPB) k_replay_gather(const uint4 *__restrict__ ring, long long cap, const long long *__restrict__ idx,
+                                                       long long B, float *states, float *next_states, uint8_t *actions,
+                                                       float *rewards, uint8_t *dones, uint8_t *mask, float *ep_return,
+                                                       int32_t *score, int *bad_index) {
+    __shared__ __align__(16) uint32_t s_pl[GATHER_S * 24];        // per sample: 3 boards x (P0[4], P1[4])
+    __shared__ ObsTables s_tb;
+    const int tid = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * GATHER_S;
+    const int n_local = (B - b0) < GATHER_S ? (int)(B - b0) : GATHER_S;
+    fill_tables<SNK_OBS_F32>(s_tb, tid);
+    // 4 threads per sample copy the 6 plane vectors + scalars
+    if (tid < n_local * 4) {
+        const int sl = tid >> 2, part = tid & 3;
+        long long i = idx[b0 + sl];
+        if (i < 0 || i >= cap) { *bad_index = 1; i = 0; }
+        const uint4 *rec = ring + i * REC_U4;
+        uint4 *dst = reinterpret_cast<uint4 *>(s_pl + sl * 24);
+        if (part < 3) { dst[2 * part] = rec[2 * part]; dst[2 * part + 1] = rec[2 * part + 1]; }
+        else {
+            const uint4 sc = rec[6];
+            const long long o = b0 + sl;
+            if (rewards) rewards[o] = __uint_as_float(sc.x);
+            if (actions) actions[o] = (uint8_t)(sc.y & 0xFF);
+            if (dones) dones[o] = (uint8_t)((sc.y >> 8) & 0xFF);
+            if (mask) { mask[3 * o] = (sc.y >> 16) & 1; mask[3 * o + 1] = (sc.y >> 17) & 1; mask[3 * o + 2] = (sc.y >> 18) & 1; }
+            if (ep_return) ep_return[o] = __uint_as_float(sc.z);
+            if (score) score[o] = (int32_t)sc.w;
+        }
+    }
+    __syncthreads();
+    // two outputs: states uses boards (0,1), next_states boards (1,2); 50 float4 units per sample each
+    const int total = n_local * 50;
+#pragma unroll 2
+    for (int which = 0; which < 2; which++) {
+        float *outp = which == 0 ? states : next_states;
+        if (outp == nullptr) continue;
+        float4 *o4 = reinterpret_cast<float4 *>(outp) + b0 * 50;
+        for (int j = tid; j < total; j += TPB) {
+            int e = (int)(((unsigned)j * 5243u) >> 18);
+            int qq = j - e * 50;
+            int f = qq >= 25;
+            int q = qq - 25 * f;
+            const uint32_t *pl = s_pl + e * 24 + (which + f) * 8;
+            int w = q >> 3, sh = (q & 7) * 4;
+            uint32_t ix = ((pl[w] >> sh) & 15u) | (((pl[4 + w] >> sh) & 15u) << 4);
+            __stcs(o4 + j, s_tb.f32[ix]);
+        }
+    }
+}
+
+// B distinct slots in [0, n): a keyed bijection of [0, 2^k) (4-round Feistel on k bits, k even) cycle-walked
+// into [0, n) and evaluated at counters 0..B-1 — sampling without replacement with no state and no rejection set.
+__device__ __forceinline__ unsigned long long feistel_perm(unsigned long long x, int half_bits, u64 key) {
+    const unsigned long long m = (1ull << half_bits) - 1ull;
+    unsigned long long l = x >> half_bits, r = x & m;
+#pragma unroll
+    for (int round = 0; round < 4; round++) {
+        unsigned long long f = splitmix64(r ^ (key + 0x9E3779B97F4A7C15ull * (u64)(round + 1))) & m;
+        unsigned long long nl = r;
+        r = l ^ f;
+        l = nl;
+    }
+    return (l << half_bits) | r;
+}
+__global__ void k_replay_sample(long long n, long long B, u64 key, long long *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int bits = 2;
+    while ((1ll << bits) < n) bits += 2;
+    unsigned long long x = (unsigned long long)i;
+    do { x = feistel_perm(x, bits / 2, key); } while (x >= (unsigned long long)n);
+    out[i] = (long long)x;
 }
 
 }  // namespace snk
@@ -720,8 +842,13 @@ static int launch_step(snk_handle h, StepArgs &a, int obs_fmt, bool select, long
     if (grid == 0) return SNK_OK;
 #define SNK_LAUNCH(FMT)                                                        \
     do {                                                                       \
-        if (select) k_step<FMT, true><<<grid, TPB, 0, st>>>(a);                \
-        else k_step<FMT, false><<<grid, TPB, 0, st>>>(a);                      \
+        if (a.sink != nullptr) {                                               \
+            if (select) k_step<FMT, true, true><<<grid, TPB, 0, st>>>(a);      \
+            else k_step<FMT, false, true><<<grid, TPB, 0, st>>>(a);            \
+        } else {                                                               \
+            if (select) k_step<FMT, true, false><<<grid, TPB, 0, st>>>(a);     \
+            else k_step<FMT, false, false><<<grid, TPB, 0, st>>>(a);           \
+        }                                                                      \
     } while (0)
     switch (obs_fmt) {
         case SNK_OBS_NONE: SNK_LAUNCH(SNK_OBS_NONE); break;
@@ -934,6 +1061,114 @@ int snk_count_errors_host(snk_handle h, int64_t *count) {
     SNK_CUDA(cudaMemcpyAsync(&c, h->d_count, 8, cudaMemcpyDeviceToHost, h->stream));
     SNK_CUDA(cudaStreamSynchronize(h->stream));
     *count = (int64_t)c;
+    return SNK_OK;
+}
+
+
+// ---- replay ring (ReplayBuffer, structs.jl:104-116; store!/sample/stack_exp, utils.jl:265-383) ----------
+struct snk_replay_s {
+    long long capacity;
+    int device;
+    uint4 *ring;             // capacity x 128-byte records
+    long long total;         // transitions ever stored since the last clear
+    u64 draws;               // sample calls so far (counter of the keyed permutation)
+    int *d_bad;
+};
+
+int snk_replay_create(snk_replay *out, int64_t capacity, int device) {
+    SNK_REQUIRE(out != nullptr, "null out");
+    SNK_REQUIRE(capacity >= 64, "batch_size (64) cannot be greater than the capacity of the buffer");   // structs.jl:113
+    *out = nullptr;
+    SNK_CUDA(cudaSetDevice(device));
+    snk_replay_s *r = new (std::nothrow) snk_replay_s();
+    if (r == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
+    memset(r, 0, sizeof(*r));
+    r->capacity = capacity; r->device = device;
+    cudaError_t e = cudaMalloc((void **)&r->ring, (size_t)capacity * 128);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&r->d_bad, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(r->d_bad, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        if (r->ring) cudaFree(r->ring);
+        delete r;
+        return fail(SNK_ERR_CUDA, "snk_replay_create: %s", cudaGetErrorString(e));
+    }
+    *out = r;
+    return SNK_OK;
+}
+int snk_replay_destroy(snk_replay r) {
+    if (r == nullptr) return SNK_OK;
+    cudaSetDevice(r->device);
+    cudaFree(r->ring);
+    cudaFree(r->d_bad);
+    delete r;
+    return SNK_OK;
+}
+int snk_replay_clear(snk_replay r) {                      // empty_buffer!, utils.jl:311-314
+    SNK_REQUIRE(r != nullptr, "null replay");
+    r->total = 0;
+    return SNK_OK;
+}
+int snk_replay_length(snk_replay r, int64_t *length, int64_t *position) {
+    SNK_REQUIRE(r != nullptr, "null replay");
+    if (length) *length = r->total < r->capacity ? r->total : r->capacity;
+    // rpb.position (1-based) only advances once the buffer is full (utils.jl:268-276)
+    if (position) *position = r->total < r->capacity ? 1 : ((r->total - r->capacity) % r->capacity) + 1;
+    return SNK_OK;
+}
+
+int snk_step_fused_store(snk_handle h, snk_replay r, const float *q, float eps, const float *u, const uint8_t *ridx,
+                         uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask,
+                         float *ep_return, int32_t *ep_score) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(r != nullptr, "null replay");
+    SNK_REQUIRE(r->device == h->device, "replay ring and env live on different devices");
+    if (!(h->flags & SNK_AUTO_RESET))
+        return fail(SNK_ERR_UNSUPPORTED, "snk_step_fused_store needs an env created with SNK_AUTO_RESET (every env must step)");
+    SNK_REQUIRE(q != nullptr || act_idx != nullptr, "need q (select) or act_idx (input)");
+    SNK_REQUIRE(obs_fmt == SNK_OBS_NONE || obs != nullptr, "obs_fmt given without an obs buffer");
+    SNK_REQUIRE(obs_fmt == SNK_OBS_NONE || ((uintptr_t)obs & 15u) == 0, "obs must be 16-byte aligned");
+    StepArgs a;
+    base_args(h, a);
+    a.q = q; a.eps = eps; a.u = u; a.ridx = ridx;
+    if (q != nullptr) a.act_out = act_idx; else a.act = act_idx;
+    a.reward = reward; a.done = done; a.obs = obs; a.mask = mask; a.ep_return = ep_return; a.ep_score = ep_score;
+    a.sink = r->ring; a.sink_base = r->total; a.sink_cap = r->capacity; a.sink_n = h->n;
+    int rc = launch_step(h, a, obs ? obs_fmt : SNK_OBS_NONE, q != nullptr, 0, h->n, h->stream);
+    h->step_counter++;
+    if (rc == SNK_OK) r->total += h->n;
+    return rc;
+}
+
+int snk_replay_gather(snk_replay r, const int64_t *idx, int64_t B, float *states, float *next_states, uint8_t *actions,
+                      float *rewards, uint8_t *dones, uint8_t *mask, float *ep_return, int32_t *score, void *cuda_stream) {
+    SNK_REQUIRE(r != nullptr && idx != nullptr && B >= 0, "bad argument");
+    SNK_REQUIRE((((uintptr_t)states | (uintptr_t)next_states) & 15u) == 0, "state buffers must be 16-byte aligned");
+    if (B == 0) return SNK_OK;
+    SNK_CUDA(cudaSetDevice(r->device));
+    k_replay_gather<<<nblocks(B, GATHER_S), TPB, 0, (cudaStream_t)cuda_stream>>>(
+        r->ring, r->capacity, (const long long *)idx, B, states, next_states, actions, rewards, dones, mask, ep_return,
+        score, r->d_bad);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_replay_sample_indices(snk_replay r, uint64_t seed, int64_t B, int64_t *idx_out, void *cuda_stream) {
+    SNK_REQUIRE(r != nullptr && idx_out != nullptr, "bad argument");
+    const long long n = r->total < r->capacity ? r->total : r->capacity;
+    // sample(rpb): min(batch, length) distinct transitions (utils.jl:280-287)
+    SNK_REQUIRE(B >= 0 && B <= n, "cannot sample more distinct transitions than the buffer holds");
+    if (B == 0) return SNK_OK;
+    SNK_CUDA(cudaSetDevice(r->device));
+    const u64 key = splitmix64(seed ^ splitmix64(r->draws++));
+    k_replay_sample<<<nblocks(B, 256), 256, 0, (cudaStream_t)cuda_stream>>>(n, B, key, (long long *)idx_out);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_replay_bad_index_host(snk_replay r, int *flag) {
+    SNK_REQUIRE(r != nullptr && flag != nullptr, "bad argument");
+    SNK_CUDA(cudaSetDevice(r->device));
+    SNK_CUDA(cudaMemcpy(flag, r->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
     return SNK_OK;
 }
 
