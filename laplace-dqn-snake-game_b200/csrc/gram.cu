@@ -403,7 +403,7 @@ static void make_plan(long long rows_a, long long rows_b, long long P, int bk, i
     pl->Nt = (long long)pl->tiles_n * BN;
     pl->kblocks = (int)((P + bk - 1) / bk);
     int tiles = pl->tiles_m * pl->tiles_n;
-    int splits = splits_req > 0 ? splits_req : (tiles >= sms ? 1 : sms / tiles);   // one work item per CTA, no second wave
+    int splits = splits_req > 0 ? splits_req : (tiles >= sms ? 1 : (2 * sms) / tiles);   // ~2 work items per CTA: the second's main loop hides the first's epilogue (measured best at K=1000: 9 splits)
     if (splits > pl->kblocks) splits = pl->kblocks;
     if (splits > 64) splits = 64;
     pl->kb_per_split = (pl->kblocks + splits - 1) / splits;
