@@ -261,6 +261,11 @@ def run_ours(args):
                 "note": "3.5 MB per step: launch-latency bound and L2-resident by construction"}
         env2.close()
 
+    # ---- BASELINE config 4: 65,536 envs acting from the Q-net, masked max-Q targets, 50k replay ring
+    cfg4 = None
+    if rank == 0 and not args.skip_config4:
+        cfg4 = bench_config4(S, dev, local)
+
     # ---- BASELINE config 5a: Gram of the deviation matrix (K=1000 snapshots x P=181,395 weights), tcgen05
     gram = None
     if rank == 0 and not args.skip_gram:
@@ -308,6 +313,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if cfg2 is not None:
             line["config2_4096_envs"] = cfg2
+        if cfg4 is not None:
+            line["config4_65536_envs"] = cfg4
         if gram is not None:
             line["gram_5a"] = gram
         if gram_sh is not None:
@@ -318,6 +325,47 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bench_config4(S, dev, local, n=65536, steps=20):
+    """One rollout step = q_net(state) -> fused eps-greedy/step!/virtual_step/obs/store! -> t_net(next_state) ->
+    masked max-Q target (utils.jl:203-208, 448-451).  Q-net = seeded Glorot init of structs.jl:127-139 (the
+    two-frame checkpoints BASELINE names are missing from the reference mount)."""
+    import torch
+    env = S.SnakeGame(n, device=local, auto_reset=True)
+    rb = S.ReplayBuffer(capacity=50000, device=local)
+    layers = S.qnet.glorot_layers(seed=0)
+    out = {"workload": "config4: %d envs, eps=0.05, Glorot-init Q-net (synthetic weights), 50k replay ring" % n}
+    for backend in S.qnet.available_backends():
+        qn = S.qnet.QNet(layers, dev, backend=backend)
+        ro = S.rollout.Rollout(env, qn, qn, rb, epsilon=0.05)
+        for _ in range(3):
+            ro.step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ro.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        # the two network forwards alone
+        x = ro.state
+        for _ in range(2):
+            qn(x)
+        e0.record()
+        for _ in range(steps):
+            qn(x)
+        e1.record()
+        torch.cuda.synchronize()
+        fwd = e0.elapsed_time(e1) / steps
+        out[backend] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "qnet_forward_ms": fwd,
+                        "qnet_tflops": 2 * 0 + 4870784.0 * n / (fwd * 1e-3) / 1e12,
+                        "note": S.qnet.BACKEND_NOTES[backend]}
+    out["replay_len"] = len(rb)
+    env.close()
+    rb.close()
+    return out
 
 
 def ncu_traffic_bytes():
@@ -424,6 +472,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-config2", action="store_true")
     ap.add_argument("--skip-gram", action="store_true")
+    ap.add_argument("--skip-config4", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

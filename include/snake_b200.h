@@ -182,6 +182,17 @@ SNK_API int snk_replay_gather(snk_replay r, const int64_t *idx, int64_t B, float
 SNK_API int snk_replay_sample_indices(snk_replay r, uint64_t seed, int64_t B, int64_t *idx_out, void *cuda_stream);
 SNK_API int snk_replay_bad_index_host(snk_replay r, int *flag);
 
+/* ---- Q-network forward  structs.jl:127-139; call sites utils.jl:165 (acting), 448 (t_net targets) -------------
+ * Conv(3x3,2=>16,relu,pad 1) -> Conv(3x3,16=>32,relu,pad 1) -> Conv(6x6,32=>64,relu) -> flatten -> Dense(1600,64,relu)
+ * -> Dense(64,3), Flux semantics (true convolution, WHCN, column-major flatten).  theta_host = Flux.destructure(q_net)
+ * (181,395 Float32: per layer weight then bias, column-major) as compute_D.jl:43,68 takes it.  obs: (10,10,2,N) f32 as
+ * snk_state / snk_step_fused emit it; q_out: (3,N) f32.  tcgen05 implicit-GEMM convolutions, bf16 operands, FP32
+ * accumulation. */
+typedef struct snk_qnet_s *snk_qnet;
+SNK_API int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device);
+SNK_API int snk_qnet_destroy(snk_qnet q);
+SNK_API int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3xN, void *cuda_stream);
+
 /* ---- Laplace deviation matrix  compute_D.jl:9-31, 66-81; la_utils.jl:14-36, 154-169 -------- */
 /* D is P x K Float64, column-major (column k = snapshot k).  Welford mean / M2 over the columns in
  * column order, var = M2 / max(K-1,1), then D .-= mean, all in Float64 without FMA contraction so

@@ -73,6 +73,8 @@ def lib():
         "snk_replay_gather": [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "snk_replay_sample_indices": [vp, C.c_uint64, i64, vp, vp],
         "snk_replay_bad_index_host": [vp, C.POINTER(i32)],
+        "snk_qnet_create": [C.POINTER(vp), vp, i64, i32], "snk_qnet_destroy": [vp],
+        "snk_qnet_forward": [vp, vp, i64, vp, vp],
         "snk_gram_workspace_bytes": [i64, i64, i32, C.POINTER(C.c_size_t)],
         "snk_gram_pack": [vp, i32, i64, i64, vp, vp],
         "snk_gram": [vp, i64, i64, i32, i32, i32, vp, vp],
@@ -334,6 +336,7 @@ def center_columns(Dt):
 
 
 from . import shard  # noqa: E402,F401
+from . import bson_io, qnet, rollout  # noqa: E402,F401
 
 
 def pinned_empty(shape, dtype):

@@ -1,0 +1,666 @@
+// qnet.cu — forward pass of the reference's Q-network (structs.jl:127-139) on the 5th-gen tensor cores.
+//
+//   Conv((3,3), 2=>16, relu; pad=1) -> Conv((3,3), 16=>32, relu; pad=1) -> Conv((6,6), 32=>64, relu) ->
+//   Flux.flatten -> Dense(1600, 64, relu) -> Dense(64, 3)          call sites: utils.jl:165 (acting), 448 (targets)
+//
+// Flux's Conv is a true convolution over WHCN arrays: with the kernel flipped once on the host,
+//   out(x, y, o) = b[o] + sum_{k1,k2,c} Wf[k1,k2,c,o] * in_pad(x + k1, y + k2, c),   x = Julia dim 1, y = dim 2.
+//
+// Kernel A (k_qnet_convs): the three convolutions for S samples per CTA iteration, activations never leave
+// shared memory.  Every conv is an implicit GEMM on tcgen05 WITHOUT im2col: activations are stored
+// "chunk-planar" ([8-channel chunk][pixel][8 x bf16], the no-swizzle K-major canonical layout, one 16-byte row
+// per pixel), so the A operand of kernel offset (k1,k2) is the same plane read at a start address shifted by a
+// constant number of pixels — a different shared-memory descriptor, no data movement:
+//   conv1/conv2: rows = 128 consecutive pixels of the zero-padded 12x12 grids of the S samples (shift = 12 k2 + k1);
+//                conv1 has only 2 real input channels, so one K=16 MMA covers two horizontally adjacent taps
+//                (leading-dimension byte offset = one pixel);
+//   conv3:       pixels are stored [y][sample][x], rows = 8-pixel groups at a 10-pixel pitch (stride byte offset
+//                160 B) over (y, sample), shift = 10 S k2 + k1; its 147 KB of weights stream through a 2-slot ring
+//                of k2-slices (cp.async.bulk + mbarrier) while 4-5 accumulator tiles stay live in TMEM.
+//   Epilogues (tcgen05.ld -> bias, relu -> bf16) write the next layer's operand plane directly.
+// Kernel B (k_qnet_head): Dense(1600,64,relu) as a TMA/tcgen05 GEMM over the conv3 activations (one 3.2 KB
+// bf16 row per sample, written by kernel A in the order the packed dense weight expects) with Dense(64,3) fused
+// into its epilogue.
+// Precision: bf16 operands, FP32 accumulation (the reference is Float32) — tolerance in tests/test_qnet_gpu.py.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.h"
+
+namespace snk {
+namespace qnet {
+
+constexpr int S = 12;                         // samples per CTA iteration
+constexpr int THREADS = 384;                  // warp 0 MMA issuer, warp 1 weight producer, warps 4..11 epilogue
+constexpr int PIX12 = 144;                    // padded 12x12 grid
+constexpr int ROWS12 = S * PIX12;             // 1728 flat positions per iteration
+constexpr int TILES12 = (ROWS12 + 127) / 128; // 14
+constexpr int A0_PIX = TILES12 * 128 + 32;    // + room for the largest shift (26) of the last tile
+constexpr int A2_PIX = ((5 * S + 15) / 16) * 160 + 5 * S * 10 + 16;   // groups of the last tile + largest shift
+constexpr int TILES3 = (5 * S + 15) / 16;     // 4 accumulator tiles of 16 (y, sample) groups
+constexpr int W3_SLICE = 6 * 2 * 2048;        // one k2 slice of the conv3 weights
+constexpr int OFF_A0 = 0;
+constexpr int OFF_A1 = OFF_A0 + A0_PIX * 16;
+constexpr int OFF_A2 = OFF_A1 + 2 * A0_PIX * 16;
+constexpr int OFF_W1 = OFF_A2 + 4 * A2_PIX * 16;
+constexpr int OFF_W2 = OFF_W1 + 3 * 2 * 512;
+constexpr int OFF_W3 = OFF_W2 + 9 * 1024;
+constexpr int OFF_BIAS = OFF_W3 + 2 * W3_SLICE;          // b1 (16) b2 (32) b3 (64) f32
+constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
+constexpr int SMEM_A = OFF_BAR + 128 + 128;              // barriers + alignment slack
+static_assert(SMEM_A <= 232448, "kernel A shared memory over the 227 KB limit");
+constexpr int TMEM_C3 = 0, TMEM_C2 = 320, TMEM_C1 = 384; // column offsets of the accumulators
+
+// packed parameter blob (device): byte offsets
+constexpr size_t P_W1 = 0, P_W2 = P_W1 + 3 * 2 * 512, P_W3 = P_W2 + 9 * 1024, P_BIAS = P_W3 + 6 * (size_t)W3_SLICE;
+constexpr size_t P_W4 = P_BIAS + 112 * 4;                // [64][1600] bf16, columns in kernel-A order
+constexpr size_t P_B4 = P_W4 + 64 * 1600 * 2, P_W5 = P_B4 + 64 * 4, P_B5 = P_W5 + 3 * 64 * 4, P_END = P_B5 + 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {     // bounded: a protocol bug traps, never hangs
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("snk qnet: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"((uint64_t)src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c_inner, int c_row) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row) : "memory");
+}
+
+// no-swizzle K-major operand descriptor: core matrix = 8 rows x 16 B; LBO = byte distance between the two 8-element
+// K chunks of one K=16 MMA, SBO = byte distance between 8-row groups (cute::UMMA::SmemDescriptor, layout_type 0)
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+struct ConvArgs {
+    const float *obs;            // (10,10,2,N) f32
+    long long n;
+    const uint8_t *params;       // packed blob
+    __nv_bfloat16 *out3;         // [N][1600] bf16: k' = (oy*5 + ox)*64 + c
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t *A0 = smem + OFF_A0, *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
+    const float *bias = (const float *)(smem + OFF_BIAS);
+    uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
+    uint64_t *acc_full = bars, *acc_empty = bars + 2, *w3_full = bars + 4, *w3_empty = bars + 6, *c3_full = bars + 8;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 10);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup: zero the activation planes (borders / K padding stay zero), stage W1, W2, biases
+    for (int i = tid; i < OFF_W1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(P_W3 / 16); i += THREADS)
+        reinterpret_cast<uint4 *>(smem + OFF_W1)[i] = reinterpret_cast<const uint4 *>(a.params)[i];
+    for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], 1); }
+        mbar_init(c3_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // pipeline state that survives across iterations
+    uint32_t acc_it = 0;       // MMA issuer / epilogue: accumulator-buffer uses so far (conv1 + conv2 tiles)
+    uint32_t w3_it = 0;        // producer / MMA issuer: W3 slices so far
+    uint32_t c3_it = 0;
+
+    const long long n_iter = (a.n + S - 1) / S;
+    for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
+        const long long s0 = it * S;
+        // ---- load the observations: pixel (x, y) of sample s -> A0[(s*144 + (y+1)*12 + (x+1))] channels 0,1
+        for (int i = tid; i < S * 100; i += THREADS) {
+            const int s = i / 100, p = i - s * 100;                 // p = x + 10 y   (Julia (r, c) = (x, y))
+            float f0 = 0.f, f1 = 0.f;
+            if (s0 + s < a.n) {
+                const float *o = a.obs + (s0 + s) * 200 + p;
+                f0 = __ldg(o);
+                f1 = __ldg(o + 100);
+            }
+            const int y = p / 10, x = p - 10 * y;
+            __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+            *reinterpret_cast<uint32_t *>(A0 + (s * PIX12 + (y + 1) * 12 + (x + 1)) * 16) = *reinterpret_cast<uint32_t *>(&h);
+        }
+        fence_proxy_async();
+        __syncthreads();
+
+        if (warp == 1 && lane == 0) {
+            // ================= conv3 weight producer, part 1: the first two k2-slices fill the 2-slot ring now and
+            // land while conv1/conv2 run (the remaining four follow in the conv3 phase) =================
+            for (int k2 = 0; k2 < 2; k2++) {
+                const uint32_t u = w3_it + k2;
+                const int b = u & 1;
+                mbar_wait(&w3_empty[b], ((u >> 1) & 1) ^ 1);
+                mbar_expect_tx(&w3_full[b], W3_SLICE);
+                bulk_load(smem + OFF_W3 + b * W3_SLICE, a.params + P_W3 + (size_t)k2 * W3_SLICE, W3_SLICE, &w3_full[b]);
+            }
+        }
+        // ================= conv1: 2 -> 16, 3x3, pad 1 =================
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int t = 0; t < TILES12; t++) {
+                    const uint32_t u = acc_it + t;
+                    const int b = u & 1;
+                    mbar_wait(&acc_empty[b], ((u >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + TMEM_C1 + b * 16;
+                    const uint32_t a_base = smem_u32(A0) + (uint32_t)(t * 128) * 16;
+#pragma unroll
+                    for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+                        for (int pr = 0; pr < 2; pr++) {
+                            // K chunk 0 = tap k1 = 2 pr, chunk 1 = the next pixel (tap 2 pr + 1; zero weights for pr = 1)
+                            const uint64_t ad = desc_nosw(a_base + (uint32_t)(k2 * 12 + 2 * pr) * 16, 16, 128);
+                            const uint64_t bd = desc_nosw(smem_u32(smem + OFF_W1) + (uint32_t)(k2 * 2 + pr) * 512, 256, 128);
+                            umma_bf16(d, ad, bd, idesc_bf16(128, 16), (k2 | pr) ? 1u : 0u);
+                        }
+                    umma_commit(&acc_full[b]);
+                }
+            }
+        } else if (warp >= 4) {
+            const int grp = (warp - 4) >> 2, q = warp & 3;
+            uint32_t my_it = acc_it;
+            for (int t = 0; t < TILES12; t++, my_it++) {
+                if ((int)(my_it & 1) != grp) continue;
+                const int b = my_it & 1;
+                mbar_wait(&acc_full[b], (my_it >> 1) & 1);
+                tc_fence_after();
+                uint32_t v[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C1 + b * 16, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[b]);
+                const int P = t * 128 + q * 32 + lane;
+                const int rem = P % PIX12, y = rem / 12, x = rem - 12 * y;
+                if (P < ROWS12 && x < 10 && y < 10) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        w[j] = pack_relu_bf16(__uint_as_float(v[2 * j]) + bias[2 * j], __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1]);
+                    uint8_t *dst = A1 + (P + 13) * 16;               // (x+1, y+1) in conv2's padded grid
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4 *>(dst + A0_PIX * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+            }
+        }
+        acc_it += TILES12;
+        fence_proxy_async();
+        __syncthreads();
+
+        // ================= conv2: 16 -> 32, 3x3, pad 1 =================
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int t = 0; t < TILES12; t++) {
+                    const uint32_t u = acc_it + t;
+                    const int b = u & 1;
+                    mbar_wait(&acc_empty[b], ((u >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + TMEM_C2 + b * 32;
+                    const uint32_t a_base = smem_u32(A1) + (uint32_t)(t * 128) * 16;
+#pragma unroll
+                    for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+                        for (int k1 = 0; k1 < 3; k1++) {
+                            const uint64_t ad = desc_nosw(a_base + (uint32_t)(k2 * 12 + k1) * 16, A0_PIX * 16, 128);
+                            const uint64_t bd = desc_nosw(smem_u32(smem + OFF_W2) + (uint32_t)(k2 * 3 + k1) * 1024, 512, 128);
+                            umma_bf16(d, ad, bd, idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
+                        }
+                    umma_commit(&acc_full[b]);
+                }
+            }
+        } else if (warp >= 4) {
+            const int grp = (warp - 4) >> 2, q = warp & 3;
+            uint32_t my_it = acc_it;
+            for (int t = 0; t < TILES12; t++, my_it++) {
+                if ((int)(my_it & 1) != grp) continue;
+                const int b = my_it & 1;
+                mbar_wait(&acc_full[b], (my_it >> 1) & 1);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C2 + b * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C2 + b * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[b]);
+                const int P = t * 128 + q * 32 + lane;
+                const int s = P / PIX12, rem = P - s * PIX12, y = rem / 12, x = rem - 12 * y;
+                if (P < ROWS12 && x < 10 && y < 10) {
+                    uint8_t *dst = A2 + ((y * S + s) * 10 + x) * 16;          // [y][sample][x]
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; c8++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            w[j] = pack_relu_bf16(__uint_as_float(v[c8 * 8 + 2 * j]) + bias[16 + c8 * 8 + 2 * j],
+                                                  __uint_as_float(v[c8 * 8 + 2 * j + 1]) + bias[16 + c8 * 8 + 2 * j + 1]);
+                        *reinterpret_cast<uint4 *>(dst + c8 * (A2_PIX * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+        acc_it += TILES12;
+        fence_proxy_async();
+        __syncthreads();
+
+        // ================= conv3: 32 -> 64, 6x6, valid =================
+        if (warp == 0) {
+            if (lane == 0) {
+                tc_fence_after();
+                for (int k2 = 0; k2 < 6; k2++) {
+                    const uint32_t u = w3_it + k2;
+                    const int b = u & 1;
+                    mbar_wait(&w3_full[b], (u >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t w_base = smem_u32(smem + OFF_W3 + b * W3_SLICE);
+                    for (int tt = 0; tt < TILES3; tt++) {
+                        const uint32_t d = tmem + TMEM_C3 + tt * 64;
+                        const uint32_t a_base = smem_u32(A2) + (uint32_t)(tt * 160 + k2 * S * 10) * 16;
+#pragma unroll
+                        for (int k1 = 0; k1 < 6; k1++)
+#pragma unroll
+                            for (int m = 0; m < 2; m++) {
+                                const uint64_t ad = desc_nosw(a_base + (uint32_t)k1 * 16 + (uint32_t)(2 * m) * (A2_PIX * 16), A2_PIX * 16, 160);
+                                const uint64_t bd = desc_nosw(w_base + (uint32_t)(k1 * 2 + m) * 2048, 1024, 128);
+                                umma_bf16(d, ad, bd, idesc_bf16(128, 64), (k2 | k1 | m) ? 1u : 0u);
+                            }
+                    }
+                    umma_commit(&w3_empty[b]);
+                }
+                umma_commit(c3_full);
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                // conv3 weight producer, part 2: slices 2..5 as the tensor core releases the ring slots
+                for (int k2 = 2; k2 < 6; k2++) {
+                    const uint32_t u = w3_it + k2;
+                    const int b = u & 1;
+                    mbar_wait(&w3_empty[b], ((u >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&w3_full[b], W3_SLICE);
+                    bulk_load(smem + OFF_W3 + b * W3_SLICE, a.params + P_W3 + (size_t)k2 * W3_SLICE, W3_SLICE, &w3_full[b]);
+                }
+            }
+        } else if (warp >= 4) {
+            const int grp = (warp - 4) >> 2, q = warp & 3;
+            mbar_wait(c3_full, c3_it & 1);
+            tc_fence_after();
+            for (int tt = grp; tt < TILES3; tt += 2) {
+                const int r = q * 32 + lane, g = tt * 16 + (r >> 3), ox = r & 7;
+                const int oy = g / S, s = g - oy * S;
+                const bool valid = ox < 5 && oy < 5 && (s0 + s) < a.n;
+                uint4 *dst = reinterpret_cast<uint4 *>(a.out3 + (s0 + s) * 1600 + (oy * 5 + ox) * 64);
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C3 + tt * 64 + h * 16, v);
+                    tmem_ld_wait();
+                    if (valid) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            w[j] = pack_relu_bf16(__uint_as_float(v[2 * j]) + bias[48 + h * 16 + 2 * j],
+                                                  __uint_as_float(v[2 * j + 1]) + bias[48 + h * 16 + 2 * j + 1]);
+                        dst[2 * h] = make_uint4(w[0], w[1], w[2], w[3]);
+                        dst[2 * h + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+        w3_it += 6;
+        c3_it++;
+        __syncthreads();                            // conv3 accumulators and A2 are free again
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ---- kernel B: Dense(1600,64,relu) + Dense(64,3) ---------------------------------------------------------
+constexpr int HB_M = 128, HB_K = 64, HB_STAGES = 6;
+constexpr int HB_STAGE_BYTES = HB_M * 128 + 64 * 128;      // A tile 16 KB + W4 tile 8 KB (SWIZZLE_128B rows of 64 bf16)
+constexpr int HB_SMEM = HB_STAGES * HB_STAGE_BYTES + 1024 + 256 + 64 * 4 + 3 * 64 * 4 + 16;
+constexpr int HB_THREADS = 192;
+
+struct HeadArgs {
+    const uint8_t *params;
+    float *q_out;               // (3, N)
+    long long n;
+};
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_constant__ CUtensorMap map_x,   // out3 [N][1600], box 128 x 64
+                                                             const __grid_constant__ CUtensorMap map_w,   // W4' [64][1600], box 64 x 64
+                                                             const HeadArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + HB_STAGES * HB_STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + HB_STAGES, *acc_full = bars + 2 * HB_STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+    float *s_b4 = (float *)(tmem_slot + 4), *s_w5 = s_b4 + 64, *s_b5 = s_w5 + 192;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long n_tiles = (a.n + HB_M - 1) / HB_M;
+    constexpr int KB = 1600 / HB_K;   // 25
+
+    for (int i = tid; i < 64; i += HB_THREADS) s_b4[i] = reinterpret_cast<const float *>(a.params + P_B4)[i];
+    for (int i = tid; i < 192; i += HB_THREADS) s_w5[i] = reinterpret_cast<const float *>(a.params + P_W5)[i];
+    if (tid < 3) s_b5[tid] = reinterpret_cast<const float *>(a.params + P_B5)[tid];
+    if (tid == 0) {
+        for (int s = 0; s < HB_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x)
+                for (int kb = 0; kb < KB; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * HB_STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], HB_STAGE_BYTES);
+                    tma_load_2d(&map_x, &full[stage], st, kb * HB_K, (int)(t * HB_M));
+                    tma_load_2d(&map_w, &full[stage], st + HB_M * 128, kb * HB_K, 0);
+                    if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < KB; kb++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + stage * HB_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < HB_K / 16; k++)
+                        umma_bf16(tmem + acc * 64, desc_sw128(base) + (uint64_t)(2 * k), desc_sw128(base + HB_M * 128) + (uint64_t)(2 * k),
+                                  idesc_bf16(128, 64), (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[stage]);
+                    if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            float q0 = s_b5[0], q1 = s_b5[1], q2 = s_b5[2];
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                uint32_t v[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * 64 + h * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int c = h * 16 + j;
+                    const float hv = fmaxf(__uint_as_float(v[j]) + s_b4[c], 0.f);     // Dense(1600,64,relu)
+                    q0 = fmaf(s_w5[c * 3 + 0], hv, q0);                              // Dense(64,3); W5 stored (3,64) column-major
+                    q1 = fmaf(s_w5[c * 3 + 1], hv, q1);
+                    q2 = fmaf(s_w5[c * 3 + 2], hv, q2);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            const long long s = t * HB_M + q * 32 + lane;
+            if (s < a.n) { a.q_out[3 * s] = q0; a.q_out[3 * s + 1] = q1; a.q_out[3 * s + 2] = q2; }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 128);
+    }
+}
+
+// ---- host: parameter packing ------------------------------------------------------------------------------
+static uint16_t f2bf(float f) {            // round-to-nearest-even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// theta = Flux.destructure(q_net): W1(3,3,2,16) b1 W2(3,3,16,32) b2 W3(6,6,32,64) b3 W4(64,1600) b4 W5(3,64) b5, column-major
+static void pack_params(const float *th, std::vector<uint8_t> &blob) {
+    blob.assign(P_END, 0);
+    const float *W1 = th, *b1 = W1 + 288, *W2 = b1 + 16, *b2 = W2 + 4608, *W3 = b2 + 32, *b3 = W3 + 73728;
+    const float *W4 = b3 + 64, *b4 = W4 + 102400, *W5 = b4 + 64, *b5 = W5 + 192;
+    auto bf = [&](size_t off) { return reinterpret_cast<uint16_t *>(blob.data() + off); };
+    // flipped kernels: Wf[k1,k2,c,o] = W[K-1-k1, K-1-k2, c, o]; Flux layout index = a1 + K*(a2 + K*(c + C*o))
+    auto w1 = [&](int k1, int k2, int c, int o) { return W1[(2 - k1) + 3 * ((2 - k2) + 3 * (c + 2 * o))]; };
+    auto w2 = [&](int k1, int k2, int c, int o) { return W2[(2 - k1) + 3 * ((2 - k2) + 3 * (c + 16 * o))]; };
+    auto w3 = [&](int k1, int k2, int c, int o) { return W3[(5 - k1) + 6 * ((5 - k2) + 6 * (c + 32 * o))]; };
+    // W1: [k2][pair][chunk][o (16)][8]: chunk 0 = tap k1 = 2*pair, chunk 1 = tap 2*pair + 1 (absent for pair 1)
+    for (int k2 = 0; k2 < 3; k2++)
+        for (int pr = 0; pr < 2; pr++)
+            for (int ch = 0; ch < 2; ch++) {
+                const int k1 = 2 * pr + ch;
+                if (k1 > 2) continue;
+                for (int o = 0; o < 16; o++)
+                    for (int c = 0; c < 2; c++)
+                        bf(P_W1)[(((k2 * 2 + pr) * 2 + ch) * 16 + o) * 8 + c] = f2bf(w1(k1, k2, c, o));
+            }
+    // W2: [k2][k1][chunk (2)][o (32)][8]
+    for (int k2 = 0; k2 < 3; k2++)
+        for (int k1 = 0; k1 < 3; k1++)
+            for (int c = 0; c < 16; c++)
+                for (int o = 0; o < 32; o++)
+                    bf(P_W2)[(((k2 * 3 + k1) * 2 + c / 8) * 32 + o) * 8 + c % 8] = f2bf(w2(k1, k2, c, o));
+    // W3: [k2][k1][m (2)][chunk (2)][o (64)][8], channel c = 16 m + 8 chunk + j
+    for (int k2 = 0; k2 < 6; k2++)
+        for (int k1 = 0; k1 < 6; k1++)
+            for (int c = 0; c < 32; c++)
+                for (int o = 0; o < 64; o++)
+                    bf(P_W3)[((((k2 * 6 + k1) * 2 + c / 16) * 2 + (c / 8) % 2) * 64 + o) * 8 + c % 8] = f2bf(w3(k1, k2, c, o));
+    float *bias = reinterpret_cast<float *>(blob.data() + P_BIAS);
+    memcpy(bias, b1, 64); memcpy(bias + 16, b2, 128); memcpy(bias + 48, b3, 256);
+    // W4 (64,1600) column-major, Flux flatten index kF = x + 5 y + 25 c  ->  [n][k' = (y*5 + x)*64 + c]
+    for (int n = 0; n < 64; n++)
+        for (int c = 0; c < 64; c++)
+            for (int y = 0; y < 5; y++)
+                for (int x = 0; x < 5; x++)
+                    bf(P_W4)[(size_t)n * 1600 + (y * 5 + x) * 64 + c] = f2bf(W4[n + 64 * (x + 5 * y + 25 * c)]);
+    memcpy(blob.data() + P_B4, b4, 256);
+    memcpy(blob.data() + P_W5, W5, 768);          // (3,64) column-major: W5[a + 3 c]
+    memcpy(blob.data() + P_B5, b5, 12);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_map_bf16(CUtensorMap *m, const void *base, long long rows, long long cols, int box_rows, int box_cols) {
+    static EncodeTiledFn enc = nullptr;
+    if (enc == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SNK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || p == nullptr) return fail(SNK_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+        enc = (EncodeTiledFn)p;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SNK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SNK_OK;
+}
+
+}  // namespace qnet
+}  // namespace snk
+
+using namespace snk;
+using namespace snk::qnet;
+
+struct snk_qnet_s {
+    int device;
+    uint8_t *params;
+    __nv_bfloat16 *out3;
+    long long out3_cap;
+    int sms;
+};
+
+extern "C" {
+
+int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device) {
+    SNK_REQUIRE(out != nullptr && theta_host != nullptr, "null argument");
+    SNK_REQUIRE(n_params == 181395, "theta must be Flux.destructure of the two-frame Q-net (181,395 parameters, structs.jl:127-139)");
+    *out = nullptr;
+    SNK_CUDA(cudaSetDevice(device));
+    std::vector<uint8_t> blob;
+    pack_params(theta_host, blob);
+    snk_qnet_s *q = new (std::nothrow) snk_qnet_s();
+    if (q == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
+    memset(q, 0, sizeof(*q));
+    q->device = device;
+    cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
+    cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
+    if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (q->params) cudaFree(q->params);
+        delete q;
+        return fail(SNK_ERR_CUDA, "snk_qnet_create: %s", cudaGetErrorString(e));
+    }
+    *out = q;
+    return SNK_OK;
+}
+
+int snk_qnet_destroy(snk_qnet q) {
+    if (q == nullptr) return SNK_OK;
+    cudaSetDevice(q->device);
+    if (q->params) cudaFree(q->params);
+    if (q->out3) cudaFree(q->out3);
+    delete q;
+    return SNK_OK;
+}
+
+int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3xN, void *cuda_stream) {
+    SNK_REQUIRE(q != nullptr && obs_f32 != nullptr && q_out_3xN != nullptr && N > 0, "bad argument");
+    SNK_CUDA(cudaSetDevice(q->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (q->out3_cap < N) {
+        if (q->out3) { SNK_CUDA(cudaStreamSynchronize(st)); SNK_CUDA(cudaFree(q->out3)); q->out3 = nullptr; }
+        long long cap = (N + 127) / 128 * 128;
+        SNK_CUDA(cudaMalloc((void **)&q->out3, (size_t)cap * 1600 * 2));
+        SNK_CUDA(cudaMemsetAsync(q->out3, 0, (size_t)cap * 1600 * 2, st));
+        q->out3_cap = cap;
+    }
+    ConvArgs ca;
+    ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = q->out3;
+    const long long n_iter = (N + S - 1) / S;
+    int grid = (int)(n_iter < q->sms ? n_iter : q->sms);
+    SNK_CUDA(cudaFuncSetAttribute(k_qnet_convs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_A));
+    k_qnet_convs<<<grid, THREADS, SMEM_A, st>>>(ca);
+    SNK_CUDA(cudaGetLastError());
+    CUtensorMap mx, mw;
+    int rc;
+    if ((rc = make_map_bf16(&mx, q->out3, q->out3_cap, 1600, HB_M, HB_K)) != SNK_OK) return rc;
+    if ((rc = make_map_bf16(&mw, q->params + P_W4, 64, 1600, 64, HB_K)) != SNK_OK) return rc;
+    HeadArgs ha;
+    ha.params = q->params; ha.q_out = q_out_3xN; ha.n = N;
+    const long long n_tiles = (N + HB_M - 1) / HB_M;
+    grid = (int)(n_tiles < q->sms ? n_tiles : q->sms);
+    SNK_CUDA(cudaFuncSetAttribute(k_qnet_head, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM));
+    k_qnet_head<<<grid, HB_THREADS, HB_SMEM, st>>>(mx, mw, ha);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+}  // extern "C"

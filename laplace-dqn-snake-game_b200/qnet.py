@@ -7,6 +7,7 @@
 the forward pass.  backend="torch" is a LIBRARY path (cuDNN / cuBLAS through torch), kept as the reference
 implementation the native kernel is checked against; it is labelled as such wherever it is timed.
 """
+import ctypes as C
 import math
 
 import numpy as np
@@ -43,8 +44,22 @@ def glorot_layers(seed=0, in_frames=2):
     return layers
 
 
+BACKEND_NOTES = {
+    "torch": "LIBRARY path: torch conv2d/linear (cuDNN/cuBLAS), fp32 — the baseline, not a kernel of this repo",
+    "torch_bf16": "LIBRARY path: torch conv2d/linear in bf16 channels_last (cuDNN/cuBLAS)",
+    "native": "this repo: tcgen05 implicit-GEMM convolutions + TMA/tcgen05 dense head (snk_qnet_forward), bf16 operands, fp32 accumulate",
+}
+
+
+def available_backends():
+    return ["native", "torch_bf16", "torch"]
+
+
 class QNet:
-    def __init__(self, layers, device, dtype=torch.float32):
+    def __init__(self, layers, device, dtype=torch.float32, backend="torch"):
+        self.backend = backend
+        if backend == "torch_bf16":
+            dtype = torch.bfloat16
         self.device, self.dtype = torch.device(device), dtype
         self.params = []
         for kind, p in layers:
@@ -55,6 +70,30 @@ class QNet:
                 self.params.append(("dense", torch.from_numpy(np.ascontiguousarray(p["W"])).to(self.device, dtype),
                                     torch.from_numpy(p["b"]).to(self.device, dtype), None))
         self.n_params = sum(w.numel() + b.numel() for _, w, b, _ in self.params)
+        self._q = None
+        if backend == "native":
+            from . import _check, lib
+            theta = np.ascontiguousarray(bson_io.destructure(layers), dtype=np.float32)
+            self._q = C.c_void_p()
+            _check(lib().snk_qnet_create(C.byref(self._q), theta.ctypes.data_as(C.c_void_p), theta.size,
+                                         self.device.index or 0))
+
+    def close(self):
+        if getattr(self, "_q", None):
+            from . import lib
+            lib().snk_qnet_destroy(self._q)
+            self._q = None
+
+    __del__ = close
+
+    def forward_native(self, obs):
+        """snk_qnet_forward: obs (N,2,10,10) float32 contiguous -> Q (N,3) float32"""
+        from . import _check, _ptr, lib
+        n = obs.shape[0]
+        out = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _check(lib().snk_qnet_forward(self._q, _ptr(obs, torch.float32, n * 200, self.device), n, _ptr(out), st))
+        return out
 
     @classmethod
     def from_trainer_bson(cls, path, device, which="q_net", dtype=torch.float32):
@@ -64,6 +103,8 @@ class QNet:
     def forward_torch(self, obs):
         """obs: (N, C, 10, 10) = Julia (10,10,C,N).  Returns Q (N, 3) float32 [= Julia (3, N)]."""
         x = obs.to(self.dtype)
+        if self.backend == "torch_bf16":
+            x = x.contiguous(memory_format=torch.channels_last)
         convs = [p for p in self.params if p[0] == "conv"]
         denses = [p for p in self.params if p[0] == "dense"]
         for _, w, b, pad in convs:
@@ -73,4 +114,5 @@ class QNet:
         x = F.linear(x, denses[1][1], denses[1][2])
         return x.float().contiguous()
 
-    __call__ = forward_torch
+    def __call__(self, obs):
+        return self.forward_native(obs) if self.backend == "native" else self.forward_torch(obs)
