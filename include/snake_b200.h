@@ -192,6 +192,8 @@ typedef struct snk_qnet_s *snk_qnet;
 SNK_API int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device);
 SNK_API int snk_qnet_destroy(snk_qnet q);
 SNK_API int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3xN, void *cuda_stream);
+/* profiling aid: device buffer (int64[8 * iterations of CTA 0]) that receives clock64 stamps of the conv phases */
+SNK_API int snk_qnet_debug_timing(snk_qnet q, long long *device_buf);
 
 /* ---- Laplace deviation matrix  compute_D.jl:9-31, 66-81; la_utils.jl:14-36, 154-169 -------- */
 /* D is P x K Float64, column-major (column k = snapshot k).  Welford mean / M2 over the columns in

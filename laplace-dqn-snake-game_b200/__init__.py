@@ -150,9 +150,12 @@ class SnakeGame:
             _check(lib().snk_set_seed(self._h, int(seed)))
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().snk_destroy(self._h)
-            self._h = C.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().snk_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:              # interpreter shutdown: module globals may already be gone
+            pass
 
     __del__ = close
 
@@ -400,9 +403,12 @@ class ReplayBuffer:
         _check(lib().snk_replay_create(C.byref(self._r), self.capacity, int(device)))
 
     def close(self):
-        if getattr(self, "_r", None) and self._r.value:
-            lib().snk_replay_destroy(self._r)
-            self._r = C.c_void_p()
+        try:
+            if getattr(self, "_r", None) and self._r.value:
+                lib().snk_replay_destroy(self._r)
+                self._r = C.c_void_p()
+        except Exception:
+            pass
 
     __del__ = close
 

@@ -53,7 +53,8 @@ constexpr int OFF_BIAS = OFF_W3 + 2 * W3_SLICE;          // b1 (16) b2 (32) b3 (
 constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
 constexpr int SMEM_A = OFF_BAR + 128 + 128;              // barriers + alignment slack
 static_assert(SMEM_A <= 232448, "kernel A shared memory over the 227 KB limit");
-constexpr int TMEM_C3 = 0, TMEM_C2 = 320, TMEM_C1 = 384; // column offsets of the accumulators
+constexpr int NACC = 4;                                  // accumulator buffers cycled by the conv1 / conv2 tiles
+constexpr int TMEM_C3 = 0, TMEM_C2 = 256, TMEM_C1 = 384; // column offsets: conv3 4 x 64 | conv2 NACC x 32 | conv1 NACC x 16
 
 // packed parameter blob (device): byte offsets
 constexpr size_t P_W1 = 0, P_W2 = P_W1 + 3 * 2 * 512, P_W3 = P_W2 + 9 * 1024, P_BIAS = P_W3 + 6 * (size_t)W3_SLICE;
@@ -139,7 +140,25 @@ struct ConvArgs {
     long long n;
     const uint8_t *params;       // packed blob
     __nv_bfloat16 *out3;         // [N][1600] bf16: k' = (oy*5 + ox)*64 + c
+    long long *timing;           // optional (debug): per-phase clock64 stamps of block 0, 8 per iteration
 };
+#define QNET_STAMP(k) do { if (a.timing != nullptr && blockIdx.x == 0 && tid == 128) a.timing[it_local * 8 + (k)] = clock64(); } while (0)
+
+// observations of S samples starting at s0 -> A0 (channels 0,1 of the padded 12x12 grids), by threads [t0, t0+nt)
+__device__ __forceinline__ void load_obs(const ConvArgs &a, long long s0, uint8_t *A0, int t, int nt) {
+    for (int i = t; i < S * 100; i += nt) {
+        const int s = i / 100, p = i - s * 100;                 // p = x + 10 y   (Julia (r, c) = (x, y))
+        float f0 = 0.f, f1 = 0.f;
+        if (s0 + s < a.n) {
+            const float *o = a.obs + (s0 + s) * 200 + p;
+            f0 = __ldg(o);
+            f1 = __ldg(o + 100);
+        }
+        const int y = p / 10, x = p - 10 * y;
+        __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+        *reinterpret_cast<uint32_t *>(A0 + (s * PIX12 + (y + 1) * 12 + (x + 1)) * 16) = *reinterpret_cast<uint32_t *>(&h);
+    }
+}
 
 __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -147,8 +166,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
     uint8_t *A0 = smem + OFF_A0, *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
     const float *bias = (const float *)(smem + OFF_BIAS);
     uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
-    uint64_t *acc_full = bars, *acc_empty = bars + 2, *w3_full = bars + 4, *w3_empty = bars + 6, *c3_full = bars + 8;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 10);
+    uint64_t *acc_full = bars, *acc_empty = bars + NACC, *w3_full = bars + 2 * NACC, *w3_empty = w3_full + 2, *c3_full = w3_empty + 2;
+    uint32_t *tmem_slot = (uint32_t *)(c3_full + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time setup: zero the activation planes (borders / K padding stay zero), stage W1, W2, biases
@@ -157,44 +176,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
         reinterpret_cast<uint4 *>(smem + OFF_W1)[i] = reinterpret_cast<const uint4 *>(a.params)[i];
     for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
     if (tid == 0) {
-        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], 1); }
         mbar_init(c3_full, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
+    __syncthreads();
+    const long long n_iter = (a.n + S - 1) / S;
+    if (blockIdx.x < n_iter) load_obs(a, (long long)blockIdx.x * S, A0, tid, THREADS);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // pipeline state that survives across iterations
-    uint32_t acc_it = 0;       // MMA issuer / epilogue: accumulator-buffer uses so far (conv1 + conv2 tiles)
-    uint32_t w3_it = 0;        // producer / MMA issuer: W3 slices so far
+    // constant parts of the operand descriptors; the start-address field counts 16-byte units = pixels
+    const uint64_t dA0 = desc_nosw(smem_u32(A0), 16, 128);                   // conv1: K chunk 1 = the next pixel
+    const uint64_t dA1 = desc_nosw(smem_u32(A1), A0_PIX * 16, 128);          // conv2: K chunks = the two channel planes
+    const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PIX * 16, 160);          // conv3: 8-pixel groups at a 10-pixel pitch
+    const uint64_t dW1 = desc_nosw(smem_u32(smem + OFF_W1), 256, 128);
+    const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);
+    const uint64_t dW3 = desc_nosw(smem_u32(smem + OFF_W3), 1024, 128);
+
+    // pipeline counters (every thread keeps the same values)
+    uint32_t acc_it = 0;       // accumulator-buffer uses so far (conv1 + conv2 tiles)
+    uint32_t w3_it = 0;        // W3 slices so far
     uint32_t c3_it = 0;
 
-    const long long n_iter = (a.n + S - 1) / S;
-    for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
+    long long it_local = 0;
+    for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, it_local++) {
         const long long s0 = it * S;
-        // ---- load the observations: pixel (x, y) of sample s -> A0[(s*144 + (y+1)*12 + (x+1))] channels 0,1
-        for (int i = tid; i < S * 100; i += THREADS) {
-            const int s = i / 100, p = i - s * 100;                 // p = x + 10 y   (Julia (r, c) = (x, y))
-            float f0 = 0.f, f1 = 0.f;
-            if (s0 + s < a.n) {
-                const float *o = a.obs + (s0 + s) * 200 + p;
-                f0 = __ldg(o);
-                f1 = __ldg(o + 100);
-            }
-            const int y = p / 10, x = p - 10 * y;
-            __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-            *reinterpret_cast<uint32_t *>(A0 + (s * PIX12 + (y + 1) * 12 + (x + 1)) * 16) = *reinterpret_cast<uint32_t *>(&h);
-        }
-        fence_proxy_async();
-        __syncthreads();
-
+        QNET_STAMP(0);
         if (warp == 1 && lane == 0) {
-            // ================= conv3 weight producer, part 1: the first two k2-slices fill the 2-slot ring now and
-            // land while conv1/conv2 run (the remaining four follow in the conv3 phase) =================
+            // conv3 weight producer, part 1: the first two k2-slices fill the 2-slot ring now and land while
+            // conv1/conv2 run (the remaining four follow in the conv3 phase)
             for (int k2 = 0; k2 < 2; k2++) {
                 const uint32_t u = w3_it + k2;
                 const int b = u & 1;
@@ -203,35 +219,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
                 bulk_load(smem + OFF_W3 + b * W3_SLICE, a.params + P_W3 + (size_t)k2 * W3_SLICE, W3_SLICE, &w3_full[b]);
             }
         }
+        QNET_STAMP(1);
         // ================= conv1: 2 -> 16, 3x3, pad 1 =================
         if (warp == 0) {
             if (lane == 0) {
                 for (int t = 0; t < TILES12; t++) {
                     const uint32_t u = acc_it + t;
-                    const int b = u & 1;
-                    mbar_wait(&acc_empty[b], ((u >> 1) & 1) ^ 1);
+                    const int b = u % NACC;
+                    mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d = tmem + TMEM_C1 + b * 16;
-                    const uint32_t a_base = smem_u32(A0) + (uint32_t)(t * 128) * 16;
+                    const uint64_t at = dA0 + (uint64_t)(t * 128);
 #pragma unroll
                     for (int k2 = 0; k2 < 3; k2++)
 #pragma unroll
-                        for (int pr = 0; pr < 2; pr++) {
-                            // K chunk 0 = tap k1 = 2 pr, chunk 1 = the next pixel (tap 2 pr + 1; zero weights for pr = 1)
-                            const uint64_t ad = desc_nosw(a_base + (uint32_t)(k2 * 12 + 2 * pr) * 16, 16, 128);
-                            const uint64_t bd = desc_nosw(smem_u32(smem + OFF_W1) + (uint32_t)(k2 * 2 + pr) * 512, 256, 128);
-                            umma_bf16(d, ad, bd, idesc_bf16(128, 16), (k2 | pr) ? 1u : 0u);
-                        }
+                        for (int pr = 0; pr < 2; pr++)       // K chunk 0 = tap k1 = 2 pr, chunk 1 = tap 2 pr + 1 (zero weights for pr = 1)
+                            umma_bf16(d, at + (uint64_t)(k2 * 12 + 2 * pr), dW1 + (uint64_t)((k2 * 2 + pr) * 32),
+                                      idesc_bf16(128, 16), (k2 | pr) ? 1u : 0u);
                     umma_commit(&acc_full[b]);
                 }
             }
         } else if (warp >= 4) {
             const int grp = (warp - 4) >> 2, q = warp & 3;
-            uint32_t my_it = acc_it;
-            for (int t = 0; t < TILES12; t++, my_it++) {
-                if ((int)(my_it & 1) != grp) continue;
-                const int b = my_it & 1;
-                mbar_wait(&acc_full[b], (my_it >> 1) & 1);
+            for (int t = 0; t < TILES12; t++) {
+                const uint32_t u = acc_it + t;
+                if ((int)(u & 1) != grp) continue;
+                const int b = u % NACC;
+                mbar_wait(&acc_full[b], (u / NACC) & 1);
                 tc_fence_after();
                 uint32_t v[16];
                 tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C1 + b * 16, v);
@@ -255,35 +269,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
         acc_it += TILES12;
         fence_proxy_async();
         __syncthreads();
+        QNET_STAMP(2);
 
         // ================= conv2: 16 -> 32, 3x3, pad 1 =================
         if (warp == 0) {
             if (lane == 0) {
                 for (int t = 0; t < TILES12; t++) {
                     const uint32_t u = acc_it + t;
-                    const int b = u & 1;
-                    mbar_wait(&acc_empty[b], ((u >> 1) & 1) ^ 1);
+                    const int b = u % NACC;
+                    mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d = tmem + TMEM_C2 + b * 32;
-                    const uint32_t a_base = smem_u32(A1) + (uint32_t)(t * 128) * 16;
+                    const uint64_t at = dA1 + (uint64_t)(t * 128);
 #pragma unroll
                     for (int k2 = 0; k2 < 3; k2++)
 #pragma unroll
-                        for (int k1 = 0; k1 < 3; k1++) {
-                            const uint64_t ad = desc_nosw(a_base + (uint32_t)(k2 * 12 + k1) * 16, A0_PIX * 16, 128);
-                            const uint64_t bd = desc_nosw(smem_u32(smem + OFF_W2) + (uint32_t)(k2 * 3 + k1) * 1024, 512, 128);
-                            umma_bf16(d, ad, bd, idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
-                        }
+                        for (int k1 = 0; k1 < 3; k1++)
+                            umma_bf16(d, at + (uint64_t)(k2 * 12 + k1), dW2 + (uint64_t)((k2 * 3 + k1) * 64),
+                                      idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
                     umma_commit(&acc_full[b]);
                 }
             }
         } else if (warp >= 4) {
             const int grp = (warp - 4) >> 2, q = warp & 3;
-            uint32_t my_it = acc_it;
-            for (int t = 0; t < TILES12; t++, my_it++) {
-                if ((int)(my_it & 1) != grp) continue;
-                const int b = my_it & 1;
-                mbar_wait(&acc_full[b], (my_it >> 1) & 1);
+            for (int t = 0; t < TILES12; t++) {
+                const uint32_t u = acc_it + t;
+                if ((int)(u & 1) != grp) continue;
+                const int b = u % NACC;
+                mbar_wait(&acc_full[b], (u / NACC) & 1);
                 tc_fence_after();
                 uint32_t v[32];
                 tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C2 + b * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -311,6 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
         acc_it += TILES12;
         fence_proxy_async();
         __syncthreads();
+        QNET_STAMP(3);
 
         // ================= conv3: 32 -> 64, 6x6, valid =================
         if (warp == 0) {
@@ -321,25 +335,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
                     const int b = u & 1;
                     mbar_wait(&w3_full[b], (u >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t w_base = smem_u32(smem + OFF_W3 + b * W3_SLICE);
+                    const uint64_t wb = dW3 + (uint64_t)(b * (W3_SLICE / 16));
                     for (int tt = 0; tt < TILES3; tt++) {
                         const uint32_t d = tmem + TMEM_C3 + tt * 64;
-                        const uint32_t a_base = smem_u32(A2) + (uint32_t)(tt * 160 + k2 * S * 10) * 16;
+                        const uint64_t at = dA2 + (uint64_t)(tt * 160 + k2 * S * 10);
 #pragma unroll
                         for (int k1 = 0; k1 < 6; k1++)
 #pragma unroll
-                            for (int m = 0; m < 2; m++) {
-                                const uint64_t ad = desc_nosw(a_base + (uint32_t)k1 * 16 + (uint32_t)(2 * m) * (A2_PIX * 16), A2_PIX * 16, 160);
-                                const uint64_t bd = desc_nosw(w_base + (uint32_t)(k1 * 2 + m) * 2048, 1024, 128);
-                                umma_bf16(d, ad, bd, idesc_bf16(128, 64), (k2 | k1 | m) ? 1u : 0u);
-                            }
+                            for (int m = 0; m < 2; m++)
+                                umma_bf16(d, at + (uint64_t)(k1 + 2 * m * A2_PIX), wb + (uint64_t)((k1 * 2 + m) * 128),
+                                          idesc_bf16(128, 64), (k2 | k1 | m) ? 1u : 0u);
                     }
                     umma_commit(&w3_empty[b]);
                 }
                 umma_commit(c3_full);
             }
-        } else if (warp == 1) {
-            if (lane == 0) {
+        } else {
+            if (warp == 1 && lane == 0) {
                 // conv3 weight producer, part 2: slices 2..5 as the tensor core releases the ring slots
                 for (int k2 = 2; k2 < 6; k2++) {
                     const uint32_t u = w3_it + k2;
@@ -349,36 +361,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
                     bulk_load(smem + OFF_W3 + b * W3_SLICE, a.params + P_W3 + (size_t)k2 * W3_SLICE, W3_SLICE, &w3_full[b]);
                 }
             }
-        } else if (warp >= 4) {
-            const int grp = (warp - 4) >> 2, q = warp & 3;
-            mbar_wait(c3_full, c3_it & 1);
-            tc_fence_after();
-            for (int tt = grp; tt < TILES3; tt += 2) {
-                const int r = q * 32 + lane, g = tt * 16 + (r >> 3), ox = r & 7;
-                const int oy = g / S, s = g - oy * S;
-                const bool valid = ox < 5 && oy < 5 && (s0 + s) < a.n;
-                uint4 *dst = reinterpret_cast<uint4 *>(a.out3 + (s0 + s) * 1600 + (oy * 5 + ox) * 64);
+            // while the tensor core works through conv3, warps 2..11 stage the NEXT iteration's observations
+            // (A0 is free: this iteration's conv1 has been consumed)
+            if (warp >= 2 && it + gridDim.x < n_iter) load_obs(a, (it + gridDim.x) * S, A0, tid - 64, THREADS - 64);
+            if (warp >= 4) {
+                const int grp = (warp - 4) >> 2, q = warp & 3;
+                mbar_wait(c3_full, c3_it & 1);
+                tc_fence_after();
+                QNET_STAMP(4);
+                for (int tt = grp; tt < TILES3; tt += 2) {
+                    const int r = q * 32 + lane, g = tt * 16 + (r >> 3), ox = r & 7;
+                    const int oy = g / S, s = g - oy * S;
+                    const bool valid = ox < 5 && oy < 5 && (s0 + s) < a.n;
+                    uint4 *dst = reinterpret_cast<uint4 *>(a.out3 + (s0 + s) * 1600 + (oy * 5 + ox) * 64);
+                    uint32_t v[64];
 #pragma unroll
-                for (int h = 0; h < 4; h++) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C3 + tt * 64 + h * 16, v);
+                    for (int h = 0; h < 4; h++)
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C3 + tt * 64 + h * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[h * 16]));
                     tmem_ld_wait();
                     if (valid) {
-                        uint32_t w[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            w[j] = pack_relu_bf16(__uint_as_float(v[2 * j]) + bias[48 + h * 16 + 2 * j],
-                                                  __uint_as_float(v[2 * j + 1]) + bias[48 + h * 16 + 2 * j + 1]);
-                        dst[2 * h] = make_uint4(w[0], w[1], w[2], w[3]);
-                        dst[2 * h + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        for (int h = 0; h < 8; h++) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                w[j] = pack_relu_bf16(__uint_as_float(v[h * 8 + 2 * j]) + bias[48 + h * 8 + 2 * j],
+                                                      __uint_as_float(v[h * 8 + 2 * j + 1]) + bias[48 + h * 8 + 2 * j + 1]);
+                            dst[h] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
                     }
                 }
+                tc_fence_before();
             }
-            tc_fence_before();
         }
         w3_it += 6;
         c3_it++;
-        __syncthreads();                            // conv3 accumulators and A2 are free again
+        fence_proxy_async();
+        __syncthreads();                            // conv3 accumulators, A2 free again; next A0 staged
+        QNET_STAMP(5);
     }
 
     tc_fence_before();
@@ -590,6 +610,7 @@ using namespace snk;
 using namespace snk::qnet;
 
 struct snk_qnet_s {
+    long long *timing;
     int device;
     uint8_t *params;
     __nv_bfloat16 *out3;
@@ -631,6 +652,13 @@ int snk_qnet_destroy(snk_qnet q) {
     return SNK_OK;
 }
 
+// debug: device buffer (8 x iterations of block 0 x int64) receiving clock64 stamps of the conv phases; NULL = off
+int snk_qnet_debug_timing(snk_qnet q, long long *device_buf) {
+    SNK_REQUIRE(q != nullptr, "null qnet");
+    q->timing = device_buf;
+    return SNK_OK;
+}
+
 int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3xN, void *cuda_stream) {
     SNK_REQUIRE(q != nullptr && obs_f32 != nullptr && q_out_3xN != nullptr && N > 0, "bad argument");
     SNK_CUDA(cudaSetDevice(q->device));
@@ -643,7 +671,7 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
         q->out3_cap = cap;
     }
     ConvArgs ca;
-    ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = q->out3;
+    ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = q->out3; ca.timing = q->timing;
     const long long n_iter = (N + S - 1) / S;
     int grid = (int)(n_iter < q->sms ? n_iter : q->sms);
     SNK_CUDA(cudaFuncSetAttribute(k_qnet_convs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_A));

@@ -154,6 +154,7 @@ class LocalPeers:
             s.pack(A[lo:lo + s.rows].contiguous())
         planes = [s.planes.ptr.value for s in self.shards]
         Ys = [s.Y.ptr.value for s in self.shards]
+        torch.cuda.synchronize()                  # "barrier": every virtual rank's planes are packed
         for s in self.shards:
             run_ring(s, planes, terms, block_k)
         torch.cuda.synchronize()

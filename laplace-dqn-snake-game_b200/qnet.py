@@ -80,8 +80,11 @@ class QNet:
 
     def close(self):
         if getattr(self, "_q", None):
-            from . import lib
-            lib().snk_qnet_destroy(self._q)
+            try:
+                from . import lib
+                lib().snk_qnet_destroy(self._q)
+            except Exception:          # interpreter shutdown: module globals may already be gone
+                pass
             self._q = None
 
     __del__ = close

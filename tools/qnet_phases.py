@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""Per-phase cycle counts of k_qnet_convs (CTA 0) via snk_qnet_debug_timing."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as graft  # noqa: E402
+
+S = graft.load_package()
+n = 65536
+env = S.SnakeGame(n, auto_reset=True)
+obs = env.assemble_state("f32")
+net = S.qnet.QNet(S.qnet.glorot_layers(0), env.device, backend="native")
+buf = torch.zeros(8 * 64, dtype=torch.int64, device="cuda")
+L = S.lib()
+L.snk_qnet_debug_timing.argtypes = [C.c_void_p, C.c_void_p]
+for _ in range(2):
+    net(obs)
+L.snk_qnet_debug_timing(net._q, C.c_void_p(buf.data_ptr()))
+net(obs)
+torch.cuda.synchronize()
+t = buf.cpu().view(-1, 8)
+names = ["obs->A0", "conv1", "conv2", "conv3 mma (wait c3_full)", "conv3 epilogue+sync"]
+for it in range(1, 6):
+    row = t[it]
+    print("iter %d:" % it, ", ".join("%s %d" % (names[k], int(row[k + 1] - row[k])) for k in range(5)),
+          "| total", int(t[it + 1][0] - row[0]))
