@@ -213,6 +213,8 @@ SNK_API int snk_center_columns(double *D, int64_t P, int64_t K, double *mean, do
 #define SNK_DTYPE_F32 1
 #define SNK_DTYPE_F64 2
 SNK_API int snk_gram_workspace_bytes(int64_t K, int64_t P, int splits, size_t *bytes);
+/* tile engine: 2 (default) = CTA pairs sharing 256x256 tiles (tcgen05 cta_group::2), 1 = single-CTA 128x256 tiles */
+SNK_API int snk_gram_config(int cta_group);
 SNK_API int snk_gram_pack(const void *A, int a_dtype, int64_t P, int64_t K, void *workspace, void *cuda_stream);
 SNK_API int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k, int splits, float *G,
                      void *cuda_stream);

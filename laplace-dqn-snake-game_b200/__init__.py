@@ -78,6 +78,7 @@ def lib():
         "snk_gram_workspace_bytes": [i64, i64, i32, C.POINTER(C.c_size_t)],
         "snk_gram_pack": [vp, i32, i64, i64, vp, vp],
         "snk_gram": [vp, i64, i64, i32, i32, i32, vp, vp],
+        "snk_gram_config": [i32],
         "snk_gram_planes_layout": [i64, i64, C.POINTER(C.c_size_t), C.POINTER(i64)],
         "snk_gram_pack_planes": [vp, i32, i64, i64, vp, vp, vp],
         "snk_gram_block_scratch_bytes": [i64, i64, i64, i32, C.POINTER(C.c_size_t)],

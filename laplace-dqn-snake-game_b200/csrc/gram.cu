@@ -301,6 +301,200 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
     }
 }
 
+// =================================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster share one 256 x 256 output tile.  Each CTA stages its own
+// 128 rows of the A-side operand and only HALF (128 rows) of each B-side operand; the pair's tensor cores read the
+// other half across the pair.  Per CTA and k-step this cuts the shared-memory operand fetch — what the single-CTA
+// kernel is bound by — from A + B to A + B/2, and the smem footprint per stage from 80 KB to 48 KB (4 stages).
+//   CTA rank r: A rows tm*256 + r*128, B rows tn*256 + r*128, accumulator rows r*128.. of the tile in its own TMEM.
+//   Only the leader (rank 0) issues tcgen05.mma.cta_group::2; both CTAs run a TMA producer whose transactions
+//   complete on the LEADER's full barrier; tcgen05.commit multicasts the stage release / accumulator-ready
+//   arrivals to both CTAs; the peer's accumulate warps release the accumulator on the leader's barrier (mapa).
+// =================================================================================================================
+constexpr int BM2 = 256;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t *bar) {      // arrives on this barrier in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint64_t *leader_bar, void *dst, int c_inner, int c_row) {
+    // the transaction bytes are credited to the LEADER CTA's barrier (peer bit of the shared::cluster address cleared)
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_row) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_rank(uint64_t *bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
+
+template <int BK, int TERMS>
+struct Cfg2 {
+    static constexpr int ROW_BYTES = BK * 2;
+    static constexpr int A_BYTES = BM * ROW_BYTES;            // 128 rows per CTA
+    static constexpr int B_BYTES = (BN / 2) * ROW_BYTES;      // half of the 256 B rows per CTA
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (TERMS > 1 ? 2 : 1);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BK, int TERMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box 128 rows x BK
+        const __grid_constant__ CUtensorMap map_b_hi,   // hi of the B side, box 128 rows x BK
+        const __grid_constant__ CUtensorMap map_b_lo,   // 2*lo of the B side, box 128 rows x BK
+        const GramArgs g) {
+    using C = Cfg2<BK, TERMS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + C::STAGES, *acc_full = bars + 2 * C::STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_tiles = g.tiles_m * g.tiles_n;
+    const int n_work = n_tiles * g.splits;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b_hi);
+        if (TERMS > 1) tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * NUM_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();                                   // barriers of BOTH CTAs are initialised before any remote arrive / TMA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs: own A rows, own half of the B rows) =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = cluster_id; w < n_work; w += n_clusters) {
+                const int split = w / n_tiles, tile = w % n_tiles;
+                const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *st = smem + stage * C::STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);      // both CTAs' bytes land here
+                    tma_load_2d_pair(&map_a, &full[stage], st, kb * BK, tm * BM2 + (int)rank * BM);
+                    tma_load_2d_pair(&map_b_hi, &full[stage], st + C::A_BYTES, kb * BK, tn * BN + (int)rank * (BN / 2));
+                    if (TERMS > 1)
+                        tma_load_2d_pair(&map_b_lo, &full[stage], st + C::A_BYTES + C::B_BYTES, kb * BK, tn * BN + (int)rank * (BN / 2));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: one thread of the leader CTA =================
+        if (lane == 0 && rank == 0) {
+            constexpr int CH = CHUNK_K / BK;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int w = cluster_id; w < n_work; w += n_clusters) {
+                const int split = w / n_tiles;
+                const int kb0 = split * g.kb_per_split;
+                const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    const int in_chunk = (kb - kb0) % CH;
+                    if (in_chunk == 0) {
+                        mbar_wait(&acc_empty[acc], acc_phase ^ 1);    // both CTAs' accumulate warps have drained this stage
+                        tc_fence_after();
+                    }
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t a_desc = make_desc<BK, TERMS>(a_addr);
+                    const uint64_t bh_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES);
+                    const uint64_t bl_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES + C::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        umma2_bf16(d_tmem, a_desc + adv, bh_desc + adv, IDESC2, (in_chunk > 0 || k > 0) ? 1u : 0u);
+                        if (TERMS > 1) umma2_bf16(d_tmem, a_desc + adv, bl_desc + adv, IDESC2, 1u);
+                    }
+                    umma2_commit_mc(&empty[stage]);                   // frees the stage in both CTAs
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (in_chunk == CH - 1 || kb == kb1 - 1) {
+                        umma2_commit_mc(&acc_full[acc]);              // chunk complete -> accumulate warps of both CTAs
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= accumulate warps (both CTAs): own 128 rows of the 256 x 256 tile =================
+        constexpr int CH = CHUNK_K / BK;
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = cluster_id; w < n_work; w += n_clusters) {
+            const int split = w / n_tiles, tile = w % n_tiles;
+            const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+            const int kb0 = split * g.kb_per_split;
+            const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
+            const int n_chunks = (kb1 - kb0 + CH - 1) / CH;
+            float r[128];
+#pragma unroll
+            for (int j = 0; j < 128; j++) r[j] = 0.f;
+            for (int ch = 0; ch < n_chunks; ch++) {
+                mbar_wait(&acc_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) r[c * 32 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_on_rank(&acc_empty[acc], 0);   // the leader's barrier counts both CTAs' warps
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            const int row = tm * BM2 + (int)rank * BM + q * 32 + lane;
+            float4 *d4 = reinterpret_cast<float4 *>(g.partials + (long long)split * g.split_stride +
+                                                    (long long)row * g.ld_part + (long long)tn * BN + half * 128);
+#pragma unroll
+            for (int j = 0; j < 32; j++) d4[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                   // neither CTA may exit while the pair still touches its smem / TMEM
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, TMEM_COLS);
+    }
+}
+
 // G[i][j] = sum_s Y_s[i][j]                         (terms = 1)
 //         = 0.5 * sum_s (Y_s[i][j] + Y_s[j][i])     (terms = 3: adds the transposed cross term)
 // Y_s tiles are fp32 in the workspace with leading dimension ld (>= K, both index orders in range).
@@ -385,9 +579,11 @@ static int make_map(CUtensorMap *m, const void *base, long long rows, long long 
 
 struct Plan {
     long long rows_a, rows_b, P, Ppad, Mt, Nt;
-    int tiles_m, tiles_n, splits, kblocks, kb_per_split, bk;
+    int tiles_m, tiles_n, splits, kblocks, kb_per_split, bk, pair;
     size_t scratch_bytes;
 };
+
+static int g_cta_group = 2;      // 2 = CTA-pair kernel (k_gram2), 1 = single-CTA kernel (k_gram)
 
 static long long pitch_of(long long P) { return (P + 63) / 64 * 64; }
 
@@ -396,14 +592,17 @@ static void make_plan(long long rows_a, long long rows_b, long long P, int bk, i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     pl->rows_a = rows_a; pl->rows_b = rows_b; pl->P = P; pl->bk = bk;
+    pl->pair = g_cta_group == 2 ? 1 : 0;
+    const int bm = pl->pair ? BM2 : BM;
+    const int units = pl->pair ? sms / 2 : sms;                 // schedulable units: CTA pairs or CTAs
     pl->Ppad = pitch_of(P);
-    pl->tiles_m = (int)((rows_a + BM - 1) / BM);
+    pl->tiles_m = (int)((rows_a + bm - 1) / bm);
     pl->tiles_n = (int)((rows_b + BN - 1) / BN);
-    pl->Mt = (long long)pl->tiles_m * BM;
+    pl->Mt = (long long)pl->tiles_m * bm;
     pl->Nt = (long long)pl->tiles_n * BN;
     pl->kblocks = (int)((P + bk - 1) / bk);
     int tiles = pl->tiles_m * pl->tiles_n;
-    int splits = splits_req > 0 ? splits_req : (tiles >= sms ? 1 : (2 * sms) / tiles);   // ~2 work items per CTA: the second's main loop hides the first's epilogue (measured best at K=1000: 9 splits)
+    int splits = splits_req > 0 ? splits_req : (tiles >= units ? 1 : (2 * units) / tiles);   // ~2 work items per CTA: the second's main loop hides the first's epilogue (measured best at K=1000: 9 splits)
     if (splits > pl->kblocks) splits = pl->kblocks;
     if (splits > 64) splits = 64;
     pl->kb_per_split = (pl->kblocks + splits - 1) / splits;
@@ -427,6 +626,18 @@ static int launch(const Plan &pl, const void *a_hi, const void *b_hi, const void
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int n_work = pl.tiles_m * pl.tiles_n * pl.splits;
+    if (pl.pair) {
+        using C2 = Cfg2<BK, TERMS>;
+        CUtensorMap mb2h, mb2l;                                  // B side in 128-row boxes (each CTA stages half a tile)
+        if ((rc = make_map(&mb2h, b_hi, pl.rows_b, pl.P, pl.Ppad, BN / 2, BK)) != SNK_OK) return rc;
+        if ((rc = make_map(&mb2l, TERMS > 1 ? b_lo : b_hi, pl.rows_b, pl.P, pl.Ppad, BN / 2, BK)) != SNK_OK) return rc;
+        int pairs = sms / 2;
+        int grid2 = 2 * (n_work < pairs ? n_work : pairs);
+        SNK_CUDA(cudaFuncSetAttribute(k_gram2<BK, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
+        k_gram2<BK, TERMS><<<grid2, NUM_THREADS, C2::SMEM_BYTES, st>>>(ma, mb2h, mb2l, g);
+        SNK_CUDA(cudaGetLastError());
+        return SNK_OK;
+    }
     int grid = n_work < sms ? n_work : sms;
     SNK_CUDA(cudaFuncSetAttribute(k_gram<BK, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     k_gram<BK, TERMS><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mbh, mbl, g);
@@ -472,6 +683,12 @@ using namespace snk::gram;
 
 extern "C" {
 
+int snk_gram_config(int cta_group) {
+    SNK_REQUIRE(cta_group == 1 || cta_group == 2, "cta_group must be 1 (single-CTA tiles) or 2 (CTA-pair tiles)");
+    g_cta_group = cta_group;
+    return SNK_OK;
+}
+
 int snk_gram_planes_layout(int64_t rows, int64_t P, size_t *plane_bytes, int64_t *pitch_elems) {
     SNK_REQUIRE(rows > 0 && P > 0, "bad argument");
     if (pitch_elems) *pitch_elems = pitch_of(P);
@@ -496,10 +713,17 @@ int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, vo
 
 int snk_gram_block_scratch_bytes(int64_t rows_a, int64_t rows_b, int64_t P, int splits, size_t *bytes) {
     SNK_REQUIRE(bytes != nullptr && rows_a > 0 && rows_b > 0 && P > 0 && splits >= 0, "bad argument");
-    Plan p64, p32;
-    make_plan(rows_a, rows_b, P, 64, splits, &p64);
-    make_plan(rows_a, rows_b, P, 32, splits, &p32);
-    *bytes = p64.scratch_bytes > p32.scratch_bytes ? p64.scratch_bytes : p32.scratch_bytes;
+    size_t best = 0;
+    const int saved = g_cta_group;
+    for (int cg = 1; cg <= 2; cg++)
+        for (int bk = 32; bk <= 64; bk += 32) {
+            Plan p;
+            g_cta_group = cg;
+            make_plan(rows_a, rows_b, P, bk, splits, &p);
+            if (p.scratch_bytes > best) best = p.scratch_bytes;
+        }
+    g_cta_group = saved;
+    *bytes = best;
     return SNK_OK;
 }
 

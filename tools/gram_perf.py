@@ -17,8 +17,10 @@ def main():
     ap.add_argument("--P", type=int, default=181395)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--variants", default="3:32:0,3:64:0,1:32:0,1:64:0")
+    ap.add_argument("--cta-group", type=int, default=2)
     args = ap.parse_args()
     S = graft.load_package()
+    S.lib().snk_gram_config(args.cta_group)
     dev = torch.device("cuda", 0)
     K, P = args.K, args.P
     g = torch.Generator(device=dev); g.manual_seed(0)
