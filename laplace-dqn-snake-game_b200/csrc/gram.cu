@@ -587,12 +587,15 @@ static int g_cta_group = 2;      // 2 = CTA-pair kernel (k_gram2), 1 = single-CT
 
 static long long pitch_of(long long P) { return (P + 63) / 64 * 64; }
 
-static void make_plan(long long rows_a, long long rows_b, long long P, int bk, int splits_req, Plan *pl) {
+static void make_plan(long long rows_a, long long rows_b, long long P, int bk, int splits_req, Plan *pl, int terms = 3) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     pl->rows_a = rows_a; pl->rows_b = rows_b; pl->P = P; pl->bk = bk;
     pl->pair = g_cta_group == 2 ? 1 : 0;
+    // measured: with plain bf16 (one MMA per k-step) a problem too small to give every CTA pair its own tile
+    // runs faster on single-CTA tiles (K=1000: 0.28 vs 0.30 ms); the hi/lo split always prefers the pair
+    if (pl->pair && terms == 1 && ((rows_a + BM2 - 1) / BM2) * ((rows_b + BN - 1) / BN) < sms / 2) pl->pair = 0;
     const int bm = pl->pair ? BM2 : BM;
     const int units = pl->pair ? sms / 2 : sms;                 // schedulable units: CTA pairs or CTAs
     pl->Ppad = pitch_of(P);
@@ -717,10 +720,12 @@ int snk_gram_block_scratch_bytes(int64_t rows_a, int64_t rows_b, int64_t P, int 
     const int saved = g_cta_group;
     for (int cg = 1; cg <= 2; cg++)
         for (int bk = 32; bk <= 64; bk += 32) {
-            Plan p;
-            g_cta_group = cg;
-            make_plan(rows_a, rows_b, P, bk, splits, &p);
-            if (p.scratch_bytes > best) best = p.scratch_bytes;
+            for (int terms = 1; terms <= 3; terms += 2) {
+                Plan p;
+                g_cta_group = cg;
+                make_plan(rows_a, rows_b, P, bk, splits, &p, terms);
+                if (p.scratch_bytes > best) best = p.scratch_bytes;
+            }
         }
     g_cta_group = saved;
     *bytes = best;
@@ -735,7 +740,7 @@ int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, const voi
     SNK_REQUIRE(block_k == 32 || block_k == 64, "block_k must be 32 or 64");
     SNK_REQUIRE(ldY >= rows_b, "ldY too small");
     Plan pl;
-    make_plan(rows_a, rows_b, P, block_k, splits, &pl);
+    make_plan(rows_a, rows_b, P, block_k, splits, &pl, terms);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = run_block(pl, terms, a_hi, b_hi, b_lo2, (float *)scratch, st);
     if (rc != SNK_OK) return rc;
@@ -782,7 +787,7 @@ int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k
     const uint8_t *ws = (const uint8_t *)workspace;
     float *scratch = (float *)(ws + 2 * plane);
     Plan pl;
-    make_plan(K, K, P, block_k, splits, &pl);
+    make_plan(K, K, P, block_k, splits, &pl, terms);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = run_block(pl, terms, ws, ws, ws + plane, scratch, st);
     if (rc != SNK_OK) return rc;
