@@ -127,6 +127,13 @@ SNK_API int snk_step_fused(snk_handle h, const float *q, float eps, const float 
 SNK_API int snk_step_fused_host(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx,
                         uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt,
                         uint8_t *mask, float *ep_return, int32_t *ep_score);
+/* T steps of step! + virtual_step + next_state in ONE launch, for action streams known up front
+ * (play_episode's actions_list mode, utils.jl:209-219; BASELINE config 2 "uniform random actions").  Small batches
+ * are launch-latency bound; here every env stays in registers across the T steps.  Step-major arrays:
+ * act (T,N) u8 indices (or absolute directions if is_abs), reward (T,N) f32, done (T,N) u8, mask (T,3,N) u8,
+ * obs (T, 10,10,2,N) in obs_fmt, ep_return / ep_score (T,N).  Outputs may be NULL. */
+SNK_API int snk_rollout_fused(snk_handle h, const uint8_t *act_TxN, int64_t T, int is_abs, float *reward, uint8_t *done,
+                              void *obs, int obs_fmt, uint8_t *mask, float *ep_return, int32_t *ep_score);
 SNK_API int snk_host_alloc(void **p, size_t bytes);   /* pinned host memory */
 SNK_API int snk_host_free(void *p);
 

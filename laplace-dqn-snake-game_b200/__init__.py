@@ -60,6 +60,7 @@ def lib():
         "snk_step": [vp, vp, vp, vp], "snk_step_abs": [vp, vp, vp, vp],
         "snk_step_fused": [vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
         "snk_step_fused_host": [vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
+        "snk_rollout_fused": [vp, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp],
         "snk_host_alloc": [C.POINTER(vp), C.c_size_t], "snk_host_free": [vp],
         "snk_state": [vp, vp, i32], "snk_losing_mask": [vp, vp],
         "snk_select_action": [vp, vp, f32, vp, vp, vp],
@@ -241,6 +242,28 @@ class SnakeGame:
             _check(lib().snk_step_fused(self._h, *args))
         else:                      # also store! every env's Experience into the device replay ring
             _check(lib().snk_step_fused_store(self._h, replay._r, *args))
+        return out
+
+    def rollout(self, actions, obs="f32", mask=True, ep_stats=False, is_abs=False, out=None):
+        """T steps in ONE launch for a known action stream (play_episode's actions_list mode, utils.jl:209-219).
+        actions: (T, N) u8.  Returns step-major arrays: reward (T,N), done (T,N), obs (T,N,2,10,10), mask (T,N,3)."""
+        T = actions.shape[0]
+        dev = self.device
+        if out is None:
+            out = {"reward": self._new((T, self.n), torch.float32), "done": self._new((T, self.n), torch.uint8)}
+            if obs:
+                _, dt, per = _OBS[obs]
+                out["obs"] = self._new((T, self.n, 2, 10, 10) if per == 200 else (T, self.n, per), dt)
+                out["obs_fmt"] = obs
+            if mask:
+                out["mask"] = self._new((T, self.n, 3), torch.uint8)
+            if ep_stats:
+                out["ep_return"] = self._new((T, self.n), torch.float32)
+                out["ep_score"] = self._new((T, self.n), torch.int32)
+        fmt = _OBS[out["obs_fmt"]][0] if out.get("obs") is not None else OBS_NONE
+        _check(lib().snk_rollout_fused(self._h, _ptr(actions, torch.uint8, T * self.n, dev), T, int(is_abs),
+                                       _ptr(out.get("reward")), _ptr(out.get("done")), _ptr(out.get("obs")), fmt,
+                                       _ptr(out.get("mask")), _ptr(out.get("ep_return")), _ptr(out.get("ep_score"))))
         return out
 
     def step_fused_host(self, host, q=False, eps=0.0):

@@ -307,6 +307,93 @@ __device__ __forceinline__ uint32_t losing_mask3(u64 occ, u64 cons, int hr, int 
     return m;
 }
 
+// ---- one env in registers ---------------------------------------------------------------------------
+struct Env {
+    u64 occ, pocc, clo, chi, cons;
+    float ret;
+    int hr, hc, tr, tc, fr, fc, pfr, pfc, pd, len, t, dn, err;
+};
+__device__ __forceinline__ void env_load(Env &e, const EnvState &s, long long i) {
+    e.occ = s.occ[i]; e.pocc = s.pocc[i]; e.clo = s.clo[i]; e.chi = s.chi[i]; e.cons = s.cons[i]; e.ret = s.ret[i];
+    const u64 misc = s.misc[i];
+    e.hr = (int)(misc >> M_HR) & 15; e.hc = (int)(misc >> M_HC) & 15;
+    e.tr = (int)(misc >> M_TR) & 15; e.tc = (int)(misc >> M_TC) & 15;
+    e.fr = (int)(misc >> M_FR) & 15; e.fc = (int)(misc >> M_FC) & 15;
+    e.pfr = (int)(misc >> M_PFR) & 15; e.pfc = (int)(misc >> M_PFC) & 15;
+    e.pd = (int)(misc >> M_PD) & 3; e.len = (int)(misc >> M_LEN) & 127; e.t = (int)(misc >> M_T) & 1023;
+    e.dn = (int)(misc >> M_DONE) & 1; e.err = (int)(misc >> M_ERR) & 15;
+}
+__device__ __forceinline__ void env_store(const Env &e, const EnvState &s, long long i) {
+    const u64 misc = ((u64)e.hr << M_HR) | ((u64)e.hc << M_HC) | ((u64)e.tr << M_TR) | ((u64)e.tc << M_TC) |
+                     ((u64)e.fr << M_FR) | ((u64)e.fc << M_FC) | ((u64)e.pfr << M_PFR) | ((u64)e.pfc << M_PFC) |
+                     ((u64)e.pd << M_PD) | ((u64)e.len << M_LEN) | ((u64)e.t << M_T) | ((u64)e.dn << M_DONE) |
+                     ((u64)e.err << M_ERR);
+    s.occ[i] = e.occ; s.pocc[i] = e.pocc; s.clo[i] = e.clo; s.chi[i] = e.chi; s.cons[i] = e.cons; s.misc[i] = misc;
+    s.ret[i] = e.ret;
+}
+// a fresh SnakeGame() (structs.jl:33-99, utils.jl:199); error bits are sticky
+__device__ __forceinline__ void env_reset(Env &e) {
+    e.occ = INIT_OCC; e.pocc = INIT_OCC; e.clo = 0; e.chi = 0; e.cons = 0; e.ret = 0.0f;
+    e.hr = 7; e.hc = 1; e.tr = 8; e.tc = 1; e.fr = 3; e.fc = 4; e.pfr = 3; e.pfc = 4; e.pd = 0; e.len = 2; e.t = 0; e.dn = 0;
+}
+// step!(game, action) + virtual_step for one live env (utils.jl:100-109, 112-132): returns the reward, m3 = the
+// next_is_suicidal bits.  aidx: index into available_actions, or an absolute direction when is_abs.
+__device__ __forceinline__ float env_advance(Env &e, int &aidx, int is_abs, u64 list_mask, const uint8_t *s_food_bit,
+                                             uint32_t &m3) {
+    int d;
+    if (is_abs) {
+        d = aidx;
+        if (d > 3) { e.err |= SNK_ENV_ERR_ACTION; d = 0; }
+    } else {
+        if (aidx > 2) { e.err |= SNK_ENV_ERR_ACTION; aidx = 0; }
+        d = av_dir(e.pd, aidx);
+    }
+    // grow_maybe! (utils.jl:66-81) on the board of the previous step
+    int dr, dc;
+    dir_delta(d, dr, dc);
+    const int nr = e.hr + dr, nc = e.hc + dc;
+    const bool wall = (nr == 0) | (nr == 9) | (nc == 0) | (nc == 9);
+    const u64 nbit = wall ? 0ull : (1ull << ((nr - 1) + 8 * (nc - 1)));
+    const bool eat = (e.fr != 0) & (nr == e.fr) & (nc == e.fc);
+    const bool reverse = d == (e.pd ^ 1);                           // utils.jl:57, third clause
+    e.pocc = e.occ; e.pfr = e.fr; e.pfc = e.fc;                    // this board becomes frame 1
+    e.chi = (e.chi << 2) | (e.clo >> 62);                           // pushfirst!(snake, new_head)
+    e.clo = (e.clo << 2) | (u64)d;
+    e.len++;
+    bool self = false;
+    float reward;
+    if (eat) {
+        reward = 1.0f;                                              // eating_reward
+        e.fr = 0; e.fc = 0;
+        int i = food_search(e.occ | nbit, e.cons, list_mask, s_food_bit);
+        if (i >= 0) {
+            e.cons |= 1ull << i;                                    // deleteat!(food_list, idx)
+            int b = s_food_bit[i];
+            e.fr = (b & 7) + 1; e.fc = (b >> 3) + 1;
+        } else if (i == -1) {
+            e.err |= SNK_ENV_ERR_FOOD;
+        }
+        e.occ |= nbit;
+    } else {
+        e.occ &= ~(1ull << ((e.tr - 1) + 8 * (e.tc - 1)));          // remove_tail!
+        int c = chain_get(e.clo, e.chi, e.len - 2), er, ec;
+        dir_delta(c, er, ec);
+        e.tr += er; e.tc += ec;
+        e.len--;
+        reward = -0.01f;                                            // male_di_vivere
+        self = (e.occ & nbit) != 0ull;                              // count(==(head), snake) > 1
+        e.occ |= nbit;
+    }
+    e.t++;
+    const bool lost = wall | self | reverse | (e.t >= 500);         // utils.jl:88 (history length > 500)
+    if (lost) reward = -1.0f;                                       // suicide_penalty
+    e.hr = nr; e.hc = nc; e.pd = d; e.dn = lost;
+    e.ret += reward;
+    m3 = 7u;
+    if (!lost) m3 = losing_mask3(e.occ, e.cons, e.hr, e.hc, e.tr, e.tc, e.fr, e.fc, e.pd, e.t, list_mask, s_food_bit, e.err);
+    return reward;
+}
+
 template <int OBS, bool SELECT, bool SINK>
 __global__ void __launch_bounds__(TPB) k_step(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) uint32_t s_planes[TPB * PLANE_WORDS];
@@ -325,18 +412,11 @@ __global__ void __launch_bounds__(TPB) k_step(const __grid_constant__ StepArgs a
 
     if (tid < n_local) {
         // ---- phase A: one thread, one env ------------------------------------------------------
-        u64 occ = a.s.occ[env], pocc = a.s.pocc[env], clo = a.s.clo[env], chi = a.s.chi[env];
-        u64 cons = a.s.cons[env], misc = a.s.misc[env];
-        float ret = a.s.ret[env];
-        int hr = (int)(misc >> M_HR) & 15, hc = (int)(misc >> M_HC) & 15;
-        int tr = (int)(misc >> M_TR) & 15, tc = (int)(misc >> M_TC) & 15;
-        int fr = (int)(misc >> M_FR) & 15, fc = (int)(misc >> M_FC) & 15;
-        int pfr = (int)(misc >> M_PFR) & 15, pfc = (int)(misc >> M_PFC) & 15;
-        int pd = (int)(misc >> M_PD) & 3, len = (int)(misc >> M_LEN) & 127, t = (int)(misc >> M_T) & 1023;
-        int dn = (int)(misc >> M_DONE) & 1, err = (int)(misc >> M_ERR) & 15;
+        Env e;
+        env_load(e, a.s, env);
         const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
-        const u64 occ_tm2 = pocc;                                   // board_{t-2}, for the transition record
-        const int fr_tm2 = pfr, fc_tm2 = pfc, pd_before = pd;
+        const u64 occ_tm2 = e.pocc;                                 // board_{t-2}, for the transition record
+        const int fr_tm2 = e.pfr, fc_tm2 = e.pfc, pd_before = e.pd;
 
         int aidx;
         if (SELECT) {
@@ -359,109 +439,115 @@ __global__ void __launch_bounds__(TPB) k_step(const __grid_constant__ StepArgs a
 
         float reward = 0.0f;
         uint32_t m3 = 7u;
-        if (!dn) {
-            int d;
-            if (a.is_abs) {
-                d = aidx;
-                if (d > 3) { err |= SNK_ENV_ERR_ACTION; d = 0; }
-            } else {
-                if (aidx > 2) { err |= SNK_ENV_ERR_ACTION; aidx = 0; }
-                d = av_dir(pd, aidx);
-            }
-            // grow_maybe! (utils.jl:66-81) on the board of the previous step
-            int dr, dc;
-            dir_delta(d, dr, dc);
-            const int nr = hr + dr, nc = hc + dc;
-            const bool wall = (nr == 0) | (nr == 9) | (nc == 0) | (nc == 9);
-            const u64 nbit = wall ? 0ull : (1ull << ((nr - 1) + 8 * (nc - 1)));
-            const bool eat = (fr != 0) & (nr == fr) & (nc == fc);
-            const bool reverse = d == (pd ^ 1);                     // utils.jl:57, third clause
-            pocc = occ; pfr = fr; pfc = fc;                        // this board becomes frame 1
-            chi = (chi << 2) | (clo >> 62);                         // pushfirst!(snake, new_head)
-            clo = (clo << 2) | (u64)d;
-            len++;
-            bool self = false;
-            if (eat) {
-                reward = 1.0f;                                      // eating_reward
-                fr = 0; fc = 0;
-                int i = food_search(occ | nbit, cons, list_mask, s_food_bit);
-                if (i >= 0) {
-                    cons |= 1ull << i;                              // deleteat!(food_list, idx)
-                    int b = s_food_bit[i];
-                    fr = (b & 7) + 1; fc = (b >> 3) + 1;
-                } else if (i == -1) {
-                    err |= SNK_ENV_ERR_FOOD;
-                }
-                occ |= nbit;
-            } else {
-                occ &= ~(1ull << ((tr - 1) + 8 * (tc - 1)));        // remove_tail!
-                int e = chain_get(clo, chi, len - 2), er, ec;
-                dir_delta(e, er, ec);
-                tr += er; tc += ec;
-                len--;
-                reward = -0.01f;                                    // male_di_vivere
-                self = (occ & nbit) != 0ull;                        // count(==(head), snake) > 1
-                occ |= nbit;
-            }
-            t++;
-            const bool lost = wall | self | reverse | (t >= 500);   // utils.jl:88 (history length > 500)
-            if (lost) reward = -1.0f;                               // suicide_penalty
-            hr = nr; hc = nc; pd = d; dn = lost;
-            ret += reward;
-            if (!lost) m3 = losing_mask3(occ, cons, hr, hc, tr, tc, fr, fc, pd, t, list_mask, s_food_bit, err);
-        }
+        if (!e.dn) reward = env_advance(e, aidx, a.is_abs, list_mask, s_food_bit, m3);
 
         if (a.reward != nullptr) a.reward[env] = reward;
-        if (a.done != nullptr) a.done[env] = (uint8_t)dn;
+        if (a.done != nullptr) a.done[env] = (uint8_t)e.dn;
         if (a.mask != nullptr) {
             a.mask[3 * env + 0] = (uint8_t)(m3 & 1u);
             a.mask[3 * env + 1] = (uint8_t)((m3 >> 1) & 1u);
             a.mask[3 * env + 2] = (uint8_t)((m3 >> 2) & 1u);
         }
-        if (a.ep_return != nullptr) a.ep_return[env] = ret;
-        if (a.ep_score != nullptr) a.ep_score[env] = len - 2;
+        if (a.ep_return != nullptr) a.ep_return[env] = e.ret;
+        if (a.ep_score != nullptr) a.ep_score[env] = e.len - 2;
 
         if (OBS != SNK_OBS_NONE) {
-            board_planes(pocc, pfr, pfc, false, 0, 0, s_planes + tid * PLANE_WORDS);
-            board_planes(occ, fr, fc, true, hr, hc, s_planes + tid * PLANE_WORDS + 8);
+            board_planes(e.pocc, e.pfr, e.pfc, false, 0, 0, s_planes + tid * PLANE_WORDS);
+            board_planes(e.occ, e.fr, e.fc, true, e.hr, e.hc, s_planes + tid * PLANE_WORDS + 8);
         }
 
         if (SINK) {
             // store!(rpb, exp) for envs in index order == ring slot (stored_so_far + env) mod capacity; when the
             // step holds more envs than the ring, the later env wins exactly as sequential store! calls would
-            const long long e = env - a.env_begin;
-            if (e + a.sink_cap >= a.sink_n) {
-                uint4 *rec = a.sink + ((a.sink_base + e) % a.sink_cap) * REC_U4;
+            const long long k = env - a.env_begin;
+            if (k + a.sink_cap >= a.sink_n) {
+                uint4 *rec = a.sink + ((a.sink_base + k) % a.sink_cap) * REC_U4;
                 uint4 p0, p1;
                 board_planes_reg(occ_tm2, fr_tm2, fc_tm2, false, 0, 0, p0, p1);
                 rec[0] = p0; rec[1] = p1;
-                board_planes_reg(pocc, pfr, pfc, false, 0, 0, p0, p1);
+                board_planes_reg(e.pocc, e.pfr, e.pfc, false, 0, 0, p0, p1);
                 rec[2] = p0; rec[3] = p1;
-                board_planes_reg(occ, fr, fc, true, hr, hc, p0, p1);
+                board_planes_reg(e.occ, e.fr, e.fc, true, e.hr, e.hc, p0, p1);
                 rec[4] = p0; rec[5] = p1;
                 rec[6] = make_uint4(__float_as_uint(reward),
-                                    (uint32_t)aidx | ((uint32_t)dn << 8) | (m3 << 16) | ((uint32_t)pd_before << 24),
-                                    __float_as_uint(ret), (uint32_t)(len - 2));
-                rec[7] = make_uint4((uint32_t)env, (uint32_t)t, 0u, 0u);
+                                    (uint32_t)aidx | ((uint32_t)e.dn << 8) | (m3 << 16) | ((uint32_t)pd_before << 24),
+                                    __float_as_uint(e.ret), (uint32_t)(e.len - 2));
+                rec[7] = make_uint4((uint32_t)env, (uint32_t)e.t, 0u, 0u);
             }
         }
 
-        if (dn && a.auto_reset) {                                   // a fresh SnakeGame() (utils.jl:199)
-            occ = INIT_OCC; pocc = INIT_OCC; clo = 0; chi = 0; cons = 0; ret = 0.0f;
-            misc = INIT_MISC | ((u64)err << M_ERR);
-        } else {
-            misc = ((u64)hr << M_HR) | ((u64)hc << M_HC) | ((u64)tr << M_TR) | ((u64)tc << M_TC) | ((u64)fr << M_FR) |
-                   ((u64)fc << M_FC) | ((u64)pfr << M_PFR) | ((u64)pfc << M_PFC) | ((u64)pd << M_PD) |
-                   ((u64)len << M_LEN) | ((u64)t << M_T) | ((u64)dn << M_DONE) | ((u64)err << M_ERR);
-        }
-        a.s.occ[env] = occ; a.s.pocc[env] = pocc; a.s.clo[env] = clo; a.s.chi[env] = chi;
-        a.s.cons[env] = cons; a.s.misc[env] = misc; a.s.ret[env] = ret;
+        if (e.dn && a.auto_reset) env_reset(e);
+        env_store(e, a.s, env);
     }
 
     if (OBS != SNK_OBS_NONE) {
         __syncthreads();
         expand_obs<OBS>(a.obs, env0, n_local, s_planes, s_tb, tid);
     }
+}
+
+// ---- T steps in one launch (small batches are launch-latency bound: the env stays in registers) ----------
+// EPB envs per CTA of TPB threads: phase A uses the first EPB threads, phase B all TPB of them.
+// Step-major I/O: act (T,N) u8; reward (T,N), done (T,N), mask (T,3,N) bytes, obs (T, N x 200) — any output NULL.
+struct RolloutArgs {
+    EnvState s;
+    const uint8_t *act;
+    float *reward;
+    uint8_t *done;
+    void *obs;
+    uint8_t *mask;
+    float *ep_return;
+    int32_t *ep_score;
+    long long n;
+    int steps, auto_reset, is_abs;
+    FoodTable food;
+};
+template <int OBS, int EPB>
+__global__ void __launch_bounds__(TPB) k_rollout(const __grid_constant__ RolloutArgs a) {
+    __shared__ __align__(16) uint32_t s_planes[EPB * PLANE_WORDS];
+    __shared__ ObsTables s_tb;
+    __shared__ uint8_t s_food_bit[MAX_FOOD];
+    const int tid = threadIdx.x;
+    const long long env0 = (long long)blockIdx.x * EPB;
+    const long long rem = a.n - env0;
+    const int n_local = rem < EPB ? (int)rem : EPB;
+    const long long env = env0 + tid;
+    const bool mine = tid < n_local;
+    if (tid < MAX_FOOD) s_food_bit[tid] = a.food.bit[tid];
+    if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid);
+    __syncthreads();
+    const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
+    Env e;
+    if (mine) env_load(e, a.s, env);
+    const size_t obs_step = (size_t)a.n * (OBS == SNK_OBS_F32 ? 800 : OBS == SNK_OBS_I8 ? 200 : OBS == SNK_OBS_I64 ? 1600 : 50);
+    for (int t = 0; t < a.steps; t++) {
+        if (mine) {
+            const long long o = (long long)t * a.n + env;
+            int aidx = a.act[o];
+            float reward = 0.0f;
+            uint32_t m3 = 7u;
+            if (!e.dn) reward = env_advance(e, aidx, a.is_abs, list_mask, s_food_bit, m3);
+            if (a.reward != nullptr) a.reward[o] = reward;
+            if (a.done != nullptr) a.done[o] = (uint8_t)e.dn;
+            if (a.mask != nullptr) {
+                uint8_t *m = a.mask + 3 * o;
+                m[0] = (uint8_t)(m3 & 1u); m[1] = (uint8_t)((m3 >> 1) & 1u); m[2] = (uint8_t)((m3 >> 2) & 1u);
+            }
+            if (a.ep_return != nullptr) a.ep_return[o] = e.ret;
+            if (a.ep_score != nullptr) a.ep_score[o] = e.len - 2;
+            if (OBS != SNK_OBS_NONE) {
+                board_planes(e.pocc, e.pfr, e.pfc, false, 0, 0, s_planes + tid * PLANE_WORDS);
+                board_planes(e.occ, e.fr, e.fc, true, e.hr, e.hc, s_planes + tid * PLANE_WORDS + 8);
+            }
+            if (e.dn && a.auto_reset) env_reset(e);
+        }
+        if (OBS != SNK_OBS_NONE) {
+            __syncthreads();
+            expand_obs<OBS>((uint8_t *)a.obs + (size_t)t * obs_step, env0, n_local, s_planes, s_tb, tid);
+            __syncthreads();
+        }
+    }
+    if (mine) env_store(e, a.s, env);
 }
 
 // ---- stand-alone views of the state ------------------------------------------------------------
@@ -906,6 +992,39 @@ int snk_step_fused(snk_handle h, const float *q, float eps, const float *u, cons
     int rc = launch_step(h, a, obs ? obs_fmt : SNK_OBS_NONE, q != nullptr, 0, h->n, h->stream);
     h->step_counter++;
     return rc;
+}
+
+int snk_rollout_fused(snk_handle h, const uint8_t *act_TxN, int64_t T, int is_abs, float *reward, uint8_t *done, void *obs,
+                      int obs_fmt, uint8_t *mask, float *ep_return, int32_t *ep_score) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(act_TxN != nullptr && T > 0 && T <= (1 << 20), "bad argument");
+    SNK_REQUIRE(obs_fmt == SNK_OBS_NONE || obs != nullptr, "obs_fmt given without an obs buffer");
+    SNK_REQUIRE(obs == nullptr || ((uintptr_t)obs & 15u) == 0, "obs must be 16-byte aligned");
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s = h->s; a.food = h->food; a.act = act_TxN; a.reward = reward; a.done = done; a.obs = obs; a.mask = mask;
+    a.ep_return = ep_return; a.ep_score = ep_score; a.n = h->n; a.steps = (int)T; a.is_abs = is_abs;
+    a.auto_reset = (h->flags & SNK_AUTO_RESET) ? 1 : 0;
+    const int fmt = obs ? obs_fmt : SNK_OBS_NONE;
+    // small batches: 32 envs per CTA so that the observation expansion of one env is spread over 4 threads
+    const bool small = h->n <= 32 * 1024;
+#define SNK_RO(FMT)                                                                                       \
+    do {                                                                                                  \
+        if (small) k_rollout<FMT, 32><<<nblocks(h->n, 32), TPB, 0, h->stream>>>(a);                       \
+        else k_rollout<FMT, TPB><<<nblocks(h->n, TPB), TPB, 0, h->stream>>>(a);                           \
+    } while (0)
+    switch (fmt) {
+        case SNK_OBS_NONE: SNK_RO(SNK_OBS_NONE); break;
+        case SNK_OBS_F32: SNK_RO(SNK_OBS_F32); break;
+        case SNK_OBS_I8: SNK_RO(SNK_OBS_I8); break;
+        case SNK_OBS_I64: SNK_RO(SNK_OBS_I64); break;
+        case SNK_OBS_PACKED2: SNK_RO(SNK_OBS_PACKED2); break;
+        default: return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
+    }
+#undef SNK_RO
+    SNK_CUDA(cudaGetLastError());
+    h->step_counter += (u64)T;
+    return SNK_OK;
 }
 
 static size_t obs_bytes_per_env(int fmt) {

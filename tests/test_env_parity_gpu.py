@@ -398,3 +398,32 @@ def test_center_columns_bit_exact():
         assert np.array_equal(bits(gm.cpu().numpy()), bits(mean)), (K, P)
         assert np.array_equal(bits(gv.cpu().numpy()), bits(var)), (K, P)
         assert np.array_equal(bits(dev.cpu().numpy().reshape(-1)), bits(want)), (K, P)
+
+
+@pytest.mark.parametrize("n,T,fmt", [(4096, 300, "f32"), (100, 700, "i8"), (33, 64, "packed2"), (70000, 20, "i8"), (1, 1100, "i64")])
+def test_multi_step_rollout_kernel_matches_oracle(n, T, fmt):
+    """snk_rollout_fused: T steps in one launch == T oracle steps (and leaves the same state behind)."""
+    S = pkg()
+    env = S.SnakeGame(n, auto_reset=True)
+    ora = O.OracleBatch(n, auto_reset=True)
+    acts = np.stack([synth_actions(n, t, seed=13) for t in range(T)])
+    out = env.rollout(torch.from_numpy(acts).cuda(), obs=fmt, mask=True, ep_stats=True)
+    got = {k: v.cpu().numpy() for k, v in out.items() if k != "obs_fmt"}
+    for t in range(T):
+        ref = ora.step(acts[t], obs=("i8", "i64", "f32"))
+        assert np.array_equal(bits(got["reward"][t]), bits(ref["reward"])), t
+        assert np.array_equal(got["done"][t], ref["done"]), t
+        assert np.array_equal(got["mask"][t], ref["mask"]), t
+        assert np.array_equal(bits(got["ep_return"][t]), bits(ref["ep_return"])), t
+        assert np.array_equal(got["ep_score"][t], ref["ep_score"]), t
+        o = got["obs"][t].reshape(n, -1)
+        if fmt == "packed2":
+            assert np.array_equal(unpack2(o), ref["obs_i8"]), t
+        else:
+            assert np.array_equal(o, ref["obs_" + fmt]), t
+    assert np.array_equal(env.assemble_state("i8").cpu().numpy().reshape(n, 200), ora.state("i8"))
+    # and a single-step call afterwards continues from the same state
+    a = synth_actions(n, T, seed=13)
+    r, d = env.step(torch.from_numpy(a).cuda())
+    ref = ora.step(a)
+    assert np.array_equal(bits(r.cpu().numpy()), bits(ref["reward"])) and np.array_equal(d.cpu().numpy(), ref["done"])
