@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -226,6 +226,20 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * E * Ke / (e2e_ms * 1e-3)
+    # same call with the int8 observation format (the reference's game.state is an integer array; 200 B/env)
+    host["obs"] = S.pinned_empty((E, 2, 10, 10), torch.int8)
+    host["obs_fmt"] = "i8"
+    for _ in range(2):
+        env.step_fused_host(host, q=True, eps=eps)
+    env.sync()
+    barrier()
+    e0.record()
+    for _ in range(Ke):
+        env.step_fused_host(host, q=True, eps=eps)
+    e1.record()
+    env.sync()
+    barrier()
+    e2e_i8_ms = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- BASELINE config 2 (4,096 envs, given actions) as a CUDA graph of steps: launch-latency regime
     cfg2 = None
@@ -320,7 +334,8 @@ def run_ours(args):
                          "traffic": None, "peak_source": peak_src, "kernel": "k_step<F32,select>",
                          "bytes_per_env_step": BYTES_PER_STEP_CONFIG3, "kernel_ms": kern_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": e2e_ms / Ke, "api": "snk_step_fused_host (pinned host buffers)"},
+                    "steps": Ke, "ms_per_step": e2e_ms / Ke, "api": "snk_step_fused_host (pinned host buffers), f32 observations",
+                    "int8_obs_variant": {"value": world * E * Ke / (e2e_i8_ms * 1e-3), "d2h_bytes_per_step": E * 209}},
             "gpu_launches": K * world,
             "clocks": clocks,
         }
@@ -479,7 +494,7 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
