@@ -11,9 +11,9 @@
 // "chunk-planar" ([8-channel chunk][pixel][8 x bf16], the no-swizzle K-major canonical layout, one 16-byte row
 // per pixel), so the A operand of kernel offset (k1,k2) is the same plane read at a start address shifted by a
 // constant number of pixels — a different shared-memory descriptor, no data movement:
-//   conv1/conv2: rows = 128 consecutive pixels of the zero-padded 12x12 grids of the S samples (shift = 12 k2 + k1);
-//                conv1 has only 2 real input channels, so one K=16 MMA covers two horizontally adjacent taps
-//                (leading-dimension byte offset = one pixel);
+//   conv1:       2 input channels, 1 % of the FLOPs: CUDA cores, straight from the Float32 observations, run by the
+//                otherwise idle warps while the tensor core works through conv3 of the previous iteration;
+//   conv2:       rows = 128 consecutive pixels of the zero-padded 12x12 grids of the S samples (shift = 12 k2 + k1);
 //   conv3:       pixels are stored [y][sample][x], rows = 8-pixel groups at a 10-pixel pitch (stride byte offset
 //                160 B) over (y, sample), shift = 10 S k2 + k1; its 147 KB of weights stream through a 2-slot ring
 //                of k2-slices (cp.async.bulk + mbarrier) while 4-5 accumulator tiles stay live in TMEM.
@@ -43,21 +43,20 @@ constexpr int A0_PIX = TILES12 * 128 + 32;    // + room for the largest shift (2
 constexpr int A2_PIX = ((5 * S + 15) / 16) * 160 + 5 * S * 10 + 16;   // groups of the last tile + largest shift
 constexpr int TILES3 = (5 * S + 15) / 16;     // 4 accumulator tiles of 16 (y, sample) groups
 constexpr int W3_SLICE = 6 * 2 * 2048;        // one k2 slice of the conv3 weights
-constexpr int OFF_A0 = 0;
-constexpr int OFF_A1 = OFF_A0 + A0_PIX * 16;
+constexpr int OFF_A1 = 0;
 constexpr int OFF_A2 = OFF_A1 + 2 * A0_PIX * 16;
-constexpr int OFF_W1 = OFF_A2 + 4 * A2_PIX * 16;
-constexpr int OFF_W2 = OFF_W1 + 3 * 2 * 512;
+constexpr int OFF_W1 = OFF_A2 + 4 * A2_PIX * 16;          // conv1 weights, fp32 [tap = k2*3+k1][c][o] (flipped), 1152 B
+constexpr int OFF_W2 = OFF_W1 + 18 * 16 * 4;
 constexpr int OFF_W3 = OFF_W2 + 9 * 1024;
 constexpr int OFF_BIAS = OFF_W3 + 2 * W3_SLICE;          // b1 (16) b2 (32) b3 (64) f32
 constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
 constexpr int SMEM_A = OFF_BAR + 128 + 128;              // barriers + alignment slack
 static_assert(SMEM_A <= 232448, "kernel A shared memory over the 227 KB limit");
 constexpr int NACC = 4;                                  // accumulator buffers cycled by the conv1 / conv2 tiles
-constexpr int TMEM_C3 = 0, TMEM_C2 = 256, TMEM_C1 = 384; // column offsets: conv3 4 x 64 | conv2 NACC x 32 | conv1 NACC x 16
+constexpr int TMEM_C3 = 0, TMEM_C2 = 256;                // column offsets: conv3 4 x 64 | conv2 NACC x 32
 
 // packed parameter blob (device): byte offsets
-constexpr size_t P_W1 = 0, P_W2 = P_W1 + 3 * 2 * 512, P_W3 = P_W2 + 9 * 1024, P_BIAS = P_W3 + 6 * (size_t)W3_SLICE;
+constexpr size_t P_W1 = 0, P_W2 = P_W1 + 18 * 16 * 4, P_W3 = P_W2 + 9 * 1024, P_BIAS = P_W3 + 6 * (size_t)W3_SLICE;
 constexpr size_t P_W4 = P_BIAS + 112 * 4;                // [64][1600] bf16, columns in kernel-A order
 constexpr size_t P_B4 = P_W4 + 64 * 1600 * 2, P_W5 = P_B4 + 64 * 4, P_B5 = P_W5 + 3 * 64 * 4, P_END = P_B5 + 16;
 
@@ -144,33 +143,62 @@ struct ConvArgs {
 };
 #define QNET_STAMP(k) do { if (a.timing != nullptr && blockIdx.x == 0 && tid == 128) a.timing[it_local * 8 + (k)] = clock64(); } while (0)
 
-// observations of S samples starting at s0 -> A0 (channels 0,1 of the padded 12x12 grids), by threads [t0, t0+nt)
-__device__ __forceinline__ void load_obs(const ConvArgs &a, long long s0, uint8_t *A0, int t, int nt) {
+// conv1 (2 -> 16 channels, 3x3, pad 1, relu) of S samples starting at s0 on the CUDA cores, straight from the
+// Float32 observations into conv2's operand plane A1 (padded 12x12 grids, chunk-planar bf16), by threads [t, t+nt).
+// It is 1 % of the network's FLOPs but cost 20 % of the time as 16-column MMAs (operand-fetch bound), and the
+// warps that run it are otherwise idle while the tensor core works through conv3 of the previous iteration.
+__device__ __forceinline__ void conv1_cuda(const ConvArgs &a, long long s0, uint8_t *A1, const float *w1f, const float *bias,
+                                           int t, int nt) {
     for (int i = t; i < S * 100; i += nt) {
         const int s = i / 100, p = i - s * 100;                 // p = x + 10 y   (Julia (r, c) = (x, y))
-        float f0 = 0.f, f1 = 0.f;
-        if (s0 + s < a.n) {
-            const float *o = a.obs + (s0 + s) * 200 + p;
-            f0 = __ldg(o);
-            f1 = __ldg(o + 100);
-        }
         const int y = p / 10, x = p - 10 * y;
-        __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-        *reinterpret_cast<uint32_t *>(A0 + (s * PIX12 + (y + 1) * 12 + (x + 1)) * 16) = *reinterpret_cast<uint32_t *>(&h);
+        float acc[16];
+#pragma unroll
+        for (int o = 0; o < 16; o++) acc[o] = bias[o];
+        if (s0 + s < a.n) {
+            const float *ob = a.obs + (s0 + s) * 200;
+#pragma unroll
+            for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+                for (int k1 = 0; k1 < 3; k1++) {
+                    const int xx = x + k1 - 1, yy = y + k2 - 1;
+                    if (xx < 0 || xx > 9 || yy < 0 || yy > 9) continue;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const float v = __ldg(ob + c * 100 + yy * 10 + xx);
+                        const float4 *w = reinterpret_cast<const float4 *>(w1f + ((k2 * 3 + k1) * 2 + c) * 16);
+#pragma unroll
+                        for (int o4 = 0; o4 < 4; o4++) {
+                            const float4 ww = w[o4];
+                            acc[4 * o4 + 0] = fmaf(v, ww.x, acc[4 * o4 + 0]);
+                            acc[4 * o4 + 1] = fmaf(v, ww.y, acc[4 * o4 + 1]);
+                            acc[4 * o4 + 2] = fmaf(v, ww.z, acc[4 * o4 + 2]);
+                            acc[4 * o4 + 3] = fmaf(v, ww.w, acc[4 * o4 + 3]);
+                        }
+                    }
+                }
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = pack_relu_bf16(acc[2 * j], acc[2 * j + 1]);
+        uint8_t *dst = A1 + (s * PIX12 + (y + 1) * 12 + (x + 1)) * 16;
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(dst + A0_PIX * 16) = make_uint4(w[4], w[5], w[6], w[7]);
     }
 }
 
 __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    uint8_t *A0 = smem + OFF_A0, *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
+    uint8_t *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
+    const float *w1f = (const float *)(smem + OFF_W1);
     const float *bias = (const float *)(smem + OFF_BIAS);
     uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
     uint64_t *acc_full = bars, *acc_empty = bars + NACC, *w3_full = bars + 2 * NACC, *w3_empty = w3_full + 2, *c3_full = w3_empty + 2;
     uint32_t *tmem_slot = (uint32_t *)(c3_full + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- one-time setup: zero the activation planes (borders / K padding stay zero), stage W1, W2, biases
+    // ---- one-time setup: zero the activation planes (borders stay zero), stage W1 (fp32), W2 (bf16), biases
     for (int i = tid; i < OFF_W1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < (int)(P_W3 / 16); i += THREADS)
         reinterpret_cast<uint4 *>(smem + OFF_W1)[i] = reinterpret_cast<const uint4 *>(a.params)[i];
@@ -184,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     __syncthreads();
     const long long n_iter = (a.n + S - 1) / S;
-    if (blockIdx.x < n_iter) load_obs(a, (long long)blockIdx.x * S, A0, tid, THREADS);
+    if (blockIdx.x < n_iter) conv1_cuda(a, (long long)blockIdx.x * S, A1, w1f, bias, tid, THREADS);   // first iteration's conv1
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -192,15 +220,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
     const uint32_t tmem = *tmem_slot;
 
     // constant parts of the operand descriptors; the start-address field counts 16-byte units = pixels
-    const uint64_t dA0 = desc_nosw(smem_u32(A0), 16, 128);                   // conv1: K chunk 1 = the next pixel
     const uint64_t dA1 = desc_nosw(smem_u32(A1), A0_PIX * 16, 128);          // conv2: K chunks = the two channel planes
     const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PIX * 16, 160);          // conv3: 8-pixel groups at a 10-pixel pitch
-    const uint64_t dW1 = desc_nosw(smem_u32(smem + OFF_W1), 256, 128);
     const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);
     const uint64_t dW3 = desc_nosw(smem_u32(smem + OFF_W3), 1024, 128);
 
     // pipeline counters (every thread keeps the same values)
-    uint32_t acc_it = 0;       // accumulator-buffer uses so far (conv1 + conv2 tiles)
+    uint32_t acc_it = 0;       // accumulator-buffer uses so far (conv2 tiles)
     uint32_t w3_it = 0;        // W3 slices so far
     uint32_t c3_it = 0;
 
@@ -210,7 +236,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
         QNET_STAMP(0);
         if (warp == 1 && lane == 0) {
             // conv3 weight producer, part 1: the first two k2-slices fill the 2-slot ring now and land while
-            // conv1/conv2 run (the remaining four follow in the conv3 phase)
+            // conv2 runs (the remaining four follow in the conv3 phase)
             for (int k2 = 0; k2 < 2; k2++) {
                 const uint32_t u = w3_it + k2;
                 const int b = u & 1;
@@ -220,55 +246,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
             }
         }
         QNET_STAMP(1);
-        // ================= conv1: 2 -> 16, 3x3, pad 1 =================
-        if (warp == 0) {
-            if (lane == 0) {
-                for (int t = 0; t < TILES12; t++) {
-                    const uint32_t u = acc_it + t;
-                    const int b = u % NACC;
-                    mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d = tmem + TMEM_C1 + b * 16;
-                    const uint64_t at = dA0 + (uint64_t)(t * 128);
-#pragma unroll
-                    for (int k2 = 0; k2 < 3; k2++)
-#pragma unroll
-                        for (int pr = 0; pr < 2; pr++)       // K chunk 0 = tap k1 = 2 pr, chunk 1 = tap 2 pr + 1 (zero weights for pr = 1)
-                            umma_bf16(d, at + (uint64_t)(k2 * 12 + 2 * pr), dW1 + (uint64_t)((k2 * 2 + pr) * 32),
-                                      idesc_bf16(128, 16), (k2 | pr) ? 1u : 0u);
-                    umma_commit(&acc_full[b]);
-                }
-            }
-        } else if (warp >= 4) {
-            const int grp = (warp - 4) >> 2, q = warp & 3;
-            for (int t = 0; t < TILES12; t++) {
-                const uint32_t u = acc_it + t;
-                if ((int)(u & 1) != grp) continue;
-                const int b = u % NACC;
-                mbar_wait(&acc_full[b], (u / NACC) & 1);
-                tc_fence_after();
-                uint32_t v[16];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C1 + b * 16, v);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[b]);
-                const int P = t * 128 + q * 32 + lane;
-                const int rem = P % PIX12, y = rem / 12, x = rem - 12 * y;
-                if (P < ROWS12 && x < 10 && y < 10) {
-                    uint32_t w[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        w[j] = pack_relu_bf16(__uint_as_float(v[2 * j]) + bias[2 * j], __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1]);
-                    uint8_t *dst = A1 + (P + 13) * 16;               // (x+1, y+1) in conv2's padded grid
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                    *reinterpret_cast<uint4 *>(dst + A0_PIX * 16) = make_uint4(w[4], w[5], w[6], w[7]);
-                }
-            }
-        }
-        acc_it += TILES12;
-        fence_proxy_async();
-        __syncthreads();
         QNET_STAMP(2);
 
         // ================= conv2: 16 -> 32, 3x3, pad 1 =================
@@ -361,9 +338,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
                     bulk_load(smem + OFF_W3 + b * W3_SLICE, a.params + P_W3 + (size_t)k2 * W3_SLICE, W3_SLICE, &w3_full[b]);
                 }
             }
-            // while the tensor core works through conv3, warps 2..11 stage the NEXT iteration's observations
-            // (A0 is free: this iteration's conv1 has been consumed)
-            if (warp >= 2 && it + gridDim.x < n_iter) load_obs(a, (it + gridDim.x) * S, A0, tid - 64, THREADS - 64);
+            // while the tensor core works through conv3, warps 2..11 run the NEXT iteration's conv1 on the CUDA cores
+            // (A1 is free: this iteration's conv2 has been consumed)
+            if (warp >= 2 && it + gridDim.x < n_iter) conv1_cuda(a, (it + gridDim.x) * S, A1, w1f, bias, tid - 64, THREADS - 64);
+            QNET_STAMP(6);
             if (warp >= 4) {
                 const int grp = (warp - 4) >> 2, q = warp & 3;
                 mbar_wait(c3_full, c3_it & 1);
@@ -397,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
         w3_it += 6;
         c3_it++;
         fence_proxy_async();
-        __syncthreads();                            // conv3 accumulators, A2 free again; next A0 staged
+        __syncthreads();                            // conv3 accumulators, A2 free again; next A1 (conv1 output) staged
         QNET_STAMP(5);
     }
 
@@ -545,16 +523,12 @@ static void pack_params(const float *th, std::vector<uint8_t> &blob) {
     auto w1 = [&](int k1, int k2, int c, int o) { return W1[(2 - k1) + 3 * ((2 - k2) + 3 * (c + 2 * o))]; };
     auto w2 = [&](int k1, int k2, int c, int o) { return W2[(2 - k1) + 3 * ((2 - k2) + 3 * (c + 16 * o))]; };
     auto w3 = [&](int k1, int k2, int c, int o) { return W3[(5 - k1) + 6 * ((5 - k2) + 6 * (c + 32 * o))]; };
-    // W1: [k2][pair][chunk][o (16)][8]: chunk 0 = tap k1 = 2*pair, chunk 1 = tap 2*pair + 1 (absent for pair 1)
+    // W1 (fp32, CUDA-core conv1): [tap = k2*3 + k1][c][o]
+    float *w1f = reinterpret_cast<float *>(blob.data() + P_W1);
     for (int k2 = 0; k2 < 3; k2++)
-        for (int pr = 0; pr < 2; pr++)
-            for (int ch = 0; ch < 2; ch++) {
-                const int k1 = 2 * pr + ch;
-                if (k1 > 2) continue;
-                for (int o = 0; o < 16; o++)
-                    for (int c = 0; c < 2; c++)
-                        bf(P_W1)[(((k2 * 2 + pr) * 2 + ch) * 16 + o) * 8 + c] = f2bf(w1(k1, k2, c, o));
-            }
+        for (int k1 = 0; k1 < 3; k1++)
+            for (int c = 0; c < 2; c++)
+                for (int o = 0; o < 16; o++) w1f[((k2 * 3 + k1) * 2 + c) * 16 + o] = w1(k1, k2, c, o);
     // W2: [k2][k1][chunk (2)][o (32)][8]
     for (int k2 = 0; k2 < 3; k2++)
         for (int k1 = 0; k1 < 3; k1++)
