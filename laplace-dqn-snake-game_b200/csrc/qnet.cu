@@ -140,6 +140,11 @@ struct ConvArgs {
     const uint8_t *params;       // packed blob
     __nv_bfloat16 *out3;         // [N][1600] bf16: k' = (oy*5 + ox)*64 + c
     long long *timing;           // optional (debug): per-phase clock64 stamps of block 0, 8 per iteration
+    // conv1 weights [tap = k2*3+k1][c][o] (flipped) and bias, by value: kernel parameters sit in the constant bank, so
+    // the FMAs of the CUDA-core conv1 take them as constant operands — no shared-memory traffic to fight the tensor
+    // core's operand fetch with
+    float w1[288];
+    float b1[16];
 };
 #define QNET_STAMP(k) do { if (a.timing != nullptr && blockIdx.x == 0 && tid == 128) a.timing[it_local * 8 + (k)] = clock64(); } while (0)
 
@@ -147,37 +152,32 @@ struct ConvArgs {
 // Float32 observations into conv2's operand plane A1 (padded 12x12 grids, chunk-planar bf16), by threads [t, t+nt).
 // It is 1 % of the network's FLOPs but cost 20 % of the time as 16-column MMAs (operand-fetch bound), and the
 // warps that run it are otherwise idle while the tensor core works through conv3 of the previous iteration.
-__device__ __forceinline__ void conv1_cuda(const ConvArgs &a, long long s0, uint8_t *A1, const float *w1f, const float *bias,
-                                           int t, int nt) {
+__device__ __forceinline__ void conv1_cuda(const ConvArgs &a, long long s0, uint8_t *A1, int t, int nt) {
     for (int i = t; i < S * 100; i += nt) {
         const int s = i / 100, p = i - s * 100;                 // p = x + 10 y   (Julia (r, c) = (x, y))
         const int y = p / 10, x = p - 10 * y;
+        // all 18 taps are fetched first (clamped address + select, no branches) so the loads are in flight together
+        const bool live = (s0 + s) < a.n;
+        const float *ob = a.obs + (live ? (s0 + s) : 0) * 200;
+        float v[18];
+#pragma unroll
+        for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+            for (int k1 = 0; k1 < 3; k1++) {
+                const int xx = x + k1 - 1, yy = y + k2 - 1;
+                const bool ok = live && xx >= 0 && xx <= 9 && yy >= 0 && yy <= 9;
+                const int off = ok ? yy * 10 + xx : 0;
+                const float t0 = __ldg(ob + off), t1 = __ldg(ob + 100 + off);
+                v[(k2 * 3 + k1) * 2] = ok ? t0 : 0.f;
+                v[(k2 * 3 + k1) * 2 + 1] = ok ? t1 : 0.f;
+            }
         float acc[16];
 #pragma unroll
-        for (int o = 0; o < 16; o++) acc[o] = bias[o];
-        if (s0 + s < a.n) {
-            const float *ob = a.obs + (s0 + s) * 200;
+        for (int o = 0; o < 16; o++) acc[o] = a.b1[o];
 #pragma unroll
-            for (int k2 = 0; k2 < 3; k2++)
+        for (int k = 0; k < 18; k++)
 #pragma unroll
-                for (int k1 = 0; k1 < 3; k1++) {
-                    const int xx = x + k1 - 1, yy = y + k2 - 1;
-                    if (xx < 0 || xx > 9 || yy < 0 || yy > 9) continue;
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const float v = __ldg(ob + c * 100 + yy * 10 + xx);
-                        const float4 *w = reinterpret_cast<const float4 *>(w1f + ((k2 * 3 + k1) * 2 + c) * 16);
-#pragma unroll
-                        for (int o4 = 0; o4 < 4; o4++) {
-                            const float4 ww = w[o4];
-                            acc[4 * o4 + 0] = fmaf(v, ww.x, acc[4 * o4 + 0]);
-                            acc[4 * o4 + 1] = fmaf(v, ww.y, acc[4 * o4 + 1]);
-                            acc[4 * o4 + 2] = fmaf(v, ww.z, acc[4 * o4 + 2]);
-                            acc[4 * o4 + 3] = fmaf(v, ww.w, acc[4 * o4 + 3]);
-                        }
-                    }
-                }
-        }
+            for (int o = 0; o < 16; o++) acc[o] = fmaf(v[k], a.w1[k * 16 + o], acc[o]);
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) w[j] = pack_relu_bf16(acc[2 * j], acc[2 * j + 1]);
@@ -187,11 +187,10 @@ __device__ __forceinline__ void conv1_cuda(const ConvArgs &a, long long s0, uint
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant__ ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint8_t *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
-    const float *w1f = (const float *)(smem + OFF_W1);
     const float *bias = (const float *)(smem + OFF_BIAS);
     uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
     uint64_t *acc_full = bars, *acc_empty = bars + NACC, *w3_full = bars + 2 * NACC, *w3_empty = w3_full + 2, *c3_full = w3_empty + 2;
@@ -212,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     __syncthreads();
     const long long n_iter = (a.n + S - 1) / S;
-    if (blockIdx.x < n_iter) conv1_cuda(a, (long long)blockIdx.x * S, A1, w1f, bias, tid, THREADS);   // first iteration's conv1
+    if (blockIdx.x < n_iter) conv1_cuda(a, (long long)blockIdx.x * S, A1, tid, THREADS);   // first iteration's conv1
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -340,7 +339,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const ConvArgs a) {
             }
             // while the tensor core works through conv3, warps 2..11 run the NEXT iteration's conv1 on the CUDA cores
             // (A1 is free: this iteration's conv2 has been consumed)
-            if (warp >= 2 && it + gridDim.x < n_iter) conv1_cuda(a, (it + gridDim.x) * S, A1, w1f, bias, tid - 64, THREADS - 64);
+            // (not warps 4 and 8: they share the MMA issuer's scheduler, and a busy scheduler slows the MMA issue)
+            if (warp >= 2 && (warp & 3) != 0 && it + gridDim.x < n_iter) {
+                const int w8 = warp - 2 - (warp > 4) - (warp > 8);                 // 2,3,5,6,7,9,10,11 -> 0..7
+                conv1_cuda(a, (it + gridDim.x) * S, A1, w8 * 32 + lane, 256);
+            }
             QNET_STAMP(6);
             if (warp >= 4) {
                 const int grp = (warp - 4) >> 2, q = warp & 3;
@@ -584,6 +587,7 @@ using namespace snk;
 using namespace snk::qnet;
 
 struct snk_qnet_s {
+    float w1[288], b1[16];
     long long *timing;
     int device;
     uint8_t *params;
@@ -605,6 +609,8 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
     if (q == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
     memset(q, 0, sizeof(*q));
     q->device = device;
+    memcpy(q->w1, blob.data() + P_W1, sizeof(q->w1));
+    memcpy(q->b1, blob.data() + P_BIAS, sizeof(q->b1));
     cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
@@ -646,6 +652,8 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
     }
     ConvArgs ca;
     ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = q->out3; ca.timing = q->timing;
+    memcpy(ca.w1, q->w1, sizeof(ca.w1));
+    memcpy(ca.b1, q->b1, sizeof(ca.b1));
     const long long n_iter = (N + S - 1) / S;
     int grid = (int)(n_iter < q->sms ? n_iter : q->sms);
     SNK_CUDA(cudaFuncSetAttribute(k_qnet_convs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_A));
