@@ -52,6 +52,8 @@ constexpr int OFF_BIAS = OFF_W3 + 2 * W3_SLICE;          // b1 (16) b2 (32) b3 (
 constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
 constexpr int SMEM_A = OFF_BAR + 128 + 128;              // barriers + alignment slack
 static_assert(SMEM_A <= 232448, "kernel A shared memory over the 227 KB limit");
+constexpr int NISSUE = 2;                                // MMA-issuing threads (lane 0 of warps 0 and 1, two schedulers):
+                                                         // with 32-cycle MMAs one thread cannot issue fast enough
 constexpr int NACC = 4;                                  // accumulator buffers cycled by the conv1 / conv2 tiles
 constexpr int TMEM_C3 = 0, TMEM_C2 = 256;                // column offsets: conv3 4 x 64 | conv2 NACC x 32
 
@@ -204,8 +206,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
     for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
     if (tid == 0) {
         for (int i = 0; i < NACC; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
-        for (int i = 0; i < 2; i++) { mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], 1); }
-        mbar_init(c3_full, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], NISSUE); }
+        mbar_init(c3_full, NISSUE);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
     for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, it_local++) {
         const long long s0 = it * S;
         QNET_STAMP(0);
-        if (warp == 1 && lane == 0) {
+        if (warp == 2 && lane == 0) {
             // conv3 weight producer, part 1: the first two k2-slices fill the 2-slot ring now and land while
             // conv2 runs (the remaining four follow in the conv3 phase)
             for (int k2 = 0; k2 < 2; k2++) {
@@ -248,10 +250,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
         QNET_STAMP(2);
 
         // ================= conv2: 16 -> 32, 3x3, pad 1 =================
-        if (warp == 0) {
+        if (warp < NISSUE) {
             if (lane == 0) {
                 for (int t = 0; t < TILES12; t++) {
                     const uint32_t u = acc_it + t;
+                    if ((int)(u % NISSUE) != warp) continue;      // issuer w owns the tiles (and accumulator buffers) of its parity
                     const int b = u % NACC;
                     mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
                     tc_fence_after();
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
         QNET_STAMP(3);
 
         // ================= conv3: 32 -> 64, 6x6, valid =================
-        if (warp == 0) {
+        if (warp < NISSUE) {
             if (lane == 0) {
                 tc_fence_after();
                 for (int k2 = 0; k2 < 6; k2++) {
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
                     mbar_wait(&w3_full[b], (u >> 1) & 1);
                     tc_fence_after();
                     const uint64_t wb = dW3 + (uint64_t)(b * (W3_SLICE / 16));
-                    for (int tt = 0; tt < TILES3; tt++) {
+                    for (int tt = warp; tt < TILES3; tt += NISSUE) {     // each issuer owns its accumulator tiles
                         const uint32_t d = tmem + TMEM_C3 + tt * 64;
                         const uint64_t at = dA2 + (uint64_t)(tt * 160 + k2 * S * 10);
 #pragma unroll
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
                 umma_commit(c3_full);
             }
         } else {
-            if (warp == 1 && lane == 0) {
+            if (warp == 2 && lane == 0) {
                 // conv3 weight producer, part 2: slices 2..5 as the tensor core releases the ring slots
                 for (int k2 = 2; k2 < 6; k2++) {
                     const uint32_t u = w3_it + k2;
@@ -339,12 +342,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
             }
             // while the tensor core works through conv3, warps 2..11 run the NEXT iteration's conv1 on the CUDA cores
             // (A1 is free: this iteration's conv2 has been consumed)
-            // (not warps 4 and 8: they share the MMA issuer's scheduler, and a busy scheduler slows the MMA issue)
-            if (warp >= 2 && (warp & 3) != 0 && it + gridDim.x < n_iter) {
-                const int w8 = warp - 2 - (warp > 4) - (warp > 8);                 // 2,3,5,6,7,9,10,11 -> 0..7
-                conv1_cuda(a, (it + gridDim.x) * S, A1, w8 * 32 + lane, 256);
+            // (only warps on the two schedulers without an MMA issuer: a busy scheduler slows the issuing thread)
+            if ((warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
+                const int w5 = warp == 3 ? 0 : (warp == 6 ? 1 : (warp == 7 ? 2 : (warp == 10 ? 3 : 4)));   // 3,6,7,10,11 -> 0..4
+                conv1_cuda(a, (it + gridDim.x) * S, A1, w5 * 32 + lane, 160);
+                if (a.timing != nullptr && blockIdx.x == 0 && warp == 11 && lane == 0) a.timing[it_local * 8 + 6] = clock64();
             }
-            QNET_STAMP(6);
             if (warp >= 4) {
                 const int grp = (warp - 4) >> 2, q = warp & 3;
                 mbar_wait(c3_full, c3_it & 1);
