@@ -427,3 +427,41 @@ def test_multi_step_rollout_kernel_matches_oracle(n, T, fmt):
     r, d = env.step(torch.from_numpy(a).cuda())
     ref = ora.step(a)
     assert np.array_equal(bits(r.cpu().numpy()), bits(ref["reward"])) and np.array_equal(d.cpu().numpy(), ref["done"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_food_lists_differential(seed):
+    """Injected food-spawn draw streams (north star): random lists of random length, duplicates included, against
+    the oracle for every output of every step; lists shorter than the reference's 50 also exercise R9."""
+    S = pkg()
+    rng = np.random.default_rng(seed)
+    n = 1536
+    n_food = int(rng.integers(3, 65))
+    food = [(int(r), int(c)) for r, c in rng.integers(2, 10, (n_food, 2))]
+    env = S.SnakeGame(n, auto_reset=True, food_list=food)
+    ora = O.OracleBatch(n, food_rc=food, auto_reset=True)
+    out = env.alloc_outputs(obs="i8", mask=True, ep_stats=True)
+    # a policy that eats a lot: prefer a non-losing action that moves towards the food, so lists get consumed
+    for t in range(250):
+        m, av = ora.losing_mask()
+        sc = ora.scalars()
+        head, foodrc = sc["head_rc"].astype(int), sc["food_rc"].astype(int)
+        best = np.zeros(n, np.int64)
+        best_score = np.full(n, 1e9)
+        for k in range(3):
+            d = av[:, k].astype(int)
+            dr = np.where(d == 0, -1, np.where(d == 1, 1, 0))
+            dc = np.where(d == 2, -1, np.where(d == 3, 1, 0))
+            dist = np.abs(head[:, 0] + dr - foodrc[:, 0]) + np.abs(head[:, 1] + dc - foodrc[:, 1])
+            score = dist + 1000.0 * m[:, k] + rng.random(n) * 0.5
+            take = score < best_score
+            best[take] = k
+            best_score[take] = score[take]
+        act = best.astype(np.uint8)
+        act[rng.random(n) < 0.1] = rng.integers(0, 3)
+        env.step_fused(act_idx=torch.from_numpy(act).cuda(), out=out)
+        ref = ora.step(act, obs=("i8",))
+        _cmp_step(out, ref, n, t, obs_key="obs_i8")
+    sc = ora.scalars()
+    assert sc["score"].max() >= min(8, n_food)                  # the greedy policy really eats through the list
+    assert np.array_equal(env.error_flags.cpu().numpy().astype(np.uint32), sc["error"])
