@@ -177,20 +177,31 @@ __device__ __forceinline__ void set_k(int r, int c, u64 &lo, u64 &hi) {
 }
 // Two bit-planes of one board, code = 2*p1 + p0: 0 empty, 1 snake, 2 food, 3 wall.  The head is drawn last
 // as snake, which reproduces update_board! overwriting the wall cell on a wall death (utils.jl:48-50).
+// nibble i of x -> byte i of the result (low nibble of each byte)
+__device__ __forceinline__ u64 spread_nibbles(uint32_t x) {
+    u64 v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    return v;
+}
+// One board -> 25 "unit bytes" in shared memory (32-byte slot): unit q covers cells 4q..4q+3, its byte holds the
+// plane-0 nibble in bits 0-3 and the plane-1 nibble in bits 4-7 — exactly the index of the 256-entry output tables,
+// so phase B needs one byte load per 16-byte store.
 __device__ __forceinline__ void board_planes(u64 occ, int fr, int fc, bool has_head, int hr, int hc, uint32_t *dst) {
     u64 slo, shi;
     to_full(occ, slo, shi);
     if (has_head) set_k(hr, hc, slo, shi);
     u64 flo = WALL_LO, fhi = WALL_HI;
     if (fr != 0) set_k(fr, fc, flo, fhi);
-    u64 p0lo = slo | WALL_LO, p0hi = shi | WALL_HI;
-    u64 p1lo = flo & ~slo, p1hi = fhi & ~shi;
-    uint4 a = make_uint4((uint32_t)p0lo, (uint32_t)(p0lo >> 32), (uint32_t)p0hi, (uint32_t)(p0hi >> 32));
-    uint4 b = make_uint4((uint32_t)p1lo, (uint32_t)(p1lo >> 32), (uint32_t)p1hi, (uint32_t)(p1hi >> 32));
-    reinterpret_cast<uint4 *>(dst)[0] = a;
-    reinterpret_cast<uint4 *>(dst)[1] = b;
+    const u64 p0lo = slo | WALL_LO, p0hi = shi | WALL_HI;
+    const u64 p1lo = flo & ~slo, p1hi = fhi & ~shi;
+    u64 *d = reinterpret_cast<u64 *>(dst);
+    d[0] = spread_nibbles((uint32_t)p0lo) | (spread_nibbles((uint32_t)p1lo) << 4);
+    d[1] = spread_nibbles((uint32_t)(p0lo >> 32)) | (spread_nibbles((uint32_t)(p1lo >> 32)) << 4);
+    d[2] = spread_nibbles((uint32_t)p0hi) | (spread_nibbles((uint32_t)p1hi) << 4);
+    d[3] = spread_nibbles((uint32_t)(p0hi >> 32)) | (spread_nibbles((uint32_t)(p1hi >> 32)) << 4);
 }
-
 __device__ __forceinline__ void board_planes_reg(u64 occ, int fr, int fc, bool has_head, int hr, int hc, uint4 &a, uint4 &b) {
     u64 slo, shi;
     to_full(occ, slo, shi);
@@ -203,8 +214,10 @@ __device__ __forceinline__ void board_planes_reg(u64 occ, int fr, int fc, bool h
     b = make_uint4((uint32_t)p1lo, (uint32_t)(p1lo >> 32), (uint32_t)p1hi, (uint32_t)(p1hi >> 32));
 }
 
-__device__ __forceinline__ int cell_code(const uint32_t *pl, int k) {
-    return (int)(((pl[k >> 5] >> (k & 31)) & 1u) | (((pl[4 + (k >> 5)] >> (k & 31)) & 1u) << 1));
+__device__ __forceinline__ int cell_code(const uint32_t *pl, int k) {     // pl = one board's 32-byte unit slot
+    const uint32_t b = reinterpret_cast<const uint8_t *>(pl)[k >> 2];
+    const int j = k & 3;
+    return (int)(((b >> j) & 1u) | (((b >> (4 + j)) & 1u) << 1));
 }
 __device__ __forceinline__ int code_value(int code) { return code == 3 ? -1 : code; }
 
@@ -250,9 +263,7 @@ __device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_loca
             int qq = j - e * 50;
             int f = qq >= 25;
             int q = qq - 25 * f;
-            const uint32_t *pl = s_planes + e * PLANE_WORDS + f * 8;
-            int w = q >> 3, sh = (q & 7) * 4;
-            uint32_t idx = ((pl[w] >> sh) & 15u) | (((pl[4 + w] >> sh) & 15u) << 4);
+            const uint32_t idx = reinterpret_cast<const uint8_t *>(s_planes)[e * (PLANE_WORDS * 4) + f * 32 + q];
             if (OBS == SNK_OBS_F32) __stcs(o32 + j, tb.f32[idx]);
             else if (OBS == SNK_OBS_I8) __stcs(o8 + j, reinterpret_cast<const uint32_t *>(tb.f32)[idx]);
             else op[j] = reinterpret_cast<const uint8_t *>(tb.f32)[idx];
