@@ -207,6 +207,9 @@ SNK_API int snk_qnet_debug_timing(snk_qnet q, long long *device_buf);
  * column order, var = M2 / max(K-1,1), then D .-= mean, all in Float64 without FMA contraction so
  * the result is bit-identical to the Julia loop.  mean/var (P) may be NULL. */
 SNK_API int snk_center_columns(double *D, int64_t P, int64_t K, double *mean, double *var, void *cuda_stream);
+/* deviation_matrix[:, position] = Float64.(theta)  (compute_D.jl:67-71): theta = Flux.destructure(q_net) as Float32 on the
+ * device, position 0-based. */
+SNK_API int snk_d_store_snapshot(double *D, int64_t P, int64_t K, int64_t position, const float *theta, void *cuda_stream);
 
 /* ---- Gram of the deviation matrix  plot_traj.jl:10-16 (svd(D), S.^2/(K-1) = eig(D'D)/(K-1)) ------------
  * G = A A^T with A = D^T: A is K x P row-major (row k = snapshot k) — byte-identical to Julia's P x K

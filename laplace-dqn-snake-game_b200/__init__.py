@@ -68,6 +68,7 @@ def lib():
         "snk_get_score": [vp, vp], "snk_get_done": [vp, vp], "snk_get_error_flags": [vp, vp],
         "snk_get_steps": [vp, vp], "snk_count_errors_host": [vp, C.POINTER(i64)],
         "snk_center_columns": [vp, i64, i64, vp, vp, vp],
+        "snk_d_store_snapshot": [vp, i64, i64, i64, vp, vp],
         "snk_replay_create": [C.POINTER(vp), i64, i32], "snk_replay_destroy": [vp], "snk_replay_clear": [vp],
         "snk_replay_length": [vp, C.POINTER(i64), C.POINTER(i64)],
         "snk_step_fused_store": [vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
@@ -362,8 +363,6 @@ def center_columns(Dt):
     return mean, var
 
 
-from . import shard  # noqa: E402,F401
-from . import bson_io, qnet, rollout  # noqa: E402,F401
 
 
 def pinned_empty(shape, dtype):
@@ -492,3 +491,7 @@ class ReplayBuffer:
         f = C.c_int(0)
         _check(lib().snk_replay_bad_index_host(self._r, C.byref(f)))
         return bool(f.value)
+
+
+from . import shard  # noqa: E402,F401
+from . import bson_io, laplace, qnet, rollout  # noqa: E402,F401

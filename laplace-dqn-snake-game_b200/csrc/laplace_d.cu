@@ -51,9 +51,23 @@ __global__ void __launch_bounds__(CENTER_TPB) k_center_columns(double *__restric
     for (; k < K; k++) D[k * P + p] = __dsub_rn(D[k * P + p], mean);
 }
 
+// deviation_matrix[:, position] = Float64.(theta)   (compute_D.jl:67-71, la_utils.jl:154-158)
+__global__ void k_store_snapshot(double *__restrict__ D, long long P, long long k, const float *__restrict__ theta) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) D[k * P + p] = (double)theta[p];
+}
+
 }  // namespace snk
 
 using namespace snk;
+
+extern "C" int snk_d_store_snapshot(double *D, int64_t P, int64_t K, int64_t position, const float *theta, void *cuda_stream) {
+    SNK_REQUIRE(D != nullptr && theta != nullptr, "null argument");
+    SNK_REQUIRE(P > 0 && position >= 0 && position < K, "position must be in 0..K-1 (0-based column)");
+    k_store_snapshot<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(D, P, position, theta);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
 
 extern "C" int snk_center_columns(double *D, int64_t P, int64_t K, double *mean, double *var, void *cuda_stream) {
     SNK_REQUIRE(D != nullptr, "null D");

@@ -83,3 +83,36 @@ def test_row_sharded_gram_with_virtual_ranks(world, K, P, terms):
     assert _rel_fro(G, ref) < tol
     single = S.gram(torch.from_numpy(A).cuda(), terms=terms).cpu().numpy()
     assert _rel_fro(G, single.astype(np.float64)) < 2e-6       # same arithmetic up to split-K summation order
+
+
+def test_plot_traj_numeric_path_matches_numpy_svd():
+    """compute_D.jl + plot_traj.jl end to end: snapshots -> D -> centring -> spectrum S.^2/(K-1), the 99 % column
+    count and the two-direction trajectory U[:, 1:2]' D, against numpy's SVD of the centred Float64 D."""
+    S = pkg()
+    K, P = 200, 30011
+    A = GO.synthetic_snapshots(K, P, seed=11)                    # (K, P) float64, values exactly representable in f32
+    dm = S.laplace.DeviationMatrix(P, K, "cuda:0")
+    for k in range(K):
+        dm.store(torch.from_numpy(A[k].astype(np.float32)).cuda())
+    assert dm.position == K and np.array_equal(dm.Dt.cpu().numpy(), A)
+    with pytest.raises(IndexError):
+        dm.store(torch.zeros(P, device="cuda"))
+    dm.center()
+    want = A.copy().reshape(-1)
+    O.center_columns(want, P, K)
+    D = want.reshape(K, P)                                       # rows = snapshots; Julia's D is this transposed
+    assert np.array_equal(dm.Dt.cpu().numpy(), D)
+    U, Sv, Vt = np.linalg.svd(D.T, full_matrices=False)          # svd(deviation_matrix), plot_traj.jl:10
+    lam_ref = Sv ** 2 / (K - 1)
+    lam, V, w = S.laplace.spectrum(dm.Dt)
+    lam = lam.cpu().numpy()
+    top = lam_ref > 1e-4 * lam_ref[0]
+    assert np.max(np.abs(lam[top] - lam_ref[top]) / lam_ref[top]) < 1e-3
+    cum = np.cumsum(lam_ref)
+    n_ref = int(np.searchsorted(cum, 0.99 * cum[-1]) + 1)
+    assert abs(S.laplace.n_cols_for_variance(torch.from_numpy(lam).cuda()) - n_ref) <= 1
+    Y = S.laplace.trajectory(w, V, 2).cpu().numpy()
+    Y_ref = U[:, :2].T @ D.T                                     # (2, K)
+    for i in range(2):
+        sgn = np.sign(np.dot(Y[i], Y_ref[i]))
+        assert np.max(np.abs(sgn * Y[i] - Y_ref[i])) < 2e-3 * np.abs(Y_ref[i]).max()
