@@ -209,6 +209,10 @@ SNK_API int snk_qnet_debug_timing(snk_qnet q, long long *device_buf);
 SNK_API int snk_center_columns(double *D, int64_t P, int64_t K, double *mean, double *var, void *cuda_stream);
 /* deviation_matrix[:, position] = Float64.(theta)  (compute_D.jl:67-71): theta = Flux.destructure(q_net) as Float32 on the
  * device, position 0-based. */
+/* sample_model (la_utils.jl:83-95): w = mean + sqrt.(|var|) .* z1 / sqrt(2) + D * z2 / sqrt(2(K-1)), all Float64 on the
+ * device; z1 (P) and z2 (K) are the injected standard-normal draws (rand(MvNormal(0, I))). */
+SNK_API int snk_laplace_sample_weights(const double *mean, const double *var, const double *D, int64_t P, int64_t K,
+                                       const double *z1, const double *z2, double *w, void *cuda_stream);
 SNK_API int snk_d_store_snapshot(double *D, int64_t P, int64_t K, int64_t position, const float *theta, void *cuda_stream);
 
 /* ---- Gram of the deviation matrix  plot_traj.jl:10-16 (svd(D), S.^2/(K-1) = eig(D'D)/(K-1)) ------------

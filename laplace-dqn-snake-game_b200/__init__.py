@@ -69,6 +69,7 @@ def lib():
         "snk_get_steps": [vp, vp], "snk_count_errors_host": [vp, C.POINTER(i64)],
         "snk_center_columns": [vp, i64, i64, vp, vp, vp],
         "snk_d_store_snapshot": [vp, i64, i64, i64, vp, vp],
+        "snk_laplace_sample_weights": [vp, vp, vp, i64, i64, vp, vp, vp, vp],
         "snk_replay_create": [C.POINTER(vp), i64, i32], "snk_replay_destroy": [vp], "snk_replay_clear": [vp],
         "snk_replay_length": [vp, C.POINTER(i64), C.POINTER(i64)],
         "snk_step_fused_store": [vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],

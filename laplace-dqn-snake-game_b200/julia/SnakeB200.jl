@@ -11,7 +11,9 @@
 module SnakeB200
 
 export BatchedSnakeGame, available_actions, step!, step_fused!, virtual_step, assemble_state!,
-       epsilon_greedy, masked_target, center_columns!, reset!, set_food_list!, score, lost
+       epsilon_greedy, masked_target, center_columns!, reset!, set_food_list!, score, lost,
+       DeviceReplayBuffer, store_step!, stack_exp, sample_indices, DeviceQNet, forward!, store_snapshot!,
+       gram!, sample_model_weights!
 
 const lib = get(ENV, "SNAKE_B200_LIB", joinpath(@__DIR__, "..", "libsnake_b200.so"))
 
@@ -143,5 +145,87 @@ epsilon_greedy(g::BatchedSnakeGame, d_q::Ptr{Float32}, epsilon::Float32, d_u::Pt
 center_columns!(d_D::Ptr{Float64}, P::Integer, K::Integer, d_mean::Ptr{Float64}, d_var::Ptr{Float64}) =
     check(ccall((:snk_center_columns, lib), Cint, (Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
                 d_D, P, K, d_mean, d_var, C_NULL))
+
+# ---- ReplayBuffer on the device (structs.jl:104-116; store! / sample / stack_exp, utils.jl:265-383) -----------
+mutable struct DeviceReplayBuffer
+    handle::Ptr{Cvoid}
+    capacity::Int
+    batch_size::Int
+    function DeviceReplayBuffer(capacity::Integer = 50000; device::Integer = 0, batch_size::Integer = 64)
+        batch_size > capacity && throw("batch_size cannot be greater than the capacity of the buffer.")   # structs.jl:113
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:snk_replay_create, lib), Cint, (Ref{Ptr{Cvoid}}, Int64, Cint), h, capacity, device))
+        r = new(h[], capacity, batch_size)
+        finalizer(x -> ccall((:snk_replay_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), r)
+        return r
+    end
+end
+function Base.length(r::DeviceReplayBuffer)
+    n = Ref{Int64}(0); p = Ref{Int64}(0)
+    check(ccall((:snk_replay_length, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), r.handle, n, p))
+    return Int(n[])
+end
+
+"""One fused step that also `store!`s every env's Experience (device pointers: q, u, ridx, outputs)."""
+store_step!(g::BatchedSnakeGame, r::DeviceReplayBuffer, d_q::Ptr{Float32}, epsilon::Float32, d_u::Ptr{Float32},
+            d_ridx::Ptr{UInt8}, d_act::Ptr{UInt8}, d_reward::Ptr{Float32}, d_done::Ptr{UInt8}, d_obs::Ptr{Float32},
+            d_mask::Ptr{UInt8}) =
+    check(ccall((:snk_step_fused_store, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float32}, Cfloat, Ptr{Float32}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Float32}, Ptr{UInt8},
+                 Ptr{Cvoid}, Cint, Ptr{UInt8}, Ptr{Float32}, Ptr{Int32}),
+                g.handle, r.handle, d_q, epsilon, d_u, d_ridx, d_act, d_reward, d_done, d_obs, OBS_F32, d_mask, C_NULL, C_NULL))
+
+"""`sample(rpb)` indices (0-based slots, distinct) into a device Int64 buffer."""
+sample_indices(r::DeviceReplayBuffer, d_idx::Ptr{Int64}, B::Integer; seed::Integer = 0) =
+    check(ccall((:snk_replay_sample_indices, lib), Cint, (Ptr{Cvoid}, UInt64, Int64, Ptr{Int64}, Ptr{Cvoid}),
+                r.handle, seed, B, d_idx, C_NULL))
+
+"""`stack_exp(batch)` on the device: states/next_states (10,10,2,B) Float32, actions (0-based), rewards, dones, mask (3,B)."""
+stack_exp(r::DeviceReplayBuffer, d_idx::Ptr{Int64}, B::Integer, d_states::Ptr{Float32}, d_next::Ptr{Float32},
+          d_actions::Ptr{UInt8}, d_rewards::Ptr{Float32}, d_dones::Ptr{UInt8}, d_mask::Ptr{UInt8}) =
+    check(ccall((:snk_replay_gather, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}, Ptr{Float32}, Ptr{UInt8}, Ptr{UInt8},
+                 Ptr{Float32}, Ptr{Int32}, Ptr{Cvoid}),
+                r.handle, d_idx, B, d_states, d_next, d_actions, d_rewards, d_dones, d_mask, C_NULL, C_NULL, C_NULL))
+
+# ---- Q-net forward (structs.jl:127-139) from Flux.destructure(q_net) ------------------------------------------
+mutable struct DeviceQNet
+    handle::Ptr{Cvoid}
+    function DeviceQNet(theta::Vector{Float32}; device::Integer = 0)     # theta, _ = Flux.destructure(model.q_net)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:snk_qnet_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ptr{Float32}, Int64, Cint), h, theta, length(theta), device))
+        q = new(h[])
+        finalizer(x -> ccall((:snk_qnet_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), q)
+        return q
+    end
+end
+"""q_net(states): d_obs (10,10,2,N) Float32 -> d_q (3,N) Float32, both on the device."""
+forward!(q::DeviceQNet, d_obs::Ptr{Float32}, N::Integer, d_q::Ptr{Float32}) =
+    check(ccall((:snk_qnet_forward, lib), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Float32}, Ptr{Cvoid}), q.handle, d_obs, N, d_q, C_NULL))
+
+# ---- Laplace deviation matrix (compute_D.jl, plot_traj.jl, la_utils.jl) ----------------------------------------
+"""deviation_matrix[:, position] = Float64.(theta) (compute_D.jl:67-71); position is 1-based like Julia's."""
+store_snapshot!(d_D::Ptr{Float64}, P::Integer, K::Integer, position::Integer, d_theta::Ptr{Float32}) =
+    check(ccall((:snk_d_store_snapshot, lib), Cint, (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float32}, Ptr{Cvoid}),
+                d_D, P, K, position - 1, d_theta, C_NULL))
+
+"""G = D'D (K x K Float32) of a centred device-resident D; eigen(G).values ./ (K-1) == svd(D).S .^ 2 ./ (K-1)."""
+function gram!(d_D::Ptr{Float64}, P::Integer, K::Integer, d_workspace::Ptr{Cvoid}, d_G::Ptr{Float32}; terms::Integer = 3)
+    check(ccall((:snk_gram_pack, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}), d_D, 2, P, K, d_workspace, C_NULL))
+    check(ccall((:snk_gram, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Cint, Cint, Cint, Ptr{Float32}, Ptr{Cvoid}),
+                d_workspace, P, K, terms, 0, 0, d_G, C_NULL))
+end
+function gram_workspace_bytes(P::Integer, K::Integer)
+    n = Ref{Csize_t}(0)
+    check(ccall((:snk_gram_workspace_bytes, lib), Cint, (Int64, Int64, Cint, Ref{Csize_t}), K, P, 0, n))
+    return Int(n[])
+end
+
+"""sample_model (la_utils.jl:83-95) with injected z1 (P), z2 (K) on the device."""
+sample_model_weights!(d_mean::Ptr{Float64}, d_var::Ptr{Float64}, d_D::Ptr{Float64}, P::Integer, K::Integer,
+                      d_z1::Ptr{Float64}, d_z2::Ptr{Float64}, d_w::Ptr{Float64}) =
+    check(ccall((:snk_laplace_sample_weights, lib), Cint,
+                (Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+                d_mean, d_var, d_D, P, K, d_z1, d_z2, d_w, C_NULL))
 
 end # module

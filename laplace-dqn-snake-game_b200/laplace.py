@@ -63,3 +63,20 @@ def n_cols_for_variance(lam, fraction=0.99):
 def trajectory(w, V, n=2):
     """Y = U[:, 1:n]' * D  (plot_traj.jl:69-70) = sqrt(w_i) * v_i', shape (n, K); rows are defined up to sign."""
     return (V[:, :n] * torch.sqrt(w[:n])).T.contiguous()
+
+
+def sample_model_weights(mean, var, Dt, z1=None, z2=None):
+    """sample_model (la_utils.jl:83-95): w = mean + sqrt.(|var|) .* z1 / sqrt(2) + D * z2 / sqrt(2 (K-1)).
+    Dt: centred (K, P) float64; z1 (P), z2 (K) standard-normal draws (generated with torch if not injected).
+    Returns the flattened weights (P,) float64 in Flux.destructure order (feed QNet / snk_qnet_create after .float())."""
+    K, P = Dt.shape
+    dev = Dt.device
+    z1 = torch.randn(P, dtype=torch.float64, device=dev) if z1 is None else z1
+    z2 = torch.randn(K, dtype=torch.float64, device=dev) if z2 is None else z2
+    w = torch.empty(P, dtype=torch.float64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _check(lib().snk_laplace_sample_weights(_ptr(mean, torch.float64, P, dev), _ptr(var, torch.float64, P, dev),
+                                                _ptr(Dt, torch.float64), P, K, _ptr(z1, torch.float64, P, dev),
+                                                _ptr(z2, torch.float64, K, dev), _ptr(w), st))
+    return w

@@ -116,3 +116,20 @@ def test_plot_traj_numeric_path_matches_numpy_svd():
     for i in range(2):
         sgn = np.sign(np.dot(Y[i], Y_ref[i]))
         assert np.max(np.abs(sgn * Y[i] - Y_ref[i])) < 2e-3 * np.abs(Y_ref[i]).max()
+
+
+def test_sample_model_weights_matches_numpy():
+    """la_utils.jl:83-95 with injected z1, z2 (the reference draws them from MvNormal(0, I))."""
+    S = pkg()
+    rng = np.random.default_rng(4)
+    K, P = 58, 181395                                            # the reference insists on K = 58 (la_utils.jl:86)
+    D = rng.normal(0, 1e-2, (K, P))
+    mean, var = rng.normal(0, 0.1, P), rng.normal(0, 1e-4, P)    # some negative "variances": compute_Gamma_diag takes abs
+    z1, z2 = rng.normal(0, 1, P), rng.normal(0, 1, K)
+    want = mean + np.sqrt(np.abs(var)) * z1 / np.sqrt(2) + (D.T @ z2) / np.sqrt(2 * (K - 1))
+    t = lambda a: torch.from_numpy(a).cuda()
+    got = S.laplace.sample_model_weights(t(mean), t(var), t(D), t(z1), t(z2)).cpu().numpy()
+    assert np.max(np.abs(got - want)) < 1e-13 * np.max(np.abs(want)) + 1e-15
+    # the sampled weights are a valid Q-net
+    net = S.qnet.QNet(S.qnet.glorot_layers(0), "cuda:0", backend="native")
+    assert got.shape == (net.n_params,)
