@@ -91,3 +91,17 @@ def test_argument_validation_without_touching_the_gpu(built):
 def test_default_food_list_is_the_pinned_xoshiro42_list(built):
     from oracle import oracle_lib as O
     assert built.default_food_list() == O.DEFAULT_FOOD_RC
+
+
+def test_product_sources_never_touch_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package (host mirror, CUDA sources, Julia
+    wrapper) may import, include, link or execute it."""
+    pkg_dir = os.path.join(ROOT, "laplace-dqn-snake-game_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".jl", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"(from|import)\s+oracle|oracle_lib|libsnake_oracle|oracle/", txt):
+                    offenders.append(os.path.join(base, f))
+    assert not offenders, offenders
