@@ -152,6 +152,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, bf16 x bf16, both K-major, M=128, N=256
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// Tile order: column panels PANEL tiles wide, swept down the rows.  The CTAs (or CTA pairs) that run concurrently then
+// cover a roughly square block of the output, so per k-step they pull ~2*sqrt(n) distinct operand tiles through L2
+// instead of n + 1 (one A row-block against every B tile).
+constexpr int PANEL = 8;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int &tm, int &tn) {
+    const int per_panel = PANEL * tiles_m;
+    const int panel = tile / per_panel, within = tile - panel * per_panel;
+    const int width = min(PANEL, tiles_n - panel * PANEL);
+    tm = within / width;
+    tn = panel * PANEL + within - tm * width;
+}
+
 struct GramArgs {
     float *partials;        // [splits][Mt][Nt] fp32, Mt = tiles_m*BM, Nt = tiles_n*BN
     int tiles_m, tiles_n, splits;
@@ -199,7 +211,8 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
                 const int n_tiles = g.tiles_m * g.tiles_n;
                 const int split = w / n_tiles, tile = w % n_tiles;      // split-major: concurrent CTAs share a k-range
-                const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+                int tm, tn;
+                tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
                 for (int kb = kb0; kb < kb1; kb++) {
@@ -261,7 +274,8 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int n_tiles = g.tiles_m * g.tiles_n;
             const int split = w / n_tiles, tile = w % n_tiles;
-            const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+            int tm, tn;
+                tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
             const int kb0 = split * g.kb_per_split;
             const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
             const int n_chunks = (kb1 - kb0 + CH - 1) / CH;
@@ -393,7 +407,8 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
             uint32_t phase = 0;
             for (int w = cluster_id; w < n_work; w += n_clusters) {
                 const int split = w / n_tiles, tile = w % n_tiles;
-                const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+                int tm, tn;
+                tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
                 for (int kb = kb0; kb < kb1; kb++) {
@@ -455,7 +470,8 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
         uint32_t acc_phase = 0;
         for (int w = cluster_id; w < n_work; w += n_clusters) {
             const int split = w / n_tiles, tile = w % n_tiles;
-            const int tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+            int tm, tn;
+                tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
             const int kb0 = split * g.kb_per_split;
             const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
             const int n_chunks = (kb1 - kb0 + CH - 1) / CH;
