@@ -24,6 +24,7 @@
 // Precision: bf16 operands, FP32 accumulation (the reference is Float32) — tolerance in tests/test_qnet_gpu.py.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <string.h>
 
 #include <new>
@@ -35,7 +36,7 @@ namespace snk {
 namespace qnet {
 
 constexpr int S = 12;                         // samples per CTA iteration
-constexpr int THREADS = 384;                  // warp 0 MMA issuer, warp 1 weight producer, warps 4..11 epilogue
+constexpr int THREADS = 512;                  // warps 0,1 MMA issuers, warp 2 weight producer, warps 4..15 = 3 epilogue groups
 constexpr int PIX12 = 144;                    // padded 12x12 grid
 constexpr int ROWS12 = S * PIX12;             // 1728 flat positions per iteration
 constexpr int TILES12 = (ROWS12 + 127) / 128; // 14
@@ -50,12 +51,17 @@ constexpr int OFF_W2 = OFF_W1 + 18 * 16 * 4;
 constexpr int OFF_W3 = OFF_W2 + 9 * 1024;
 constexpr int OFF_BIAS = OFF_W3 + 2 * W3_SLICE;          // b1 (16) b2 (32) b3 (64) f32
 constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
-constexpr int SMEM_A = OFF_BAR + 128 + 128;              // barriers + alignment slack
+constexpr int SMEM_A = OFF_BAR + 256 + 128;              // barriers (17 x 8 B + TMEM slot) + alignment slack
 static_assert(SMEM_A <= 232448, "kernel A shared memory over the 227 KB limit");
+#ifndef QNET_SEQ_CONV1
+#define QNET_SEQ_CONV1 0
+#endif
 constexpr int NISSUE = 2;                                // MMA-issuing threads (lane 0 of warps 0 and 1, two schedulers):
                                                          // with 32-cycle MMAs one thread cannot issue fast enough
-constexpr int NACC = 4;                                  // accumulator buffers cycled by the conv1 / conv2 tiles
-constexpr int TMEM_C3 = 0, TMEM_C2 = 256;                // column offsets: conv3 4 x 64 | conv2 NACC x 32
+constexpr int NGRP = 3;                                  // epilogue groups of 4 warps (one per TMEM lane quarter): conv2 is
+                                                         // bound by the fixed latency of its per-tile epilogue
+constexpr int NACC = 6;                                  // accumulator buffers cycled by the conv1 / conv2 tiles
+constexpr int TMEM_C3 = 0, TMEM_C2 = 256;                // column offsets: conv3 4 x 64 | conv2 NACC x 32 (256 + 192 <= 512)
 
 // packed parameter blob (device): byte offsets
 constexpr size_t P_W1 = 0, P_W2 = P_W1 + 18 * 16 * 4, P_W3 = P_W2 + 9 * 1024, P_BIAS = P_W3 + 6 * (size_t)W3_SLICE;
@@ -145,8 +151,8 @@ struct ConvArgs {
     // conv1 weights [tap = k2*3+k1][c][o] (flipped) and bias, by value: kernel parameters sit in the constant bank, so
     // the FMAs of the CUDA-core conv1 take them as constant operands — no shared-memory traffic to fight the tensor
     // core's operand fetch with
-    float w1[288];
-    float b1[16];
+    __half2 w1h[144];            // [tap*2 + c][o/2]: fp16 pairs for the packed HFMA2 path (inputs are -1..2 exactly; fp16
+    __half2 b1h[8];              // accumulation over 18 taps errs ~1e-3, below the bf16 rounding of the result)
 };
 #define QNET_STAMP(k) do { if (a.timing != nullptr && blockIdx.x == 0 && tid == 128) a.timing[it_local * 8 + (k)] = clock64(); } while (0)
 
@@ -154,38 +160,52 @@ struct ConvArgs {
 // Float32 observations into conv2's operand plane A1 (padded 12x12 grids, chunk-planar bf16), by threads [t, t+nt).
 // It is 1 % of the network's FLOPs but cost 20 % of the time as 16-column MMAs (operand-fetch bound), and the
 // warps that run it are otherwise idle while the tensor core works through conv3 of the previous iteration.
+// the 18 input taps of pixel item i (clamped address + select, no branches: all loads in flight together)
+__device__ __forceinline__ void conv1_taps(const ConvArgs &a, long long s0, int i, float (&v)[18]) {
+    const int s = i / 100, p = i - s * 100;                     // p = x + 10 y   (Julia (r, c) = (x, y))
+    const int y = p / 10, x = p - 10 * y;
+    const bool live = (s0 + s) < a.n;
+    const float *ob = a.obs + (live ? (s0 + s) : 0) * 200;
+#pragma unroll
+    for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+        for (int k1 = 0; k1 < 3; k1++) {
+            const int xx = x + k1 - 1, yy = y + k2 - 1;
+            const bool ok = live && xx >= 0 && xx <= 9 && yy >= 0 && yy <= 9;
+            const int off = ok ? yy * 10 + xx : 0;
+            const float t0 = __ldg(ob + off), t1 = __ldg(ob + 100 + off);
+            v[(k2 * 3 + k1) * 2] = ok ? t0 : 0.f;
+            v[(k2 * 3 + k1) * 2 + 1] = ok ? t1 : 0.f;
+        }
+}
 __device__ __forceinline__ void conv1_cuda(const ConvArgs &a, long long s0, uint8_t *A1, int t, int nt) {
+    // software pipeline: the taps of the thread's next pixel are loading while this pixel is computed
+    float v[18], vn[18];
+    if (t < S * 100) conv1_taps(a, s0, t, v);
     for (int i = t; i < S * 100; i += nt) {
-        const int s = i / 100, p = i - s * 100;                 // p = x + 10 y   (Julia (r, c) = (x, y))
+        if (i + nt < S * 100) conv1_taps(a, s0, i + nt, vn);
+        const int s = i / 100, p = i - s * 100;
         const int y = p / 10, x = p - 10 * y;
-        // all 18 taps are fetched first (clamped address + select, no branches) so the loads are in flight together
-        const bool live = (s0 + s) < a.n;
-        const float *ob = a.obs + (live ? (s0 + s) : 0) * 200;
-        float v[18];
+        __half2 acc2[8];
 #pragma unroll
-        for (int k2 = 0; k2 < 3; k2++)
+        for (int o = 0; o < 8; o++) acc2[o] = a.b1h[o];
 #pragma unroll
-            for (int k1 = 0; k1 < 3; k1++) {
-                const int xx = x + k1 - 1, yy = y + k2 - 1;
-                const bool ok = live && xx >= 0 && xx <= 9 && yy >= 0 && yy <= 9;
-                const int off = ok ? yy * 10 + xx : 0;
-                const float t0 = __ldg(ob + off), t1 = __ldg(ob + 100 + off);
-                v[(k2 * 3 + k1) * 2] = ok ? t0 : 0.f;
-                v[(k2 * 3 + k1) * 2 + 1] = ok ? t1 : 0.f;
-            }
+        for (int k = 0; k < 18; k++) {
+            const __half2 vv = __float2half2_rn(v[k]);
+#pragma unroll
+            for (int o = 0; o < 8; o++) acc2[o] = __hfma2(vv, a.w1h[k * 8 + o], acc2[o]);
+        }
         float acc[16];
 #pragma unroll
-        for (int o = 0; o < 16; o++) acc[o] = a.b1[o];
-#pragma unroll
-        for (int k = 0; k < 18; k++)
-#pragma unroll
-            for (int o = 0; o < 16; o++) acc[o] = fmaf(v[k], a.w1[k * 16 + o], acc[o]);
+        for (int o = 0; o < 8; o++) { const float2 f = __half22float2(acc2[o]); acc[2 * o] = f.x; acc[2 * o + 1] = f.y; }
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) w[j] = pack_relu_bf16(acc[2 * j], acc[2 * j + 1]);
         uint8_t *dst = A1 + (s * PIX12 + (y + 1) * 12 + (x + 1)) * 16;
         *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4 *>(dst + A0_PIX * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+        for (int k = 0; k < 18; k++) v[k] = vn[k];
     }
 }
 
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
             const int grp = (warp - 4) >> 2, q = warp & 3;
             for (int t = 0; t < TILES12; t++) {
                 const uint32_t u = acc_it + t;
-                if ((int)(u & 1) != grp) continue;
+                if ((int)(u % NGRP) != grp) continue;
                 const int b = u % NACC;
                 mbar_wait(&acc_full[b], (u / NACC) & 1);
                 tc_fence_after();
@@ -343,17 +363,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
             // while the tensor core works through conv3, warps 2..11 run the NEXT iteration's conv1 on the CUDA cores
             // (A1 is free: this iteration's conv2 has been consumed)
             // (only warps on the two schedulers without an MMA issuer: a busy scheduler slows the issuing thread)
-            if ((warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
-                const int w5 = warp == 3 ? 0 : (warp == 6 ? 1 : (warp == 7 ? 2 : (warp == 10 ? 3 : 4)));   // 3,6,7,10,11 -> 0..4
-                conv1_cuda(a, (it + gridDim.x) * S, A1, w5 * 32 + lane, 160);
-                if (a.timing != nullptr && blockIdx.x == 0 && warp == 11 && lane == 0) a.timing[it_local * 8 + 6] = clock64();
+            if (!QNET_SEQ_CONV1 && (warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
+                const int w7 = warp == 3 ? 0 : 2 * ((warp - 4) >> 2) + (warp & 1) + 1;      // 3,6,7,10,11,14,15 -> 0..6
+                conv1_cuda(a, (it + gridDim.x) * S, A1, w7 * 32 + lane, 224);
+                if (a.timing != nullptr && blockIdx.x == 0 && warp == 15 && lane == 0) a.timing[it_local * 8 + 6] = clock64();
             }
             if (warp >= 4) {
                 const int grp = (warp - 4) >> 2, q = warp & 3;
                 mbar_wait(c3_full, c3_it & 1);
                 tc_fence_after();
                 QNET_STAMP(4);
-                for (int tt = grp; tt < TILES3; tt += 2) {
+                for (int tt = grp; tt < TILES3; tt += NGRP) {
                     const int r = q * 32 + lane, g = tt * 16 + (r >> 3), ox = r & 7;
                     const int oy = g / S, s = g - oy * S;
                     const bool valid = ox < 5 && oy < 5 && (s0 + s) < a.n;
@@ -383,6 +403,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
         fence_proxy_async();
         __syncthreads();                            // conv3 accumulators, A2 free again; next A1 (conv1 output) staged
         QNET_STAMP(5);
+        if (QNET_SEQ_CONV1 && it + gridDim.x < n_iter) {
+            conv1_cuda(a, (it + gridDim.x) * S, A1, tid, THREADS);
+            fence_proxy_async();
+            __syncthreads();
+        }
+        QNET_STAMP(7);
     }
 
     tc_fence_before();
@@ -590,7 +616,7 @@ using namespace snk;
 using namespace snk::qnet;
 
 struct snk_qnet_s {
-    float w1[288], b1[16];
+    __half2 w1h[144], b1h[8];
     long long *timing;
     int device;
     uint8_t *params;
@@ -612,8 +638,12 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
     if (q == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
     memset(q, 0, sizeof(*q));
     q->device = device;
-    memcpy(q->w1, blob.data() + P_W1, sizeof(q->w1));
-    memcpy(q->b1, blob.data() + P_BIAS, sizeof(q->b1));
+    {
+        const float *w1f = reinterpret_cast<const float *>(blob.data() + P_W1);
+        const float *b1f = reinterpret_cast<const float *>(blob.data() + P_BIAS);
+        for (int i = 0; i < 144; i++) q->w1h[i] = __floats2half2_rn(w1f[2 * i], w1f[2 * i + 1]);
+        for (int i = 0; i < 8; i++) q->b1h[i] = __floats2half2_rn(b1f[2 * i], b1f[2 * i + 1]);
+    }
     cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
@@ -655,8 +685,8 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
     }
     ConvArgs ca;
     ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = q->out3; ca.timing = q->timing;
-    memcpy(ca.w1, q->w1, sizeof(ca.w1));
-    memcpy(ca.b1, q->b1, sizeof(ca.b1));
+    memcpy(ca.w1h, q->w1h, sizeof(ca.w1h));
+    memcpy(ca.b1h, q->b1h, sizeof(ca.b1h));
     const long long n_iter = (N + S - 1) / S;
     int grid = (int)(n_iter < q->sms ? n_iter : q->sms);
     SNK_CUDA(cudaFuncSetAttribute(k_qnet_convs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_A));

@@ -27,4 +27,4 @@ names = ["obs->A0", "conv1", "conv2", "conv3 mma (wait c3_full)", "conv3 epilogu
 for it in range(1, 6):
     row = t[it]
     print("iter %d:" % it, ", ".join("%s %d" % (names[k], int(row[k + 1] - row[k])) for k in range(5)),
-          "| next conv1 done at +%d of the conv3 phase" % int(row[6] - row[3]), "| total", int(t[it + 1][0] - row[0]))
+          "| next conv1 done at +%d of the conv3 phase" % int(row[6] - row[3]), "| seq conv1 %d" % int(row[7] - row[5]), "| total", int(t[it + 1][0] - row[0]))
