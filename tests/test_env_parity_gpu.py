@@ -465,3 +465,22 @@ def test_random_food_lists_differential(seed):
     sc = ora.scalars()
     assert sc["score"].max() >= min(8, n_food)                  # the greedy policy really eats through the list
     assert np.array_equal(env.error_flags.cpu().numpy().astype(np.uint32), sc["error"])
+
+
+def test_multi_step_rollout_absolute_dirs_no_auto_reset():
+    """rollout kernel with absolute directions (reverse moves lose) and frozen lost envs."""
+    S = pkg()
+    n, T = 300, 80
+    env = S.SnakeGame(n, auto_reset=False)
+    ora = O.OracleBatch(n, auto_reset=False)
+    rng = np.random.default_rng(21)
+    dirs = rng.integers(0, 4, (T, n)).astype(np.uint8)
+    out = env.rollout(torch.from_numpy(dirs).cuda(), obs="i8", mask=True, ep_stats=True, is_abs=True)
+    got = {k: v.cpu().numpy() for k, v in out.items() if k != "obs_fmt"}
+    for t in range(T):
+        ref = ora.step(dirs[t], is_abs=True, obs=("i8",))
+        assert np.array_equal(bits(got["reward"][t]), bits(ref["reward"])), t
+        assert np.array_equal(got["done"][t], ref["done"]), t
+        assert np.array_equal(got["mask"][t], ref["mask"]), t
+        assert np.array_equal(got["obs"][t].reshape(n, 200), ref["obs_i8"]), t
+    assert got["done"][-1].all()
