@@ -520,6 +520,10 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10):
         return ts[len(ts) // 2]
 
     out["pack_ms"] = timed(lambda: plan.pack(A))
+    Dc = A.clone()
+    out["center_ms"] = timed(lambda: S.center_columns(Dc))       # Welford + centring of the Float64 D (3 passes over 1.45 GB)
+    out["center_hbm_frac"] = 3 * 8.0 * K * P / (out["center_ms"] * 1e-3) / 1e9 / peaks()[0]
+    del Dc
     G = torch.empty(K, K, dtype=torch.float32, device=dev)
     for terms in (3, 1):
         ms = timed(lambda: plan.gram(terms, 0, out=G))
