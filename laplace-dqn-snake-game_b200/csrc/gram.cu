@@ -23,7 +23,7 @@
 //                           item the registers go to the partial tile in the workspace
 // Two TMEM accumulator stages (2 x 256 columns): the tensor core fills one while the other is drained.
 // Work item = (128 x 256 output tile, split of the contraction); partial tiles are reduced (deterministically)
-// by k_gram_reduce, which also symmetrises.
+// by k_gram_finish, which also symmetrises.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string.h>
@@ -92,7 +92,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c_inner, int c_row) {
     asm volatile(
@@ -511,35 +510,6 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
     }
 }
 
-// G[i][j] = sum_s Y_s[i][j]                         (terms = 1)
-//         = 0.5 * sum_s (Y_s[i][j] + Y_s[j][i])     (terms = 3: adds the transposed cross term)
-// Y_s tiles are fp32 in the workspace with leading dimension ld (>= K, both index orders in range).
-__global__ void k_gram_reduce(const float *__restrict__ part, int splits, long long split_stride, long long ld, int K,
-                              int symmetrise, float *__restrict__ G) {
-    __shared__ float tile[32][33];
-    const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
-    // transposed block first (coalesced read of Y[bj + ty.., bi + tx]), through smem
-    if (symmetrise) {
-        for (int r = ty; r < 32; r += 8) {
-            int i = bj + r, j = bi + tx;
-            float acc = 0.f;
-            if (i < K && j < K)
-                for (int s = 0; s < splits; s++) acc += part[s * split_stride + (long long)i * ld + j];
-            tile[r][tx] = acc;
-        }
-        __syncthreads();
-    }
-    for (int r = ty; r < 32; r += 8) {
-        int i = bi + r, j = bj + tx;
-        if (i < K && j < K) {
-            float acc = 0.f;
-            for (int s = 0; s < splits; s++) acc += part[s * split_stride + (long long)i * ld + j];
-            G[(long long)i * K + j] = symmetrise ? 0.5f * (acc + tile[tx][r]) : acc;
-        }
-    }
-}
-
 // D (P x K column-major, i.e. row k of A contiguous) -> hi[k][p], lo2[k][p] bf16 with row pitch Ppad
 template <typename T>
 __global__ void k_gram_pack(const T *__restrict__ A, long long P, long long K, long long Ppad,
@@ -670,17 +640,23 @@ static int run_block(const Plan &pl, int terms, const void *a_hi, const void *b_
     return terms == 1 ? launch<32, 1>(pl, a_hi, b_hi, b_lo, scratch, st) : launch<32, 3>(pl, a_hi, b_hi, b_lo, scratch, st);
 }
 
-// out[i][j] = sum_s part[s][i][j]   (+ optionally 0.5*(. + yt[j][i]) with yt another row-major block, maybe in peer memory)
+// out[i][j] = sum_s part[s][i][j], or 0.5 * (that + sum_s yt[s][j][i]) when a transposed source is given: the hi/lo
+// split computes Y = hi hi^T + hi (2 lo)^T and G = (Y + Y^T)/2.  yt is row-major with leading dimension ld_yt and may be
+// the same partial buffer (single GPU) or a block in a PEER's memory (row-sharded Gram: plain loads over NVLink).
+// The partials are summed in split order: deterministic.
 __global__ void k_gram_finish(const float *__restrict__ part, int splits, long long split_stride, long long ld_part,
-                              const float *__restrict__ yt, long long ld_yt, int rows_a, int rows_b,
-                              float *__restrict__ out, long long ld_out) {
+                              const float *__restrict__ yt, int yt_splits, long long yt_split_stride, long long ld_yt,
+                              int rows_a, int rows_b, float *__restrict__ out, long long ld_out) {
     __shared__ float tile[32][33];
     const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
     if (yt != nullptr) {
         for (int r = ty; r < 32; r += 8) {                 // coalesced read of yt[bj + r][bi + tx]
             int i = bj + r, j = bi + tx;
-            tile[r][tx] = (i < rows_b && j < rows_a) ? yt[(long long)i * ld_yt + j] : 0.f;
+            float acc = 0.f;
+            if (i < rows_b && j < rows_a)
+                for (int s = 0; s < yt_splits; s++) acc += yt[s * yt_split_stride + (long long)i * ld_yt + j];
+            tile[r][tx] = acc;
         }
         __syncthreads();
     }
@@ -761,7 +737,7 @@ int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, const voi
     int rc = run_block(pl, terms, a_hi, b_hi, b_lo2, (float *)scratch, st);
     if (rc != SNK_OK) return rc;
     dim3 rb(32, 8), rg((unsigned)((rows_b + 31) / 32), (unsigned)((rows_a + 31) / 32));
-    k_gram_finish<<<rg, rb, 0, st>>>((const float *)scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, nullptr, 0, (int)rows_a,
+    k_gram_finish<<<rg, rb, 0, st>>>((const float *)scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, nullptr, 0, 0, 0, (int)rows_a,
                                      (int)rows_b, Y, ldY);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
@@ -771,7 +747,7 @@ int snk_gram_symmetrize_block(const float *Y, int64_t ldY, const float *YT, int6
                               float *G, int64_t ldG, void *cuda_stream) {
     SNK_REQUIRE(Y && YT && G && rows_a > 0 && rows_b > 0, "bad argument");
     dim3 rb(32, 8), rg((unsigned)((rows_b + 31) / 32), (unsigned)((rows_a + 31) / 32));
-    k_gram_finish<<<rg, rb, 0, (cudaStream_t)cuda_stream>>>(Y, 1, 0, ldY, YT, ldYT, (int)rows_a, (int)rows_b, G, ldG);
+    k_gram_finish<<<rg, rb, 0, (cudaStream_t)cuda_stream>>>(Y, 1, 0, ldY, YT, 1, 0, ldYT, (int)rows_a, (int)rows_b, G, ldG);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }
@@ -809,7 +785,8 @@ int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k
     if (rc != SNK_OK) return rc;
     // G = sum of the split partials; for the hi/lo split also G = (Y + Y^T)/2, Y^T read from the same partials
     dim3 rb(32, 8), rg((unsigned)((K + 31) / 32), (unsigned)((K + 31) / 32));
-    k_gram_reduce<<<rg, rb, 0, st>>>(scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, (int)K, terms > 1 ? 1 : 0, G);
+    k_gram_finish<<<rg, rb, 0, st>>>(scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, terms > 1 ? scratch : nullptr, pl.splits,
+                                     pl.Mt * pl.Nt, pl.Nt, (int)K, (int)K, G, K);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }
