@@ -530,7 +530,11 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10):
         err = float((G.double() - ref).norm() / ref.norm())
         mma = (2 if terms == 3 else 1) * 2.0 * K * K * P / (ms * 1e-3) / 1e12
         out["terms%d" % terms] = {"ms": ms, "useful_tflops": 2.0 * K * K * P / (ms * 1e-3) / 1e12, "mma_tflops": mma,
-                                  "frac_of_measured_bf16_peak": mma / peak, "rel_fro_err_vs_fp64": err}
+                                  "frac_of_measured_bf16_peak": mma / peak, "rel_fro_err_vs_fp64": err,
+                                  "roofline": {"bound": "tensor", "achieved": mma, "peak": peak, "unit": "TFLOP/s",
+                                               "frac": mma / peak, "traffic": 726.4e6 if terms == 3 else 363.2e6,
+                                               "note": "time covers k_gram + the split-K/symmetrise pass; traffic = ncu dram bytes of "
+                                                       "k_gram (profiles/r01_ncu_gram_5a_*.csv): the bf16 planes read once"}}
     Ab = A.to(torch.bfloat16)
     ms = timed(lambda: torch.matmul(Ab, Ab.T))
     out["cublas_bf16_same_shape_ms"] = ms

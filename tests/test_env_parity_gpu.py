@@ -484,3 +484,15 @@ def test_multi_step_rollout_absolute_dirs_no_auto_reset():
         assert np.array_equal(got["mask"][t], ref["mask"]), t
         assert np.array_equal(got["obs"][t].reshape(n, 200), ref["obs_i8"]), t
     assert got["done"][-1].all()
+
+
+def test_config1_trace_file_from_cuda_matches_pinned_hash():
+    import hashlib
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import trace_config1
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "g7_config1_trace.json")))
+    text = "\n".join(trace_config1.trace_lines(10000, cuda=True)) + "\n"
+    assert hashlib.sha256(text.encode()).hexdigest() == gold["sha256"]

@@ -123,3 +123,17 @@ def test_history_modes_agree():
         ra, rb = a.step(act), b.step(act)
         for k in ("reward", "done", "mask", "obs_f32", "ep_return", "ep_score"):
             assert np.array_equal(ra[k], rb[k]), (t, k)
+
+
+def test_config1_trace_is_stable():
+    """BASELINE config 1 (1 env, 10,000 random-action steps): the oracle's trace is pinned by hash so that the
+    oracle cannot drift silently; tools/trace_config1.py --cuda and bench_ref/trace_config1.jl write the same file."""
+    import hashlib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import trace_config1
+    gold = json.load(open(os.path.join(G, "g7_config1_trace.json")))
+    lines = trace_config1.trace_lines(10000)
+    text = "\n".join(lines) + "\n"
+    assert len(lines) == gold["n_lines"] and lines[:3] == gold["first"] and lines[-1] == gold["last"]
+    assert hashlib.sha256(text.encode()).hexdigest() == gold["sha256"]
