@@ -16,7 +16,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnake_b200.so")
+LIB_PATH = os.environ.get("SNAKE_B200_LIB", os.path.join(_HERE, "libsnake_b200.so"))   # same override as julia/SnakeB200.jl
 
 OBS_NONE, OBS_F32, OBS_I8, OBS_I64, OBS_PACKED2 = 0, 1, 2, 3, 4
 AUTO_RESET = 1
