@@ -54,7 +54,17 @@ int fail(int code, const char *fmt, ...) {
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int TPB = 128;          // envs (= threads) per CTA
+#ifndef SNK_TPB
+#define SNK_TPB 256            // measured on B200 at 2^20 envs: 256 threads ~1-2 % faster than 128, 64 and 512 slower
+#endif
+#ifndef SNK_MINB
+#define SNK_MINB 1
+#endif
+#ifndef SNK_UNROLL
+#define SNK_UNROLL 2
+#endif
+constexpr int PHASE_B_UNROLL = SNK_UNROLL;
+constexpr int TPB = SNK_TPB;      // envs (= threads) per CTA (tuning knobs: -DSNK_TPB / -DSNK_MINB / -DSNK_UNROLL)
 constexpr int MAX_FOOD = 64;
 constexpr int PLANE_WORDS = 16;   // per env in smem: [frame 0/1][plane 0/1][4 x u32]
 
@@ -242,9 +252,9 @@ struct ObsTables {
     float4 f32[256];         // (n1<<4 | n0) -> 4 cells as Float32
 };
 template <int OBS>
-__device__ __forceinline__ void fill_tables(ObsTables &tb, int tid) {
+__device__ __forceinline__ void fill_tables(ObsTables &tb, int tid, int nt = TPB) {
     if (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I8 || OBS == SNK_OBS_PACKED2) {
-        for (int i = tid; i < 256; i += TPB) {
+        for (int i = tid; i < 256; i += nt) {
             int n0 = i & 15, n1 = i >> 4;
             float v[4];
             uint32_t bytes = 0, packed = 0;
@@ -261,7 +271,11 @@ __device__ __forceinline__ void fill_tables(ObsTables &tb, int tid) {
     }
 }
 
-template <int OBS>
+template <bool STREAM, typename T>
+__device__ __forceinline__ void obs_store(T *p, const T &v) {
+    if (STREAM) __stcs(p, v); else SNK_OBS_STORE(p, v);
+}
+template <int OBS, int NT = TPB, int UNROLL = PHASE_B_UNROLL, bool STREAM = false>
 __device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_local, const uint32_t *s_planes,
                                            const ObsTables &tb, int tid) {
     if (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I8 || OBS == SNK_OBS_PACKED2) {
@@ -270,22 +284,22 @@ __device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_loca
         float4 *o32 = reinterpret_cast<float4 *>(obs) + env0 * 50;
         uint32_t *o8 = reinterpret_cast<uint32_t *>(obs) + env0 * 50;
         uint8_t *op = reinterpret_cast<uint8_t *>(obs) + env0 * 50;
-#pragma unroll 5
-        for (int j = tid; j < total; j += TPB) {
+#pragma unroll UNROLL
+        for (int j = tid; j < total; j += NT) {
             int e = (int)(((unsigned)j * 5243u) >> 18);     // j / 50 for j < 2^15
             int qq = j - e * 50;
             int f = qq >= 25;
             int q = qq - 25 * f;
             const uint32_t idx = reinterpret_cast<const uint8_t *>(s_planes)[e * (PLANE_WORDS * 4) + f * 32 + q];
-            if (OBS == SNK_OBS_F32) SNK_OBS_STORE(o32 + j, tb.f32[idx]);
-            else if (OBS == SNK_OBS_I8) SNK_OBS_STORE(o8 + j, reinterpret_cast<const uint32_t *>(tb.f32)[idx]);
+            if (OBS == SNK_OBS_F32) obs_store<STREAM>(o32 + j, tb.f32[idx]);
+            else if (OBS == SNK_OBS_I8) obs_store<STREAM>(o8 + j, reinterpret_cast<const uint32_t *>(tb.f32)[idx]);
             else op[j] = reinterpret_cast<const uint8_t *>(tb.f32)[idx];
         }
     } else if (OBS == SNK_OBS_I64) {
         // unit = 2 consecutive cells (16 bytes); 100 units per env
         const int total = n_local * 100;
         longlong2 *o = reinterpret_cast<longlong2 *>(obs) + env0 * 100;
-        for (int j = tid; j < total; j += TPB) {
+        for (int j = tid; j < total; j += NT) {
             int e = j / 100;
             int p = j - e * 100;
             int f = p >= 50;
@@ -294,7 +308,7 @@ __device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_loca
             longlong2 v;
             v.x = code_value(cell_code(pl, k));
             v.y = code_value(cell_code(pl, k + 1));
-            SNK_OBS_STORE(o + j, v);
+            obs_store<STREAM>(o + j, v);
         }
     }
 }
@@ -419,7 +433,7 @@ __device__ __forceinline__ float env_advance(Env &e, int &aidx, int is_abs, u64 
 }
 
 template <int OBS, bool SELECT, bool SINK>
-__global__ void __launch_bounds__(TPB) k_step(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(TPB, SNK_MINB) k_step(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) uint32_t s_planes[TPB * PLANE_WORDS];
     __shared__ ObsTables s_tb;
     __shared__ uint8_t s_food_bit[MAX_FOOD];
@@ -526,8 +540,9 @@ struct RolloutArgs {
     int steps, auto_reset, is_abs;
     FoodTable food;
 };
+constexpr int RTPB = 128;         // threads per CTA of the rollout kernel (latency-bound: tuned separately from k_step)
 template <int OBS, int EPB>
-__global__ void __launch_bounds__(TPB) k_rollout(const __grid_constant__ RolloutArgs a) {
+__global__ void __launch_bounds__(RTPB) k_rollout(const __grid_constant__ RolloutArgs a) {
     __shared__ __align__(16) uint32_t s_planes[EPB * PLANE_WORDS];
     __shared__ ObsTables s_tb;
     __shared__ uint8_t s_food_bit[MAX_FOOD];
@@ -538,7 +553,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(const __grid_constant__ Rollout
     const long long env = env0 + tid;
     const bool mine = tid < n_local;
     if (tid < MAX_FOOD) s_food_bit[tid] = a.food.bit[tid];
-    if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid);
+    if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid, RTPB);
     __syncthreads();
     const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
     Env e;
@@ -567,7 +582,7 @@ __global__ void __launch_bounds__(TPB) k_rollout(const __grid_constant__ Rollout
         }
         if (OBS != SNK_OBS_NONE) {
             __syncthreads();
-            expand_obs<OBS>((uint8_t *)a.obs + (size_t)t * obs_step, env0, n_local, s_planes, s_tb, tid);
+            expand_obs<OBS, RTPB, 5, true>((uint8_t *)a.obs + (size_t)t * obs_step, env0, n_local, s_planes, s_tb, tid);
             __syncthreads();
         }
     }
@@ -687,7 +702,7 @@ __global__ void k_masked_target(const float *q, const uint8_t *mask, const float
 // One CTA per 32 samples; the records' planes go to shared memory, then states (10,10,2,B) and next_states are
 // streamed out with the same nibble->float4 table as the step kernel.
 constexpr int GATHER_S = 32;
-__global__ void __launch_bounds__(TPB) k_replay_gather(const uint4 *__restrict__ ring, long long cap, const long long *__restrict__ idx,
+__global__ void __launch_bounds__(128) k_replay_gather(const uint4 *__restrict__ ring, long long cap, const long long *__restrict__ idx,
                                                        long long B, float *states, float *next_states, uint8_t *actions,
                                                        float *rewards, uint8_t *dones, uint8_t *mask, float *ep_return,
                                                        int32_t *score, int *bad_index) {
@@ -696,7 +711,7 @@ __global__ void __launch_bounds__(TPB) k_replay_gather(const uint4 *__restrict__
     const int tid = threadIdx.x;
     const long long b0 = (long long)blockIdx.x * GATHER_S;
     const int n_local = (B - b0) < GATHER_S ? (int)(B - b0) : GATHER_S;
-    fill_tables<SNK_OBS_F32>(s_tb, tid);
+    fill_tables<SNK_OBS_F32>(s_tb, tid, 128);
     // 4 threads per sample copy the 6 plane vectors + scalars
     if (tid < n_local * 4) {
         const int sl = tid >> 2, part = tid & 3;
@@ -724,7 +739,7 @@ __global__ void __launch_bounds__(TPB) k_replay_gather(const uint4 *__restrict__
         float *outp = which == 0 ? states : next_states;
         if (outp == nullptr) continue;
         float4 *o4 = reinterpret_cast<float4 *>(outp) + b0 * 50;
-        for (int j = tid; j < total; j += TPB) {
+        for (int j = tid; j < total; j += 128) {
             int e = (int)(((unsigned)j * 5243u) >> 18);
             int qq = j - e * 50;
             int f = qq >= 25;
@@ -1034,8 +1049,8 @@ int snk_rollout_fused(snk_handle h, const uint8_t *act_TxN, int64_t T, int is_ab
     const bool small = h->n <= 32 * 1024;
 #define SNK_RO(FMT)                                                                                       \
     do {                                                                                                  \
-        if (small) k_rollout<FMT, 32><<<nblocks(h->n, 32), TPB, 0, h->stream>>>(a);                       \
-        else k_rollout<FMT, TPB><<<nblocks(h->n, TPB), TPB, 0, h->stream>>>(a);                           \
+        if (small) k_rollout<FMT, 32><<<nblocks(h->n, 32), RTPB, 0, h->stream>>>(a);                      \
+        else k_rollout<FMT, RTPB><<<nblocks(h->n, RTPB), RTPB, 0, h->stream>>>(a);                        \
     } while (0)
     switch (fmt) {
         case SNK_OBS_NONE: SNK_RO(SNK_OBS_NONE); break;
@@ -1288,7 +1303,7 @@ int snk_replay_gather(snk_replay r, const int64_t *idx, int64_t B, float *states
     SNK_REQUIRE((((uintptr_t)states | (uintptr_t)next_states) & 15u) == 0, "state buffers must be 16-byte aligned");
     if (B == 0) return SNK_OK;
     SNK_CUDA(cudaSetDevice(r->device));
-    k_replay_gather<<<nblocks(B, GATHER_S), TPB, 0, (cudaStream_t)cuda_stream>>>(
+    k_replay_gather<<<nblocks(B, GATHER_S), 128, 0, (cudaStream_t)cuda_stream>>>(
         r->ring, r->capacity, (const long long *)idx, B, states, next_states, actions, rewards, dones, mask, ep_return,
         score, r->d_bad);
     SNK_CUDA(cudaGetLastError());
