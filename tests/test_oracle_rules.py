@@ -163,3 +163,35 @@ def test_welford_matches_numpy_and_is_centred():
     one = rng.normal(0, 1, (1, 7)).reshape(-1)
     m1, v1 = O.center_columns(one, 7, 1)
     assert (v1 == 0).all() and (one == 0).all()
+
+
+def test_board_invariants_under_arbitrary_action_streams():
+    """hypothesis-driven: for any stream of action indices the oracle keeps the board invariants of the reference
+    (snake cells = score + 2 on live boards, at most one food, walls intact until a wall death overwrites one cell,
+    rewards in {+1, -0.01, -1}, a lost game reports trues(3))."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=0, max_value=2), min_size=1, max_size=120), st.integers(0, 2 ** 16))
+    def run(actions, seed):
+        g = O.OracleGame()
+        rng = np.random.default_rng(seed)
+        for a in actions:
+            av = g.available_actions()
+            g.step(int(av[a]))
+            b = g.board
+            r = np.float32(g.reward)
+            assert r in (np.float32(1.0), np.float32(-0.01), np.float32(-1.0))
+            assert (b == 2).sum() <= 1
+            border = np.ones((10, 10), bool); border[1:9, 1:9] = False
+            if g.lost:
+                assert r == np.float32(-1.0)
+                assert (b[border] != -1).sum() <= 1
+                assert g.virtual_step()[1].tolist() == [1, 1, 1]
+                break
+            assert (b[border] == -1).all()
+            assert (b == 1).sum() == g.score + 2
+            if rng.random() < 0.2:
+                av2, lost = g.virtual_step()
+                assert set(av2.tolist()) <= {0, 1, 2, 3} and len(set(av2.tolist())) == 3
+    run()
