@@ -77,8 +77,8 @@ SNK_API int snk_destroy(snk_handle h);
 /* every env back to the constructor state (R1): walls, food (4,5), snake [(8,2),(9,2)], prev_dir U */
 SNK_API int snk_reset(snk_handle h);
 /* food_list injection (structs.jl:70).  cells_rc_host: n pairs (row, col), 1-based, 2..9; n <= 64.
- * Default = the 50 cells Xoshiro(42) yields (snk_default_food_list).  Takes effect at the next reset
- * of each env; call snk_reset to apply it everywhere. */
+ * Default = the 50 cells Xoshiro(42) yields (snk_default_food_list_host).  The table is swapped immediately, but the
+ * consumed-entry bitmaps of running episodes refer to the old list: call snk_reset right after. */
 SNK_API int snk_set_food_list_host(snk_handle h, const uint8_t *cells_rc_host, int n);
 SNK_API int snk_default_food_list_host(uint8_t *cells_rc_host /* 100 bytes */, int *n);
 /* A handle starts on its own non-blocking stream.  snk_set_stream adopts an external one (cudaStream_t /
@@ -199,7 +199,8 @@ typedef struct snk_qnet_s *snk_qnet;
 SNK_API int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device);
 SNK_API int snk_qnet_destroy(snk_qnet q);
 SNK_API int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3xN, void *cuda_stream);
-/* profiling aid: device buffer (int64[8 * iterations of CTA 0]) that receives clock64 stamps of the conv phases */
+/* profiling aid: device buffer of int64[8 * (1 + N / (12 * #SMs))] that receives clock64 stamps of the conv phases of
+ * CTA 0 on every later forward; NULL switches it off */
 SNK_API int snk_qnet_debug_timing(snk_qnet q, long long *device_buf);
 
 /* ---- Laplace deviation matrix  compute_D.jl:9-31, 66-81; la_utils.jl:14-36, 154-169 -------- */
