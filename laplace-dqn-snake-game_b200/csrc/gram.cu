@@ -510,21 +510,41 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
     }
 }
 
-// D (P x K column-major, i.e. row k of A contiguous) -> hi[k][p], lo2[k][p] bf16 with row pitch Ppad
+// D (P x K column-major, i.e. row k of A contiguous) -> hi[k][p], lo2[k][p] bf16 with row pitch Ppad.
+// One thread packs 8 consecutive elements: eight coalesced scalar loads (rows of odd length start unaligned), one
+// 16-byte store per plane.  HBM-bound: reads the source once, writes 4 bytes per element.
 template <typename T>
 __global__ void k_gram_pack(const T *__restrict__ A, long long P, long long K, long long Ppad,
                             __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo2) {
     const long long k = blockIdx.y;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < Ppad; p += (long long)gridDim.x * blockDim.x) {
-        __nv_bfloat16 h = __float2bfloat16_rn(0.f), l = h;
-        if (p < P) {
-            const double a = (double)A[k * P + p];
-            h = __double2bfloat16(a);
-            const double rem = a - (double)__bfloat162float(h);
-            l = __double2bfloat16(2.0 * rem);                 // 2*lo: exact scaling, folds the 1/2 of (Y + Y^T)/2
+    const T *row = A + k * P;
+    for (long long p8 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; p8 < Ppad; p8 += (long long)gridDim.x * blockDim.x * 8) {
+        T a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = (p8 + j < P) ? row[p8 + j] : (T)0;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            __nv_bfloat16 hh[2], ll[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                // 2*lo: exact scaling, folds the 1/2 of (Y + Y^T)/2.  For fp32 input the remainder a - hi is exact in fp32,
+                // so the fp32 path gives the same bits as the fp64 one without the emulated double->bf16 conversions.
+                if constexpr (sizeof(T) == 4) {
+                    const float v = (float)a[2 * j + e];
+                    hh[e] = __float2bfloat16_rn(v);
+                    ll[e] = __float2bfloat16_rn(2.0f * (v - __bfloat162float(hh[e])));
+                } else {
+                    const double v = (double)a[2 * j + e];
+                    hh[e] = __double2bfloat16(v);
+                    ll[e] = __double2bfloat16(2.0 * (v - (double)__bfloat162float(hh[e])));
+                }
+            }
+            h[j] = (uint32_t)__bfloat16_as_ushort(hh[0]) | ((uint32_t)__bfloat16_as_ushort(hh[1]) << 16);
+            l[j] = (uint32_t)__bfloat16_as_ushort(ll[0]) | ((uint32_t)__bfloat16_as_ushort(ll[1]) << 16);
         }
-        hi[k * Ppad + p] = h;
-        lo2[k * Ppad + p] = l;
+        *reinterpret_cast<uint4 *>(hi + k * Ppad + p8) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(lo2 + k * Ppad + p8) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -695,7 +715,7 @@ int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, vo
     SNK_REQUIRE(A != nullptr && hi != nullptr && lo2 != nullptr && rows > 0 && P > 0, "bad argument");
     SNK_REQUIRE(a_dtype == SNK_DTYPE_F64 || a_dtype == SNK_DTYPE_F32, "a_dtype must be SNK_DTYPE_F64 or SNK_DTYPE_F32");
     const long long Ppad = pitch_of(P);
-    dim3 grid((unsigned)((Ppad + 1023) / 1024 < 64 ? (Ppad + 1023) / 1024 : 64), (unsigned)rows);
+    dim3 grid((unsigned)((Ppad / 8 + 255) / 256 < 96 ? (Ppad / 8 + 255) / 256 : 96), (unsigned)rows);
     if (a_dtype == SNK_DTYPE_F64)
         k_gram_pack<double><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const double *)A, P, rows, Ppad, (__nv_bfloat16 *)hi,
                                                                          (__nv_bfloat16 *)lo2);
