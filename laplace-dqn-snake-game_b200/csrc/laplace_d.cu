@@ -6,49 +6,110 @@
 // followed by `D .-= mean` and var = m2 ./ max(n-1, 1), in Float64 with explicit round-to-nearest
 // intrinsics so that no multiply-add is contracted: the results are bit-identical to the Julia loop.
 // The column order is a true sequential dependency, so the parallel axis is p (coalesced: thread p reads
-// D[p + k P]); 8 columns are loaded ahead of the dependent arithmetic to keep HBM requests in flight.
+// D[p + k P]); 16 columns per thread are kept in flight through a shared-memory cp.async ring.  The per-column
+// division by the running count uses a shared table of correctly rounded reciprocals plus one exact-remainder
+// correction (div_by_count) instead of the ~20-instruction IEEE division sequence.
 #include "common.h"
 
 namespace snk {
 
 constexpr int CENTER_TPB = 128;
-constexpr int CENTER_AHEAD = 8;
+constexpr int CENTER_DEPTH = 16;   // columns in flight per thread (16 KB of ring per CTA)
+constexpr int CENTER_GROUP = 4;    // columns per cp.async commit group
+constexpr long long CENTER_FAST_MAX_K = 1ll << 20;
 
-__global__ void __launch_bounds__(CENTER_TPB) k_center_columns(double *__restrict__ D, long long P, long long K,
+// d / n for an integer count n <= 2^20 with y = RN(1/n), bit-identical to the IEEE quotient:
+//   q = RN(d y);  r = d - n q (exact: a multiple of ulp(q) below 2^12 ulps, one fma);  result = RN(q + r y).
+// q + r y differs from the true quotient Q = q + r/n by less than 2^-52 ulp(Q), while Q = d/n is never a rounding
+// midpoint (an odd 54-bit significand times n does not fit 53 bits) and lies at least ulp/(2n) >= 2^-21 ulp away from
+// one, so the last rounding returns RN(Q).  The argument needs r and r y free of underflow/overflow, hence the
+// magnitude window; zeros, subnormals, huge values, Inf and NaN take the IEEE division.
+__device__ __forceinline__ double div_by_count(double d, double n, double y) {
+    const double ad = fabs(d);
+    if (ad > 0x1p-900 && ad < 0x1p+900) {
+        const double q = __dmul_rn(d, y);
+        const double r = __fma_rn(-q, n, d);
+        return __fma_rn(r, y, q);
+    }
+    return __ddiv_rn(d, n);
+}
+
+// Column ring in shared memory: every thread keeps CENTER_DEPTH columns of its own row in flight with 8-byte cp.async
+// copies (rows of odd length leave columns only 8-byte aligned, which rules out 16-byte and bulk/TMA copies), one
+// commit group per CENTER_GROUP columns.  A thread only ever reads the slots it filled itself, so the ring needs no
+// block barrier; the register file holds just the running statistics, which keeps 10 CTAs resident per SM.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Calls body(k, x) for k = 0..K-1 in order with x = D[p + k P], streaming the row through the ring.
+template <typename Body>
+__device__ __forceinline__ void stream_row(const double *__restrict__ D, long long P, long long K, long long p,
+                                           double (*ring)[CENTER_TPB], Body body) {
+    constexpr int NG = CENTER_DEPTH / CENTER_GROUP;
+    double *mine = &ring[0][threadIdx.x];        // slot s of this thread = mine[s * CENTER_TPB]
+    const double *src = D + p;                   // next column to request
+    long long left = K;                          // columns not requested yet
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+#pragma unroll
+        for (int j = 0; j < CENTER_GROUP; j++)
+            if (left > 0) { cp_async8(mine + (g * CENTER_GROUP + j) * CENTER_TPB, src); src += P; left--; }
+        cp_async_commit();
+    }
+    int slot = 0;
+    for (long long k = 0; k < K; k += CENTER_GROUP) {
+        cp_async_wait<NG - 1>();
+        double x[CENTER_GROUP];
+#pragma unroll
+        for (int j = 0; j < CENTER_GROUP; j++) x[j] = mine[(slot + j) * CENTER_TPB];
+#pragma unroll
+        for (int j = 0; j < CENTER_GROUP; j++)
+            if (left > 0) { cp_async8(mine + (slot + j) * CENTER_TPB, src); src += P; left--; }
+        cp_async_commit();
+#pragma unroll
+        for (int j = 0; j < CENTER_GROUP; j++)
+            if (k + j < K) body(k + j, x[j]);
+        slot = (slot + CENTER_GROUP) % CENTER_DEPTH;
+    }
+    cp_async_wait<0>();
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(CENTER_TPB, 10) k_center_columns(double *__restrict__ D, long long P, long long K,
                                                                double *__restrict__ mean_out,
                                                                double *__restrict__ var_out) {
-    const long long p = (long long)blockIdx.x * CENTER_TPB + threadIdx.x;
-    if (p >= P) return;
-    double mean = 0.0, m2 = 0.0;
-    long long k = 0;
-    for (; k + CENTER_AHEAD <= K; k += CENTER_AHEAD) {
-        double x[CENTER_AHEAD];
-#pragma unroll
-        for (int j = 0; j < CENTER_AHEAD; j++) x[j] = __ldcs(D + (k + j) * P + p);
-#pragma unroll
-        for (int j = 0; j < CENTER_AHEAD; j++) {
-            double d = __dsub_rn(x[j], mean);
-            mean = __dadd_rn(mean, __ddiv_rn(d, (double)(k + j + 1)));
-            m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(x[j], mean)));
+    __shared__ double ring[CENTER_DEPTH][CENTER_TPB];
+    __shared__ double rcp[CENTER_TPB];          // RN(1/n) for the CENTER_TPB columns being processed
+    const long long p_raw = (long long)blockIdx.x * CENTER_TPB + threadIdx.x;
+    const bool active = p_raw < P;
+    const long long p = active ? p_raw : P - 1;  // idle lanes shadow the last row (loads only) so the block barriers stay uniform
+    double mean = 0.0, m2 = 0.0, n = 0.0;       // n: running column count (exact in Float64)
+    int kt = 0;                                  // column index inside the current reciprocal table
+    stream_row(D, P, K, p, ring, [&](long long k, double x) {
+        if (FAST && kt == 0) {                   // uniform across the block: every thread walks k in step
+            __syncthreads();
+            rcp[threadIdx.x] = __drcp_rn((double)(k + threadIdx.x + 1));
+            __syncthreads();
         }
-    }
-    for (; k < K; k++) {
-        double x = __ldcs(D + k * P + p);
-        double d = __dsub_rn(x, mean);
-        mean = __dadd_rn(mean, __ddiv_rn(d, (double)(k + 1)));
+        n += 1.0;
+        const double d = __dsub_rn(x, mean);
+        mean = __dadd_rn(mean, FAST ? div_by_count(d, n, rcp[kt]) : __ddiv_rn(d, n));
         m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(x, mean)));
+        kt = (kt + 1) % CENTER_TPB;
+    });
+    if (active) {
+        if (mean_out != nullptr) mean_out[p] = mean;
+        if (var_out != nullptr) var_out[p] = __ddiv_rn(m2, (double)(K - 1 > 1 ? K - 1 : 1));
     }
-    if (mean_out != nullptr) mean_out[p] = mean;
-    if (var_out != nullptr) var_out[p] = __ddiv_rn(m2, (double)(K - 1 > 1 ? K - 1 : 1));
-    k = 0;
-    for (; k + CENTER_AHEAD <= K; k += CENTER_AHEAD) {
-        double x[CENTER_AHEAD];
-#pragma unroll
-        for (int j = 0; j < CENTER_AHEAD; j++) x[j] = __ldcs(D + (k + j) * P + p);
-#pragma unroll
-        for (int j = 0; j < CENTER_AHEAD; j++) D[(k + j) * P + p] = __dsub_rn(x[j], mean);
-    }
-    for (; k < K; k++) D[k * P + p] = __dsub_rn(D[k * P + p], mean);
+    double *dst = D + p;
+    stream_row(D, P, K, p, ring, [&](long long, double x) {
+        if (active) *dst = __dsub_rn(x, mean);
+        dst += P;
+    });
 }
 
 // deviation_matrix[:, position] = Float64.(theta)   (compute_D.jl:67-71, la_utils.jl:154-158)
@@ -96,7 +157,8 @@ extern "C" int snk_center_columns(double *D, int64_t P, int64_t K, double *mean,
     SNK_REQUIRE(D != nullptr, "null D");
     SNK_REQUIRE(P > 0 && K > 0, "P and K must be positive");
     unsigned grid = (unsigned)((P + CENTER_TPB - 1) / CENTER_TPB);
-    k_center_columns<<<grid, CENTER_TPB, 0, (cudaStream_t)cuda_stream>>>(D, P, K, mean, var);
+    if (K <= CENTER_FAST_MAX_K) k_center_columns<true><<<grid, CENTER_TPB, 0, (cudaStream_t)cuda_stream>>>(D, P, K, mean, var);
+    else k_center_columns<false><<<grid, CENTER_TPB, 0, (cudaStream_t)cuda_stream>>>(D, P, K, mean, var);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }

@@ -400,6 +400,47 @@ def test_center_columns_bit_exact():
         assert np.array_equal(bits(dev.cpu().numpy().reshape(-1)), bits(want)), (K, P)
 
 
+def test_center_columns_bit_exact_edge_values():
+    """The reciprocal-table division inside k_center_columns must return the IEEE quotient for every input: wide-exponent
+    random significands (2e7 divisions by n = 1..1000), signed zeros, subnormals, huge magnitudes, repeated values
+    (d == 0), and Inf/NaN rows."""
+    S = pkg()
+    rng = np.random.default_rng(21)
+    K, P = 1000, 20000
+    sig = rng.integers(0, 1 << 52, (K, P), dtype=np.uint64)
+    expo = rng.integers(1023 - 40, 1023 + 40, (K, P), dtype=np.uint64)
+    sign = rng.integers(0, 2, (K, P), dtype=np.uint64)
+    Dt = ((sign << np.uint64(63)) | (expo << np.uint64(52)) | sig).view(np.float64)
+    Dt[:, 0] = 0.0
+    Dt[:, 1] = -0.0
+    Dt[::2, 2] = -0.0
+    Dt[1::2, 2] = 0.0
+    Dt[:, 3] = 1.5                                            # d == 0 from the second column on
+    Dt[:, 4] = rng.integers(1, 1 << 40, K).astype(np.uint64).view(np.float64)   # subnormals
+    Dt[:, 5] *= 1e-300
+    Dt[:, 6] *= 1e+290
+    Dt[:, 7] = np.where(np.arange(K) == 500, np.inf, Dt[:, 7])
+    Dt[:, 8] = np.where(np.arange(K) == 3, np.nan, Dt[:, 8])
+    Dt[:, 9] = 2.0 ** -1000 * (1 + np.arange(K))
+    Dt[:, 10] = np.float64(1) + np.arange(K) * 2.0 ** -52      # neighbouring floats: tiny exact differences
+    Dt = np.ascontiguousarray(Dt)
+    want = Dt.copy().reshape(-1)
+    with np.errstate(all="ignore"):
+        mean, var = O.center_columns(want, P, K)
+    dev = torch.from_numpy(Dt).cuda()
+    gm, gv = S.center_columns(dev)
+    got = dev.cpu().numpy().reshape(-1)
+
+    def same(a, b):
+        a, b = np.asarray(a), np.asarray(b)
+        nan = np.isnan(a) & np.isnan(b)                      # NaN payload/sign is not part of the contract
+        return np.array_equal(bits(a)[~nan], bits(b)[~nan]) and np.array_equal(np.isnan(a), np.isnan(b))
+
+    assert same(gm.cpu().numpy(), mean)
+    assert same(gv.cpu().numpy(), var)
+    assert same(got, want)
+
+
 @pytest.mark.parametrize("n,T,fmt", [(4096, 300, "f32"), (100, 700, "i8"), (33, 64, "packed2"), (70000, 20, "i8"), (1, 1100, "i64")])
 def test_multi_step_rollout_kernel_matches_oracle(n, T, fmt):
     """snk_rollout_fused: T steps in one launch == T oracle steps (and leaves the same state behind)."""
