@@ -13,9 +13,21 @@
 
 namespace snk {
 
-constexpr int CENTER_TPB = 128;
-constexpr int CENTER_DEPTH = 16;   // columns in flight per thread (16 KB of ring per CTA)
-constexpr int CENTER_GROUP = 4;    // columns per cp.async commit group
+#ifndef SNK_CENTER_TPB
+#define SNK_CENTER_TPB 128
+#endif
+#ifndef SNK_CENTER_DEPTH
+#define SNK_CENTER_DEPTH 16
+#endif
+#ifndef SNK_CENTER_GROUP
+#define SNK_CENTER_GROUP 2
+#endif
+#ifndef SNK_CENTER_MINB
+#define SNK_CENTER_MINB 10
+#endif
+constexpr int CENTER_TPB = SNK_CENTER_TPB;
+constexpr int CENTER_DEPTH = SNK_CENTER_DEPTH;   // columns in flight per thread (16 KB of ring per CTA)
+constexpr int CENTER_GROUP = SNK_CENTER_GROUP;    // columns per cp.async commit group
 constexpr long long CENTER_FAST_MAX_K = 1ll << 20;
 
 // d / n for an integer count n <= 2^20 with y = RN(1/n), bit-identical to the IEEE quotient:
@@ -79,7 +91,7 @@ __device__ __forceinline__ void stream_row(const double *__restrict__ D, long lo
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(CENTER_TPB, 10) k_center_columns(double *__restrict__ D, long long P, long long K,
+__global__ void __launch_bounds__(CENTER_TPB, SNK_CENTER_MINB) k_center_columns(double *__restrict__ D, long long P, long long K,
                                                                double *__restrict__ mean_out,
                                                                double *__restrict__ var_out) {
     __shared__ double ring[CENTER_DEPTH][CENTER_TPB];
