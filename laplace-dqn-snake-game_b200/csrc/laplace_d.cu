@@ -131,15 +131,20 @@ __global__ void k_store_snapshot(double *__restrict__ D, long long P, long long 
 }
 
 // sample_model (la_utils.jl:83-95):  w = mean + 1/sqrt(2) * sqrt.(Gamma_diag) * z1 + 1/sqrt(2(K-1)) * D * z2
-// with Gamma_diag = |var| (compute_Gamma_diag, la_utils.jl:74-81).  One thread per parameter p; D z2 is accumulated in
+// with Gamma_diag = |var| (compute_Gamma_diag, la_utils.jl:74-81).  One thread per parameter p (row streamed through the
+// same cp.async ring as k_center_columns: HBM-bound, D is read once); D z2 is accumulated in
 // column order in Float64 (the reference's BLAS gemv order is unspecified: parity is to ~1e-15 relative, not bit-exact).
-__global__ void k_laplace_sample(const double *__restrict__ mean, const double *__restrict__ var, const double *__restrict__ D,
-                                 long long P, long long K, const double *__restrict__ z1, const double *__restrict__ z2,
-                                 double *__restrict__ w) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
+__global__ void __launch_bounds__(CENTER_TPB, SNK_CENTER_MINB) k_laplace_sample(const double *__restrict__ mean, const double *__restrict__ var,
+                                                                                 const double *__restrict__ D, long long P, long long K,
+                                                                                 const double *__restrict__ z1, const double *__restrict__ z2,
+                                                                                 double *__restrict__ w) {
+    __shared__ double ring[CENTER_DEPTH][CENTER_TPB];
+    const long long p_raw = (long long)blockIdx.x * CENTER_TPB + threadIdx.x;
+    const bool active = p_raw < P;
+    const long long p = active ? p_raw : P - 1;
     double acc = 0.0;
-    for (long long k = 0; k < K; k++) acc = fma(D[k * P + p], z2[k], acc);
+    stream_row(D, P, K, p, ring, [&](long long k, double x) { acc = fma(x, __ldg(z2 + k), acc); });
+    if (!active) return;
     const double g = fabs(var[p]);
     w[p] = mean[p] + (1.0 / sqrt(2.0)) * sqrt(g) * z1[p] + (1.0 / sqrt(2.0 * (double)(K - 1))) * acc;
 }
@@ -152,7 +157,7 @@ extern "C" int snk_laplace_sample_weights(const double *mean, const double *var,
                                           const double *z1, const double *z2, double *w, void *cuda_stream) {
     SNK_REQUIRE(mean && var && D && z1 && z2 && w, "null argument");
     SNK_REQUIRE(P > 0 && K > 1, "need P > 0 and K > 1");
-    k_laplace_sample<<<(unsigned)((P + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(mean, var, D, P, K, z1, z2, w);
+    k_laplace_sample<<<(unsigned)((P + CENTER_TPB - 1) / CENTER_TPB), CENTER_TPB, 0, (cudaStream_t)cuda_stream>>>(mean, var, D, P, K, z1, z2, w);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }

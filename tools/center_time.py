@@ -28,3 +28,15 @@ ts = sorted(ts[2:])
 chk = int(A.view(torch.int64).sum().item()) ^ int(m.view(torch.int64).sum().item()) ^ int(v.view(torch.int64).sum().item())
 print("%s center_ms median %.4f min %.4f  hbm_frac %.3f  checksum %x" % (os.environ.get("SNAKE_B200_LIB", "default"), ts[len(ts) // 2], ts[0],
       3 * 8.0 * K * P / (ts[len(ts) // 2] * 1e-3) / 1e9 / 6455.6, chk & 0xFFFFFFFFFFFF))
+
+z1 = torch.randn(P, dtype=torch.float64, device=dev)
+z2 = torch.randn(K, dtype=torch.float64, device=dev)
+ts = []
+for i in range(8):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); w = S.laplace.sample_model_weights(m, v, A, z1, z2); e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ts = sorted(ts[2:])
+print("sample_model_weights ms median %.4f  hbm_frac %.3f" % (ts[len(ts) // 2], 8.0 * K * P / (ts[len(ts) // 2] * 1e-3) / 1e9 / 6455.6))
