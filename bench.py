@@ -478,7 +478,24 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
             times.append(t)
     want = float((J[0].double() ** 2).sum().item())
     got = float(G[0, rank * R].item())
+    Gring = G.clone()
     dg.close()
+    # baseline: the same block Grams behind library collectives (NCCL all-gather of the planes, all-to-all of Y^T blocks)
+    ag = GS.AllGatherGram([R] * world, P, dev)
+    times_ag = []
+    for it in range(iters + 1):
+        torch.cuda.synchronize()
+        dist.barrier(device_ids=[local])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Ga = ag.run(J, terms=3)
+        e1.record()
+        torch.cuda.synchronize()
+        t = max_over_ranks(e0.elapsed_time(e1))
+        if it > 0:
+            times_ag.append(t)
+    same = bool(torch.equal(Ga, Gring))
+    ag.close()
     ms = sorted(times)[len(times) // 2]
     Kt = R * world
     useful = 2.0 * Kt * Kt * P
@@ -486,6 +503,7 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
             "K_total": Kt, "ms": ms, "useful_tflops_total": useful / (ms * 1e-3) / 1e12,
             "mma_tflops_per_gpu": 2 * useful / world / (ms * 1e-3) / 1e12,
             "diag_rel_err_sample": abs(got - want) / want,
+            "nccl_allgather_baseline_ms": sorted(times_ag)[len(times_ag) // 2], "nccl_allgather_same_bits_rank0": same,
             "exchange": "planes ring: cudaMemcpyAsync from peer-mapped (cudaIpc) memory on a copy stream under the MMA main loop; "
                         "transpose exchange: peer loads inside the symmetrise kernel; torch.distributed only for handles/barriers",
             "timed": "pack + barriers + ring + block Grams + symmetrise; buffers and IPC mappings set up once"}

@@ -214,6 +214,64 @@ class DistributedGram:
         self.shard.free()
 
 
+class AllGatherGram:
+    """The same row-sharded Gram through library collectives — the baseline the planes ring is measured against
+    (BASELINE config 5b names "NCCL all-gather"): NCCL all-gather of every rank's packed planes (materialised:
+    world x 2 planes per GPU), the block Grams against the gathered planes, an NCCL all-to-all of the transposed Y
+    blocks, and the local symmetrise kernel.  Same kernels, same result bits as DistributedGram; the exchange is
+    a separate phase here instead of running under the MMA main loop."""
+
+    def __init__(self, rows_all, P, device, splits=0, group=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.rows_all, self.P, self.splits = list(rows_all), int(P), splits
+        self.rows, self.K = self.rows_all[self.rank], sum(self.rows_all)
+        self.col0 = [sum(self.rows_all[:r]) for r in range(self.world)]
+        self.device = torch.device(device)
+        max_rows = max(self.rows_all)
+        pb, pitch = C.c_size_t(0), C.c_int64(0)
+        _check(lib().snk_gram_planes_layout(max_rows, self.P, C.byref(pb), C.byref(pitch)))
+        self.plane_bytes = pb.value
+        sb = C.c_size_t(0)
+        _check(lib().snk_gram_block_scratch_bytes(self.rows, max_rows, self.P, splits, C.byref(sb)))
+        self.all_planes = torch.empty(self.world, 2 * self.plane_bytes, dtype=torch.uint8, device=self.device)
+        self.scratch = torch.empty(max(sb.value, 256), dtype=torch.uint8, device=self.device)
+        self.Y = torch.empty(self.rows, self.K, dtype=torch.float32, device=self.device)
+        self.G = torch.empty(self.rows, self.K, dtype=torch.float32, device=self.device)
+
+    def run(self, A_rows, terms=3, block_k=0):
+        L = lib()
+        assert tuple(A_rows.shape) == (self.rows, self.P)
+        dt = {torch.float64: DTYPE_F64, torch.float32: DTYPE_F32}[A_rows.dtype]
+        mine = self.all_planes[self.rank]
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _check(L.snk_gram_pack_planes(_ptr(A_rows, device=self.device), dt, self.P, self.rows, C.c_void_p(mine.data_ptr()),
+                                          C.c_void_p(mine.data_ptr() + self.plane_bytes), st))
+            dist.all_gather_into_tensor(self.all_planes.view(-1), mine, group=self.group)
+            for p in ring_schedule(self.rank, self.world):
+                b_hi = self.all_planes[p].data_ptr()
+                _check(L.snk_gram_block(C.c_void_p(mine.data_ptr()), self.rows, C.c_void_p(b_hi), C.c_void_p(b_hi + self.plane_bytes),
+                                        self.rows_all[p], self.P, terms, block_k, self.splits, C.c_void_p(self.scratch.data_ptr()),
+                                        C.c_void_p(self.Y.data_ptr() + 4 * self.col0[p]), self.K, st))
+            if terms == 1:
+                self.G.copy_(self.Y)
+                return self.G
+            send = [self.Y[:, self.col0[p]:self.col0[p] + self.rows_all[p]].contiguous() for p in range(self.world)]
+            recv = [torch.empty(self.rows_all[p], self.rows, dtype=torch.float32, device=self.device) for p in range(self.world)]
+            dist.all_to_all(recv, send, group=self.group)
+            for p in range(self.world):
+                _check(L.snk_gram_symmetrize_block(C.c_void_p(self.Y.data_ptr() + 4 * self.col0[p]), self.K,
+                                                   C.c_void_p(recv[p].data_ptr()), self.rows, self.rows, self.rows_all[p],
+                                                   C.c_void_p(self.G.data_ptr() + 4 * self.col0[p]), self.K, st))
+        return self.G
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self.all_planes = self.scratch = self.Y = self.G = None
+
+
 def gram_distributed(A_rows, rows_all, terms=3, block_k=0, splits=0, group=None):
     """One-shot G[rows_rank, :] for this rank.  A_rows: this rank's (rows, P) CUDA tensor."""
     dg = DistributedGram(rows_all, A_rows.shape[1], A_rows.device, splits, group)

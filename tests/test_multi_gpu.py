@@ -27,6 +27,7 @@ def test_row_sharded_gram_over_nvlink_matches_fp64():
     lines = _torchrun(2, "tools/gram_dist.py", "--check-only")
     d = json.loads(lines[-1])
     assert d["world"] == 2 and max(d["small_rel_fro_err"]) < 1e-5
+    assert all(d["nccl_allgather_same_bits"])      # library-collective baseline == planes ring, bit for bit
 
 
 @needs2

@@ -45,10 +45,16 @@ def main():
     err = float((G.double() - ref).norm() / ref.norm())
     errs = [None] * world
     dist.all_gather_object(errs, err)
+    # the library-collective baseline (NCCL all-gather + all-to-all) must give the same bits
+    ag = GS.AllGatherGram(rows_all, P, dev)
+    G2 = ag.run(A[lo:lo + rows_all[rank]].to(dev).contiguous(), terms=args.terms).clone()
+    ag.close()
+    same = [None] * world
+    dist.all_gather_object(same, bool(torch.equal(G2, G)))
 
     if args.check_only:
         if rank == 0:
-            print(json.dumps({"world": world, "terms": args.terms, "small_rel_fro_err": errs}))
+            print(json.dumps({"world": world, "terms": args.terms, "small_rel_fro_err": errs, "nccl_allgather_same_bits": same}))
         dist.destroy_process_group()
         return
 
@@ -70,7 +76,22 @@ def main():
         if it > 0:
             times.append(float(t.item()))
     diag = float(Gb[0, rank * R].item()), float((J[0].double() ** 2).sum().item())
+    Gring = Gb.clone()
     dg.close()
+    times_ag = []
+    ag = GS.AllGatherGram(rows_all, P, dev)
+    for it in range(args.iters + 1):
+        torch.cuda.synchronize(); dist.barrier(device_ids=[local])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Ga = ag.run(J, terms=args.terms)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it > 0:
+            times_ag.append(float(t.item()))
+    same_big = bool(torch.equal(Ga, Gring))
+    ag.close()
     if rank == 0:
         ms = sorted(times)[len(times) // 2]
         Kt = R * world
@@ -78,7 +99,8 @@ def main():
         print(json.dumps({"world": world, "terms": args.terms, "small_rel_fro_err": errs, "rows_per_rank": R, "K_total": Kt,
                           "P": P, "ms": ms, "useful_tflops_total": useful / (ms * 1e-3) / 1e12,
                           "mma_tflops_per_gpu": useful * (2 if args.terms == 3 else 1) / world / (ms * 1e-3) / 1e12,
-                          "diag_check": diag,
+                          "diag_check": diag, "nccl_allgather_ms": sorted(times_ag)[len(times_ag) // 2],
+                          "nccl_allgather_same_bits": same, "nccl_allgather_same_bits_5b_size_rank0": same_big,
                           "note": "time = pack + barriers + planes ring over NVLink + block Grams + peer-read symmetrise (buffers/IPC set up once)"}))
     dist.destroy_process_group()
 
