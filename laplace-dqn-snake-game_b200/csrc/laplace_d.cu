@@ -22,8 +22,11 @@ namespace snk {
 #ifndef SNK_CENTER_GROUP
 #define SNK_CENTER_GROUP 2
 #endif
+#ifndef SNK_CENTER_CARVE
+#define SNK_CENTER_CARVE (-1)   /* percent of the L1/shared array given to shared memory; -1 = driver default */
+#endif
 #ifndef SNK_CENTER_MINB
-#define SNK_CENTER_MINB 10
+#define SNK_CENTER_MINB 7    /* 72 registers, no spills: measured faster than 10 CTAs/SM at 48 registers with spills */
 #endif
 constexpr int CENTER_TPB = SNK_CENTER_TPB;
 constexpr int CENTER_DEPTH = SNK_CENTER_DEPTH;   // columns in flight per thread (16 KB of ring per CTA)
@@ -49,7 +52,7 @@ __device__ __forceinline__ double div_by_count(double d, double n, double y) {
 // Column ring in shared memory: every thread keeps CENTER_DEPTH columns of its own row in flight with 8-byte cp.async
 // copies (rows of odd length leave columns only 8-byte aligned, which rules out 16-byte and bulk/TMA copies), one
 // commit group per CENTER_GROUP columns.  A thread only ever reads the slots it filled itself, so the ring needs no
-// block barrier; the register file holds just the running statistics, which keeps 10 CTAs resident per SM.
+// block barrier and the register file holds just the running statistics.
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -57,35 +60,48 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Calls body(k, x) for k = 0..K-1 in order with x = D[p + k P], streaming the row through the ring.
-template <typename Body>
+// Streams row p of D through the ring: for every block of CENTER_DEPTH columns starting at kb calls begin(kb) once and
+// then body(kb, c, x) for c = 0..CENTER_DEPTH-1 (while kb + c < K) in column order, x = D[p + (kb + c) P].  The block
+// is fully unrolled, so ring slots are compile-time offsets and the tail tests are uniform integer compares.
+template <typename Begin, typename Body>
 __device__ __forceinline__ void stream_row(const double *__restrict__ D, long long P, long long K, long long p,
-                                           double (*ring)[CENTER_TPB], Body body) {
+                                           double (*ring)[CENTER_TPB], Begin begin, Body body) {
     constexpr int NG = CENTER_DEPTH / CENTER_GROUP;
+    static_assert(CENTER_DEPTH % CENTER_GROUP == 0, "ring depth must be a whole number of commit groups");
     double *mine = &ring[0][threadIdx.x];        // slot s of this thread = mine[s * CENTER_TPB]
-    const double *src = D + p;                   // next column to request
-    long long left = K;                          // columns not requested yet
+    const double *src = D + p;                   // next column to request (runs ahead past the end, never dereferenced there)
 #pragma unroll
     for (int g = 0; g < NG; g++) {
 #pragma unroll
-        for (int j = 0; j < CENTER_GROUP; j++)
-            if (left > 0) { cp_async8(mine + (g * CENTER_GROUP + j) * CENTER_TPB, src); src += P; left--; }
+        for (int j = 0; j < CENTER_GROUP; j++) {
+            const int c = g * CENTER_GROUP + j;
+            if (c < K) cp_async8(mine + c * CENTER_TPB, src);
+            src += P;
+        }
         cp_async_commit();
     }
-    int slot = 0;
-    for (long long k = 0; k < K; k += CENTER_GROUP) {
-        cp_async_wait<NG - 1>();
-        double x[CENTER_GROUP];
+    for (long long kb = 0; kb < K; kb += CENTER_DEPTH) {
+        const int rem = (int)(K - kb < 2 * CENTER_DEPTH ? K - kb : 2 * CENTER_DEPTH);   // columns from kb on, clamped
+        begin(kb);
 #pragma unroll
-        for (int j = 0; j < CENTER_GROUP; j++) x[j] = mine[(slot + j) * CENTER_TPB];
+        for (int g = 0; g < NG; g++) {
+            cp_async_wait<NG - 1>();
+            double x[CENTER_GROUP];
 #pragma unroll
-        for (int j = 0; j < CENTER_GROUP; j++)
-            if (left > 0) { cp_async8(mine + (slot + j) * CENTER_TPB, src); src += P; left--; }
-        cp_async_commit();
+            for (int j = 0; j < CENTER_GROUP; j++) x[j] = mine[(g * CENTER_GROUP + j) * CENTER_TPB];
 #pragma unroll
-        for (int j = 0; j < CENTER_GROUP; j++)
-            if (k + j < K) body(k + j, x[j]);
-        slot = (slot + CENTER_GROUP) % CENTER_DEPTH;
+            for (int j = 0; j < CENTER_GROUP; j++) {
+                const int c = g * CENTER_GROUP + j;
+                if (CENTER_DEPTH + c < rem) cp_async8(mine + c * CENTER_TPB, src);
+                src += P;
+            }
+            cp_async_commit();
+#pragma unroll
+            for (int j = 0; j < CENTER_GROUP; j++) {
+                const int c = g * CENTER_GROUP + j;
+                if (c < rem) body(kb, c, x[j]);
+            }
+        }
     }
     cp_async_wait<0>();
 }
@@ -94,34 +110,39 @@ template <bool FAST>
 __global__ void __launch_bounds__(CENTER_TPB, SNK_CENTER_MINB) k_center_columns(double *__restrict__ D, long long P, long long K,
                                                                double *__restrict__ mean_out,
                                                                double *__restrict__ var_out) {
+    static_assert(CENTER_TPB % CENTER_DEPTH == 0, "the reciprocal table is refreshed on ring-block boundaries");
     __shared__ double ring[CENTER_DEPTH][CENTER_TPB];
     __shared__ double rcp[CENTER_TPB];          // RN(1/n) for the CENTER_TPB columns being processed
     const long long p_raw = (long long)blockIdx.x * CENTER_TPB + threadIdx.x;
     const bool active = p_raw < P;
     const long long p = active ? p_raw : P - 1;  // idle lanes shadow the last row (loads only) so the block barriers stay uniform
     double mean = 0.0, m2 = 0.0, n = 0.0;       // n: running column count (exact in Float64)
-    int kt = 0;                                  // column index inside the current reciprocal table
-    stream_row(D, P, K, p, ring, [&](long long k, double x) {
-        if (FAST && kt == 0) {                   // uniform across the block: every thread walks k in step
-            __syncthreads();
-            rcp[threadIdx.x] = __drcp_rn((double)(k + threadIdx.x + 1));
-            __syncthreads();
-        }
-        n += 1.0;
-        const double d = __dsub_rn(x, mean);
-        mean = __dadd_rn(mean, FAST ? div_by_count(d, n, rcp[kt]) : __ddiv_rn(d, n));
-        m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(x, mean)));
-        kt = (kt + 1) % CENTER_TPB;
-    });
+    int kt = 0;                                  // first table entry of the current ring block
+    stream_row(D, P, K, p, ring,
+        [&](long long kb) {
+            kt = (int)(kb % CENTER_TPB);
+            if (FAST && kt == 0) {               // uniform across the block: every thread walks the columns in step
+                __syncthreads();
+                rcp[threadIdx.x] = __drcp_rn((double)(kb + threadIdx.x + 1));
+                __syncthreads();
+            }
+        },
+        [&](long long, int c, double x) {
+            n += 1.0;
+            const double d = __dsub_rn(x, mean);
+            mean = __dadd_rn(mean, FAST ? div_by_count(d, n, rcp[kt + c]) : __ddiv_rn(d, n));
+            m2 = __dadd_rn(m2, __dmul_rn(d, __dsub_rn(x, mean)));
+        });
     if (active) {
         if (mean_out != nullptr) mean_out[p] = mean;
         if (var_out != nullptr) var_out[p] = __ddiv_rn(m2, (double)(K - 1 > 1 ? K - 1 : 1));
     }
     double *dst = D + p;
-    stream_row(D, P, K, p, ring, [&](long long, double x) {
-        if (active) *dst = __dsub_rn(x, mean);
-        dst += P;
-    });
+    stream_row(D, P, K, p, ring, [](long long) {},
+        [&](long long, int, double x) {
+            if (active) *dst = __dsub_rn(x, mean);
+            dst += P;
+        });
 }
 
 // deviation_matrix[:, position] = Float64.(theta)   (compute_D.jl:67-71, la_utils.jl:154-158)
@@ -143,7 +164,7 @@ __global__ void __launch_bounds__(CENTER_TPB, SNK_CENTER_MINB) k_laplace_sample(
     const bool active = p_raw < P;
     const long long p = active ? p_raw : P - 1;
     double acc = 0.0;
-    stream_row(D, P, K, p, ring, [&](long long k, double x) { acc = fma(x, __ldg(z2 + k), acc); });
+    stream_row(D, P, K, p, ring, [](long long) {}, [&](long long kb, int c, double x) { acc = fma(x, __ldg(z2 + kb + c), acc); });
     if (!active) return;
     const double g = fabs(var[p]);
     w[p] = mean[p] + (1.0 / sqrt(2.0)) * sqrt(g) * z1[p] + (1.0 / sqrt(2.0 * (double)(K - 1))) * acc;
@@ -157,6 +178,11 @@ extern "C" int snk_laplace_sample_weights(const double *mean, const double *var,
                                           const double *z1, const double *z2, double *w, void *cuda_stream) {
     SNK_REQUIRE(mean && var && D && z1 && z2 && w, "null argument");
     SNK_REQUIRE(P > 0 && K > 1, "need P > 0 and K > 1");
+    static const bool carve = [] {
+        cudaFuncSetAttribute(k_laplace_sample, cudaFuncAttributePreferredSharedMemoryCarveout, SNK_CENTER_CARVE);
+        return true;
+    }();
+    (void)carve;
     k_laplace_sample<<<(unsigned)((P + CENTER_TPB - 1) / CENTER_TPB), CENTER_TPB, 0, (cudaStream_t)cuda_stream>>>(mean, var, D, P, K, z1, z2, w);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
@@ -174,6 +200,14 @@ extern "C" int snk_center_columns(double *D, int64_t P, int64_t K, double *mean,
     SNK_REQUIRE(D != nullptr, "null D");
     SNK_REQUIRE(P > 0 && K > 0, "P and K must be positive");
     unsigned grid = (unsigned)((P + CENTER_TPB - 1) / CENTER_TPB);
+    // Carve-out left at the driver default (-1): measured 0.81 ms at the config-5a size for 50-60 % and the default alike;
+    // the maximum carve-out is 25 % slower (the 8-byte-aligned columns share sectors between warps and want the L1).
+    static const bool carve = [] {
+        cudaFuncSetAttribute(k_center_columns<true>, cudaFuncAttributePreferredSharedMemoryCarveout, SNK_CENTER_CARVE);
+        cudaFuncSetAttribute(k_center_columns<false>, cudaFuncAttributePreferredSharedMemoryCarveout, SNK_CENTER_CARVE);
+        return true;
+    }();
+    (void)carve;
     if (K <= CENTER_FAST_MAX_K) k_center_columns<true><<<grid, CENTER_TPB, 0, (cudaStream_t)cuda_stream>>>(D, P, K, mean, var);
     else k_center_columns<false><<<grid, CENTER_TPB, 0, (cudaStream_t)cuda_stream>>>(D, P, K, mean, var);
     SNK_CUDA(cudaGetLastError());
