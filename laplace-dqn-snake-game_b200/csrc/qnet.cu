@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
     uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
     uint64_t *acc_full = bars, *acc_empty = bars + NACC, *w3_full = bars + 2 * NACC, *w3_empty = w3_full + 2, *c3_full = w3_empty + 2;
     uint32_t *tmem_slot = (uint32_t *)(c3_full + 1);
+    uint64_t *a1_full = c3_full + 2;          // the overlapped conv1 has staged the next iteration's A1 (7 warps arrive)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time setup: zero the activation planes (borders stay zero), stage W1 (fp32), W2 (bf16), biases
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
         for (int i = 0; i < NACC; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         for (int i = 0; i < 2; i++) { mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], NISSUE); }
         mbar_init(c3_full, NISSUE);
+        mbar_init(a1_full, 7);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -272,6 +274,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
         // ================= conv2: 16 -> 32, 3x3, pad 1 =================
         if (warp < NISSUE) {
             if (lane == 0) {
+                // There is no block barrier at the end of an iteration: these MMAs queue up behind conv3's while the
+                // epilogue warps are still draining the conv3 accumulators.  A1 comes from the overlapped conv1.
+                if (!QNET_SEQ_CONV1 && it_local > 0) mbar_wait(a1_full, (uint32_t)(it_local - 1) & 1);
                 for (int t = 0; t < TILES12; t++) {
                     const uint32_t u = acc_it + t;
                     if ((int)(u % NISSUE) != warp) continue;      // issuer w owns the tiles (and accumulator buffers) of its parity
@@ -366,6 +371,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
             if (!QNET_SEQ_CONV1 && (warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
                 const int w7 = warp == 3 ? 0 : 2 * ((warp - 4) >> 2) + (warp & 1) + 1;      // 3,6,7,10,11,14,15 -> 0..6
                 conv1_cuda(a, (it + gridDim.x) * S, A1, w7 * 32 + lane, 224);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a1_full);
                 if (a.timing != nullptr && blockIdx.x == 0 && warp == 15 && lane == 0) a.timing[it_local * 8 + 6] = clock64();
             }
             if (warp >= 4) {
@@ -400,8 +408,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
         }
         w3_it += 6;
         c3_it++;
-        fence_proxy_async();
-        __syncthreads();                            // conv3 accumulators, A2 free again; next A1 (conv1 output) staged
+        // No barrier here in the overlapped build: A2 and the conv3 accumulators are handed over through c3_full (the
+        // epilogue warps pass it before they touch A2 again) and the barrier after the next conv2; A1 through a1_full.
+        if (QNET_SEQ_CONV1) {
+            fence_proxy_async();
+            __syncthreads();
+        }
         QNET_STAMP(5);
         if (QNET_SEQ_CONV1 && it + gridDim.x < n_iter) {
             conv1_cuda(a, (it + gridDim.x) * S, A1, tid, THREADS);
