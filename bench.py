@@ -151,6 +151,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: keep this rank's pinned host buffers and copy threads on the GPU's own NUMA node
+    affinity = {"bound": False, "reason": "--no-numa-bind"} if args.no_numa_bind else S.shard.bind_host_near_gpu(local)
     if world > 1:
         # NCCL prints its version banner to stdout from C when the communicator is created; stdout must carry only
         # the one JSON line, so fd 1 points at stderr until the first collective has run
@@ -377,6 +379,7 @@ def run_ours(args):
                          "bytes_per_env_step": BYTES_PER_STEP_CONFIG3, "kernel_ms": kern_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step": e2e_ms / Ke, "api": "snk_step_fused_host (pinned host buffers), f32 observations",
+                    "host_affinity_rank0": affinity,
                     "int8_obs_variant": {"value": world * E * Ke / (e2e_i8_ms * 1e-3), "d2h_bytes_per_step": E * 209}},
             "gpu_launches": K * world,
             "clocks": clocks,
@@ -568,6 +571,7 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU (weak scaling)")
     ap.add_argument("--total-envs", type=int, default=0, help="strong scaling: this many envs in total, sharded over the ranks")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the CPUs next to its GPU")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-config2", action="store_true")
     ap.add_argument("--skip-gram", action="store_true")

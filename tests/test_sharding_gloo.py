@@ -115,3 +115,13 @@ def test_sharded_gram_schedule_two_ranks():
         assert p.exitcode == 0
     # only lo*lo^T is dropped: relative error ~ (2^-24)^2
     assert all(err < 1e-12 for _, err in res), res
+
+
+def test_cpulist_parsing_and_affinity_helper_never_raises():
+    pkg()
+    from snake_b200 import shard
+    assert shard.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert shard.parse_cpulist("5") == [5]
+    assert shard.parse_cpulist("") == []
+    info = shard.bind_host_near_gpu(0)          # no GPU here: reports why nothing was bound
+    assert info["bound"] is False and "reason" in info
