@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -66,7 +67,7 @@ constexpr int TMEM_C3 = 0, TMEM_C2 = 256;                // column offsets: conv
 // packed parameter blob (device): byte offsets
 constexpr size_t P_W1 = 0, P_W2 = P_W1 + 18 * 16 * 4, P_W3 = P_W2 + 9 * 1024, P_BIAS = P_W3 + 6 * (size_t)W3_SLICE;
 constexpr size_t P_W4 = P_BIAS + 112 * 4;                // [64][1600] bf16, columns in kernel-A order
-constexpr size_t P_B4 = P_W4 + 64 * 1600 * 2, P_W5 = P_B4 + 64 * 4, P_B5 = P_W5 + 3 * 64 * 4, P_END = P_B5 + 16;
+constexpr size_t P_B4 = P_W4 + 64 * 1600 * 2, P_W5 = P_B4 + 64 * 4, P_B5 = P_W5 + 3 * 64 * 4, P_W3B = P_B5 + 16, P_END = P_W3B + 36 * 4096;   // P_W3B: conv3 weights as stacked-tap M operands (engine 16)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -431,6 +432,325 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant
     }
 }
 
+// ---- kernel A, engine 16: conv3 with the WEIGHTS as the M operand -------------------------------------------
+// The engine above is bound by the tensor core's shared-memory operand fetch: 6 KB per 128x64x16 MMA of which 5/8 of
+// the rows are real outputs.  Here 16 samples go through one iteration and conv3 is turned around:
+//   M = 128 = the 64 output channels of kernel row k2 = 2j (lanes 0..63) stacked on those of k2 = 2j+1 (lanes 64..127),
+//   N = 80  = the 5 output columns x 16 samples of ONE input row r (conv3's input is stored [r][x][sample], so the 5
+//             consecutive pixels starting at tap column k1 are 10 contiguous 8-sample core matrices),
+//   accumulator tile t (80 TMEM columns, t = 0..5) takes input rows r = t + 2j: its lower lanes hold the even-k2 part of
+//   output row t, its upper lanes the odd-k2 part of output row t-1;  out[y] = lower(T_y) + upper(T_{y+1}).
+// 6.5 KB of operands per 128x80x16 MMA with 5/6 of it useful: 1.7x more useful MACs per operand byte.  The six
+// accumulators fill 480 of the 512 TMEM columns, so conv2 (16 buffers x 32 columns) time-shares them: conv2 -> barrier ->
+// conv3 (+ next conv1 on the CUDA cores) -> conv3 epilogue -> barrier.  conv2's rows are [pixel][sample] so that its
+// epilogue writes conv3's layout with consecutive lanes on consecutive 16-byte units.
+namespace e16 {
+constexpr int S = 16;
+constexpr int ROWS12 = S * PIX12;             // 2304 flat positions [pixel][sample] = 18 tiles exactly
+constexpr int TILES12 = ROWS12 / 128;
+constexpr int A1_PLANE = ROWS12 * 16;         // bytes per 8-channel plane; shifted reads of the last tile run into the
+                                              // following plane / region (their rows are discarded outputs)
+constexpr int A2_PLANE = 100 * S * 16;        // [r][x][sample]
+#ifndef E16_NSLOT
+#define E16_NSLOT 8
+#endif
+#ifndef E16_NOLOAD
+#define E16_NOLOAD 0   /* timing experiment: skip the weight loads */
+#endif
+constexpr int NSLOT = E16_NSLOT;                      // ring of 4 KB conv3 weight blocks
+constexpr int NBLK = 36;                      // (j, k1, m) blocks per iteration
+constexpr int NACC = 16;                      // conv2 accumulator buffers (all 512 columns)
+constexpr int OFF_A1 = 0;
+constexpr int OFF_A2 = OFF_A1 + 2 * A1_PLANE;
+constexpr int OFF_W1 = OFF_A2 + 4 * A2_PLANE;
+constexpr int OFF_W2 = OFF_W1 + 18 * 16 * 4;
+constexpr int OFF_W3 = OFF_W2 + 9 * 1024;
+constexpr int OFF_BIAS = OFF_W3 + NSLOT * 4096;
+constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
+constexpr int SMEM = OFF_BAR + 512 + 128;
+static_assert(SMEM <= 232448, "engine 16 shared memory over the 227 KB limit");
+static_assert(5 * 80 * 64 * 4 <= 4 * A2_PLANE, "epilogue scratch must fit in the conv3 input planes");
+// B-descriptor offset (16-byte units) of weight block be = (j*6 + k1)*2 + m for tile 0: ((2j)*10 + k1)*S + 2m*(A2_PLANE/16)
+__constant__ uint32_t c_boff[NBLK] = {0, 3200, 16, 3216, 32, 3232, 48, 3248, 64, 3264, 80, 3280, 320, 3520, 336, 3536, 352, 3552, 368, 3568, 384, 3584, 400, 3600, 640, 3840, 656, 3856, 672, 3872, 688, 3888, 704, 3904, 720, 3920};
+
+// conv1 on the CUDA cores, one thread per (sample, image row y, half row): the 3 x 7 x 2 input patch is loaded once (42
+// loads in flight together) and the five pixels are accumulated weight-major, so every conv1 weight is fetched from the
+// constant bank once per five pixels.  (A pixel-at-a-time loop spent its time on 72 LDC.64 per 144 HFMA2.)
+// Writes conv2's operand plane A1 ([pixel of the padded 12x12 grid][sample], chunk-planar bf16).
+__device__ __forceinline__ void conv1_pixmajor(const ConvArgs &a, long long s0, uint8_t *A1, int t, int nt) {
+#pragma unroll 1
+    for (int item = t; item < S * 20; item += nt) {
+        const int s = item / 20, r = item - 20 * s, y = r >> 1, x0 = (r & 1) * 5;
+        const bool live = (s0 + s) < a.n;
+        const float *ob = a.obs + (live ? (s0 + s) : 0) * 200;
+        __half2 in[3][7][2];                                     // [k2][column x0 - 1 + j][c], value broadcast to both halves
+#pragma unroll
+        for (int k2 = 0; k2 < 3; k2++) {
+            const int yy = y + k2 - 1;
+            const bool rok = live && yy >= 0 && yy <= 9;
+            const float *row = ob + (rok ? yy * 10 : 0);
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                const int xx = x0 - 1 + j;
+                const bool ok = rok && xx >= 0 && xx <= 9;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const float f = __ldg(row + c * 100 + (ok ? xx : 0));
+                    in[k2][j][c] = __float2half2_rn(ok ? f : 0.f);
+                }
+            }
+        }
+        __half2 acc[5][8];
+#pragma unroll
+        for (int px = 0; px < 5; px++)
+#pragma unroll
+            for (int o = 0; o < 8; o++) acc[px][o] = a.b1h[o];
+#pragma unroll
+        for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+            for (int k1 = 0; k1 < 3; k1++)
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+#pragma unroll
+                    for (int o = 0; o < 8; o++) {
+                        const __half2 w = a.w1h[((k2 * 3 + k1) * 2 + c) * 8 + o];
+#pragma unroll
+                        for (int px = 0; px < 5; px++) acc[px][o] = __hfma2(in[k2][px + k1][c], w, acc[px][o]);
+                    }
+        uint8_t *dst = A1 + (((y + 1) * 12 + (x0 + 1)) * S + s) * 16;
+#pragma unroll
+        for (int px = 0; px < 5; px++) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float2 f = __half22float2(acc[px][j]); w[j] = pack_relu_bf16(f.x, f.y); }
+            *reinterpret_cast<uint4 *>(dst + px * S * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(dst + px * S * 16 + A1_PLANE) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_constant__ ConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
+    const float *bias = (const float *)(smem + OFF_BIAS);
+    uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
+    uint64_t *acc_full = bars, *acc_empty = bars + NACC, *w3_full = bars + 2 * NACC, *w3_empty = w3_full + NSLOT, *c3_full = w3_empty + NSLOT;
+    uint32_t *tmem_slot = (uint32_t *)(c3_full + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < OFF_A2 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // A1 borders stay zero
+    for (int i = tid; i < (int)(P_W3 / 16); i += THREADS)
+        reinterpret_cast<uint4 *>(smem + OFF_W1)[i] = reinterpret_cast<const uint4 *>(a.params)[i];
+    for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
+    if (tid == 0) {
+        for (int i = 0; i < NACC; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < NSLOT; i++) { mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], NISSUE); }
+        mbar_init(c3_full, NISSUE);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    __syncthreads();
+    const long long n_iter = (a.n + S - 1) / S;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const uint64_t dA1 = desc_nosw(smem_u32(A1), A1_PLANE, 128);             // conv2 A: 8-sample core matrices, contiguous
+    const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PLANE, 128);             // conv3 B (N operand): likewise
+    const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);
+    const uint64_t dW3 = desc_nosw(smem_u32(smem + OFF_W3), 2048, 128);      // conv3 A: 128 stacked rows, K chunks 2 KB apart
+
+    uint32_t acc_it = 0, w3_it = 0, c3_it = 0;
+    // The loop starts one pass early: pass -1 only runs the conv1 of the first real iteration, through the same (single)
+    // call site as the overlapped conv1 of every later pass — the kernel's code has to stay small (see conv1_pixmajor).
+    long long it_local = -1;
+    for (long long it = (long long)blockIdx.x - gridDim.x; it < n_iter; it += gridDim.x, it_local++) {
+        const bool real = it_local >= 0;
+        const long long s0 = it * S;
+        if (real) QNET_STAMP(0);
+        if (real && warp == 2 && lane == 0) {
+            // weight producer, part 1: fill the ring while conv2 runs
+            for (int bi = 0; bi < NSLOT; bi++) {
+                const uint32_t u = w3_it + bi;
+                const int b = u % NSLOT;
+                mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
+                if (E16_NOLOAD) { mbar_arrive(&w3_full[b]); continue; }
+                mbar_expect_tx(&w3_full[b], 4096);
+                bulk_load(smem + OFF_W3 + b * 4096, a.params + P_W3B + (size_t)bi * 4096, 4096, &w3_full[b]);
+            }
+        }
+
+        // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][sample] =================
+        if (!real) {
+        } else if (warp < NISSUE) {
+            if (lane == 0) {
+                tc_fence_after();
+                for (int t = 0; t < TILES12; t++) {
+                    const uint32_t u = acc_it + t;
+                    if ((int)(u % NISSUE) != warp) continue;
+                    const int b = u % NACC;
+                    mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + b * 32;
+                    const uint64_t at = dA1 + (uint64_t)(t * 128);
+#pragma unroll
+                    for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+                        for (int k1 = 0; k1 < 3; k1++)
+                            umma_bf16(d, at + (uint64_t)((k2 * 12 + k1) * S), dW2 + (uint64_t)((k2 * 3 + k1) * 64),
+                                      idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
+                    umma_commit(&acc_full[b]);
+                }
+            }
+        } else if (warp >= 4) {
+            const int grp = (warp - 4) >> 2, q = warp & 3;
+            for (int t = 0; t < TILES12; t++) {
+                const uint32_t u = acc_it + t;
+                if ((int)(u % NGRP) != grp) continue;
+                const int b = u % NACC;
+                mbar_wait(&acc_full[b], (u / NACC) & 1);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + b * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + b * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[b]);
+                const int P = t * 128 + q * 32 + lane;
+                const int pix = P / S, s = P - pix * S, y = pix / 12, x = pix - 12 * y;
+                if (x < 10 && y < 10) {
+                    uint8_t *dst = A2 + ((y * 10 + x) * S + s) * 16;          // [r][x][sample]
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; c8++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            w[j] = pack_relu_bf16(__uint_as_float(v[c8 * 8 + 2 * j]) + bias[16 + c8 * 8 + 2 * j],
+                                                  __uint_as_float(v[c8 * 8 + 2 * j + 1]) + bias[16 + c8 * 8 + 2 * j + 1]);
+                        *reinterpret_cast<uint4 *>(dst + c8 * A2_PLANE) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+        if (real) acc_it += TILES12;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (real) QNET_STAMP(3);
+
+        // ================= conv3: 32 -> 64, 6x6, valid; weights are the M operand =================
+        if (warp < NISSUE) {
+            if (real && lane == 0) {
+                tc_fence_after();
+                // The B-descriptor offset of every block comes from a constant table: deriving j, k1, m and the offsets at
+                // run time cost ~160 cycles of dependent integer work per MMA in the single issuing thread (twice what the
+                // tensor core needs), and a fully unrolled loop is 26 KB of code.  Blocks are waited for in pairs.
+                const uint64_t bbase = dA2 + (uint64_t)(warp * 10 * S);     // issuer w owns tiles t = w, w + 2, w + 4
+                const uint32_t dbase = tmem + warp * 80;
+                const uint32_t ring0 = w3_it % NSLOT;
+#pragma unroll 2
+                for (int bi = 0; bi < NBLK; bi += 2) {
+                    const uint32_t b0 = (ring0 + bi) % NSLOT, b1 = b0 + 1;  // ring0 and bi are even
+                    const uint32_t par = ((w3_it + bi) / NSLOT) & 1;       // both blocks share the ring pass
+                    const uint64_t o0 = bbase + c_boff[bi], o1 = bbase + c_boff[bi + 1];
+                    const uint64_t w0 = dW3 + (uint64_t)(b0 * 256), w1 = w0 + 256;
+                    mbar_wait(&w3_full[b0], par);
+                    mbar_wait(&w3_full[b1], par);
+                    tc_fence_after();
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        umma_bf16(dbase + i * 160, w0, o0 + (uint64_t)(i * 20 * S), idesc_bf16(128, 80), bi ? 1u : 0u);
+                        umma_bf16(dbase + i * 160, w1, o1 + (uint64_t)(i * 20 * S), idesc_bf16(128, 80), 1u);
+                    }
+                    umma_commit(&w3_empty[b0]);
+                    umma_commit(&w3_empty[b1]);
+                }
+                umma_commit(c3_full);
+            }
+        } else {
+            if (real && warp == 2 && lane == 0) {
+                for (int bi = NSLOT; bi < NBLK; bi++) {
+                    const uint32_t u = w3_it + bi;
+                    const int b = u % NSLOT;
+                    mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
+                    if (E16_NOLOAD) { mbar_arrive(&w3_full[b]); continue; }
+                    mbar_expect_tx(&w3_full[b], 4096);
+                    bulk_load(smem + OFF_W3 + b * 4096, a.params + P_W3B + (size_t)bi * 4096, 4096, &w3_full[b]);
+                }
+            }
+            // next iteration's conv1 on the CUDA cores, by warps of the two schedulers without an MMA issuer
+            if ((warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
+                const int w7 = warp == 3 ? 0 : 2 * ((warp - 4) >> 2) + (warp & 1) + 1;      // 3,6,7,10,11,14,15 -> 0..6
+                conv1_pixmajor(a, (it + gridDim.x) * S, A1, w7 * 32 + lane, 224);
+                if (real && a.timing != nullptr && blockIdx.x == 0 && warp == 11 && lane == 0) a.timing[it_local * 8 + 6] = clock64();
+            }
+            if (real && warp >= 4) {
+                const int grp = (warp - 4) >> 2, q = warp & 3;
+                mbar_wait(c3_full, c3_it & 1);
+                tc_fence_after();
+                QNET_STAMP(4);
+                float *scratch = reinterpret_cast<float *>(A2);             // [y][column = x*16 + s][oc]: conv3 no longer reads A2
+                // out[y] = lower lanes of tile y + upper lanes of tile y + 1.  Warp quarter q owns lanes 32q..32q+31, i.e.
+                // output channels (q & 1)*32 + lane of the lower (q < 2) or upper (q >= 2) half.  For even y the upper half
+                // is parked in shared memory and the lower-lane warps finish the row; for odd y the other way round, so all
+                // twelve warps read TMEM (64 B/cycle, the bound here) and convert in both phases.
+                const int oc = (q & 1) * 32 + lane;
+                const uint32_t my = tmem + ((uint32_t)(q * 32) << 16) + (q >= 2 ? 80 : 0);   // + y*80: my half of output row y
+                for (int y = grp; y < 5; y += NGRP) {
+                    if (((y & 1) == 0) != (q >= 2)) continue;              // this half is parked for even y by q >= 2, for odd y by q < 2
+#pragma unroll 1
+                    for (int h = 0; h < 5; h++) {
+                        uint32_t v[16];
+                        tmem_ld16(my + y * 80 + h * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) scratch[(y * 80 + h * 16 + i) * 64 + oc] = __uint_as_float(v[i]);
+                    }
+                }
+                asm volatile("bar.sync 1, 384;" ::: "memory");
+                QNET_STAMP(1);
+                const float bo = bias[48 + oc];
+                const int live = (int)(a.n - s0 < 16 ? a.n - s0 : 16);
+                for (int y = grp; y < 5; y += NGRP) {
+                    if (((y & 1) == 0) == (q >= 2)) continue;
+#pragma unroll 1
+                    for (int h = 0; h < 5; h++) {                            // h = output column x
+                        uint32_t v[16];
+                        tmem_ld16(my + y * 80 + h * 16, v);
+                        float other[16];                                     // all loads first: the stores below may alias as far
+#pragma unroll                                                               // as the compiler knows, and would serialise them
+                        for (int i = 0; i < 16; i++) other[i] = scratch[(y * 80 + h * 16 + i) * 64 + oc];
+                        tmem_ld_wait();
+                        __nv_bfloat16 *dst = a.out3 + s0 * 1600 + (y * 5 + h) * 64 + oc;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {                       // i = sample
+                            const float r = __uint_as_float(v[i]) + other[i] + bo;
+                            if (i < live) dst[i * 1600] = __float2bfloat16_rn(fmaxf(r, 0.f));
+                        }
+                    }
+                }
+                QNET_STAMP(2);
+                tc_fence_before();
+            }
+        }
+        if (real) { w3_it += NBLK; c3_it++; }
+        fence_proxy_async();
+        __syncthreads();                            // conv3 accumulators drained (conv2 reuses the columns), A1/A2 handed over
+        if (real) { QNET_STAMP(5); QNET_STAMP(7); }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+}  // namespace e16
+
 // ---- kernel B: Dense(1600,64,relu) + Dense(64,3) ---------------------------------------------------------
 constexpr int HB_M = 128, HB_K = 64, HB_STAGES = 6;
 constexpr int HB_STAGE_BYTES = HB_M * 128 + 64 * 128;      // A tile 16 KB + W4 tile 8 KB (SWIZZLE_128B rows of 64 bf16)
@@ -585,6 +905,15 @@ static void pack_params(const float *th, std::vector<uint8_t> &blob) {
             for (int c = 0; c < 32; c++)
                 for (int o = 0; o < 64; o++)
                     bf(P_W3)[((((k2 * 6 + k1) * 2 + c / 16) * 2 + (c / 8) % 2) * 64 + o) * 8 + c % 8] = f2bf(w3(k1, k2, c, o));
+    // W3 for engine 16: 36 blocks (j, k1, m) of 128 stacked rows x 16 channels, canonical K-major core matrices:
+    // row R = 64 h + o carries kernel row k2 = 2 j + h; [K chunk (2)][row group (16)][row (8)][8 channels]
+    for (int j = 0; j < 3; j++)
+        for (int k1 = 0; k1 < 6; k1++)
+            for (int m = 0; m < 2; m++)
+                for (int R = 0; R < 128; R++)
+                    for (int kk = 0; kk < 16; kk++)
+                        bf(P_W3B)[(size_t)((j * 6 + k1) * 2 + m) * 2048 + (((kk / 8) * 16 + R / 8) * 8 + R % 8) * 8 + kk % 8] =
+                            f2bf(w3(k1, 2 * j + R / 64, 16 * m + kk, R % 64));
     float *bias = reinterpret_cast<float *>(blob.data() + P_BIAS);
     memcpy(bias, b1, 64); memcpy(bias + 16, b2, 128); memcpy(bias + 48, b3, 256);
     // W4 (64,1600) column-major, Flux flatten index kF = x + 5 y + 25 c  ->  [n][k' = (y*5 + x)*64 + c]
@@ -635,6 +964,7 @@ struct snk_qnet_s {
     __nv_bfloat16 *out3;
     long long out3_cap;
     int sms;
+    int engine;                  // 16: stacked-tap conv3, 16 samples per iteration; 12: the first engine (SNK_QNET_ENGINE=12)
 };
 
 extern "C" {
@@ -657,6 +987,10 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
         for (int i = 0; i < 8; i++) q->b1h[i] = __floats2half2_rn(b1f[2 * i], b1f[2 * i + 1]);
     }
     cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
+    {
+        const char *e = getenv("SNK_QNET_ENGINE");
+        q->engine = (e != nullptr && atoi(e) == 16) ? 16 : 12;
+    }
     cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -699,10 +1033,18 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
     ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = q->out3; ca.timing = q->timing;
     memcpy(ca.w1h, q->w1h, sizeof(ca.w1h));
     memcpy(ca.b1h, q->b1h, sizeof(ca.b1h));
-    const long long n_iter = (N + S - 1) / S;
-    int grid = (int)(n_iter < q->sms ? n_iter : q->sms);
-    SNK_CUDA(cudaFuncSetAttribute(k_qnet_convs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_A));
-    k_qnet_convs<<<grid, THREADS, SMEM_A, st>>>(ca);
+    int grid;
+    if (q->engine == 16) {
+        const long long n_iter = (N + e16::S - 1) / e16::S;
+        grid = (int)(n_iter < q->sms ? n_iter : q->sms);
+        SNK_CUDA(cudaFuncSetAttribute(e16::k_qnet_convs16, cudaFuncAttributeMaxDynamicSharedMemorySize, e16::SMEM));
+        e16::k_qnet_convs16<<<grid, THREADS, e16::SMEM, st>>>(ca);
+    } else {
+        const long long n_iter = (N + S - 1) / S;
+        grid = (int)(n_iter < q->sms ? n_iter : q->sms);
+        SNK_CUDA(cudaFuncSetAttribute(k_qnet_convs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_A));
+        k_qnet_convs<<<grid, THREADS, SMEM_A, st>>>(ca);
+    }
     SNK_CUDA(cudaGetLastError());
     CUtensorMap mx, mw;
     int rc;

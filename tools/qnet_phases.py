@@ -28,3 +28,15 @@ for it in range(1, 6):
     row = t[it]
     print("iter %d:" % it, ", ".join("%s %d" % (names[k], int(row[k + 1] - row[k])) for k in range(5)),
           "| next conv1 done at +%d of the conv3 phase" % int(row[6] - row[3]), "| seq conv1 %d" % int(row[7] - row[5]), "| total", int(t[it + 1][0] - row[0]))
+
+if os.environ.get("RAW"):
+    # engine 16 stamps: 0 start, 3 conv2 done, 4 c3_full seen, 1 upper halves dumped, 2 warp 4 finalised, 5 end barrier, 6 conv1 done, 7 end
+    for it in range(1, 5):
+        r = [int(x) for x in t[it]]
+        print("raw iter %d: conv2 %d | conv3 mma %d | dump+bar %d | finalise(warp4) %d | to end barrier %d | conv1 done +%d | tail %d | total %d" % (
+            it, r[3] - r[0], r[4] - r[3], r[1] - r[4], r[2] - r[1], r[5] - r[2], r[6] - r[3], r[7] - r[1], int(t[it + 1][0]) - r[0]))
+
+if os.environ.get("RAW2"):
+    for it in range(1, 4):
+        r = [int(x) for x in t[it]]
+        print("raw2 iter %d: c3_full->bar %d | bar->first tmem load done %d | scratch loads done %d | rest to end barrier %d" % (it, r[1] - r[4], r[7] - r[1], r[2] - r[7], r[5] - r[2]))
