@@ -113,6 +113,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -538,6 +543,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
     uint64_t *acc_full = bars, *acc_empty = bars + NACC, *w3_full = bars + 2 * NACC, *w3_empty = w3_full + NSLOT, *c3_full = w3_empty + NSLOT;
     uint32_t *tmem_slot = (uint32_t *)(c3_full + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int uwarp = __shfl_sync(0xffffffffu, warp, 0);      // the same value, provably warp-uniform for the compiler
 
     for (int i = tid; i < OFF_A2 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // A1 borders stay zero
     for (int i = tid; i < (int)(P_W3 / 16); i += THREADS)
@@ -585,16 +591,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
         // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][sample] =================
         if (!real) {
         } else if (warp < NISSUE) {
-            if (lane == 0) {
+            tc_fence_after();
+            for (int t = 0; t < TILES12; t++) {
+                const uint32_t u = acc_it + t;
+                if ((int)(u % NISSUE) != uwarp) continue;                   // issuer w owns the tiles of its parity
+                const int b = u % NACC;
+                mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
                 tc_fence_after();
-                for (int t = 0; t < TILES12; t++) {
-                    const uint32_t u = acc_it + t;
-                    if ((int)(u % NISSUE) != warp) continue;
-                    const int b = u % NACC;
-                    mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d = tmem + b * 32;
-                    const uint64_t at = dA1 + (uint64_t)(t * 128);
+                const uint32_t d = tmem + b * 32;
+                const uint64_t at = dA1 + (uint64_t)(t * 128);
+                if (elect_one()) {
 #pragma unroll
                     for (int k2 = 0; k2 < 3; k2++)
 #pragma unroll
@@ -603,6 +609,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
                                       idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
                     umma_commit(&acc_full[b]);
                 }
+                __syncwarp();
             }
         } else if (warp >= 4) {
             const int grp = (warp - 4) >> 2, q = warp & 3;
@@ -643,13 +650,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
 
         // ================= conv3: 32 -> 64, 6x6, valid; weights are the M operand =================
         if (warp < NISSUE) {
-            if (real && lane == 0) {
+            if (real) {
+                // The whole issuer warp runs this loop with warp-uniform values and one elected lane issues: descriptors
+                // then live in uniform registers.  (Issued from an `if (lane == 0)` branch every tcgen05.mma was wrapped in
+                // an ELECT + 5 R2UR.BROADCAST sequence, ~15 dependent instructions per MMA.)  The B-descriptor offset of a
+                // block comes from a constant table; blocks are waited for in pairs.
                 tc_fence_after();
-                // The B-descriptor offset of every block comes from a constant table: deriving j, k1, m and the offsets at
-                // run time cost ~160 cycles of dependent integer work per MMA in the single issuing thread (twice what the
-                // tensor core needs), and a fully unrolled loop is 26 KB of code.  Blocks are waited for in pairs.
-                const uint64_t bbase = dA2 + (uint64_t)(warp * 10 * S);     // issuer w owns tiles t = w, w + 2, w + 4
-                const uint32_t dbase = tmem + warp * 80;
+                const uint64_t bbase = dA2 + (uint64_t)(uwarp * 10 * S);    // issuer w owns tiles t = w, w + 2, w + 4
+                const uint32_t dbase = tmem + uwarp * 80;
                 const uint32_t ring0 = w3_it % NSLOT;
 #pragma unroll 2
                 for (int bi = 0; bi < NBLK; bi += 2) {
@@ -660,15 +668,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
                     mbar_wait(&w3_full[b0], par);
                     mbar_wait(&w3_full[b1], par);
                     tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        umma_bf16(dbase + i * 160, w0, o0 + (uint64_t)(i * 20 * S), idesc_bf16(128, 80), bi ? 1u : 0u);
-                        umma_bf16(dbase + i * 160, w1, o1 + (uint64_t)(i * 20 * S), idesc_bf16(128, 80), 1u);
+                        for (int i = 0; i < 3; i++) {
+                            umma_bf16(dbase + i * 160, w0, o0 + (uint64_t)(i * 20 * S), idesc_bf16(128, 80), bi ? 1u : 0u);
+                            umma_bf16(dbase + i * 160, w1, o1 + (uint64_t)(i * 20 * S), idesc_bf16(128, 80), 1u);
+                        }
+                        umma_commit(&w3_empty[b0]);
+                        umma_commit(&w3_empty[b1]);
                     }
-                    umma_commit(&w3_empty[b0]);
-                    umma_commit(&w3_empty[b1]);
+                    __syncwarp();
                 }
-                umma_commit(c3_full);
+                if (elect_one()) umma_commit(c3_full);
+                __syncwarp();
             }
         } else {
             if (real && warp == 2 && lane == 0) {
