@@ -976,7 +976,7 @@ struct snk_qnet_s {
     __nv_bfloat16 *out3;
     long long out3_cap;
     int sms;
-    int engine;                  // 16: stacked-tap conv3, 16 samples per iteration; 12: the first engine (SNK_QNET_ENGINE=12)
+    int engine;                  // 16 (default): stacked-tap conv3, 16 samples per iteration; 12: the first engine (SNK_QNET_ENGINE=12)
 };
 
 extern "C" {
@@ -988,9 +988,8 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
     SNK_CUDA(cudaSetDevice(device));
     std::vector<uint8_t> blob;
     pack_params(theta_host, blob);
-    snk_qnet_s *q = new (std::nothrow) snk_qnet_s();
+    snk_qnet_s *q = new (std::nothrow) snk_qnet_s();      // value-initialised: every member zero
     if (q == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
-    memset(q, 0, sizeof(*q));
     q->device = device;
     {
         const float *w1f = reinterpret_cast<const float *>(blob.data() + P_W1);
@@ -1001,7 +1000,7 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
     cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
     {
         const char *e = getenv("SNK_QNET_ENGINE");
-        q->engine = (e != nullptr && atoi(e) == 16) ? 16 : 12;
+        q->engine = (e != nullptr && atoi(e) == 12) ? 12 : 16;
     }
     cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
@@ -1043,8 +1042,8 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
     }
     ConvArgs ca;
     ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = q->out3; ca.timing = q->timing;
-    memcpy(ca.w1h, q->w1h, sizeof(ca.w1h));
-    memcpy(ca.b1h, q->b1h, sizeof(ca.b1h));
+    for (int i = 0; i < 144; i++) ca.w1h[i] = q->w1h[i];
+    for (int i = 0; i < 8; i++) ca.b1h[i] = q->b1h[i];
     int grid;
     if (q->engine == 16) {
         const long long n_iter = (N + e16::S - 1) / e16::S;
