@@ -763,6 +763,310 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
 }
 }  // namespace e16
 
+// ---- kernel A, engine 17: conv3 weights stationary in tensor memory -------------------------------------------
+// Engine 16's conv3 is still bound by the tensor core's shared-memory operand fetch (6.5 KB per 40-cycle MMA) and keeps
+// all six accumulator tiles live, so its epilogue cannot overlap anything.  Here the 36 stacked-tap weight blocks
+// (128 rows x 16 channels = 8 TMEM columns each, 288 columns in all) are written into tensor memory ONCE per CTA with
+// tcgen05.st and every conv3 MMA takes its A operand from there (tcgen05.mma [d], [a_tmem], b_desc: lane = row, 32-bit
+// column j = K elements 2j, 2j+1 — tools/probes/probe_ts_mma.cu).  Per MMA only the 2.5 KB of B (80 pixel-samples) come
+// from shared memory: conv3 becomes math-bound, needs no weight ring, and because the weights no longer stream the six
+// output tiles are computed ONE AFTER THE OTHER into two 80-column accumulators, tile t+1's MMAs under tile t's epilogue.
+//   TMEM: [0,288) conv3 weights | [288,448) 2 conv3 accumulators | [448,512) 2 conv2 accumulators.
+//   tile t (input rows t, t+2, t+4): lanes 0..63 = even-k2 part of output row t, lanes 64..127 = odd-k2 part of row t-1.
+//   Epilogue of tile t: the lower-lane warps park their half in shared memory (two 20 KB buffers), the upper-lane warps add
+//   the half parked one tile earlier, bias, relu, and write output row t-1.
+// Warp roles: 0 = MMA issuer (conv2 even tiles, all of conv3), 1 = conv2 odd tiles, 4..11 = conv2 epilogue (group g drains
+// buffer g) and conv3 tile epilogues (columns 0..47 | 48..79), {1,2,3,12..15} = the next iteration's conv1 on the CUDA cores.
+// One block barrier per iteration (conv2 -> conv3); everything else is handed over through mbarriers, so conv2 of the next
+// iteration starts under the last conv3 epilogue.
+namespace e17 {
+constexpr int S = e16::S, ROWS12 = e16::ROWS12, TILES12 = e16::TILES12, A1_PLANE = e16::A1_PLANE, A2_PLANE = e16::A2_PLANE;
+constexpr int TM_W3 = 0, TM_C3 = 288, TM_C2 = 448;
+constexpr int SCR = 80 * 64 * 4;              // one parked half tile: [column = x*16 + sample][oc] fp32
+constexpr int NC1W = 7;                       // warps running conv1
+constexpr int OFF_A1 = 0;
+constexpr int OFF_A2 = OFF_A1 + 2 * A1_PLANE;
+constexpr int OFF_W2 = OFF_A2 + 4 * A2_PLANE;
+constexpr int OFF_SCR = OFF_W2 + 9 * 1024;
+constexpr int OFF_BIAS = OFF_SCR + 2 * SCR;
+constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
+constexpr int SMEM = OFF_BAR + 256 + 128;
+static_assert(SMEM <= 232448, "engine 17 shared memory over the 227 KB limit");
+static_assert(TILES12 % 2 == 0, "tile -> issuer / buffer / epilogue group mapping assumes an even tile count");
+
+// debug stamps of CTA 0 (snk_qnet_debug_timing): 64 slots per iteration, first 8 iterations; the buffer holds 512 int64
+#define E17_STAMP(slot) do { if (a.timing != nullptr && blockIdx.x == 0 && lane == 0 && it_local >= 0 && it_local < 8) a.timing[it_local * 64 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+#ifndef E17_NOSTORE
+#define E17_NOSTORE 0   /* timing experiment: conv3 epilogue without its global stores */
+#endif
+// 16 parked values of one thread (one per sample, 256 B apart) in one statement: the loads issue back to back
+__device__ __forceinline__ void lds16_stride256(uint32_t saddr, float (&o)[16]) {
+    asm volatile(
+        "ld.shared.f32 %0, [%16];\n\tld.shared.f32 %1, [%16+256];\n\tld.shared.f32 %2, [%16+512];\n\tld.shared.f32 %3, [%16+768];\n\t"
+        "ld.shared.f32 %4, [%16+1024];\n\tld.shared.f32 %5, [%16+1280];\n\tld.shared.f32 %6, [%16+1536];\n\tld.shared.f32 %7, [%16+1792];\n\t"
+        "ld.shared.f32 %8, [%16+2048];\n\tld.shared.f32 %9, [%16+2304];\n\tld.shared.f32 %10, [%16+2560];\n\tld.shared.f32 %11, [%16+2816];\n\t"
+        "ld.shared.f32 %12, [%16+3072];\n\tld.shared.f32 %13, [%16+3328];\n\tld.shared.f32 %14, [%16+3584];\n\tld.shared.f32 %15, [%16+3840];"
+        : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7]), "=f"(o[8]), "=f"(o[9]),
+          "=f"(o[10]), "=f"(o[11]), "=f"(o[12]), "=f"(o[13]), "=f"(o[14]), "=f"(o[15])
+        : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float hi, float lo) {      // {bf16(max(hi,0)), bf16(max(lo,0))}
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 &lo, const uint4 &hi) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs17(const __grid_constant__ ConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
+    const float *bias = (const float *)(smem + OFF_BIAS);
+    uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
+    uint64_t *acc_full = bars, *acc_empty = bars + 2, *c3_full = bars + 4, *c3_empty = bars + 6, *a1_full = bars + 8, *c3_done = bars + 9;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 10);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int uwarp = __shfl_sync(0xffffffffu, warp, 0);      // the same value, provably warp-uniform for the compiler
+
+    for (int i = tid; i < OFF_A2 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // A1 borders stay zero
+    for (int i = tid; i < 9 * 1024 / 16; i += THREADS)
+        reinterpret_cast<uint4 *>(smem + OFF_W2)[i] = reinterpret_cast<const uint4 *>(a.params + P_W2)[i];
+    for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&c3_full[i], 1); mbar_init(&c3_empty[i], 8); }
+        mbar_init(a1_full, NC1W);
+        mbar_init(c3_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    {
+        // conv3 weights -> tensor memory: block be = (j*6 + k1)*2 + m at columns 8 be; a thread writes the 16 channels of
+        // the stacked row (= TMEM lane) 32 q + lane of its warp's lane quarter q
+        const int q = warp & 3;
+        for (int be = warp >> 2; be < 36; be += THREADS / 128) {
+            const uint8_t *src = a.params + P_W3B + (size_t)be * 4096 + (q * 32 + lane) * 16;
+            const uint4 lo = *reinterpret_cast<const uint4 *>(src), hi = *reinterpret_cast<const uint4 *>(src + 2048);
+            tmem_st8(tmem + ((uint32_t)(q * 32) << 16) + TM_W3 + be * 8, lo, hi);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    const long long n_iter = (a.n + S - 1) / S;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint64_t dA1 = desc_nosw(smem_u32(A1), A1_PLANE, 128);             // conv2 A: 8-sample core matrices, contiguous
+    const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PLANE, 128);             // conv3 B (N operand): likewise
+    const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);
+    const bool conv1_warp = (warp >= 1 && warp <= 3) || warp >= 12;
+    const int w7 = warp <= 3 ? warp - 1 : warp - 9;                           // 1,2,3,12,13,14,15 -> 0..6
+
+    uint32_t acc_it = 0, c3_it = 0;
+    // The loop starts one pass early: pass -1 only runs the conv1 of the first real iteration, through the same (single)
+    // call site as the overlapped conv1 of every later pass.
+    long long it_local = -1;
+    for (long long it = (long long)blockIdx.x - gridDim.x; it < n_iter; it += gridDim.x, it_local++) {
+        const bool real = it_local >= 0;
+        const long long s0 = it * S;
+        if (real) {
+            if (warp == 4) E17_STAMP(0);
+            // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][sample] =================
+            if (warp < 2) {
+                mbar_wait(a1_full, (uint32_t)it_local & 1);                   // conv1 of this iteration has written A1
+                tc_fence_after();
+                for (int t = uwarp; t < TILES12; t += 2) {                    // issuer w owns the tiles (and the buffer) of its parity
+                    const uint32_t u = acc_it + t;
+                    mbar_wait(&acc_empty[uwarp], ((u >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + TM_C2 + uwarp * 32;
+                    const uint64_t at = dA1 + (uint64_t)(t * 128);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+                            for (int k1 = 0; k1 < 3; k1++)
+                                umma_bf16(d, at + (uint64_t)((k2 * 12 + k1) * S), dW2 + (uint64_t)((k2 * 3 + k1) * 64),
+                                          idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
+                        umma_commit(&acc_full[uwarp]);
+                    }
+                    __syncwarp();
+                }
+            } else if (warp >= 4 && warp < 12) {
+                // group g drains accumulator buffer g: a waiter has to see EVERY phase of its mbarrier (parity waits only tell
+                // adjacent phases apart), so the number of epilogue groups equals the number of buffers
+                const int grp = (warp - 4) >> 2, q = warp & 3;
+                if (it_local > 0) mbar_wait(c3_done, ((uint32_t)it_local - 1) & 1);   // the previous conv3 has read A2
+                for (int t = grp; t < TILES12; t += 2) {
+                    const uint32_t u = acc_it + t;
+                    const int b = grp;
+                    mbar_wait(&acc_full[b], (u >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + b * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + b * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[b]);
+                    const int P = t * 128 + q * 32 + lane;
+                    const int pix = P / S, s = P - pix * S, y = pix / 12, x = pix - 12 * y;
+                    if (x < 10 && y < 10) {
+                        uint8_t *dst = A2 + ((y * 10 + x) * S + s) * 16;          // [r][x][sample]
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; c8++) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                w[j] = pack_relu_bf16(__uint_as_float(v[c8 * 8 + 2 * j]) + bias[16 + c8 * 8 + 2 * j],
+                                                      __uint_as_float(v[c8 * 8 + 2 * j + 1]) + bias[16 + c8 * 8 + 2 * j + 1]);
+                            *reinterpret_cast<uint4 *>(dst + c8 * A2_PLANE) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            }
+            acc_it += TILES12;
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();                        // A2 complete; every conv2 MMA has completed (its epilogue ran), A1 is free
+            if (warp == 4) E17_STAMP(3);
+        }
+
+        // ================= conv3: 32 -> 64, 6x6, valid; stationary weights, tile after tile =================
+        if (warp == 0) {
+            if (real) {
+                tc_fence_after();
+#pragma unroll 1
+                for (int t = 0; t < 6; t++) {
+                    const uint32_t u = c3_it + t;
+                    const int b = t & 1;
+                    mbar_wait(&c3_empty[b], ((u >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    E17_STAMP(8 + t);
+                    const uint32_t d = tmem + TM_C3 + b * 80;
+                    const uint64_t bt = dA2 + (uint64_t)(t * 10 * S);       // input row t (16-byte units: one per pixel-sample)
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < 3; j++)
+#pragma unroll
+                            for (int k1 = 0; k1 < 6; k1++)
+#pragma unroll
+                                for (int m = 0; m < 2; m++)
+                                    umma_bf16_ts(d, tmem + TM_W3 + ((j * 6 + k1) * 2 + m) * 8,
+                                                 bt + (uint64_t)((2 * j * 10 + k1) * S + 2 * m * (A2_PLANE / 16)),
+                                                 idesc_bf16(128, 80), (j | k1 | m) ? 1u : 0u);
+                        umma_commit(&c3_full[b]);
+                        if (t == 5) umma_commit(c3_done);
+                    }
+                    __syncwarp();
+                    E17_STAMP(16 + t);
+                }
+            }
+        } else {
+            // next iteration's conv1 on the CUDA cores (A1 is free: see the barrier above)
+            if (conv1_warp && it + gridDim.x < n_iter) {
+                e16::conv1_pixmajor(a, (it + gridDim.x) * S, A1, w7 * 32 + lane, NC1W * 32);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a1_full);
+                if (warp == 13) E17_STAMP(6);
+            }
+            if (real && warp >= 4 && warp < 12) {
+                // Tile t: lanes 0..63 (warps q = 0,1) hold the even-k2 part of output row t, lanes 64..127 (q = 2,3) the odd-k2
+                // part of row t-1.  The q < 2 warps park their half (+ bias) in one of two shared-memory buffers; one tile later
+                // the q >= 2 warps add it to theirs, relu, and write the finished row.  A thread and the thread that parked for
+                // it have the same lane index, so one 128-thread named barrier per group and tile orders the hand-over:
+                // passing it at tile t means tile t-1's half is parked and tile t-2's has been read.
+                const int grp = (warp - 4) >> 2, q = warp & 3;
+                const int c_lo = grp == 0 ? 0 : 3, c_hi = grp == 0 ? 3 : 5;  // 16-column chunks (= output column x) of this group
+                const int oc = (q & 1) * 32 + lane;
+                const float bo = bias[48 + oc];
+                const int live = (int)(a.n - s0 < 16 ? a.n - s0 : 16);
+                const uint32_t scr = smem_u32(smem + OFF_SCR) + oc * 4;
+#pragma unroll 1
+                for (int t = 0; t < 6; t++) {
+                    const uint32_t u = c3_it + t;
+                    const int b = t & 1;
+                    mbar_wait(&c3_full[b], (u >> 1) & 1);
+                    tc_fence_after();
+                    if (warp == 6) E17_STAMP(24 + t);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    const uint32_t my = tmem + ((uint32_t)(q * 32) << 16) + TM_C3 + b * 80;
+                    if (q < 2 && t < 5) {
+                        const uint32_t park = scr + (uint32_t)((t & 1) * SCR);
+#pragma unroll 1
+                        for (int h = c_lo; h < c_hi; h++) {
+                            uint32_t v[16];
+                            tmem_ld16(my + h * 16, v);
+                            tmem_ld_wait();
+                            if (h == c_hi - 1) {                                 // accumulator drained
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&c3_empty[b]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; i++) sts_f32(park + (h * 16 + i) * 256, __uint_as_float(v[i]) + bo);
+                        }
+                        if (warp == 4) E17_STAMP(56 + t);
+                    } else if (q >= 2 && t >= 1) {
+                        const uint32_t park = scr + (uint32_t)(((t - 1) & 1) * SCR);
+                        const int y = t - 1;
+                        if (warp == 6) E17_STAMP(32 + t);
+#pragma unroll 1
+                        for (int h = c_lo; h < c_hi; h++) {                      // h = output column x
+                            uint32_t v[16];
+                            float other[16];
+                            tmem_ld16(my + h * 16, v);
+                            lds16_stride256(park + h * 16 * 256, other);
+                            tmem_ld_wait();
+                            if (h == c_hi - 1) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&c3_empty[b]);
+                                if (warp == 6) E17_STAMP(40 + t);
+                            }
+                            uint16_t *dst = reinterpret_cast<uint16_t *>(a.out3 + s0 * 1600 + (y * 5 + h) * 64 + oc);
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {                    // i = sample
+                                const uint32_t pk = cvt_relu_bf16x2(__uint_as_float(v[i + 1]) + other[i + 1], __uint_as_float(v[i]) + other[i]);
+                                if (E17_NOSTORE) continue;
+                                if (i < live) dst[i * 1600] = (uint16_t)pk;
+                                if (i + 1 < live) dst[(i + 1) * 1600] = (uint16_t)(pk >> 16);
+                            }
+                        }
+                        if (warp == 6) E17_STAMP(48 + t);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&c3_empty[b]);
+                    }
+                }
+            }
+        }
+        if (real) c3_it += 6;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+}  // namespace e17
+
 // ---- kernel B: Dense(1600,64,relu) + Dense(64,3) ---------------------------------------------------------
 constexpr int HB_M = 128, HB_K = 64, HB_STAGES = 6;
 constexpr int HB_STAGE_BYTES = HB_M * 128 + 64 * 128;      // A tile 16 KB + W4 tile 8 KB (SWIZZLE_128B rows of 64 bf16)
@@ -942,7 +1246,7 @@ static void pack_params(const float *th, std::vector<uint8_t> &blob) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_map_bf16(CUtensorMap *m, const void *base, long long rows, long long cols, int box_rows, int box_cols) {
+static int tensor_map_encoder(EncodeTiledFn *out) {
     static EncodeTiledFn enc = nullptr;
     if (enc == nullptr) {
         void *p = nullptr;
@@ -951,6 +1255,13 @@ static int make_map_bf16(CUtensorMap *m, const void *base, long long rows, long 
         if (qres != cudaDriverEntryPointSuccess || p == nullptr) return fail(SNK_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
         enc = (EncodeTiledFn)p;
     }
+    *out = enc;
+    return SNK_OK;
+}
+static int make_map_bf16(CUtensorMap *m, const void *base, long long rows, long long cols, int box_rows, int box_cols) {
+    EncodeTiledFn enc;
+    int rc = tensor_map_encoder(&enc);
+    if (rc != SNK_OK) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
@@ -961,7 +1272,6 @@ static int make_map_bf16(CUtensorMap *m, const void *base, long long rows, long 
     if (r != CUDA_SUCCESS) return fail(SNK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return SNK_OK;
 }
-
 }  // namespace qnet
 }  // namespace snk
 
@@ -976,7 +1286,8 @@ struct snk_qnet_s {
     __nv_bfloat16 *out3;
     long long out3_cap;
     int sms;
-    int engine;                  // 16 (default): stacked-tap conv3, 16 samples per iteration; 12: the first engine (SNK_QNET_ENGINE=12)
+    int engine;                  // SNK_QNET_ENGINE: 17 (default) conv3 weights stationary in tensor memory, tile-by-tile conv3;
+                                 // 16: stacked-tap conv3 with streamed weights; 12: the first engine
 };
 
 extern "C" {
@@ -1000,7 +1311,8 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
     cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
     {
         const char *e = getenv("SNK_QNET_ENGINE");
-        q->engine = (e != nullptr && atoi(e) == 12) ? 12 : 16;
+        const int v = e != nullptr ? atoi(e) : 0;
+        q->engine = (v == 12 || v == 16) ? v : 17;
     }
     cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
@@ -1045,7 +1357,12 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
     for (int i = 0; i < 144; i++) ca.w1h[i] = q->w1h[i];
     for (int i = 0; i < 8; i++) ca.b1h[i] = q->b1h[i];
     int grid;
-    if (q->engine == 16) {
+    if (q->engine == 17) {
+        const long long n_iter = (N + e17::S - 1) / e17::S;
+        grid = (int)(n_iter < q->sms ? n_iter : q->sms);
+        SNK_CUDA(cudaFuncSetAttribute(e17::k_qnet_convs17, cudaFuncAttributeMaxDynamicSharedMemorySize, e17::SMEM));
+        e17::k_qnet_convs17<<<grid, THREADS, e17::SMEM, st>>>(ca);
+    } else if (q->engine == 16) {
         const long long n_iter = (N + e16::S - 1) / e16::S;
         grid = (int)(n_iter < q->sms ? n_iter : q->sms);
         SNK_CUDA(cudaFuncSetAttribute(e16::k_qnet_convs16, cudaFuncAttributeMaxDynamicSharedMemorySize, e16::SMEM));

@@ -30,10 +30,10 @@ def _real_obs(n, steps=12):
     return out["obs"].clone()
 
 
-@pytest.mark.parametrize("engine", [16, 12])
+@pytest.mark.parametrize("engine", [17, 16, 12])
 @pytest.mark.parametrize("n", [1, 12, 13, 16, 17, 100, 257, 5000])
 def test_native_forward_matches_oracle(n, engine, monkeypatch):
-    """both conv engines (snk_qnet_create reads SNK_QNET_ENGINE; 16 = default) at ragged sizes around their
+    """both conv engines (snk_qnet_create reads SNK_QNET_ENGINE; 17 = default) at ragged sizes around their
     samples-per-iteration (12 / 16) and one size that gives every CTA several iterations"""
     monkeypatch.setenv("SNK_QNET_ENGINE", str(engine))
     S = pkg()
