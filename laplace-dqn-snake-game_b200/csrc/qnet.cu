@@ -482,10 +482,16 @@ __constant__ uint32_t c_boff[NBLK] = {0, 3200, 16, 3216, 32, 3232, 48, 3248, 64,
 // loads in flight together) and the five pixels are accumulated weight-major, so every conv1 weight is fetched from the
 // constant bank once per five pixels.  (A pixel-at-a-time loop spent its time on 72 LDC.64 per 144 HFMA2.)
 // Writes conv2's operand plane A1 ([pixel of the padded 12x12 grid][sample], chunk-planar bf16).
+// SPREAD = false: a warp's lanes are consecutive half rows of one sample (coalesced loads, but every 16-byte store of the
+// warp lands in the same bank group: 20-way conflicts).  SPREAD = true: a warp is 8 samples x 4 half rows, so each quarter
+// warp stores 8 consecutive samples of one pixel = one conflict-free 128-byte wavefront (loads touch ~10 lines instead of ~7).
+template <bool SPREAD = false>
 __device__ __forceinline__ void conv1_pixmajor(const ConvArgs &a, long long s0, uint8_t *A1, int t, int nt) {
 #pragma unroll 1
     for (int item = t; item < S * 20; item += nt) {
-        const int s = item / 20, r = item - 20 * s, y = r >> 1, x0 = (r & 1) * 5;
+        const int s = SPREAD ? 8 * ((item >> 5) & 1) + (item & 7) : item / 20;
+        const int r = SPREAD ? 4 * (item >> 6) + ((item >> 3) & 3) : item - 20 * s;
+        const int y = r >> 1, x0 = (r & 1) * 5;
         const bool live = (s0 + s) < a.n;
         const float *ob = a.obs + (live ? (s0 + s) : 0) * 200;
         __half2 in[3][7][2];                                     // [k2][column x0 - 1 + j][c], value broadcast to both halves
@@ -776,14 +782,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
 //   Epilogue of tile t: the lower-lane warps park their half in shared memory (two 20 KB buffers), the upper-lane warps add
 //   the half parked one tile earlier, bias, relu, and write output row t-1.
 // Warp roles: 0 = MMA issuer (conv2 even tiles, all of conv3), 1 = conv2 odd tiles, 4..11 = conv2 epilogue (group g drains
-// buffer g) and conv3 tile epilogues (columns 0..47 | 48..79), {1,2,3,12..15} = the next iteration's conv1 on the CUDA cores.
+// buffer g) and conv3 tile epilogues (columns 0..47 | 48..79), 2, 3 and 12.. = the next iteration's conv1 on the CUDA cores (ten warps: its 320 items in one pass).
 // One block barrier per iteration (conv2 -> conv3); everything else is handed over through mbarriers, so conv2 of the next
 // iteration starts under the last conv3 epilogue.
 namespace e17 {
 constexpr int S = e16::S, ROWS12 = e16::ROWS12, TILES12 = e16::TILES12, A1_PLANE = e16::A1_PLANE, A2_PLANE = e16::A2_PLANE;
 constexpr int TM_W3 = 0, TM_C3 = 288, TM_C2 = 448;
 constexpr int SCR = 80 * 64 * 4;              // one parked half tile: [column = x*16 + sample][oc] fp32
-constexpr int NC1W = 7;                       // warps running conv1
+#ifndef E17_WARPS
+#define E17_WARPS 20
+#endif
+#ifndef E17_SPREAD
+#define E17_SPREAD 1   /* conv1 lane mapping, see conv1_pixmajor */
+#endif
+constexpr int NWARPS = E17_WARPS, NTHREADS = NWARPS * 32;
+constexpr int NC1W = NWARPS - 10;             // warps running conv1: 2, 3 and 12.. (320 items = 10 warps: one pass)
 constexpr int OFF_A1 = 0;
 constexpr int OFF_A2 = OFF_A1 + 2 * A1_PLANE;
 constexpr int OFF_W2 = OFF_A2 + 4 * A2_PLANE;
@@ -825,7 +838,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 &lo, const 
                  ::"r"(taddr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs17(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_constant__ ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint8_t *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
@@ -836,10 +849,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs17(const __grid_consta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int uwarp = __shfl_sync(0xffffffffu, warp, 0);      // the same value, provably warp-uniform for the compiler
 
-    for (int i = tid; i < OFF_A2 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // A1 borders stay zero
-    for (int i = tid; i < 9 * 1024 / 16; i += THREADS)
+    for (int i = tid; i < OFF_A2 / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // A1 borders stay zero
+    for (int i = tid; i < 9 * 1024 / 16; i += NTHREADS)
         reinterpret_cast<uint4 *>(smem + OFF_W2)[i] = reinterpret_cast<const uint4 *>(a.params + P_W2)[i];
-    for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
+    for (int i = tid; i < 112; i += NTHREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
     if (tid == 0) {
         for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&c3_full[i], 1); mbar_init(&c3_empty[i], 8); }
         mbar_init(a1_full, NC1W);
@@ -856,7 +869,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs17(const __grid_consta
         // conv3 weights -> tensor memory: block be = (j*6 + k1)*2 + m at columns 8 be; a thread writes the 16 channels of
         // the stacked row (= TMEM lane) 32 q + lane of its warp's lane quarter q
         const int q = warp & 3;
-        for (int be = warp >> 2; be < 36; be += THREADS / 128) {
+        for (int be = warp >> 2; be < 36; be += NTHREADS / 128) {
             const uint8_t *src = a.params + P_W3B + (size_t)be * 4096 + (q * 32 + lane) * 16;
             const uint4 lo = *reinterpret_cast<const uint4 *>(src), hi = *reinterpret_cast<const uint4 *>(src + 2048);
             tmem_st8(tmem + ((uint32_t)(q * 32) << 16) + TM_W3 + be * 8, lo, hi);
@@ -871,8 +884,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs17(const __grid_consta
     const uint64_t dA1 = desc_nosw(smem_u32(A1), A1_PLANE, 128);             // conv2 A: 8-sample core matrices, contiguous
     const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PLANE, 128);             // conv3 B (N operand): likewise
     const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);
-    const bool conv1_warp = (warp >= 1 && warp <= 3) || warp >= 12;
-    const int w7 = warp <= 3 ? warp - 1 : warp - 9;                           // 1,2,3,12,13,14,15 -> 0..6
+    const bool conv1_warp = warp == 2 || warp == 3 || warp >= 12;
+    const int w7 = warp <= 3 ? warp - 2 : warp - 10;                          // 2, 3, 12, 13, ... -> 0, 1, 2, 3, ...
 
     uint32_t acc_it = 0, c3_it = 0;
     // The loop starts one pass early: pass -1 only runs the conv1 of the first real iteration, through the same (single)
@@ -977,7 +990,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs17(const __grid_consta
         } else {
             // next iteration's conv1 on the CUDA cores (A1 is free: see the barrier above)
             if (conv1_warp && it + gridDim.x < n_iter) {
-                e16::conv1_pixmajor(a, (it + gridDim.x) * S, A1, w7 * 32 + lane, NC1W * 32);
+                e16::conv1_pixmajor<E17_SPREAD != 0>(a, (it + gridDim.x) * S, A1, w7 * 32 + lane, NC1W * 32);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a1_full);
@@ -1361,7 +1374,7 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
         const long long n_iter = (N + e17::S - 1) / e17::S;
         grid = (int)(n_iter < q->sms ? n_iter : q->sms);
         SNK_CUDA(cudaFuncSetAttribute(e17::k_qnet_convs17, cudaFuncAttributeMaxDynamicSharedMemorySize, e17::SMEM));
-        e17::k_qnet_convs17<<<grid, THREADS, e17::SMEM, st>>>(ca);
+        e17::k_qnet_convs17<<<grid, e17::NTHREADS, e17::SMEM, st>>>(ca);
     } else if (q->engine == 16) {
         const long long n_iter = (N + e16::S - 1) / e16::S;
         grid = (int)(n_iter < q->sms ? n_iter : q->sms);
