@@ -777,7 +777,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
 // column j = K elements 2j, 2j+1 — tools/probes/probe_ts_mma.cu).  Per MMA only the 2.5 KB of B (80 pixel-samples) come
 // from shared memory: conv3 becomes math-bound, needs no weight ring, and because the weights no longer stream the six
 // output tiles are computed ONE AFTER THE OTHER into two 80-column accumulators, tile t+1's MMAs under tile t's epilogue.
-//   TMEM: [0,288) conv3 weights | [288,448) 2 conv3 accumulators | [448,512) 2 conv2 accumulators.
+//   TMEM: [0,288) conv3 weights | [288,448) 2 conv3 accumulators | [448,512) 2 conv2 accumulators (conv2 also borrows the
+//   first 32 columns of each conv3 accumulator while conv3 is not running: 4 conv2 buffers).
 //   tile t (input rows t, t+2, t+4): lanes 0..63 = even-k2 part of output row t, lanes 64..127 = odd-k2 part of row t-1.
 //   Epilogue of tile t: the lower-lane warps park their half in shared memory (two 20 KB buffers), the upper-lane warps add
 //   the half parked one tile earlier, bias, relu, and write output row t-1.
@@ -786,7 +787,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
 // One block barrier per iteration (conv2 -> conv3); everything else is handed over through mbarriers, so conv2 of the next
 // iteration starts under the last conv3 epilogue.
 namespace e17 {
-constexpr int S = e16::S, ROWS12 = e16::ROWS12, TILES12 = e16::TILES12, A1_PLANE = e16::A1_PLANE, A2_PLANE = e16::A2_PLANE;
+constexpr int S = e16::S, A1_PLANE = e16::A1_PLANE, A2_PLANE = e16::A2_PLANE;
+// conv2 output rows are [pixel p = 12 y + x of the padded grid][sample]: the real outputs (y < 10) are p < 120, i.e. the first
+// 1920 rows = 15 tiles exactly; the last three tiles of the 12x12 grid (y = 10, 11) hold nothing and are not computed
+constexpr int TILES2 = 120 * S / 128;
+static_assert(TILES2 * 128 == 120 * S, "conv2 tiles must end on the last real output row");
 constexpr int TM_W3 = 0, TM_C3 = 288, TM_C2 = 448;
 constexpr int SCR = 80 * 64 * 4;              // one parked half tile: [column = x*16 + sample][oc] fp32
 #ifndef E17_WARPS
@@ -805,7 +810,6 @@ constexpr int OFF_BIAS = OFF_SCR + 2 * SCR;
 constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
 constexpr int SMEM = OFF_BAR + 256 + 128;
 static_assert(SMEM <= 232448, "engine 17 shared memory over the 227 KB limit");
-static_assert(TILES12 % 2 == 0, "tile -> issuer / buffer / epilogue group mapping assumes an even tile count");
 
 // debug stamps of CTA 0 (snk_qnet_debug_timing): 64 slots per iteration, first 8 iterations; the buffer holds 512 int64
 #define E17_STAMP(slot) do { if (a.timing != nullptr && blockIdx.x == 0 && lane == 0 && it_local >= 0 && it_local < 8) a.timing[it_local * 64 + (slot)] = clock64(); } while (0)
@@ -844,8 +848,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
     uint8_t *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
     const float *bias = (const float *)(smem + OFF_BIAS);
     uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
-    uint64_t *acc_full = bars, *acc_empty = bars + 2, *c3_full = bars + 4, *c3_empty = bars + 6, *a1_full = bars + 8, *c3_done = bars + 9;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 10);
+    uint64_t *acc_full = bars, *acc_empty = bars + 4, *c3_full = bars + 8, *c3_empty = bars + 10, *a1_full = bars + 12, *c3_done = bars + 13;
+    uint64_t *c3_drained = bars + 14;                         // [2]: the last two conv3 tiles of an iteration have left their accumulators
+    uint32_t *tmem_slot = (uint32_t *)(bars + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int uwarp = __shfl_sync(0xffffffffu, warp, 0);      // the same value, provably warp-uniform for the compiler
 
@@ -854,7 +859,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
         reinterpret_cast<uint4 *>(smem + OFF_W2)[i] = reinterpret_cast<const uint4 *>(a.params + P_W2)[i];
     for (int i = tid; i < 112; i += NTHREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
     if (tid == 0) {
-        for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); mbar_init(&c3_full[i], 1); mbar_init(&c3_empty[i], 8); }
+        for (int i = 0; i < 4; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&c3_full[i], 1); mbar_init(&c3_empty[i], 8); mbar_init(&c3_drained[i], 8); }
         mbar_init(a1_full, NC1W);
         mbar_init(c3_done, 1);
         fence_barrier_init();
@@ -900,11 +906,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
             if (warp < 2) {
                 mbar_wait(a1_full, (uint32_t)it_local & 1);                   // conv1 of this iteration has written A1
                 tc_fence_after();
-                for (int t = uwarp; t < TILES12; t += 2) {                    // issuer w owns the tiles (and the buffer) of its parity
-                    const uint32_t u = acc_it + t;
-                    mbar_wait(&acc_empty[uwarp], ((u >> 1) & 1) ^ 1);
+                // Four accumulators: 0, 1 are conv2's own columns, 2, 3 borrow the first 32 columns of the two conv3 accumulators
+                // (idle during conv2 once the last two conv3 tiles of the previous iteration have been drained).  Running tile
+                // index u -> buffer u & 3, issuer u & 1 (so an issuer alternates between two buffers and is always one tile ahead
+                // of the epilogue), epilogue group u & 1.
+                for (int t = (uwarp - acc_it) & 1; t < TILES2; t += 2) {
+                    const uint32_t u = acc_it + t, bsel = u & 3;
+                    if (bsel >= 2 && it_local > 0 && t < 4) mbar_wait(&c3_drained[bsel - 2], ((uint32_t)it_local - 1) & 1);
+                    mbar_wait(&acc_empty[bsel], ((u >> 2) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t d = tmem + TM_C2 + uwarp * 32;
+                    const uint32_t d = tmem + (bsel < 2 ? TM_C2 + bsel * 32 : TM_C3 + (bsel - 2) * 80);
                     const uint64_t at = dA1 + (uint64_t)(t * 128);
                     if (elect_one()) {
 #pragma unroll
@@ -913,23 +924,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
                             for (int k1 = 0; k1 < 3; k1++)
                                 umma_bf16(d, at + (uint64_t)((k2 * 12 + k1) * S), dW2 + (uint64_t)((k2 * 3 + k1) * 64),
                                           idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
-                        umma_commit(&acc_full[uwarp]);
+                        umma_commit(&acc_full[bsel]);
                     }
                     __syncwarp();
                 }
             } else if (warp >= 4 && warp < 12) {
-                // group g drains accumulator buffer g: a waiter has to see EVERY phase of its mbarrier (parity waits only tell
-                // adjacent phases apart), so the number of epilogue groups equals the number of buffers
+                // a waiter has to see EVERY phase of its mbarrier (parity waits only tell adjacent phases apart): group g drains
+                // buffers g and g + 2 in strict alternation, nobody else waits on their barriers
                 const int grp = (warp - 4) >> 2, q = warp & 3;
                 if (it_local > 0) mbar_wait(c3_done, ((uint32_t)it_local - 1) & 1);   // the previous conv3 has read A2
-                for (int t = grp; t < TILES12; t += 2) {
+                for (int t = (grp - acc_it) & 1; t < TILES2; t += 2) {
                     const uint32_t u = acc_it + t;
-                    const int b = grp;
-                    mbar_wait(&acc_full[b], (u >> 1) & 1);
+                    const int b = u & 3;                                        // group g sees every phase of buffers g and g + 2
+                    mbar_wait(&acc_full[b], (u >> 2) & 1);
                     tc_fence_after();
                     uint32_t v[32];
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + b * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TM_C2 + b * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                    const uint32_t src = tmem + ((uint32_t)(q * 32) << 16) + (b < 2 ? TM_C2 + b * 32 : TM_C3 + (b - 2) * 80);
+                    tmem_ld16(src, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                    tmem_ld16(src + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -950,7 +962,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
                     }
                 }
             }
-            acc_it += TILES12;
+            acc_it += TILES2;
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();                        // A2 complete; every conv2 MMA has completed (its epilogue ran), A1 is free
@@ -1027,7 +1039,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
                             if (h == c_hi - 1) {                                 // accumulator drained
                                 tc_fence_before();
                                 __syncwarp();
-                                if (lane == 0) mbar_arrive(&c3_empty[b]);
+                                if (lane == 0) { mbar_arrive(&c3_empty[b]); if (t >= 4) mbar_arrive(&c3_drained[b]); }
                             }
 #pragma unroll
                             for (int i = 0; i < 16; i++) sts_f32(park + (h * 16 + i) * 256, __uint_as_float(v[i]) + bo);
@@ -1047,7 +1059,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
                             if (h == c_hi - 1) {
                                 tc_fence_before();
                                 __syncwarp();
-                                if (lane == 0) mbar_arrive(&c3_empty[b]);
+                                if (lane == 0) { mbar_arrive(&c3_empty[b]); if (t >= 4) mbar_arrive(&c3_drained[b]); }
                                 if (warp == 6) E17_STAMP(40 + t);
                             }
                             uint16_t *dst = reinterpret_cast<uint16_t *>(a.out3 + s0 * 1600 + (y * 5 + h) * 64 + oc);
@@ -1063,7 +1075,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
                     } else {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&c3_empty[b]);
+                        if (lane == 0) { mbar_arrive(&c3_empty[b]); if (t >= 4) mbar_arrive(&c3_drained[b]); }
                     }
                 }
             }
