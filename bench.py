@@ -40,6 +40,12 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bf16_peak_tflops():
+    """dense bf16 TFLOP/s of this pool's B200 (burst figure: the kernels it is used for are timed alone)"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["bf16_tflops"]) if os.path.exists(p) else 1590.0
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -434,9 +440,15 @@ def bench_config4(S, dev, local, n=65536, steps=20):
         e1.record()
         torch.cuda.synchronize()
         fwd = e0.elapsed_time(e1) / steps
+        tflops = 4870784.0 * n / (fwd * 1e-3) / 1e12            # 4,870,784 FLOP per sample (useful)
         out[backend] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "qnet_forward_ms": fwd,
-                        "qnet_tflops": 2 * 0 + 4870784.0 * n / (fwd * 1e-3) / 1e12,
-                        "note": S.qnet.BACKEND_NOTES[backend]}
+                        "qnet_tflops": tflops, "note": S.qnet.BACKEND_NOTES[backend]}
+        if backend == "native":
+            peak = bf16_peak_tflops()
+            out[backend]["roofline"] = {
+                "bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
+                "note": "useful FLOP of the five layers / time of snk_qnet_forward (conv kernel + dense head); ncu of the conv "
+                        "kernel: profiles/r01_ncu_qnet_full.csv (tensor pipe % of active cycles)"}
     out["replay_len"] = len(rb)
     env.close()
     rb.close()
@@ -522,8 +534,7 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10):
     ref = A @ A.T
     plan = S.GramPlan(K, P, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+    peak = bf16_peak_tflops()
     out = {"workload": "config5a: Gram G = D'D of K=%d snapshots x P=%d weights (compute_D.jl D, plot_traj.jl spectrum)" % (K, P),
            "flop_useful": 2.0 * K * K * P, "peak_bf16_tflops_burst": peak}
 
