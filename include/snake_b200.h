@@ -194,13 +194,16 @@ SNK_API int snk_replay_bad_index_host(snk_replay r, int *flag);
  * -> Dense(64,3), Flux semantics (true convolution, WHCN, column-major flatten).  theta_host = Flux.destructure(q_net)
  * (181,395 Float32: per layer weight then bias, column-major) as compute_D.jl:43,68 takes it.  obs: (10,10,2,N) f32 as
  * snk_state / snk_step_fused emit it; q_out: (3,N) f32.  tcgen05 implicit-GEMM convolutions, bf16 operands, FP32
- * accumulation. */
+ * accumulation.  The environment variable SNK_QNET_ENGINE, read by snk_qnet_create, selects the convolution kernel:
+ * 17 (default; conv3 weights stationary in tensor memory), 16 or 12 (earlier engines, same results within the stated
+ * tolerance; kept for comparison). */
 typedef struct snk_qnet_s *snk_qnet;
 SNK_API int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device);
 SNK_API int snk_qnet_destroy(snk_qnet q);
 SNK_API int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3xN, void *cuda_stream);
-/* profiling aid: device buffer of int64[8 * (1 + N / (12 * #SMs))] that receives clock64 stamps of the conv phases of
- * CTA 0 on every later forward; NULL switches it off */
+/* profiling aid: device buffer of 512 int64 that receives clock64 stamps of the conv phases of CTA 0 on every later
+ * forward (engine 17: 64 slots for each of its first 8 iterations, tools/qnet_phases17.py; engines 12/16: 8 slots per
+ * iteration, tools/qnet_phases.py); NULL switches it off */
 SNK_API int snk_qnet_debug_timing(snk_qnet q, long long *device_buf);
 
 /* ---- Laplace deviation matrix  compute_D.jl:9-31, 66-81; la_utils.jl:14-36, 154-169 -------- */

@@ -127,6 +127,18 @@ def load_trainer_nets(path):
     return chain_layers(bf, mf[0]), chain_layers(bf, mf[1])
 
 
+def load_deviation_matrix(path):
+    """The centred D of compute_D.jl:84 (`BSON.@save ... deviation_matrix = deviation_matrix`), read back the way
+    plot_traj.jl:7 does: a (P, K) Float64 numpy array in Julia's shape.  `DeviationMatrix.from_numpy` takes it."""
+    bf = BsonFile(path)
+    if "deviation_matrix" not in bf.doc:
+        raise ValueError("no `deviation_matrix` in %s (keys: %s)" % (path, sorted(k for k in bf.doc if k != "_backrefs")))
+    D = bf.array(bf.doc["deviation_matrix"])
+    if D.ndim != 2 or D.dtype != np.float64:
+        raise ValueError("deviation_matrix must be a Float64 matrix, found %s %s" % (D.dtype, D.shape))
+    return D
+
+
 def destructure(layers):
     """Flux.destructure order: per layer weight then bias, each column-major (compute_D.jl:43,68)."""
     parts = []

@@ -36,6 +36,20 @@ class DeviationMatrix:
                                               _ptr(theta, torch.float32, self.P, self.device), st))
         self.position += 1
 
+    @classmethod
+    def from_numpy(cls, D, device):
+        """An already collected D (P x K Float64 in Julia's shape, e.g. bson_io.load_deviation_matrix of a
+        ./D_matrices/*.bson written by compute_D.jl:84) -> device; plot_traj.jl:7 starts from such a file."""
+        import numpy as np
+        D = np.asarray(D, dtype=np.float64)
+        if D.ndim != 2:
+            raise ValueError("D must be a (P, K) matrix")
+        P, K = D.shape
+        self = cls(P, K, device)
+        self.Dt.copy_(torch.from_numpy(np.ascontiguousarray(D.T)))      # Julia column k = row k here
+        self.position = K
+        return self
+
     def center(self):
         """Welford over the columns, D .-= mean   (compute_D.jl:76-81); returns (mean, var)"""
         self.mean, self.var = center_columns(self.Dt)

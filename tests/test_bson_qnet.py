@@ -100,6 +100,24 @@ def test_bson_round_trip_and_destructure_order():
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BSON), reason="reference checkpoint only exists in the build container")
+def test_reads_a_deviation_matrix_file(tmp_path):
+    """./D_matrices/<name>.bson as compute_D.jl:84 writes it and plot_traj.jl:7 loads it (none is committed in the reference,
+    so the file is produced by the BSON.jl-style writer above): Float64 (P, K), Julia column-major."""
+    pkg()
+    from snake_b200 import bson_io
+    rng = np.random.default_rng(5)
+    D = rng.normal(size=(37, 6))
+    arr = {"tag": "array", "type": _dtype(["Core", "Float64"]), "size": [37, 6], "data": np.asfortranarray(D).astype("<f8").tobytes(order="F")}
+    path = tmp_path / "D_test.bson"
+    path.write_bytes(_doc([_enc(arr, "deviation_matrix")]))
+    got = bson_io.load_deviation_matrix(str(path))
+    assert got.dtype == np.float64 and got.shape == (37, 6) and np.array_equal(got, D)
+    bad = tmp_path / "other.bson"
+    bad.write_bytes(_doc([_enc(arr, "buffer")]))
+    with pytest.raises(ValueError):
+        bson_io.load_deviation_matrix(str(bad))
+
+
 def test_reads_the_committed_reference_checkpoint():
     pkg()
     from snake_b200 import bson_io

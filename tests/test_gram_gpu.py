@@ -118,6 +118,21 @@ def test_plot_traj_numeric_path_matches_numpy_svd():
         assert np.max(np.abs(sgn * Y[i] - Y_ref[i])) < 2e-3 * np.abs(Y_ref[i]).max()
 
 
+def test_deviation_matrix_from_a_loaded_file_shape():
+    """plot_traj.jl:7 starts from a stored D (P x K Float64, already centred): from_numpy keeps Julia's column k as row k and the
+    spectrum of the loaded matrix matches numpy's SVD."""
+    S = pkg()
+    K, P = 64, 5003
+    A = GO.synthetic_snapshots(K, P, seed=3)
+    A = A - A.mean(axis=0, keepdims=True)                         # centred, as compute_D.jl:84 saves it
+    dm = S.laplace.DeviationMatrix.from_numpy(np.asfortranarray(A.T), "cuda:0")     # Julia shape (P, K)
+    assert dm.position == K and np.array_equal(dm.Dt.cpu().numpy(), A)
+    lam, V, w = S.laplace.spectrum(dm.Dt)
+    lam_ref = np.linalg.svd(A.T, compute_uv=False) ** 2 / (K - 1)
+    top = lam_ref > 1e-4 * lam_ref[0]
+    assert np.max(np.abs(lam.cpu().numpy()[top] - lam_ref[top]) / lam_ref[top]) < 1e-3
+
+
 def test_sample_model_weights_matches_numpy():
     """la_utils.jl:83-95 with injected z1, z2 (the reference draws them from MvNormal(0, I))."""
     S = pkg()

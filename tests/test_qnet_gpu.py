@@ -72,6 +72,19 @@ def test_native_forward_random_inputs_and_linearity_in_last_layer():
     assert np.allclose(q2 - q, np.array([1.0, -2.0, 0.5]), atol=1e-5)
 
 
+def test_one_handle_many_batch_sizes():
+    """the same snk_qnet handle called with growing and shrinking N (the conv3 activation buffer is re-allocated on growth)"""
+    S = pkg()
+    layers = _layers(seed=11)
+    net = S.qnet.QNet(layers, torch.device("cuda", 0), backend="native")
+    ref = S.qnet.QNet(layers, torch.device("cuda", 0), backend="torch")
+    for n in (100, 5000, 17, 2368, 2369):          # 2368 = 148 SMs x 16 samples: exactly one iteration per CTA, then one more
+        obs = _real_obs(n, steps=5)
+        q, want = net(obs).cpu().numpy(), ref(obs).cpu().numpy()
+        assert q.shape == (n, 3)
+        assert np.abs(q - want).max() / np.abs(want).max() < 1.5e-2, n
+
+
 def test_rollout_with_native_qnet_runs_config4_shape():
     S = pkg()
     n = 4096
