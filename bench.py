@@ -236,11 +236,12 @@ def run_ours(args):
             barrier()
             if rank == 0:
                 sampler.start()
-            K = max(R, K // R * R)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
             for _ in range(K // R):
                 graph.replay()
+            for i in range(K % R):                       # EXACTLY K steps: the remainder as plain launches
+                one_step(i)
             e1.record(st)
             st.synchronize()
         barrier()
