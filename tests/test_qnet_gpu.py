@@ -72,6 +72,23 @@ def test_native_forward_random_inputs_and_linearity_in_last_layer():
     assert np.allclose(q2 - q, np.array([1.0, -2.0, 0.5]), atol=1e-5)
 
 
+def test_native_forward_at_the_config4_batch():
+    """65,536 samples = 28 iterations per CTA: every hand-over between iterations (accumulator reuse, the borrowed conv2 buffers,
+    the parked halves) is exercised many times; compared with the Float32 library path on every sample, twice (a second call
+    must give the same bits: no state leaks from one launch into the next)."""
+    S = pkg()
+    layers = _layers(seed=21)
+    obs = _real_obs(65536, steps=20)
+    net = S.qnet.QNet(layers, obs.device, backend="native")
+    q1 = net(obs).clone()
+    q2 = net(obs)
+    assert torch.equal(q1, q2)
+    want = S.qnet.QNet(layers, obs.device, backend="torch")(obs)
+    scale = want.abs().max()
+    assert ((q1 - want).abs().max() / scale).item() < 1.5e-2
+    assert torch.isfinite(q1).all()
+
+
 def test_one_handle_many_batch_sizes():
     """the same snk_qnet handle called with growing and shrinking N (the conv3 activation buffer is re-allocated on growth)"""
     S = pkg()
