@@ -1144,7 +1144,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * HB_STAGE_BYTES;
                     mbar_expect_tx(&full[stage], HB_STAGE_BYTES);
-                    tma_load_2d(&map_x, &full[stage], st, kb * HB_K, (int)(t * HB_M));
+                    tma_load_2d(&map_x, &full[stage], st, kb * HB_K, (int)((n_tiles - 1 - t) * HB_M));   // newest rows first, see below
                     tma_load_2d(&map_w, &full[stage], st + HB_M * 128, kb * HB_K, 0);
                     if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -1196,7 +1196,9 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
-            const long long s = t * HB_M + q * 32 + lane;
+            // tiles are taken from the END of the batch: the conv kernel wrote out3 in sample order and the last ~100 MB of it
+            // are still in L2 when this kernel starts; reading front to back would evict them before they are reached
+            const long long s = (n_tiles - 1 - t) * HB_M + q * 32 + lane;
             if (s < a.n) { a.q_out[3 * s] = q0; a.q_out[3 * s + 1] = q1; a.q_out[3 * s + 2] = q2; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
