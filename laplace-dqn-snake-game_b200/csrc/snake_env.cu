@@ -346,14 +346,23 @@ __device__ __forceinline__ uint32_t losing_mask3(u64 occ, u64 cons, int hr, int 
 }
 
 // ---- one env in registers ---------------------------------------------------------------------------
+constexpr int CHI_FROM_LEN = 32;          // see env_load
 struct Env {
     u64 occ, pocc, clo, chi, cons;
     float ret;
     int hr, hc, tr, tc, fr, fc, pfr, pfc, pd, len, t, dn, err;
 };
+// POCC_ALWAYS = false: the previous board is only read for an env that is frozen (done, no auto-reset) — a live env overwrites
+// it with the current board before anything looks at it (env_advance), so the 8 bytes are not fetched for it
+// CHI_LAZY = true: the second word of the direction chain (entries 32..63) only carries live entries for a snake of 34 or more
+// segments, and an entry that is live when it crosses from clo into chi does so at length >= 33: the word is fetched (and,
+// see env_store, written back) only from length 32 on.  Below that its content in memory is never looked at by anybody.
+template <bool POCC_ALWAYS = true, bool CHI_LAZY = false>
 __device__ __forceinline__ void env_load(Env &e, const EnvState &s, long long i) {
-    e.occ = s.occ[i]; e.pocc = s.pocc[i]; e.clo = s.clo[i]; e.chi = s.chi[i]; e.cons = s.cons[i]; e.ret = s.ret[i];
+    e.occ = s.occ[i]; e.clo = s.clo[i]; e.cons = s.cons[i]; e.ret = s.ret[i];
     const u64 misc = s.misc[i];
+    e.pocc = (POCC_ALWAYS || ((misc >> M_DONE) & 1ull)) ? s.pocc[i] : 0ull;
+    e.chi = (!CHI_LAZY || ((int)(misc >> M_LEN) & 127) >= CHI_FROM_LEN) ? s.chi[i] : 0ull;
     e.hr = (int)(misc >> M_HR) & 15; e.hc = (int)(misc >> M_HC) & 15;
     e.tr = (int)(misc >> M_TR) & 15; e.tc = (int)(misc >> M_TC) & 15;
     e.fr = (int)(misc >> M_FR) & 15; e.fc = (int)(misc >> M_FC) & 15;
@@ -361,12 +370,13 @@ __device__ __forceinline__ void env_load(Env &e, const EnvState &s, long long i)
     e.pd = (int)(misc >> M_PD) & 3; e.len = (int)(misc >> M_LEN) & 127; e.t = (int)(misc >> M_T) & 1023;
     e.dn = (int)(misc >> M_DONE) & 1; e.err = (int)(misc >> M_ERR) & 15;
 }
-__device__ __forceinline__ void env_store(const Env &e, const EnvState &s, long long i) {
+__device__ __forceinline__ void env_store(const Env &e, const EnvState &s, long long i, bool store_chi = true) {
     const u64 misc = ((u64)e.hr << M_HR) | ((u64)e.hc << M_HC) | ((u64)e.tr << M_TR) | ((u64)e.tc << M_TC) |
                      ((u64)e.fr << M_FR) | ((u64)e.fc << M_FC) | ((u64)e.pfr << M_PFR) | ((u64)e.pfc << M_PFC) |
                      ((u64)e.pd << M_PD) | ((u64)e.len << M_LEN) | ((u64)e.t << M_T) | ((u64)e.dn << M_DONE) |
                      ((u64)e.err << M_ERR);
-    s.occ[i] = e.occ; s.pocc[i] = e.pocc; s.clo[i] = e.clo; s.chi[i] = e.chi; s.cons[i] = e.cons; s.misc[i] = misc;
+    s.occ[i] = e.occ; s.pocc[i] = e.pocc; s.clo[i] = e.clo; s.cons[i] = e.cons; s.misc[i] = misc;
+    if (store_chi) s.chi[i] = e.chi;
     s.ret[i] = e.ret;
 }
 // a fresh SnakeGame() (structs.jl:33-99, utils.jl:199); error bits are sticky
@@ -451,7 +461,8 @@ __global__ void __launch_bounds__(TPB, SNK_MINB) k_step(const __grid_constant__ 
     if (tid < n_local) {
         // ---- phase A: one thread, one env ------------------------------------------------------
         Env e;
-        env_load(e, a.s, env);
+        env_load<SINK, true>(e, a.s, env);                         // the transition record needs board_{t-2}
+        const bool chi_live = e.len >= CHI_FROM_LEN;
         const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
         const u64 occ_tm2 = e.pocc;                                 // board_{t-2}, for the transition record
         const int fr_tm2 = e.pfr, fc_tm2 = e.pfc, pd_before = e.pd;
@@ -515,7 +526,7 @@ __global__ void __launch_bounds__(TPB, SNK_MINB) k_step(const __grid_constant__ 
         }
 
         if (e.dn && a.auto_reset) env_reset(e);
-        env_store(e, a.s, env);
+        env_store(e, a.s, env, chi_live || e.len >= CHI_FROM_LEN);
     }
 
     if (OBS != SNK_OBS_NONE) {

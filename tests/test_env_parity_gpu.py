@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import oracle_lib as O
-from tests.util import bits, pkg, synth_actions, unpack2
+from tests.util import G2_ACTIONS, ROOT, bits, pkg, synth_actions, unpack2
 
 pytestmark = pytest.mark.gpu
 
@@ -140,6 +140,40 @@ def test_step_abs_reverse_move_loses():
     e1 = S.SnakeGame(1, auto_reset=False)
     r, dn = e1.step_abs(torch.tensor([S.D], dtype=torch.uint8, device="cuda"))
     assert r.item() == -1.0 and dn.item() == 1
+
+
+def test_g2_golden_game_of_the_reference_replays_on_the_gpu():
+    """The reference's own artefact as the judge of the CUDA path: the 240 frames of trainer_gifs/very_long_double_training3.gif
+    (its best game: 237 moves, 33 apples, snake length 35 — the only test where the second 64-bit word of the direction chain
+    carries live entries) must come out of the fused kernel frame by frame, and rewards / masks / scores must match the oracle."""
+    import os
+    S = pkg()
+    boards = np.load(os.path.join(ROOT, "tests", "golden", "g2_boards_double3.npy"))      # (240, 10, 10) Int, [row][col]
+    n = 67
+    env = S.SnakeGame(n, auto_reset=False)
+    ora = O.OracleBatch(n, auto_reset=False)
+    out = env.alloc_outputs(obs="i8", mask=True, ep_stats=True)
+    dirs = ["UDLR".index(c) for c in G2_ACTIONS]
+    assert len(dirs) == 237
+    for t, d in enumerate(dirs, start=1):
+        av = ora.available_actions()                                   # (n, 3) direction codes in available_actions order
+        idx = np.argmax(av == d, axis=1).astype(np.uint8)
+        assert (av[np.arange(n), idx] == d).all()                      # the GIF's move is one of the three offered
+        env.step_fused(act_idx=torch.from_numpy(idx).cuda(), out=out)
+        ref = ora.step(idx, obs=("i8",))
+        _cmp_step(out, ref, n, t, obs_key="obs_i8")
+        st = out["obs"].cpu().numpy().reshape(n, 2, 10, 10)            # Julia (10,10,2,n) column-major = [n][frame][col][row]
+        assert (st[:, 0].transpose(0, 2, 1) == boards[t]).all(), t     # older frame
+        assert (st[:, 1].transpose(0, 2, 1) == boards[t + 1]).all(), t  # newest frame = the GIF's next frame
+    assert out["done"].all() and (out["ep_score"].cpu().numpy() == 33).all() and env.count_errors() == 0
+    # the same game through the one-launch rollout kernel with absolute directions (play_snake.jl's control)
+    env2 = S.SnakeGame(n, auto_reset=False)
+    acts = torch.tensor(dirs, dtype=torch.uint8).repeat(n, 1).T.contiguous().cuda()        # (T, n)
+    ro = env2.rollout(acts, obs="i8", mask=True, ep_stats=True, is_abs=True)
+    last = ro["obs"][-1].cpu().numpy().reshape(n, 2, 10, 10)
+    assert (last[:, 1].transpose(0, 2, 1) == boards[238]).all()
+    assert (ro["ep_score"][-1].cpu().numpy() == 33).all() and ro["done"][-1].all()
+    assert int((bits(ro["reward"].cpu().numpy()) == 0x3F800000).sum()) == 33 * n
 
 
 def _cycle_dirs(t):

@@ -10,6 +10,7 @@ import numpy as np
 
 from oracle import oracle_lib as O
 from oracle.xoshiro_food import default_food_list
+from tests.util import G2_ACTIONS
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -83,10 +84,7 @@ def test_g2_score33_trajectory_replays_exactly():
     # frame 239 is the padding copy (utils.jl:223)
     assert np.array_equal(boards[239], boards[238])
     acts = "".join("UDLR"[a] for a in actions)
-    assert acts == (
-        "UURUURRDDDRURULLLLDDRRRRULULLULLDDRRDRRRULULLULURURRDDRRDDDLULDLLUULLURULURRRDRDDRDDLDLLLURRULULUULURRRRD"
-        "RRURDDLLDRDDLDLLLLLUUUURRDDRRUUULLLLURRRRRDRDLDRDRDLLLDLDLLUULUUURRDRUULLURRRRRRDLDLDRDRDLLDLLLULLURRRULLUL"
-        "URRRURDRRDLDLDRRRDLLDLDLD")
+    assert acts == G2_ACTIONS
     # skip-and-keep food rule R5: (7,7) is skipped twice while occupied and used later
     assert foods == [(7, 5), (5, 7), (7, 3), (6, 7), (5, 4), (4, 4), (6, 2), (7, 7), (5, 5), (4, 3), (2, 6),
                      (3, 6), (5, 8), (7, 4), (5, 4), (4, 3), (2, 2), (4, 6), (7, 3), (7, 5), (6, 5), (4, 9),

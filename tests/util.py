@@ -40,3 +40,11 @@ def unpack2(packed):
     p = np.asarray(packed, dtype=np.uint8)
     codes = np.stack([(p >> (2 * j)) & 3 for j in range(4)], axis=-1).reshape(p.shape[0], -1)
     return np.where(codes == 3, -1, codes).astype(np.int8)
+
+
+# The reference's best game (README.md:54-58, trainer_gifs/very_long_double_training3.gif): 237 absolute moves, 33 apples,
+# death on the bottom wall.  Recovered frame by frame in tests/test_oracle_golden.py::test_g2_score33_trajectory_replays_exactly.
+G2_ACTIONS = (
+    "UURUURRDDDRURULLLLDDRRRRULULLULLDDRRDRRRULULLULURURRDDRRDDDLULDLLUULLURULURRRDRDDRDDLDLLLURRULULUULURRRRD"
+    "RRURDDLLDRDDLDLLLLLUUUURRDDRRUUULLLLURRRRRDRDLDRDRDLLLDLDLLUULUUURRDRUULLURRRRRRDLDLDRDRDLLDLLLULLURRRULLUL"
+    "URRRURDRRDLDLDRRRDLLDLDLD")
