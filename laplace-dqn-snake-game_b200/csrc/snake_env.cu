@@ -370,13 +370,14 @@ __device__ __forceinline__ void env_load(Env &e, const EnvState &s, long long i)
     e.pd = (int)(misc >> M_PD) & 3; e.len = (int)(misc >> M_LEN) & 127; e.t = (int)(misc >> M_T) & 1023;
     e.dn = (int)(misc >> M_DONE) & 1; e.err = (int)(misc >> M_ERR) & 15;
 }
-__device__ __forceinline__ void env_store(const Env &e, const EnvState &s, long long i, bool store_chi = true) {
+__device__ __forceinline__ void env_store(const Env &e, const EnvState &s, long long i, bool store_chi = true, bool store_cons = true) {
     const u64 misc = ((u64)e.hr << M_HR) | ((u64)e.hc << M_HC) | ((u64)e.tr << M_TR) | ((u64)e.tc << M_TC) |
                      ((u64)e.fr << M_FR) | ((u64)e.fc << M_FC) | ((u64)e.pfr << M_PFR) | ((u64)e.pfc << M_PFC) |
                      ((u64)e.pd << M_PD) | ((u64)e.len << M_LEN) | ((u64)e.t << M_T) | ((u64)e.dn << M_DONE) |
                      ((u64)e.err << M_ERR);
-    s.occ[i] = e.occ; s.pocc[i] = e.pocc; s.clo[i] = e.clo; s.cons[i] = e.cons; s.misc[i] = misc;
+    s.occ[i] = e.occ; s.pocc[i] = e.pocc; s.clo[i] = e.clo; s.misc[i] = misc;
     if (store_chi) s.chi[i] = e.chi;
+    if (store_cons) s.cons[i] = e.cons;
     s.ret[i] = e.ret;
 }
 // a fresh SnakeGame() (structs.jl:33-99, utils.jl:199); error bits are sticky
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(TPB, SNK_MINB) k_step(const __grid_constant__ 
         Env e;
         env_load<SINK, true>(e, a.s, env);                         // the transition record needs board_{t-2}
         const bool chi_live = e.len >= CHI_FROM_LEN;
+        const u64 cons_loaded = e.cons;                             // changes only when an apple is eaten or the env resets
         const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
         const u64 occ_tm2 = e.pocc;                                 // board_{t-2}, for the transition record
         const int fr_tm2 = e.pfr, fc_tm2 = e.pfc, pd_before = e.pd;
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(TPB, SNK_MINB) k_step(const __grid_constant__ 
         }
 
         if (e.dn && a.auto_reset) env_reset(e);
-        env_store(e, a.s, env, chi_live || e.len >= CHI_FROM_LEN);
+        env_store(e, a.s, env, chi_live || e.len >= CHI_FROM_LEN, e.cons != cons_loaded);
     }
 
     if (OBS != SNK_OBS_NONE) {
