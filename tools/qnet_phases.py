@@ -1,10 +1,13 @@
 #!/usr/bin/env python3
-"""Per-phase cycle counts of k_qnet_convs (CTA 0) via snk_qnet_debug_timing."""
+"""Per-phase cycle counts of the Q-net conv kernel of engines 12 / 16 (CTA 0) via snk_qnet_debug_timing.
+SNK_QNET_ENGINE=12 (default here) or 16 with RAW=1; engine 17, the library default, has its own tool: qnet_phases17.py."""
 import ctypes as C
 import os
 import sys
 
 import torch
+
+os.environ.setdefault("SNK_QNET_ENGINE", "12")
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as graft  # noqa: E402
