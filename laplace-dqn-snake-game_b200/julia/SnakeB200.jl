@@ -13,7 +13,10 @@ module SnakeB200
 export BatchedSnakeGame, available_actions, step!, step_fused!, virtual_step, assemble_state!,
        epsilon_greedy, masked_target, center_columns!, reset!, set_food_list!, score, lost,
        DeviceReplayBuffer, store_step!, stack_exp, sample_indices, DeviceQNet, forward!, store_snapshot!,
-       gram!, sample_model_weights!
+       gram!, sample_model_weights!, empty_buffer!,
+       step_device!, step_abs_device!, step_fused_device!, rollout_device!, state_device!, losing_mask_device!,
+       lost_device!, steps_device!, error_flags_device!, count_errors, seed!, set_stream!, num_envs, library_version,
+       default_food_list
 
 const lib = get(ENV, "SNAKE_B200_LIB", joinpath(@__DIR__, "..", "libsnake_b200.so"))
 
@@ -160,6 +163,8 @@ mutable struct DeviceReplayBuffer
         return r
     end
 end
+"""empty_buffer! (utils.jl:311): forget every stored Experience."""
+empty_buffer!(r::DeviceReplayBuffer) = check(ccall((:snk_replay_clear, lib), Cint, (Ptr{Cvoid},), r.handle))
 function Base.length(r::DeviceReplayBuffer)
     n = Ref{Int64}(0); p = Ref{Int64}(0)
     check(ccall((:snk_replay_length, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), r.handle, n, p))
@@ -227,5 +232,71 @@ sample_model_weights!(d_mean::Ptr{Float64}, d_var::Ptr{Float64}, d_D::Ptr{Float6
     check(ccall((:snk_laplace_sample_weights, lib), Cint,
                 (Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
                 d_mean, d_var, d_D, P, K, d_z1, d_z2, d_w, C_NULL))
+
+# ---- device-pointer forms of the per-call API (for CUDA.jl users: pass `pointer(cuarray)`) ----------------------------
+# Everything below takes device pointers, enqueues on the handle's stream and returns; call sync(g) before reading.
+
+"""step!(game, action) for N games (utils.jl:100-109): d_act holds 0-based indices into available_actions."""
+step_device!(g::BatchedSnakeGame, d_act::Ptr{UInt8}, d_reward::Ptr{Float32}, d_done::Ptr{UInt8}) =
+    check(ccall((:snk_step, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Float32}, Ptr{UInt8}), g.handle, d_act, d_reward, d_done))
+
+"""play_snake.jl:96-111 control: d_dir holds absolute directions 0:3 (U,D,L,R); the reverse of prev_dir loses (utils.jl:57)."""
+step_abs_device!(g::BatchedSnakeGame, d_dir::Ptr{UInt8}, d_reward::Ptr{Float32}, d_done::Ptr{UInt8}) =
+    check(ccall((:snk_step_abs, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Float32}, Ptr{UInt8}), g.handle, d_dir, d_reward, d_done))
+
+"""One fused launch on device buffers: epsilon_greedy (when d_q != C_NULL; d_u / d_ridx = injected draws or C_NULL) ->
+step! -> virtual_step -> assemble_state!.  Any output pointer may be C_NULL.  obs_fmt: OBS_F32 / OBS_I8 / OBS_I64 / OBS_PACKED2."""
+step_fused_device!(g::BatchedSnakeGame, d_q::Ptr{Float32}, epsilon::Real, d_u::Ptr{Float32}, d_ridx::Ptr{UInt8},
+                   d_act::Ptr{UInt8}, d_reward::Ptr{Float32}, d_done::Ptr{UInt8}, d_obs::Ptr{Cvoid}, obs_fmt::Integer,
+                   d_mask::Ptr{UInt8}, d_ep_return::Ptr{Float32}, d_ep_score::Ptr{Int32}) =
+    check(ccall((:snk_step_fused, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Float32}, Cfloat, Ptr{Float32}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Float32}, Ptr{UInt8},
+                 Ptr{Cvoid}, Cint, Ptr{UInt8}, Ptr{Float32}, Ptr{Int32}),
+                g.handle, d_q, epsilon, d_u, d_ridx, d_act, d_reward, d_done, d_obs, obs_fmt, d_mask, d_ep_return, d_ep_score))
+
+"""play_episode(...; actions_list = ...) (utils.jl:209-219) for N games: T scripted steps in ONE launch; d_act is (N,T)
+column-major = step-major; outputs are step-major too ((N,T), (3,N,T), (10,10,2,N,T)); any output may be C_NULL."""
+rollout_device!(g::BatchedSnakeGame, d_act::Ptr{UInt8}, T::Integer, is_abs::Bool, d_reward::Ptr{Float32}, d_done::Ptr{UInt8},
+                d_obs::Ptr{Cvoid}, obs_fmt::Integer, d_mask::Ptr{UInt8}, d_ep_return::Ptr{Float32}, d_ep_score::Ptr{Int32}) =
+    check(ccall((:snk_rollout_fused, lib), Cint,
+                (Ptr{Cvoid}, Ptr{UInt8}, Int64, Cint, Ptr{Float32}, Ptr{UInt8}, Ptr{Cvoid}, Cint, Ptr{UInt8}, Ptr{Float32}, Ptr{Int32}),
+                g.handle, d_act, T, is_abs ? 1 : 0, d_reward, d_done, d_obs, obs_fmt, d_mask, d_ep_return, d_ep_score))
+
+"""assemble_state! (utils.jl:135-149) into a device buffer in the chosen format."""
+state_device!(g::BatchedSnakeGame, d_obs::Ptr{Cvoid}, obs_fmt::Integer = OBS_F32) =
+    check(ccall((:snk_state, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), g.handle, d_obs, obs_fmt))
+
+"""virtual_step (utils.jl:112-132) of the current states: (3,N) UInt8, 1 = that action loses."""
+losing_mask_device!(g::BatchedSnakeGame, d_mask::Ptr{UInt8}) =
+    check(ccall((:snk_losing_mask, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, d_mask))
+
+lost_device!(g::BatchedSnakeGame, d_done::Ptr{UInt8}) = check(ccall((:snk_get_done, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, d_done))
+steps_device!(g::BatchedSnakeGame, d_steps::Ptr{Int32}) = check(ccall((:snk_get_steps, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}), g.handle, d_steps))
+"""per-env sticky error bits (ERR_FOOD where the reference would throw BoundsError, utils.jl:23,37; ERR_ACTION for an index > 2)."""
+error_flags_device!(g::BatchedSnakeGame, d_flags::Ptr{UInt8}) =
+    check(ccall((:snk_get_error_flags, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, d_flags))
+function count_errors(g::BatchedSnakeGame)
+    n = Ref{Int64}(0)
+    check(ccall((:snk_count_errors_host, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), g.handle, n))
+    return n[]
+end
+
+"""seed of the internal counter-based draws used when epsilon_greedy gets no injected u / ridx (the reference uses the global RNG)."""
+seed!(g::BatchedSnakeGame, seed::Integer) = check(ccall((:snk_set_seed, lib), Cint, (Ptr{Cvoid}, UInt64), g.handle, UInt64(seed)))
+"""run the handle's work on a caller-owned CUDA stream (e.g. CUDA.stream().handle); C_NULL = the legacy default stream."""
+set_stream!(g::BatchedSnakeGame, stream::Ptr{Cvoid}) = check(ccall((:snk_set_stream, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, stream))
+num_envs(g::BatchedSnakeGame) = Int(ccall((:snk_num_envs, lib), Int64, (Ptr{Cvoid},), g.handle))
+library_version() = Int(ccall((:snk_version, lib), Cint, ()))
+
+"""the 50 food cells of Xoshiro(42) (structs.jl:33,70) as the library holds them: vector of (row, col), 1-based."""
+function default_food_list()
+    cells = zeros(UInt8, 2, 64)
+    n = Ref{Cint}(0)
+    check(ccall((:snk_default_food_list_host, lib), Cint, (Ptr{UInt8}, Ref{Cint}), cells, n))
+    return [(Int(cells[1, i]), Int(cells[2, i])) for i in 1:n[]]
+end
+
+# Not bound here: snk_gram_block / snk_gram_symmetrize_block / snk_gram_pack_planes / snk_ipc_* / snk_copy_async — the
+# building blocks of the row-sharded multi-GPU Gram, orchestrated one process per GPU by gram_sharded.py.
 
 end # module

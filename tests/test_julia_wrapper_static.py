@@ -28,14 +28,19 @@ def _split_top(s):
     return out
 
 
+rets = {}       # symbol -> C return type, filled by c_declarations()
+
+
 def c_declarations():
     src = re.sub(r"/\*.*?\*/", " ", open(HEADER).read(), flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
     handles = set(re.findall(r"typedef\s+struct\s+\w+\s*\*\s*(\w+)\s*;", src))
     decls = {}
+    rets.clear()
     for ret, name, params in re.findall(r"SNK_API\s+([\w\s\*]+?)\s*\**\s*(snk_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         ps = [] if params.strip() in ("", "void") else _split_top(" ".join(params.split()))
         decls[name] = ps
+        rets[name] = " ".join(ret.split())
     return decls, handles
 
 
@@ -85,6 +90,7 @@ def test_every_ccall_matches_a_header_declaration():
         for k, (cp, jt) in enumerate(zip(params, types)):
             if not _compatible(cp, jt, handles):
                 problems.append("%s (line %d): argument %d is `%s` in C but `%s` in Julia" % (name, line, k + 1, cp, jt))
-        if name != "snk_last_error" and ret != "Cint":
-            problems.append("%s (line %d): returns int, bound as %s" % (name, line, ret))
+        want = {"int": "Cint", "int64_t": "Int64", "const char": "Cstring"}[rets[name]]
+        if ret != want:
+            problems.append("%s (line %d): returns %s, bound as %s" % (name, line, rets[name], ret))
     assert not problems, "\n".join(problems)
