@@ -60,7 +60,10 @@ def parse_document(b, o=0, as_list=False):
 class BsonFile:
     def __init__(self, path_or_bytes):
         raw = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else open(path_or_bytes, "rb").read()
-        self.doc, _ = parse_document(raw)
+        try:
+            self.doc, _ = parse_document(raw)
+        except (IndexError, struct.error, UnicodeDecodeError, KeyError, OverflowError, MemoryError) as e:
+            raise ValueError("corrupt or truncated BSON document (%s: %s)" % (type(e).__name__, e)) from e
         self.backrefs = self.doc.get("_backrefs", [])
 
     def deref(self, x):

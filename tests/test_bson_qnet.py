@@ -100,6 +100,18 @@ def test_bson_round_trip_and_destructure_order():
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BSON), reason="reference checkpoint only exists in the build container")
+def test_truncated_or_damaged_files_raise_value_error():
+    pkg()
+    from snake_b200 import bson_io
+    good = _trainer_bson(*[[("dense", {"W": np.ones((3, 4), np.float32), "b": np.zeros(3, np.float32)})]] * 2)
+    bson_io.BsonFile(good)
+    for cut in (0, 3, 17, len(good) // 2, len(good) - 1):
+        with pytest.raises(ValueError):
+            bson_io.BsonFile(good[:cut])
+    with pytest.raises(ValueError):
+        bson_io.BsonFile(struct.pack("<i", 2 ** 30) + good[4:])          # declared length beyond the buffer
+
+
 def test_reads_a_deviation_matrix_file(tmp_path):
     """./D_matrices/<name>.bson as compute_D.jl:84 writes it and plot_traj.jl:7 loads it (none is committed in the reference,
     so the file is produced by the BSON.jl-style writer above): Float64 (P, K), Julia column-major."""
