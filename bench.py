@@ -254,6 +254,28 @@ def run_ours(args):
     value = world * E * K / (total_ms * 1e-3)
     n_err = env.count_errors()
 
+    # ---- the same fused step with the other observation formats (report all three byte counts)
+    variants = {}
+    if rank == 0 and not use_graph and not args.skip_variants:
+        for name, fmt, nbytes in (("int8_obs", "i8", BYTES_PER_STEP_CONFIG3 - 800 + 200), ("no_obs", None, BYTES_PER_STEP_CONFIG3 - 800)):
+            out_v = env.alloc_outputs(obs=fmt, mask=True)
+            Kv = min(K, 400)
+            for i in range(5):
+                env.step_fused(q=qs[i % R], eps=eps, u=us[i % R], ridx=rs[i % R], out=out_v)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(Kv):
+                env.step_fused(q=qs[i % R], eps=eps, u=us[i % R], ridx=rs[i % R], out=out_v)
+            a1.record()
+            torch.cuda.synchronize()
+            ms_v = a0.elapsed_time(a1) / Kv
+            variants[name] = {"value": E / (ms_v * 1e-3), "unit": UNIT, "ms_per_step": ms_v, "bytes_per_env_step": nbytes,
+                              "hbm_frac": E * nbytes / (ms_v * 1e-3) / 1e9 / peaks()[0]}
+            del out_v
+        variants["note"] = ("single GPU, device-timed like `value`; int8 observations (the reference's game.state is an integer array) "
+                            "and no observation at all (reward / done / mask only): the smaller the output, the more the kernel is "
+                            "bound by its per-env arithmetic and latency instead of HBM")
+
     # ---- e2e: the host-buffer C-ABI call, pinned host tensors, copies inside the timed region
     Ke = max(2, min(K, args.e2e_steps))
     host = {"obs_fmt": "f32", "q": S.pinned_empty((E, 3), torch.float32), "u": S.pinned_empty((E,), torch.float32),
@@ -393,6 +415,8 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if variants:
+            line["obs_format_variants"] = variants
         if cfg2 is not None:
             line["config2_4096_envs"] = cfg2
         if cfg4 is not None:
@@ -588,6 +612,7 @@ def main():
     ap.add_argument("--skip-config2", action="store_true")
     ap.add_argument("--skip-gram", action="store_true")
     ap.add_argument("--skip-config4", action="store_true")
+    ap.add_argument("--skip-variants", action="store_true", help="skip the int8-observation / no-observation timings")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
