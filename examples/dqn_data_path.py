@@ -30,8 +30,8 @@ def main():
         q_layers, t_layers = S.bson_io.load_trainer_nets(args.bson)
     else:
         q_layers = t_layers = S.qnet.glorot_layers(seed=0)           # Flux default init (structs.jl:127-139)
-    q_net = S.qnet.QNet(q_layers, dev, backend="native")
-    t_net = S.qnet.QNet(t_layers, dev, backend="native")
+    q_net = S.qnet.QNet(q_layers, dev, precision="f32")
+    t_net = S.qnet.QNet(t_layers, dev, precision="f32")
     env = S.SnakeGame(args.envs, auto_reset=True)
     rb = S.ReplayBuffer(capacity=50000, batch_size=64)
     ro = S.rollout.Rollout(env, q_net, t_net, rb, epsilon=args.epsilon)

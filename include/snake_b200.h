@@ -18,9 +18,14 @@
  *     `(10,10,2,N)` column-major exactly as `stack_exp` builds them (utils.jl:348-362):
  *     element (r,c,f,n), 1-based, lives at (r-1) + 10(c-1) + 100(f-1) + 200(n-1);
  *     frame f=1 is the older board, f=2 the newer one;
- *   - calls enqueue work on the handle's CUDA stream and return; snk_sync() waits;
+ *   - calls enqueue work on the handle's CUDA stream and return; snk_sync() waits.  This includes
+ *     snk_step_fused_host / snk_step_fused_store_host: their host buffers are read and written
+ *     asynchronously — call snk_sync() before reading an output or reusing an input buffer.
+ *     The per-call getters whose names end in `_host` (snk_state_host, snk_losing_mask_host, ...)
+ *     return when the data has arrived;
+ *   - every call runs on its handle's device and restores the caller's current device;
  *   - one handle per host thread; there is no hidden global state besides the
- *     thread-local error string;
+ *     thread-local error string and the tile-engine switch snk_gram_config;
  *   - there is no CPU fallback: without a CUDA device snk_create fails.
  *
  * Codes
@@ -39,7 +44,7 @@
 extern "C" {
 #endif
 
-#define SNK_VERSION 100
+#define SNK_VERSION 200
 
 #if defined(__GNUC__)
 #define SNK_API __attribute__((visibility("default")))
@@ -53,7 +58,7 @@ extern "C" {
 #define SNK_ERR_CUDA (-2)      /* a CUDA runtime call failed */
 #define SNK_ERR_NODEVICE (-3)  /* no CUDA device / not a Blackwell part */
 #define SNK_ERR_UNSUPPORTED (-4)
-#define SNK_ERR_NCCL (-5)
+#define SNK_ERR_TIMEOUT (-5)   /* a peer of the row-sharded Gram did not reach a barrier */
 
 /* snk_create flags */
 #define SNK_AUTO_RESET 1u      /* a lost env is re-initialised (a fresh SnakeGame(), utils.jl:199) after its terminal outputs */
@@ -95,6 +100,7 @@ SNK_API int snk_version(void);
 
 /* ---- available_actions(game)  utils.jl:7-10 ---------------------------------------------- */
 SNK_API int snk_available_actions(snk_handle h, uint8_t *dirs_3xN);
+SNK_API int snk_available_actions_host(snk_handle h, uint8_t *dirs_3xN_host);
 
 /* ---- step!(game, action)  utils.jl:100-109 (+ grow_maybe!, sample_food!, check_collision,
  *      update_board!, move_wrapper!: utils.jl:13-96) ---------------------------------------
@@ -114,6 +120,8 @@ SNK_API int snk_step_abs(snk_handle h, const uint8_t *dir, float *reward, uint8_
  *                        are NULL they come from the internal generator.  act_idx then is an
  *                        optional OUTPUT (N) u8.
  *          q == NULL  -> act_idx (N) u8 is the INPUT action index.
+ *          The internal generator is keyed by (seed, env, number of step calls so far); the call count is a launch
+ *          argument, so a CUDA graph replays the SAME draws: inject u / ridx when capturing steps into a graph.
  * Outputs (any may be NULL): reward (N) f32, done (N) u8,
  *          obs: next_state (board_{t-1}, board_t) in obs_fmt, the terminal pair when done;
  *          mask (3,N) u8: next_is_suicidal (trues(3) when done);
@@ -122,8 +130,11 @@ SNK_API int snk_step_abs(snk_handle h, const uint8_t *dir, float *reward, uint8_
 SNK_API int snk_step_fused(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx,
                    uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt,
                    uint8_t *mask, float *ep_return, int32_t *ep_score);
-/* same call with HOST buffers (pinned memory recommended: snk_host_alloc): copies the inputs up,
- * runs the fused kernel in env chunks and streams the outputs back, overlapped. */
+/* same call with HOST buffers (pinned memory recommended: snk_host_alloc): env chunks are pipelined three deep — the
+ * inputs of chunk c+1 go up while the kernel of chunk c runs and the outputs of chunk c-1 come down.  ASYNCHRONOUS:
+ * returns after enqueueing; snk_sync(h) before reading an output or overwriting an input.  obs_fmt SNK_OBS_PACKED2
+ * (50 B/env, lossless) is the format meant for this entry: the reference casts to Float32 only the 64 transitions a
+ * minibatch samples (utils.jl:361-362) — snk_replay_gather_host does that for the device replay ring. */
 SNK_API int snk_step_fused_host(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx,
                         uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt,
                         uint8_t *mask, float *ep_return, int32_t *ep_score);
@@ -140,11 +151,17 @@ SNK_API int snk_host_free(void *p);
 /* ---- assemble_state! / assemble_states_vector  utils.jl:135-149 --------------------------- */
 /* current two-frame state (board_{t-1}, board_t) of every env, in obs_fmt */
 SNK_API int snk_state(snk_handle h, void *obs, int obs_fmt);
+SNK_API int snk_state_host(snk_handle h, void *obs_host, int obs_fmt);        /* returns when the data has arrived */
+/* obs = the next_state output of the fused step that produced `done`: rows of envs that step re-initialised (done != 0,
+ * SNK_AUTO_RESET) are overwritten with the constructor state (init, init) (structs.jl:53-55) — obs then is the acting
+ * state of the next step for every env, without re-expanding all N (a batched play_episode loop, utils.jl:203-208) */
+SNK_API int snk_patch_reset_obs(snk_handle h, const uint8_t *done, void *obs, int obs_fmt);
 
 /* ---- virtual_step(game, model)  utils.jl:112-132 ------------------------------------------ */
 /* next_is_suicidal for the CURRENT state: for each available action, would step! lose?
  * trues(3) for a lost env.  Includes the history-length rule (all true after 499 steps). */
 SNK_API int snk_losing_mask(snk_handle h, uint8_t *mask_3xN);
+SNK_API int snk_losing_mask_host(snk_handle h, uint8_t *mask_3xN_host);
 
 /* ---- epsilon_greedy(game, model, eps)  utils.jl:153-172 ----------------------------------- */
 /* out[i] = ridx[i] if u[i] < eps else argmax(q[:,i]) (Julia argmax: first maximum, NaN wins). */
@@ -163,6 +180,11 @@ SNK_API int snk_get_score(snk_handle h, int32_t *score);          /* game.score 
 SNK_API int snk_get_done(snk_handle h, uint8_t *done);            /* game.lost   structs.jl:28 */
 SNK_API int snk_get_error_flags(snk_handle h, uint8_t *flags);    /* SNK_ENV_ERR_* */
 SNK_API int snk_get_steps(snk_handle h, int32_t *steps);          /* steps taken in the current episode */
+/* the same into HOST arrays (game.score / game.lost as a Julia host reads them); return when the data has arrived */
+SNK_API int snk_get_score_host(snk_handle h, int32_t *score_host);
+SNK_API int snk_get_done_host(snk_handle h, uint8_t *done_host);
+SNK_API int snk_get_error_flags_host(snk_handle h, uint8_t *flags_host);
+SNK_API int snk_get_steps_host(snk_handle h, int32_t *steps_host);
 /* number of envs with any error bit set (synchronises) */
 SNK_API int snk_count_errors_host(snk_handle h, int64_t *count);
 
@@ -186,6 +208,14 @@ SNK_API int snk_step_fused_store(snk_handle h, snk_replay r, const float *q, flo
 SNK_API int snk_replay_gather(snk_replay r, const int64_t *idx, int64_t B, float *states, float *next_states,
                               uint8_t *actions, float *rewards, uint8_t *dones, uint8_t *mask, float *ep_return,
                               int32_t *score, void *cuda_stream);
+/* host-buffer forms: the fused step + store! with HOST buffers (asynchronous like snk_step_fused_host), and stack_exp of
+ * the slots idx_host[0..B) into HOST arrays (expanded to Float32 on the device, 1,613 B per sample over PCIe; returns
+ * when the data has arrived) — together the data path of one train! iteration (utils.jl:436-443) for a host trainer */
+SNK_API int snk_step_fused_store_host(snk_handle h, snk_replay r, const float *q, float eps, const float *u,
+                                      const uint8_t *ridx, uint8_t *act_idx, float *reward, uint8_t *done, void *obs,
+                                      int obs_fmt, uint8_t *mask, float *ep_return, int32_t *ep_score);
+SNK_API int snk_replay_gather_host(snk_replay r, const int64_t *idx_host, int64_t B, float *states, float *next_states,
+                                   uint8_t *actions, float *rewards, uint8_t *dones, uint8_t *mask, void *cuda_stream);
 SNK_API int snk_replay_sample_indices(snk_replay r, uint64_t seed, int64_t B, int64_t *idx_out, void *cuda_stream);
 SNK_API int snk_replay_bad_index_host(snk_replay r, int *flag);
 
@@ -193,17 +223,26 @@ SNK_API int snk_replay_bad_index_host(snk_replay r, int *flag);
  * Conv(3x3,2=>16,relu,pad 1) -> Conv(3x3,16=>32,relu,pad 1) -> Conv(6x6,32=>64,relu) -> flatten -> Dense(1600,64,relu)
  * -> Dense(64,3), Flux semantics (true convolution, WHCN, column-major flatten).  theta_host = Flux.destructure(q_net)
  * (181,395 Float32: per layer weight then bias, column-major) as compute_D.jl:43,68 takes it.  obs: (10,10,2,N) f32 as
- * snk_state / snk_step_fused emit it; q_out: (3,N) f32.  tcgen05 implicit-GEMM convolutions, bf16 operands, FP32
- * accumulation.  The environment variable SNK_QNET_ENGINE, read by snk_qnet_create, selects the convolution kernel:
- * 17 (default; conv3 weights stationary in tensor memory), 16 or 12 (earlier engines, same results within the stated
- * tolerance; kept for comparison). */
+ * snk_state / snk_step_fused emit it; q_out: (3,N) f32.  tcgen05 implicit-GEMM convolutions with FP32 accumulation;
+ * `precision` chooses the operand format:
+ *   SNK_QNET_F32   Float32-faithful (the reference network is Float32): weights and activations as fp16 (hi, lo) pairs
+ *                  = 22 significant bits, all four partial products on the tensor cores.  Stated tolerance against a
+ *                  Float64 evaluation: 2e-5 of max|Q|; argmax identical to it wherever the top-2 gap exceeds 1e-4 of
+ *                  max|Q|.  Activations must stay inside the fp16 range (|x| <= 65504): snk_qnet_overflow_host tells.
+ *   SNK_QNET_BF16  bf16 operands: 3-4x faster, 1.5e-2 of max|Q| — a greedy action can differ from the reference's; for
+ *                  throughput studies, not for parity. */
+#define SNK_QNET_BF16 0
+#define SNK_QNET_F32 1
 typedef struct snk_qnet_s *snk_qnet;
-SNK_API int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device);
+SNK_API int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device, int precision);
 SNK_API int snk_qnet_destroy(snk_qnet q);
 SNK_API int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3xN, void *cuda_stream);
-/* profiling aid: device buffer of 512 int64 that receives clock64 stamps of the conv phases of CTA 0 on every later
- * forward (engine 17: 64 slots for each of its first 8 iterations, tools/qnet_phases17.py; engines 12/16: 8 slots per
- * iteration, tools/qnet_phases.py); NULL switches it off */
+SNK_API int snk_qnet_precision(snk_qnet q, int *precision);
+/* SNK_QNET_F32: *flag = 1 if a forward since the last call produced an activation outside the fp16 range (its Q-values are
+ * then not valid); reads and clears the flag, synchronises the device */
+SNK_API int snk_qnet_overflow_host(snk_qnet q, int *flag);
+/* profiling aid (SNK_QNET_BF16): device buffer of 512 int64 that receives clock64 stamps of the conv phases of CTA 0 on every
+ * later forward (64 slots for each of its first 8 iterations, tools/qnet_phases17.py); NULL switches it off */
 SNK_API int snk_qnet_debug_timing(snk_qnet q, long long *device_buf);
 
 /* ---- Laplace deviation matrix  compute_D.jl:9-31, 66-81; la_utils.jl:14-36, 154-169 -------- */

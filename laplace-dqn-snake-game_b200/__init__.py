@@ -63,6 +63,12 @@ def lib():
         "snk_rollout_fused": [vp, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp],
         "snk_host_alloc": [C.POINTER(vp), C.c_size_t], "snk_host_free": [vp],
         "snk_state": [vp, vp, i32], "snk_losing_mask": [vp, vp],
+        "snk_state_host": [vp, vp, i32], "snk_losing_mask_host": [vp, vp], "snk_available_actions_host": [vp, vp],
+        "snk_patch_reset_obs": [vp, vp, vp, i32],
+        "snk_get_score_host": [vp, vp], "snk_get_done_host": [vp, vp], "snk_get_error_flags_host": [vp, vp],
+        "snk_get_steps_host": [vp, vp],
+        "snk_step_fused_store_host": [vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp],
+        "snk_replay_gather_host": [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp],
         "snk_select_action": [vp, vp, f32, vp, vp, vp],
         "snk_masked_target": [vp, vp, vp, vp, f64, f32, vp, vp, i64, vp],
         "snk_get_score": [vp, vp], "snk_get_done": [vp, vp], "snk_get_error_flags": [vp, vp],
@@ -76,8 +82,9 @@ def lib():
         "snk_replay_gather": [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "snk_replay_sample_indices": [vp, C.c_uint64, i64, vp, vp],
         "snk_replay_bad_index_host": [vp, C.POINTER(i32)],
-        "snk_qnet_create": [C.POINTER(vp), vp, i64, i32], "snk_qnet_destroy": [vp],
-        "snk_qnet_forward": [vp, vp, i64, vp, vp],
+        "snk_qnet_create": [C.POINTER(vp), vp, i64, i32, i32], "snk_qnet_destroy": [vp],
+        "snk_qnet_forward": [vp, vp, i64, vp, vp], "snk_qnet_precision": [vp, C.POINTER(i32)],
+        "snk_qnet_overflow_host": [vp, C.POINTER(i32)], "snk_qnet_debug_timing": [vp, vp],
         "snk_gram_workspace_bytes": [i64, i64, i32, C.POINTER(C.c_size_t)],
         "snk_gram_pack": [vp, i32, i64, i64, vp, vp],
         "snk_gram": [vp, i64, i64, i32, i32, i32, vp, vp],
@@ -268,23 +275,58 @@ class SnakeGame:
                                        _ptr(out.get("mask")), _ptr(out.get("ep_return")), _ptr(out.get("ep_score"))))
         return out
 
-    def step_fused_host(self, host, q=False, eps=0.0):
+    def step_fused_host(self, host, q=False, eps=0.0, replay=None):
         """Same through HOST (pinned) tensors: `host` is a dict of CPU tensors with the keys of
-        alloc_outputs() plus the inputs ('act_idx', or 'q' [+ 'u', 'ridx'])."""
+        alloc_outputs() plus the inputs ('act_idx', or 'q' [+ 'u', 'ridx']).  ASYNCHRONOUS: call sync() before
+        reading an output or overwriting an input.  replay: also store! every transition into the device ring."""
         fmt = _OBS[host["obs_fmt"]][0] if host.get("obs") is not None else OBS_NONE
         g = lambda k: _ptr(host.get(k))
-        _check(lib().snk_step_fused_host(
-            self._h, g("q") if q else None, float(eps), g("u") if q else None, g("ridx") if q else None,
-            g("act_idx"), g("reward"), g("done"), g("obs"), fmt, g("mask"), g("ep_return"), g("ep_score")))
+        args = (g("q") if q else None, float(eps), g("u") if q else None, g("ridx") if q else None,
+                g("act_idx"), g("reward"), g("done"), g("obs"), fmt, g("mask"), g("ep_return"), g("ep_score"))
+        if replay is None:
+            _check(lib().snk_step_fused_host(self._h, *args))
+        else:
+            _check(lib().snk_step_fused_store_host(self._h, replay._r, *args))
         return host
 
     # -- utils.jl:135-149 -----------------------------------------------------------------------
-    def assemble_state(self, fmt="f32"):
+    def assemble_state(self, fmt="f32", out=None):
         """(board_{t-1}, board_t) of every env: (N,2,10,10) [= Julia (10,10,2,N)]"""
         code, dt, per = _OBS[fmt]
-        out = self._new((self.n, 2, 10, 10) if per == 200 else (self.n, per), dt)
-        _check(lib().snk_state(self._h, _ptr(out), code))
+        if out is None:
+            out = self._new((self.n, 2, 10, 10) if per == 200 else (self.n, per), dt)
+        _check(lib().snk_state(self._h, _ptr(out, dt, self.n * per, self.device), code))
         return out
+
+    def patch_reset_obs(self, done, obs, fmt="f32"):
+        """rows of `obs` (a step's next_state output) of the envs that step re-initialised become (init, init): obs then is
+        the acting state of the next step (snk_patch_reset_obs)"""
+        code, dt, per = _OBS[fmt]
+        _check(lib().snk_patch_reset_obs(self._h, _ptr(done, torch.uint8, self.n, self.device),
+                                         _ptr(obs, dt, self.n * per, self.device), code))
+        return obs
+
+    # host-array forms of the per-call API (what a Julia host calls where the reference reads a field of `game`)
+    def _host(self, fn, shape, dtype, *extra):
+        out = torch.empty(shape, dtype=dtype)
+        _check(fn(self._h, C.c_void_p(out.data_ptr()), *extra))
+        return out
+
+    def assemble_state_host(self, fmt="f32"):
+        code, dt, per = _OBS[fmt]
+        return self._host(lib().snk_state_host, (self.n, 2, 10, 10) if per == 200 else (self.n, per), dt, code)
+
+    def virtual_step_host(self):
+        return self._host(lib().snk_losing_mask_host, (self.n, 3), torch.uint8)
+
+    def available_actions_host(self):
+        return self._host(lib().snk_available_actions_host, (self.n, 3), torch.uint8)
+
+    def score_host(self):
+        return self._host(lib().snk_get_score_host, (self.n,), torch.int32)
+
+    def lost_host(self):
+        return self._host(lib().snk_get_done_host, (self.n,), torch.uint8)
 
     # -- utils.jl:112-132 -----------------------------------------------------------------------
     def virtual_step(self):
@@ -487,6 +529,20 @@ class ReplayBuffer:
 
     def sample(self):
         return self.stack_exp(self.sample_indices())
+
+    def stack_exp_host(self, idx_host, out=None):
+        """stack_exp for 0-based slots given as a CPU int64 tensor, into HOST tensors (pinned if `out` holds pinned
+        tensors): what a host-side trainer receives per minibatch (utils.jl:442-443).  Returns when the data is there."""
+        B = idx_host.numel()
+        if out is None:
+            out = {"states": torch.empty(B, 2, 10, 10, dtype=torch.float32), "next_states": torch.empty(B, 2, 10, 10, dtype=torch.float32),
+                   "actions": torch.empty(B, dtype=torch.uint8), "rewards": torch.empty(B, dtype=torch.float32),
+                   "dones": torch.empty(B, dtype=torch.uint8), "mask": torch.empty(B, 3, dtype=torch.uint8)}
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        p = lambda k: C.c_void_p(out[k].data_ptr())
+        _check(lib().snk_replay_gather_host(self._r, C.c_void_p(idx_host.data_ptr()), B, p("states"), p("next_states"),
+                                            p("actions"), p("rewards"), p("dones"), p("mask"), st))
+        return out
 
     def bad_index(self):
         f = C.c_int(0)

@@ -149,9 +149,3 @@ def destructure(layers):
         if kind in ("conv", "dense"):
             parts += [p["W"].reshape(-1, order="F"), p["b"].reshape(-1, order="F")]
     return np.concatenate(parts)
-
-
-def conv_weight_to_torch(W):
-    """Flux (k1,k2,cin,cout) true-convolution kernel -> torch cross-correlation weight [cout,cin,kh,kw] for
-    inputs stored (N,C,d2,d1):  wt[o,c,kh,kw] = W[K1-1-kw, K2-1-kh, c, o]."""
-    return np.ascontiguousarray(np.transpose(W[::-1, ::-1, :, :], (3, 2, 1, 0)))

@@ -26,4 +26,20 @@ int fail(int code, const char *fmt, ...);
 
 typedef unsigned long long u64;
 
+// Every ABI entry runs on its handle's device and leaves the caller's current device as it found it (a process driving
+// several GPUs, e.g. from torch, must not have its device changed behind its back).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != device) prev = cur;
+        cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 }  // namespace snk

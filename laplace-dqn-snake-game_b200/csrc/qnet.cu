@@ -6,25 +6,34 @@
 // Flux's Conv is a true convolution over WHCN arrays: with the kernel flipped once on the host,
 //   out(x, y, o) = b[o] + sum_{k1,k2,c} Wf[k1,k2,c,o] * in_pad(x + k1, y + k2, c),   x = Julia dim 1, y = dim 2.
 //
-// Kernel A (k_qnet_convs): the three convolutions for S samples per CTA iteration, activations never leave
-// shared memory.  Every conv is an implicit GEMM on tcgen05 WITHOUT im2col: activations are stored
-// "chunk-planar" ([8-channel chunk][pixel][8 x bf16], the no-swizzle K-major canonical layout, one 16-byte row
-// per pixel), so the A operand of kernel offset (k1,k2) is the same plane read at a start address shifted by a
+// Kernel A: the three convolutions for 16 sample slots per CTA iteration, activations never leave shared memory.
+// Every conv is an implicit GEMM on tcgen05 WITHOUT im2col: activations are stored "chunk-planar"
+// ([8-channel chunk][pixel][sample slot][8 x 16-bit], the no-swizzle K-major canonical layout, one 16-byte row per
+// pixel-sample), so the operand of kernel offset (k1,k2) is the same plane read at a start address shifted by a
 // constant number of pixels — a different shared-memory descriptor, no data movement:
-//   conv1:       2 input channels, 1 % of the FLOPs: CUDA cores, straight from the Float32 observations, run by the
-//                otherwise idle warps while the tensor core works through conv3 of the previous iteration;
-//   conv2:       rows = 128 consecutive pixels of the zero-padded 12x12 grids of the S samples (shift = 12 k2 + k1);
-//   conv3:       pixels are stored [y][sample][x], rows = 8-pixel groups at a 10-pixel pitch (stride byte offset
-//                160 B) over (y, sample), shift = 10 S k2 + k1; its 147 KB of weights stream through a 2-slot ring
-//                of k2-slices (cp.async.bulk + mbarrier) while 4-5 accumulator tiles stay live in TMEM.
-//   Epilogues (tcgen05.ld -> bias, relu -> bf16) write the next layer's operand plane directly.
-// Kernel B (k_qnet_head): Dense(1600,64,relu) as a TMA/tcgen05 GEMM over the conv3 activations (one 3.2 KB
-// bf16 row per sample, written by kernel A in the order the packed dense weight expects) with Dense(64,3) fused
+//   conv1: 2 input channels, 1 % of the FLOPs: CUDA cores, straight from the Float32 observations, run by otherwise idle
+//          warps while the tensor core works through conv3 of the previous iteration;
+//   conv2: rows (M) = 128 consecutive (pixel, slot) positions of the zero-padded 12x12 grids, shift = (12 k2 + k1) * 16;
+//   conv3: the WEIGHTS are the M operand (two kernel rows stacked: lanes 0..63 = 64 output channels of k2 = 2j, lanes
+//          64..127 = those of k2 = 2j+1), N = 80 = 5 output columns x 16 slots of one input row.
+// Kernel B (k_qnet_head): Dense(1600,64,relu) as a TMA/tcgen05 GEMM over the conv3 activations with Dense(64,3) fused
 // into its epilogue.
-// Precision: bf16 operands, FP32 accumulation (the reference is Float32) — tolerance in tests/test_qnet_gpu.py.
+//
+// Two precisions (snk_qnet_create's `precision` argument):
+//   SNK_QNET_BF16 (engine 17, k_qnet_convs17): bf16 operands, FP32 accumulation, conv3 weights stationary in tensor
+//          memory; the fast mode (1.5e-2 of max|Q| against Float64 — NOT the reference's Float32 fidelity).
+//   SNK_QNET_F32  (k_qnet_convs_split): Float32-faithful.  Every weight and every activation is split into two fp16 numbers
+//          (x = hi + lo, 22 significant bits) and all four partial products go through the tensor cores with FP32
+//          accumulation:  the two halves of an ACTIVATION live in two different sample slots (slot s = hi of sample s,
+//          slot s + 8 = 2^11 * lo of sample s; the layers are linear up to the epilogue, so the slots are simply two
+//          independent "virtual samples" whose accumulators the epilogue adds: real = acc[s] + 2^-11 acc[s + 8]), the two
+//          halves of a WEIGHT are two MMAs into the same accumulator (lo first, so that the tensor core's truncating
+//          FP32 accumulation hits the small terms while the accumulator is small).  8 real samples per iteration, 4x the
+//          MMAs of the bf16 mode per sample; conv1 and Dense(64,3) are plain FP32 FMAs.  Tolerance: tests/test_qnet_gpu.py.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,38 +45,23 @@
 namespace snk {
 namespace qnet {
 
-constexpr int S = 12;                         // samples per CTA iteration
-constexpr int THREADS = 512;                  // warps 0,1 MMA issuers, warp 2 weight producer, warps 4..15 = 3 epilogue groups
+constexpr int THREADS = 512;                  // split engine: warps 0,1 MMA issuers, warp 2 weight producer, warps 4..15 = 3 epilogue groups
 constexpr int PIX12 = 144;                    // padded 12x12 grid
-constexpr int ROWS12 = S * PIX12;             // 1728 flat positions per iteration
-constexpr int TILES12 = (ROWS12 + 127) / 128; // 14
-constexpr int A0_PIX = TILES12 * 128 + 32;    // + room for the largest shift (26) of the last tile
-constexpr int A2_PIX = ((5 * S + 15) / 16) * 160 + 5 * S * 10 + 16;   // groups of the last tile + largest shift
-constexpr int TILES3 = (5 * S + 15) / 16;     // 4 accumulator tiles of 16 (y, sample) groups
-constexpr int W3_SLICE = 6 * 2 * 2048;        // one k2 slice of the conv3 weights
-constexpr int OFF_A1 = 0;
-constexpr int OFF_A2 = OFF_A1 + 2 * A0_PIX * 16;
-constexpr int OFF_W1 = OFF_A2 + 4 * A2_PIX * 16;          // conv1 weights, fp32 [tap = k2*3+k1][c][o] (flipped), 1152 B
-constexpr int OFF_W2 = OFF_W1 + 18 * 16 * 4;
-constexpr int OFF_W3 = OFF_W2 + 9 * 1024;
-constexpr int OFF_BIAS = OFF_W3 + 2 * W3_SLICE;          // b1 (16) b2 (32) b3 (64) f32
-constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
-constexpr int SMEM_A = OFF_BAR + 256 + 128;              // barriers (17 x 8 B + TMEM slot) + alignment slack
-static_assert(SMEM_A <= 232448, "kernel A shared memory over the 227 KB limit");
-#ifndef QNET_SEQ_CONV1
-#define QNET_SEQ_CONV1 0
-#endif
-constexpr int NISSUE = 2;                                // MMA-issuing threads (lane 0 of warps 0 and 1, two schedulers):
-                                                         // with 32-cycle MMAs one thread cannot issue fast enough
-constexpr int NGRP = 3;                                  // epilogue groups of 4 warps (one per TMEM lane quarter): conv2 is
-                                                         // bound by the fixed latency of its per-tile epilogue
-constexpr int NACC = 6;                                  // accumulator buffers cycled by the conv1 / conv2 tiles
-constexpr int TMEM_C3 = 0, TMEM_C2 = 256;                // column offsets: conv3 4 x 64 | conv2 NACC x 32 (256 + 192 <= 512)
+constexpr int NISSUE = 2;                     // MMA-issuing warps (two schedulers): with small MMAs one thread cannot issue fast enough
+constexpr int NGRP = 3;                       // epilogue groups of 4 warps (one per TMEM lane quarter)
 
 // packed parameter blob (device): byte offsets
-constexpr size_t P_W1 = 0, P_W2 = P_W1 + 18 * 16 * 4, P_W3 = P_W2 + 9 * 1024, P_BIAS = P_W3 + 6 * (size_t)W3_SLICE;
-constexpr size_t P_W4 = P_BIAS + 112 * 4;                // [64][1600] bf16, columns in kernel-A order
-constexpr size_t P_B4 = P_W4 + 64 * 1600 * 2, P_W5 = P_B4 + 64 * 4, P_B5 = P_W5 + 3 * 64 * 4, P_W3B = P_B5 + 16, P_END = P_W3B + 36 * 4096;   // P_W3B: conv3 weights as stacked-tap M operands (engine 16)
+constexpr size_t P_W1 = 0;                                   // conv1 weights fp32 [tap = k2*3+k1][c][o] (flipped), host-side source of the kernel params
+constexpr size_t P_W2 = P_W1 + 18 * 16 * 4;                  // bf16 [k2][k1][chunk (2)][o (32)][8]
+constexpr size_t P_BIAS = P_W2 + 9 * 1024;                   // b1 (16) b2 (32) b3 (64) f32
+constexpr size_t P_W4 = P_BIAS + 112 * 4;                    // [64][1600] bf16, columns in kernel-A order
+constexpr size_t P_B4 = P_W4 + 64 * 1600 * 2, P_W5 = P_B4 + 64 * 4, P_B5 = P_W5 + 3 * 64 * 4;
+constexpr size_t P_W3B = P_B5 + 16;                          // bf16 conv3 weights as 36 stacked-tap M operands of 4 KB
+// Float32-faithful mode: fp16 (lo, hi) pairs of the same layouts
+constexpr size_t P_S_W2 = P_W3B + 36 * 4096;                 // [part (lo, hi)][k2][k1][chunk][o][8] fp16
+constexpr size_t P_S_W3 = P_S_W2 + 2 * 9 * 1024;             // 72 blocks of 4 KB: 36 lo blocks, then 36 hi blocks
+constexpr size_t P_S_W4 = P_S_W3 + 72 * 4096;                // [64][3200] fp16: columns [0,1600) = lo, [1600,3200) = hi
+constexpr size_t P_END = P_S_W4 + 64 * 3200 * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -147,336 +141,51 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b, 0.f));
     return *reinterpret_cast<uint32_t *>(&h);
 }
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {      // a_format = b_format = 0 (F16), FP32 accumulator
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 struct ConvArgs {
     const float *obs;            // (10,10,2,N) f32
     long long n;
     const uint8_t *params;       // packed blob
     __nv_bfloat16 *out3;         // [N][1600] bf16: k' = (oy*5 + ox)*64 + c
-    long long *timing;           // optional (debug): per-phase clock64 stamps of block 0, 8 per iteration
+    long long *timing;           // optional (debug): clock64 stamps of block 0
     // conv1 weights [tap = k2*3+k1][c][o] (flipped) and bias, by value: kernel parameters sit in the constant bank, so
     // the FMAs of the CUDA-core conv1 take them as constant operands — no shared-memory traffic to fight the tensor
     // core's operand fetch with
     __half2 w1h[144];            // [tap*2 + c][o/2]: fp16 pairs for the packed HFMA2 path (inputs are -1..2 exactly; fp16
     __half2 b1h[8];              // accumulation over 18 taps errs ~1e-3, below the bf16 rounding of the result)
 };
-#define QNET_STAMP(k) do { if (a.timing != nullptr && blockIdx.x == 0 && tid == 128) a.timing[it_local * 8 + (k)] = clock64(); } while (0)
+// Float32-faithful mode
+struct SplitArgs {
+    const float *obs;            // (10,10,2,N) f32
+    long long n;
+    const uint8_t *params;
+    __half *out3;                // [2 N][1600] fp16: row 2 s = hi, row 2 s + 1 = 2^11 * lo of sample s; k' = (oy*5 + ox)*64 + c
+    int *overflow;               // set to 1 when an activation left the fp16 range (|x| > 65504): the result is not valid
+    float w1f[288];              // conv1 weights [tap*2 + c][o] fp32 (constant-bank FFMA operands)
+    float b1f[16];
+};
 
-// conv1 (2 -> 16 channels, 3x3, pad 1, relu) of S samples starting at s0 on the CUDA cores, straight from the
-// Float32 observations into conv2's operand plane A1 (padded 12x12 grids, chunk-planar bf16), by threads [t, t+nt).
-// It is 1 % of the network's FLOPs but cost 20 % of the time as 16-column MMAs (operand-fetch bound), and the
-// warps that run it are otherwise idle while the tensor core works through conv3 of the previous iteration.
-// the 18 input taps of pixel item i (clamped address + select, no branches: all loads in flight together)
-__device__ __forceinline__ void conv1_taps(const ConvArgs &a, long long s0, int i, float (&v)[18]) {
-    const int s = i / 100, p = i - s * 100;                     // p = x + 10 y   (Julia (r, c) = (x, y))
-    const int y = p / 10, x = p - 10 * y;
-    const bool live = (s0 + s) < a.n;
-    const float *ob = a.obs + (live ? (s0 + s) : 0) * 200;
-#pragma unroll
-    for (int k2 = 0; k2 < 3; k2++)
-#pragma unroll
-        for (int k1 = 0; k1 < 3; k1++) {
-            const int xx = x + k1 - 1, yy = y + k2 - 1;
-            const bool ok = live && xx >= 0 && xx <= 9 && yy >= 0 && yy <= 9;
-            const int off = ok ? yy * 10 + xx : 0;
-            const float t0 = __ldg(ob + off), t1 = __ldg(ob + 100 + off);
-            v[(k2 * 3 + k1) * 2] = ok ? t0 : 0.f;
-            v[(k2 * 3 + k1) * 2 + 1] = ok ? t1 : 0.f;
-        }
-}
-__device__ __forceinline__ void conv1_cuda(const ConvArgs &a, long long s0, uint8_t *A1, int t, int nt) {
-    // software pipeline: the taps of the thread's next pixel are loading while this pixel is computed
-    float v[18], vn[18];
-    if (t < S * 100) conv1_taps(a, s0, t, v);
-    for (int i = t; i < S * 100; i += nt) {
-        if (i + nt < S * 100) conv1_taps(a, s0, i + nt, vn);
-        const int s = i / 100, p = i - s * 100;
-        const int y = p / 10, x = p - 10 * y;
-        __half2 acc2[8];
-#pragma unroll
-        for (int o = 0; o < 8; o++) acc2[o] = a.b1h[o];
-#pragma unroll
-        for (int k = 0; k < 18; k++) {
-            const __half2 vv = __float2half2_rn(v[k]);
-#pragma unroll
-            for (int o = 0; o < 8; o++) acc2[o] = __hfma2(vv, a.w1h[k * 8 + o], acc2[o]);
-        }
-        float acc[16];
-#pragma unroll
-        for (int o = 0; o < 8; o++) { const float2 f = __half22float2(acc2[o]); acc[2 * o] = f.x; acc[2 * o + 1] = f.y; }
-        uint32_t w[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) w[j] = pack_relu_bf16(acc[2 * j], acc[2 * j + 1]);
-        uint8_t *dst = A1 + (s * PIX12 + (y + 1) * 12 + (x + 1)) * 16;
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4 *>(dst + A0_PIX * 16) = make_uint4(w[4], w[5], w[6], w[7]);
-#pragma unroll
-        for (int k = 0; k < 18; k++) v[k] = vn[k];
-    }
-}
-
-__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs(const __grid_constant__ ConvArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    uint8_t *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
-    const float *bias = (const float *)(smem + OFF_BIAS);
-    uint64_t *bars = (uint64_t *)(smem + OFF_BAR);
-    uint64_t *acc_full = bars, *acc_empty = bars + NACC, *w3_full = bars + 2 * NACC, *w3_empty = w3_full + 2, *c3_full = w3_empty + 2;
-    uint32_t *tmem_slot = (uint32_t *)(c3_full + 1);
-    uint64_t *a1_full = c3_full + 2;          // the overlapped conv1 has staged the next iteration's A1 (7 warps arrive)
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // ---- one-time setup: zero the activation planes (borders stay zero), stage W1 (fp32), W2 (bf16), biases
-    for (int i = tid; i < OFF_W1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < (int)(P_W3 / 16); i += THREADS)
-        reinterpret_cast<uint4 *>(smem + OFF_W1)[i] = reinterpret_cast<const uint4 *>(a.params)[i];
-    for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
-    if (tid == 0) {
-        for (int i = 0; i < NACC; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
-        for (int i = 0; i < 2; i++) { mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], NISSUE); }
-        mbar_init(c3_full, NISSUE);
-        mbar_init(a1_full, 7);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
-    __syncthreads();
-    const long long n_iter = (a.n + S - 1) / S;
-    if (blockIdx.x < n_iter) conv1_cuda(a, (long long)blockIdx.x * S, A1, tid, THREADS);   // first iteration's conv1
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    // constant parts of the operand descriptors; the start-address field counts 16-byte units = pixels
-    const uint64_t dA1 = desc_nosw(smem_u32(A1), A0_PIX * 16, 128);          // conv2: K chunks = the two channel planes
-    const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PIX * 16, 160);          // conv3: 8-pixel groups at a 10-pixel pitch
-    const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);
-    const uint64_t dW3 = desc_nosw(smem_u32(smem + OFF_W3), 1024, 128);
-
-    // pipeline counters (every thread keeps the same values)
-    uint32_t acc_it = 0;       // accumulator-buffer uses so far (conv2 tiles)
-    uint32_t w3_it = 0;        // W3 slices so far
-    uint32_t c3_it = 0;
-
-    long long it_local = 0;
-    for (long long it = blockIdx.x; it < n_iter; it += gridDim.x, it_local++) {
-        const long long s0 = it * S;
-        QNET_STAMP(0);
-        if (warp == 2 && lane == 0) {
-            // conv3 weight producer, part 1: the first two k2-slices fill the 2-slot ring now and land while
-            // conv2 runs (the remaining four follow in the conv3 phase)
-            for (int k2 = 0; k2 < 2; k2++) {
-                const uint32_t u = w3_it + k2;
-                const int b = u & 1;
-                mbar_wait(&w3_empty[b], ((u >> 1) & 1) ^ 1);
-                mbar_expect_tx(&w3_full[b], W3_SLICE);
-                bulk_load(smem + OFF_W3 + b * W3_SLICE, a.params + P_W3 + (size_t)k2 * W3_SLICE, W3_SLICE, &w3_full[b]);
-            }
-        }
-        QNET_STAMP(1);
-        QNET_STAMP(2);
-
-        // ================= conv2: 16 -> 32, 3x3, pad 1 =================
-        if (warp < NISSUE) {
-            if (lane == 0) {
-                // There is no block barrier at the end of an iteration: these MMAs queue up behind conv3's while the
-                // epilogue warps are still draining the conv3 accumulators.  A1 comes from the overlapped conv1.
-                if (!QNET_SEQ_CONV1 && it_local > 0) mbar_wait(a1_full, (uint32_t)(it_local - 1) & 1);
-                for (int t = 0; t < TILES12; t++) {
-                    const uint32_t u = acc_it + t;
-                    if ((int)(u % NISSUE) != warp) continue;      // issuer w owns the tiles (and accumulator buffers) of its parity
-                    const int b = u % NACC;
-                    mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d = tmem + TMEM_C2 + b * 32;
-                    const uint64_t at = dA1 + (uint64_t)(t * 128);
-#pragma unroll
-                    for (int k2 = 0; k2 < 3; k2++)
-#pragma unroll
-                        for (int k1 = 0; k1 < 3; k1++)
-                            umma_bf16(d, at + (uint64_t)(k2 * 12 + k1), dW2 + (uint64_t)((k2 * 3 + k1) * 64),
-                                      idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
-                    umma_commit(&acc_full[b]);
-                }
-            }
-        } else if (warp >= 4) {
-            const int grp = (warp - 4) >> 2, q = warp & 3;
-            for (int t = 0; t < TILES12; t++) {
-                const uint32_t u = acc_it + t;
-                if ((int)(u % NGRP) != grp) continue;
-                const int b = u % NACC;
-                mbar_wait(&acc_full[b], (u / NACC) & 1);
-                tc_fence_after();
-                uint32_t v[32];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C2 + b * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C2 + b * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[b]);
-                const int P = t * 128 + q * 32 + lane;
-                const int s = P / PIX12, rem = P - s * PIX12, y = rem / 12, x = rem - 12 * y;
-                if (P < ROWS12 && x < 10 && y < 10) {
-                    uint8_t *dst = A2 + ((y * S + s) * 10 + x) * 16;          // [y][sample][x]
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; c8++) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            w[j] = pack_relu_bf16(__uint_as_float(v[c8 * 8 + 2 * j]) + bias[16 + c8 * 8 + 2 * j],
-                                                  __uint_as_float(v[c8 * 8 + 2 * j + 1]) + bias[16 + c8 * 8 + 2 * j + 1]);
-                        *reinterpret_cast<uint4 *>(dst + c8 * (A2_PIX * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-            }
-        }
-        acc_it += TILES12;
-        fence_proxy_async();
-        __syncthreads();
-        QNET_STAMP(3);
-
-        // ================= conv3: 32 -> 64, 6x6, valid =================
-        if (warp < NISSUE) {
-            if (lane == 0) {
-                tc_fence_after();
-                for (int k2 = 0; k2 < 6; k2++) {
-                    const uint32_t u = w3_it + k2;
-                    const int b = u & 1;
-                    mbar_wait(&w3_full[b], (u >> 1) & 1);
-                    tc_fence_after();
-                    const uint64_t wb = dW3 + (uint64_t)(b * (W3_SLICE / 16));
-                    for (int tt = warp; tt < TILES3; tt += NISSUE) {     // each issuer owns its accumulator tiles
-                        const uint32_t d = tmem + TMEM_C3 + tt * 64;
-                        const uint64_t at = dA2 + (uint64_t)(tt * 160 + k2 * S * 10);
-#pragma unroll
-                        for (int k1 = 0; k1 < 6; k1++)
-#pragma unroll
-                            for (int m = 0; m < 2; m++)
-                                umma_bf16(d, at + (uint64_t)(k1 + 2 * m * A2_PIX), wb + (uint64_t)((k1 * 2 + m) * 128),
-                                          idesc_bf16(128, 64), (k2 | k1 | m) ? 1u : 0u);
-                    }
-                    umma_commit(&w3_empty[b]);
-                }
-                umma_commit(c3_full);
-            }
-        } else {
-            if (warp == 2 && lane == 0) {
-                // conv3 weight producer, part 2: slices 2..5 as the tensor core releases the ring slots
-                for (int k2 = 2; k2 < 6; k2++) {
-                    const uint32_t u = w3_it + k2;
-                    const int b = u & 1;
-                    mbar_wait(&w3_empty[b], ((u >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&w3_full[b], W3_SLICE);
-                    bulk_load(smem + OFF_W3 + b * W3_SLICE, a.params + P_W3 + (size_t)k2 * W3_SLICE, W3_SLICE, &w3_full[b]);
-                }
-            }
-            // while the tensor core works through conv3, warps 2..11 run the NEXT iteration's conv1 on the CUDA cores
-            // (A1 is free: this iteration's conv2 has been consumed)
-            // (only warps on the two schedulers without an MMA issuer: a busy scheduler slows the issuing thread)
-            if (!QNET_SEQ_CONV1 && (warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
-                const int w7 = warp == 3 ? 0 : 2 * ((warp - 4) >> 2) + (warp & 1) + 1;      // 3,6,7,10,11,14,15 -> 0..6
-                conv1_cuda(a, (it + gridDim.x) * S, A1, w7 * 32 + lane, 224);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a1_full);
-                if (a.timing != nullptr && blockIdx.x == 0 && warp == 15 && lane == 0) a.timing[it_local * 8 + 6] = clock64();
-            }
-            if (warp >= 4) {
-                const int grp = (warp - 4) >> 2, q = warp & 3;
-                mbar_wait(c3_full, c3_it & 1);
-                tc_fence_after();
-                QNET_STAMP(4);
-                for (int tt = grp; tt < TILES3; tt += NGRP) {
-                    const int r = q * 32 + lane, g = tt * 16 + (r >> 3), ox = r & 7;
-                    const int oy = g / S, s = g - oy * S;
-                    const bool valid = ox < 5 && oy < 5 && (s0 + s) < a.n;
-                    uint4 *dst = reinterpret_cast<uint4 *>(a.out3 + (s0 + s) * 1600 + (oy * 5 + ox) * 64);
-                    uint32_t v[64];
-#pragma unroll
-                    for (int h = 0; h < 4; h++)
-                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_C3 + tt * 64 + h * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[h * 16]));
-                    tmem_ld_wait();
-                    if (valid) {
-#pragma unroll
-                        for (int h = 0; h < 8; h++) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                w[j] = pack_relu_bf16(__uint_as_float(v[h * 8 + 2 * j]) + bias[48 + h * 8 + 2 * j],
-                                                      __uint_as_float(v[h * 8 + 2 * j + 1]) + bias[48 + h * 8 + 2 * j + 1]);
-                            dst[h] = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                    }
-                }
-                tc_fence_before();
-            }
-        }
-        w3_it += 6;
-        c3_it++;
-        // No barrier here in the overlapped build: A2 and the conv3 accumulators are handed over through c3_full (the
-        // epilogue warps pass it before they touch A2 again) and the barrier after the next conv2; A1 through a1_full.
-        if (QNET_SEQ_CONV1) {
-            fence_proxy_async();
-            __syncthreads();
-        }
-        QNET_STAMP(5);
-        if (QNET_SEQ_CONV1 && it + gridDim.x < n_iter) {
-            conv1_cuda(a, (it + gridDim.x) * S, A1, tid, THREADS);
-            fence_proxy_async();
-            __syncthreads();
-        }
-        QNET_STAMP(7);
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 512);
-    }
-}
-
-// ---- kernel A, engine 16: conv3 with the WEIGHTS as the M operand -------------------------------------------
-// The engine above is bound by the tensor core's shared-memory operand fetch: 6 KB per 128x64x16 MMA of which 5/8 of
-// the rows are real outputs.  Here 16 samples go through one iteration and conv3 is turned around:
+// ---- shared layout of the 16-slot engines ----------------------------------------------------------------------
+// 16 sample slots go through one iteration.  conv2's rows are [pixel of the padded 12x12 grid][slot] so that its epilogue
+// writes conv3's layout ([input row r][x][slot]) with consecutive lanes on consecutive 16-byte units.  conv3 is turned around:
 //   M = 128 = the 64 output channels of kernel row k2 = 2j (lanes 0..63) stacked on those of k2 = 2j+1 (lanes 64..127),
-//   N = 80  = the 5 output columns x 16 samples of ONE input row r (conv3's input is stored [r][x][sample], so the 5
-//             consecutive pixels starting at tap column k1 are 10 contiguous 8-sample core matrices),
+//   N = 80  = the 5 output columns x 16 slots of ONE input row r (the 5 consecutive pixels starting at tap column k1 are
+//             10 contiguous 8-slot core matrices),
 //   accumulator tile t (80 TMEM columns, t = 0..5) takes input rows r = t + 2j: its lower lanes hold the even-k2 part of
 //   output row t, its upper lanes the odd-k2 part of output row t-1;  out[y] = lower(T_y) + upper(T_{y+1}).
-// 6.5 KB of operands per 128x80x16 MMA with 5/6 of it useful: 1.7x more useful MACs per operand byte.  The six
-// accumulators fill 480 of the 512 TMEM columns, so conv2 (16 buffers x 32 columns) time-shares them: conv2 -> barrier ->
-// conv3 (+ next conv1 on the CUDA cores) -> conv3 epilogue -> barrier.  conv2's rows are [pixel][sample] so that its
-// epilogue writes conv3's layout with consecutive lanes on consecutive 16-byte units.
 namespace e16 {
 constexpr int S = 16;
-constexpr int ROWS12 = S * PIX12;             // 2304 flat positions [pixel][sample] = 18 tiles exactly
-constexpr int TILES12 = ROWS12 / 128;
+constexpr int ROWS12 = S * PIX12;             // 2304 flat positions [pixel][slot] = 18 tiles exactly
 constexpr int A1_PLANE = ROWS12 * 16;         // bytes per 8-channel plane; shifted reads of the last tile run into the
                                               // following plane / region (their rows are discarded outputs)
-constexpr int A2_PLANE = 100 * S * 16;        // [r][x][sample]
-#ifndef E16_NSLOT
-#define E16_NSLOT 8
-#endif
-#ifndef E16_NOLOAD
-#define E16_NOLOAD 0   /* timing experiment: skip the weight loads */
-#endif
-constexpr int NSLOT = E16_NSLOT;                      // ring of 4 KB conv3 weight blocks
-constexpr int NBLK = 36;                      // (j, k1, m) blocks per iteration
-constexpr int NACC = 16;                      // conv2 accumulator buffers (all 512 columns)
-constexpr int OFF_A1 = 0;
-constexpr int OFF_A2 = OFF_A1 + 2 * A1_PLANE;
-constexpr int OFF_W1 = OFF_A2 + 4 * A2_PLANE;
-constexpr int OFF_W2 = OFF_W1 + 18 * 16 * 4;
-constexpr int OFF_W3 = OFF_W2 + 9 * 1024;
-constexpr int OFF_BIAS = OFF_W3 + NSLOT * 4096;
-constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
-constexpr int SMEM = OFF_BAR + 512 + 128;
-static_assert(SMEM <= 232448, "engine 16 shared memory over the 227 KB limit");
-static_assert(5 * 80 * 64 * 4 <= 4 * A2_PLANE, "epilogue scratch must fit in the conv3 input planes");
-// B-descriptor offset (16-byte units) of weight block be = (j*6 + k1)*2 + m for tile 0: ((2j)*10 + k1)*S + 2m*(A2_PLANE/16)
-__constant__ uint32_t c_boff[NBLK] = {0, 3200, 16, 3216, 32, 3232, 48, 3248, 64, 3264, 80, 3280, 320, 3520, 336, 3536, 352, 3552, 368, 3568, 384, 3584, 400, 3600, 640, 3840, 656, 3856, 672, 3872, 688, 3888, 704, 3904, 720, 3920};
+constexpr int A2_PLANE = 100 * S * 16;        // [r][x][slot]
+// conv2 output rows are [pixel p = 12 y + x of the padded grid][slot]: the real outputs (y < 10) are p < 120, i.e. the first
+// 1920 rows = 15 tiles exactly; the last three tiles of the 12x12 grid (y = 10, 11) hold nothing and are not computed
+constexpr int TILES2 = 120 * S / 128;
+static_assert(TILES2 * 128 == 120 * S, "conv2 tiles must end on the last real output row");
 
 // conv1 on the CUDA cores, one thread per (sample, image row y, half row): the 3 x 7 x 2 input patch is loaded once (42
 // loads in flight together) and the five pixels are accumulated weight-major, so every conv1 weight is fetched from the
@@ -539,8 +248,116 @@ __device__ __forceinline__ void conv1_pixmajor(const ConvArgs &a, long long s0, 
         }
     }
 }
+}  // namespace e16
 
-__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_constant__ ConvArgs a) {
+// ---- kernel A, Float32-faithful mode: fp16 (hi, lo) split operands, weights streamed through shared memory ---------
+// 8 real samples per iteration occupy the 16 slots: slot s = fp16(x), slot s + 8 = fp16(2^11 (x - fp16(x))) of sample s's
+// activations x.  Both halves run through the same MMAs as two independent "virtual samples" (every layer is linear up to
+// its epilogue); the epilogue adds the two accumulators (real = acc[s] + 2^-11 acc[s+8]), applies bias and relu in FP32
+// and splits the result again for the next layer.  Each weight is two fp16 numbers as well (w = hi + lo, lo unscaled:
+// it shares the accumulator with hi): every MMA of the bf16 engines is issued twice, with the lo weights first.  Both
+// halves of the conv3 weights (2 x 147 KB) cannot stay in tensor memory, so they stream through a ring of 4 KB blocks
+// (cp.async.bulk + mbarrier), 72 blocks per iteration; the six 80-column conv3 accumulators fill 480 of the 512 TMEM
+// columns and conv2 (16 buffers x 32 columns) time-shares them:  conv2 -> barrier -> conv3 (+ next conv1 on the CUDA
+// cores) -> conv3 epilogue -> barrier.
+// Error budget against Float64 (tests/test_qnet_gpu.py): operands carry 22 bits (2^-22 relative each), products of fp16
+// numbers are exact in FP32, the accumulator adds with truncation (measured in round 1: ~3e-8 relative per MMA step;
+// 18 / 72 / 100 steps of the large terms per layer).  |activation| must stay below 65504 (fp16 range); the kernel
+// raises a flag otherwise (snk_qnet_overflow_host).
+namespace split {
+constexpr int S = e16::S, SR = 8;             // 16 slots = 8 real samples x (hi, lo)
+constexpr int A1_PLANE = e16::A1_PLANE, A2_PLANE = e16::A2_PLANE, TILES2 = e16::TILES2;
+constexpr int NSLOT = 8;                      // ring of 4 KB conv3 weight blocks
+constexpr int NBLK = 72;                      // (part, j, k1, m) blocks per iteration: 36 lo, then 36 hi
+constexpr int NACC = 16;                      // conv2 accumulator buffers (all 512 columns)
+constexpr int OFF_A1 = 0;
+constexpr int OFF_A2 = OFF_A1 + 2 * A1_PLANE;
+constexpr int OFF_W2 = OFF_A2 + 4 * A2_PLANE;
+constexpr int OFF_W3 = OFF_W2 + 2 * 9 * 1024;
+constexpr int OFF_BIAS = OFF_W3 + NSLOT * 4096;
+constexpr int OFF_BAR = OFF_BIAS + 112 * 4;
+constexpr int SMEM = OFF_BAR + 512 + 128;
+static_assert(SMEM <= 232448, "split engine shared memory over the 227 KB limit");
+static_assert(5 * 40 * 64 * 4 <= 4 * A2_PLANE, "epilogue scratch must fit in the conv3 input planes");
+static_assert(NBLK % NSLOT == 0 && NSLOT % 2 == 0, "the issuer waits for ring slots in aligned pairs");
+constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;      // 2^11: keeps the low halves in fp16's normal range
+// B-descriptor offset (16-byte units) of weight block be = (j*6 + k1)*2 + m for tile 0: ((2j)*10 + k1)*S + 2m*(A2_PLANE/16)
+__constant__ uint32_t c_boff[36] = {0, 3200, 16, 3216, 32, 3232, 48, 3248, 64, 3264, 80, 3280, 320, 3520, 336, 3536, 352, 3552, 368, 3568, 384, 3584, 400, 3600, 640, 3840, 656, 3856, 672, 3872, 688, 3888, 704, 3904, 720, 3920};
+
+// x >= 0 (after relu) -> the fp16 bits of its high half, or of 2^11 x its low half
+__device__ __forceinline__ unsigned short split_half(float r, bool want_lo) {
+    const __half h = __float2half_rn(r);
+    const __half l = __float2half_rn((r - __half2float(h)) * LO_SCALE);
+    return __half_as_ushort(want_lo ? l : h);
+}
+
+// conv1 (2 -> 16 channels, 3x3, pad 1, relu) of the 8 real samples starting at s0 in plain FP32 on the CUDA cores, one
+// thread per (sample, image row y, half row) as in e16::conv1_pixmajor, the 16 output channels in two passes of 8 (one
+// 16-byte unit of a chunk plane each) to stay inside the register budget.  A quarter warp = 8 samples of one half row, so
+// its 16-byte stores form conflict-free 128-byte wavefronts.  Writes both halves of conv2's operand plane A1.
+__device__ __forceinline__ void conv1_f32_split(const SplitArgs &a, long long s0, uint8_t *A1, int t, int nt, float &amax) {
+#pragma unroll 1
+    for (int item = t; item < SR * 20; item += nt) {
+        const int s = item & 7, r = item >> 3;
+        const int y = r >> 1, x0 = (r & 1) * 5;
+        const bool live = (s0 + s) < a.n;
+        const float *ob = a.obs + (live ? (s0 + s) : 0) * 200;
+        float in[3][7][2];                                       // [k2][column x0 - 1 + j][c]
+#pragma unroll
+        for (int k2 = 0; k2 < 3; k2++) {
+            const int yy = y + k2 - 1;
+            const bool rok = live && yy >= 0 && yy <= 9;
+            const float *row = ob + (rok ? yy * 10 : 0);
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                const int xx = x0 - 1 + j;
+                const bool ok = rok && xx >= 0 && xx <= 9;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const float f = __ldg(row + c * 100 + (ok ? xx : 0));
+                    in[k2][j][c] = ok ? f : 0.f;
+                }
+            }
+        }
+        uint8_t *dst = A1 + (((y + 1) * 12 + (x0 + 1)) * S + s) * 16;
+#pragma unroll
+        for (int o8 = 0; o8 < 2; o8++) {
+            float acc[5][8];
+#pragma unroll
+            for (int px = 0; px < 5; px++)
+#pragma unroll
+                for (int o = 0; o < 8; o++) acc[px][o] = a.b1f[o8 * 8 + o];
+#pragma unroll
+            for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+                for (int k1 = 0; k1 < 3; k1++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++)
+#pragma unroll
+                        for (int o = 0; o < 8; o++) {
+                            const float w = a.w1f[((k2 * 3 + k1) * 2 + c) * 16 + o8 * 8 + o];
+#pragma unroll
+                            for (int px = 0; px < 5; px++) acc[px][o] = fmaf(in[k2][px + k1][c], w, acc[px][o]);
+                        }
+#pragma unroll
+            for (int px = 0; px < 5; px++) {
+                uint32_t wh[4], wl[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float r0 = fmaxf(acc[px][2 * j], 0.f), r1 = fmaxf(acc[px][2 * j + 1], 0.f);
+                    amax = fmaxf(amax, fmaxf(r0, r1));
+                    wh[j] = (uint32_t)split_half(r0, false) | ((uint32_t)split_half(r1, false) << 16);
+                    wl[j] = (uint32_t)split_half(r0, true) | ((uint32_t)split_half(r1, true) << 16);
+                }
+                uint8_t *d = dst + px * S * 16 + o8 * A1_PLANE;
+                *reinterpret_cast<uint4 *>(d) = make_uint4(wh[0], wh[1], wh[2], wh[3]);               // slot s: high halves
+                *reinterpret_cast<uint4 *>(d + SR * 16) = make_uint4(wl[0], wl[1], wl[2], wl[3]);     // slot s + 8: low halves
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_constant__ SplitArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint8_t *A1 = smem + OFF_A1, *A2 = smem + OFF_A2;
@@ -550,10 +367,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
     uint32_t *tmem_slot = (uint32_t *)(c3_full + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int uwarp = __shfl_sync(0xffffffffu, warp, 0);      // the same value, provably warp-uniform for the compiler
+    float amax = 0.f;                                         // largest activation this thread has produced (fp16 range check)
 
     for (int i = tid; i < OFF_A2 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // A1 borders stay zero
-    for (int i = tid; i < (int)(P_W3 / 16); i += THREADS)
-        reinterpret_cast<uint4 *>(smem + OFF_W1)[i] = reinterpret_cast<const uint4 *>(a.params)[i];
+    for (int i = tid; i < 2 * 9 * 1024 / 16; i += THREADS)
+        reinterpret_cast<uint4 *>(smem + OFF_W2)[i] = reinterpret_cast<const uint4 *>(a.params + P_S_W2)[i];
     for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
     if (tid == 0) {
         for (int i = 0; i < NACC; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
@@ -563,42 +381,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     __syncthreads();
-    const long long n_iter = (a.n + S - 1) / S;
+    const long long n_iter = (a.n + SR - 1) / SR;
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const uint64_t dA1 = desc_nosw(smem_u32(A1), A1_PLANE, 128);             // conv2 A: 8-sample core matrices, contiguous
+    const uint64_t dA1 = desc_nosw(smem_u32(A1), A1_PLANE, 128);             // conv2 A: 8-slot core matrices, contiguous
     const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PLANE, 128);             // conv3 B (N operand): likewise
-    const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);
+    const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);       // + 576 (16-byte units): the hi half
     const uint64_t dW3 = desc_nosw(smem_u32(smem + OFF_W3), 2048, 128);      // conv3 A: 128 stacked rows, K chunks 2 KB apart
 
     uint32_t acc_it = 0, w3_it = 0, c3_it = 0;
     // The loop starts one pass early: pass -1 only runs the conv1 of the first real iteration, through the same (single)
-    // call site as the overlapped conv1 of every later pass — the kernel's code has to stay small (see conv1_pixmajor).
+    // call site as the overlapped conv1 of every later pass.
     long long it_local = -1;
     for (long long it = (long long)blockIdx.x - gridDim.x; it < n_iter; it += gridDim.x, it_local++) {
         const bool real = it_local >= 0;
-        const long long s0 = it * S;
-        if (real) QNET_STAMP(0);
+        const long long s0 = it * SR;
         if (real && warp == 2 && lane == 0) {
             // weight producer, part 1: fill the ring while conv2 runs
             for (int bi = 0; bi < NSLOT; bi++) {
                 const uint32_t u = w3_it + bi;
                 const int b = u % NSLOT;
                 mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
-                if (E16_NOLOAD) { mbar_arrive(&w3_full[b]); continue; }
                 mbar_expect_tx(&w3_full[b], 4096);
-                bulk_load(smem + OFF_W3 + b * 4096, a.params + P_W3B + (size_t)bi * 4096, 4096, &w3_full[b]);
+                bulk_load(smem + OFF_W3 + b * 4096, a.params + P_S_W3 + (size_t)bi * 4096, 4096, &w3_full[b]);
             }
         }
 
-        // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][sample] =================
+        // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][slot]; lo weights, then hi weights =================
         if (!real) {
         } else if (warp < NISSUE) {
             tc_fence_after();
-            for (int t = 0; t < TILES12; t++) {
+            for (int t = 0; t < TILES2; t++) {
                 const uint32_t u = acc_it + t;
                 if ((int)(u % NISSUE) != uwarp) continue;                   // issuer w owns the tiles of its parity
                 const int b = u % NACC;
@@ -608,18 +425,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
                 const uint64_t at = dA1 + (uint64_t)(t * 128);
                 if (elect_one()) {
 #pragma unroll
-                    for (int k2 = 0; k2 < 3; k2++)
+                    for (int part = 0; part < 2; part++)
 #pragma unroll
-                        for (int k1 = 0; k1 < 3; k1++)
-                            umma_bf16(d, at + (uint64_t)((k2 * 12 + k1) * S), dW2 + (uint64_t)((k2 * 3 + k1) * 64),
-                                      idesc_bf16(128, 32), (k2 | k1) ? 1u : 0u);
+                        for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+                            for (int k1 = 0; k1 < 3; k1++)
+                                umma_bf16(d, at + (uint64_t)((k2 * 12 + k1) * S), dW2 + (uint64_t)(part * 576 + (k2 * 3 + k1) * 64),
+                                          idesc_f16(128, 32), (part | k2 | k1) ? 1u : 0u);
                     umma_commit(&acc_full[b]);
                 }
                 __syncwarp();
             }
         } else if (warp >= 4) {
             const int grp = (warp - 4) >> 2, q = warp & 3;
-            for (int t = 0; t < TILES12; t++) {
+            const bool is_lo = (lane & 8) != 0;                             // this lane's row is a low-half slot
+            for (int t = 0; t < TILES2; t++) {
                 const uint32_t u = acc_it + t;
                 if ((int)(u % NGRP) != grp) continue;
                 const int b = u % NACC;
@@ -632,44 +452,51 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[b]);
-                const int P = t * 128 + q * 32 + lane;
-                const int pix = P / S, s = P - pix * S, y = pix / 12, x = pix - 12 * y;
-                if (x < 10 && y < 10) {
-                    uint8_t *dst = A2 + ((y * 10 + x) * S + s) * 16;          // [r][x][sample]
+                const int P = t * 128 + q * 32 + lane;                      // row = [pixel][slot]; slot = lane & 15
+                const int pix = P / S, y = pix / 12, x = pix - 12 * y;
+                // lanes l and l ^ 8 hold the two halves of one sample: both form the same FP32 sum, each keeps its own half
+                uint32_t w[16];
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; c8++) {
-                        uint32_t w[4];
+                for (int j = 0; j < 32; j += 2) {
+                    float r[2];
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            w[j] = pack_relu_bf16(__uint_as_float(v[c8 * 8 + 2 * j]) + bias[16 + c8 * 8 + 2 * j],
-                                                  __uint_as_float(v[c8 * 8 + 2 * j + 1]) + bias[16 + c8 * 8 + 2 * j + 1]);
-                        *reinterpret_cast<uint4 *>(dst + c8 * A2_PLANE) = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int e = 0; e < 2; e++) {
+                        const float mine = __uint_as_float(v[j + e]);
+                        const float other = __shfl_xor_sync(0xffffffffu, mine, 8);
+                        const float hi = is_lo ? other : mine, lo = is_lo ? mine : other;
+                        r[e] = fmaxf(fmaf(lo, LO_UNSCALE, hi) + bias[16 + j + e], 0.f);
                     }
+                    if (x < 10 && y < 10) amax = fmaxf(amax, fmaxf(r[0], r[1]));     // other rows are discarded garbage
+                    w[j >> 1] = (uint32_t)split_half(r[0], is_lo) | ((uint32_t)split_half(r[1], is_lo) << 16);
+                }
+                if (x < 10 && y < 10) {
+                    uint8_t *dst = A2 + ((y * 10 + x) * S + (lane & 15)) * 16;  // [r][x][slot]
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; c8++)
+                        *reinterpret_cast<uint4 *>(dst + c8 * A2_PLANE) = make_uint4(w[c8 * 4], w[c8 * 4 + 1], w[c8 * 4 + 2], w[c8 * 4 + 3]);
                 }
             }
         }
-        if (real) acc_it += TILES12;
+        if (real) acc_it += TILES2;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (real) QNET_STAMP(3);
 
-        // ================= conv3: 32 -> 64, 6x6, valid; weights are the M operand =================
+        // ================= conv3: 32 -> 64, 6x6, valid; weights are the M operand, 36 lo blocks then 36 hi blocks =================
         if (warp < NISSUE) {
             if (real) {
                 // The whole issuer warp runs this loop with warp-uniform values and one elected lane issues: descriptors
-                // then live in uniform registers.  (Issued from an `if (lane == 0)` branch every tcgen05.mma was wrapped in
-                // an ELECT + 5 R2UR.BROADCAST sequence, ~15 dependent instructions per MMA.)  The B-descriptor offset of a
-                // block comes from a constant table; blocks are waited for in pairs.
+                // then live in uniform registers.  The B-descriptor offset of a block comes from a constant table; blocks
+                // are waited for in pairs.
                 tc_fence_after();
                 const uint64_t bbase = dA2 + (uint64_t)(uwarp * 10 * S);    // issuer w owns tiles t = w, w + 2, w + 4
                 const uint32_t dbase = tmem + uwarp * 80;
-                const uint32_t ring0 = w3_it % NSLOT;
 #pragma unroll 2
                 for (int bi = 0; bi < NBLK; bi += 2) {
-                    const uint32_t b0 = (ring0 + bi) % NSLOT, b1 = b0 + 1;  // ring0 and bi are even
+                    const uint32_t b0 = (w3_it + bi) % NSLOT, b1 = b0 + 1;  // w3_it and bi are even
                     const uint32_t par = ((w3_it + bi) / NSLOT) & 1;       // both blocks share the ring pass
-                    const uint64_t o0 = bbase + c_boff[bi], o1 = bbase + c_boff[bi + 1];
+                    const int be = bi >= 36 ? bi - 36 : bi;
+                    const uint64_t o0 = bbase + c_boff[be], o1 = bbase + c_boff[be + 1];
                     const uint64_t w0 = dW3 + (uint64_t)(b0 * 256), w1 = w0 + 256;
                     mbar_wait(&w3_full[b0], par);
                     mbar_wait(&w3_full[b1], par);
@@ -677,8 +504,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
                     if (elect_one()) {
 #pragma unroll
                         for (int i = 0; i < 3; i++) {
-                            umma_bf16(dbase + i * 160, w0, o0 + (uint64_t)(i * 20 * S), idesc_bf16(128, 80), bi ? 1u : 0u);
-                            umma_bf16(dbase + i * 160, w1, o1 + (uint64_t)(i * 20 * S), idesc_bf16(128, 80), 1u);
+                            umma_bf16(dbase + i * 160, w0, o0 + (uint64_t)(i * 20 * S), idesc_f16(128, 80), bi ? 1u : 0u);
+                            umma_bf16(dbase + i * 160, w1, o1 + (uint64_t)(i * 20 * S), idesc_f16(128, 80), 1u);
                         }
                         umma_commit(&w3_empty[b0]);
                         umma_commit(&w3_empty[b1]);
@@ -694,27 +521,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
                     const uint32_t u = w3_it + bi;
                     const int b = u % NSLOT;
                     mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
-                    if (E16_NOLOAD) { mbar_arrive(&w3_full[b]); continue; }
                     mbar_expect_tx(&w3_full[b], 4096);
-                    bulk_load(smem + OFF_W3 + b * 4096, a.params + P_W3B + (size_t)bi * 4096, 4096, &w3_full[b]);
+                    bulk_load(smem + OFF_W3 + b * 4096, a.params + P_S_W3 + (size_t)bi * 4096, 4096, &w3_full[b]);
                 }
             }
             // next iteration's conv1 on the CUDA cores, by warps of the two schedulers without an MMA issuer
             if ((warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
                 const int w7 = warp == 3 ? 0 : 2 * ((warp - 4) >> 2) + (warp & 1) + 1;      // 3,6,7,10,11,14,15 -> 0..6
-                conv1_pixmajor(a, (it + gridDim.x) * S, A1, w7 * 32 + lane, 224);
-                if (real && a.timing != nullptr && blockIdx.x == 0 && warp == 11 && lane == 0) a.timing[it_local * 8 + 6] = clock64();
+                conv1_f32_split(a, (it + gridDim.x) * SR, A1, w7 * 32 + lane, 224, amax);
             }
             if (real && warp >= 4) {
                 const int grp = (warp - 4) >> 2, q = warp & 3;
                 mbar_wait(c3_full, c3_it & 1);
                 tc_fence_after();
-                QNET_STAMP(4);
-                float *scratch = reinterpret_cast<float *>(A2);             // [y][column = x*16 + s][oc]: conv3 no longer reads A2
+                float *scratch = reinterpret_cast<float *>(A2);             // [y][column = x*8 + sample][oc]: conv3 no longer reads A2
                 // out[y] = lower lanes of tile y + upper lanes of tile y + 1.  Warp quarter q owns lanes 32q..32q+31, i.e.
                 // output channels (q & 1)*32 + lane of the lower (q < 2) or upper (q >= 2) half.  For even y the upper half
-                // is parked in shared memory and the lower-lane warps finish the row; for odd y the other way round, so all
-                // twelve warps read TMEM (64 B/cycle, the bound here) and convert in both phases.
+                // is parked in shared memory and the lower-lane warps finish the row; for odd y the other way round.  Each
+                // half is first reduced over its two slots: column x*16 + s holds the high-half slot of sample s, + 8 the low one.
                 const int oc = (q & 1) * 32 + lane;
                 const uint32_t my = tmem + ((uint32_t)(q * 32) << 16) + (q >= 2 ? 80 : 0);   // + y*80: my half of output row y
                 for (int y = grp; y < 5; y += NGRP) {
@@ -725,41 +549,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
                         tmem_ld16(my + y * 80 + h * 16, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; i++) scratch[(y * 80 + h * 16 + i) * 64 + oc] = __uint_as_float(v[i]);
+                        for (int i = 0; i < 8; i++)
+                            scratch[(y * 40 + h * 8 + i) * 64 + oc] = fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i]));
                     }
                 }
                 asm volatile("bar.sync 1, 384;" ::: "memory");
-                QNET_STAMP(1);
                 const float bo = bias[48 + oc];
-                const int live = (int)(a.n - s0 < 16 ? a.n - s0 : 16);
+                const int live = (int)(a.n - s0 < SR ? a.n - s0 : SR);
                 for (int y = grp; y < 5; y += NGRP) {
                     if (((y & 1) == 0) == (q >= 2)) continue;
 #pragma unroll 1
                     for (int h = 0; h < 5; h++) {                            // h = output column x
                         uint32_t v[16];
                         tmem_ld16(my + y * 80 + h * 16, v);
-                        float other[16];                                     // all loads first: the stores below may alias as far
+                        float other[8];                                      // all loads first: the stores below may alias as far
 #pragma unroll                                                               // as the compiler knows, and would serialise them
-                        for (int i = 0; i < 16; i++) other[i] = scratch[(y * 80 + h * 16 + i) * 64 + oc];
+                        for (int i = 0; i < 8; i++) other[i] = scratch[(y * 40 + h * 8 + i) * 64 + oc];
                         tmem_ld_wait();
-                        __nv_bfloat16 *dst = a.out3 + s0 * 1600 + (y * 5 + h) * 64 + oc;
+                        unsigned short *dst = reinterpret_cast<unsigned short *>(a.out3) + 2 * s0 * 1600 + (y * 5 + h) * 64 + oc;
 #pragma unroll
-                        for (int i = 0; i < 16; i++) {                       // i = sample
-                            const float r = __uint_as_float(v[i]) + other[i] + bo;
-                            if (i < live) dst[i * 1600] = __float2bfloat16_rn(fmaxf(r, 0.f));
+                        for (int i = 0; i < 8; i++) {                        // i = sample
+                            const float r = fmaxf(fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i])) + other[i] + bo, 0.f);
+                            if (i < live) {
+                                amax = fmaxf(amax, r);
+                                dst[(2 * i) * 1600] = split_half(r, false);
+                                dst[(2 * i + 1) * 1600] = split_half(r, true);
+                            }
                         }
                     }
                 }
-                QNET_STAMP(2);
                 tc_fence_before();
             }
         }
         if (real) { w3_it += NBLK; c3_it++; }
         fence_proxy_async();
         __syncthreads();                            // conv3 accumulators drained (conv2 reuses the columns), A1/A2 handed over
-        if (real) { QNET_STAMP(5); QNET_STAMP(7); }
     }
 
+    if (amax > 65504.f) *a.overflow = 1;
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -767,7 +594,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs16(const __grid_consta
         tmem_dealloc(tmem, 512);
     }
 }
-}  // namespace e16
+}  // namespace split
 
 // ---- kernel A, engine 17: conv3 weights stationary in tensor memory -------------------------------------------
 // Engine 16's conv3 is still bound by the tensor core's shared-memory operand fetch (6.5 KB per 40-cycle MMA) and keeps
@@ -1093,8 +920,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
 }  // namespace e17
 
 // ---- kernel B: Dense(1600,64,relu) + Dense(64,3) ---------------------------------------------------------
+// SPLIT = false: X = out3 [N][1600] bf16, W4' [64][1600] bf16.
+// SPLIT = true (Float32-faithful): X = out3 [2N][1600] fp16 (row 2s = hi, row 2s+1 = 2^11 lo of sample s), W4' [64][3200]
+// fp16 (lo | hi): 50 k-blocks, the 25 lo-weight blocks first; lanes l and l ^ 1 of the epilogue hold the two halves of one
+// sample and add their accumulators.  A 128-row tile then covers 64 samples.
 constexpr int HB_M = 128, HB_K = 64, HB_STAGES = 6;
-constexpr int HB_STAGE_BYTES = HB_M * 128 + 64 * 128;      // A tile 16 KB + W4 tile 8 KB (SWIZZLE_128B rows of 64 bf16)
+constexpr int HB_STAGE_BYTES = HB_M * 128 + 64 * 128;      // A tile 16 KB + W4 tile 8 KB (SWIZZLE_128B rows of 64 16-bit elements)
 constexpr int HB_SMEM = HB_STAGES * HB_STAGE_BYTES + 1024 + 256 + 64 * 4 + 3 * 64 * 4 + 16;
 constexpr int HB_THREADS = 192;
 
@@ -1108,8 +939,9 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_constant__ CUtensorMap map_x,   // out3 [N][1600], box 128 x 64
-                                                             const __grid_constant__ CUtensorMap map_w,   // W4' [64][1600], box 64 x 64
+template <bool SPLIT>
+__global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_constant__ CUtensorMap map_x,   // out3, box 128 x 64
+                                                             const __grid_constant__ CUtensorMap map_w,   // W4', box 64 x 64
                                                              const HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1118,8 +950,11 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
     uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
     float *s_b4 = (float *)(tmem_slot + 4), *s_w5 = s_b4 + 64, *s_b5 = s_w5 + 192;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long n_tiles = (a.n + HB_M - 1) / HB_M;
-    constexpr int KB = 1600 / HB_K;   // 25
+    const long long n_rows = SPLIT ? 2 * a.n : a.n;
+    const long long n_tiles = (n_rows + HB_M - 1) / HB_M;
+    constexpr int KB1 = 1600 / HB_K;            // 25 k-blocks per weight half
+    constexpr int KB = SPLIT ? 2 * KB1 : KB1;
+    constexpr uint32_t IDESC = SPLIT ? idesc_f16(128, 64) : idesc_bf16(128, 64);
 
     for (int i = tid; i < 64; i += HB_THREADS) s_b4[i] = reinterpret_cast<const float *>(a.params + P_B4)[i];
     for (int i = tid; i < 192; i += HB_THREADS) s_w5[i] = reinterpret_cast<const float *>(a.params + P_W5)[i];
@@ -1144,7 +979,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * HB_STAGE_BYTES;
                     mbar_expect_tx(&full[stage], HB_STAGE_BYTES);
-                    tma_load_2d(&map_x, &full[stage], st, kb * HB_K, (int)((n_tiles - 1 - t) * HB_M));   // newest rows first, see below
+                    tma_load_2d(&map_x, &full[stage], st, (kb % KB1) * HB_K, (int)((n_tiles - 1 - t) * HB_M));   // newest rows first, see below
                     tma_load_2d(&map_w, &full[stage], st + HB_M * 128, kb * HB_K, 0);
                     if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -1163,7 +998,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
 #pragma unroll
                     for (int k = 0; k < HB_K / 16; k++)
                         umma_bf16(tmem + acc * 64, desc_sw128(base) + (uint64_t)(2 * k), desc_sw128(base + HB_M * 128) + (uint64_t)(2 * k),
-                                  idesc_bf16(128, 64), (kb | k) ? 1u : 0u);
+                                  IDESC, (kb | k) ? 1u : 0u);
                     umma_commit(&empty[stage]);
                     if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -1187,7 +1022,13 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const int c = h * 16 + j;
-                    const float hv = fmaxf(__uint_as_float(v[j]) + s_b4[c], 0.f);     // Dense(1600,64,relu)
+                    float x = __uint_as_float(v[j]);
+                    if (SPLIT) {                                                      // even lane: high-half row, odd lane: low-half row
+                        const float other = __shfl_xor_sync(0xffffffffu, x, 1);
+                        const float hi = (lane & 1) ? other : x, lo = (lane & 1) ? x : other;
+                        x = fmaf(lo, 1.0f / 2048.0f, hi);
+                    }
+                    const float hv = fmaxf(x + s_b4[c], 0.f);                        // Dense(1600,64,relu)
                     q0 = fmaf(s_w5[c * 3 + 0], hv, q0);                              // Dense(64,3); W5 stored (3,64) column-major
                     q1 = fmaf(s_w5[c * 3 + 1], hv, q1);
                     q2 = fmaf(s_w5[c * 3 + 2], hv, q2);
@@ -1198,8 +1039,9 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
             // tiles are taken from the END of the batch: the conv kernel wrote out3 in sample order and the last ~100 MB of it
             // are still in L2 when this kernel starts; reading front to back would evict them before they are reached
-            const long long s = (n_tiles - 1 - t) * HB_M + q * 32 + lane;
-            if (s < a.n) { a.q_out[3 * s] = q0; a.q_out[3 * s + 1] = q1; a.q_out[3 * s + 2] = q2; }
+            const long long row = (n_tiles - 1 - t) * HB_M + q * 32 + lane;
+            const long long s = SPLIT ? row >> 1 : row;
+            if (s < a.n && !(SPLIT && (lane & 1))) { a.q_out[3 * s] = q0; a.q_out[3 * s + 1] = q1; a.q_out[3 * s + 2] = q2; }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -1219,6 +1061,12 @@ static uint16_t f2bf(float f) {            // round-to-nearest-even
     u += 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
+// w = hi + lo in fp16 (lo unscaled): part 0 = lo, part 1 = hi
+static uint16_t f2h_part(float w, int part) {
+    const __half h = __float2half_rn(w);
+    if (part) return __half_as_ushort(h);
+    return __half_as_ushort(__float2half_rn(w - __half2float(h)));
+}
 
 // theta = Flux.destructure(q_net): W1(3,3,2,16) b1 W2(3,3,16,32) b2 W3(6,6,32,64) b3 W4(64,1600) b4 W5(3,64) b5, column-major
 static void pack_params(const float *th, std::vector<uint8_t> &blob) {
@@ -1236,35 +1084,39 @@ static void pack_params(const float *th, std::vector<uint8_t> &blob) {
         for (int k1 = 0; k1 < 3; k1++)
             for (int c = 0; c < 2; c++)
                 for (int o = 0; o < 16; o++) w1f[((k2 * 3 + k1) * 2 + c) * 16 + o] = w1(k1, k2, c, o);
-    // W2: [k2][k1][chunk (2)][o (32)][8]
+    // W2: [k2][k1][chunk (2)][o (32)][8]; the fp16 pair: [part][...]
     for (int k2 = 0; k2 < 3; k2++)
         for (int k1 = 0; k1 < 3; k1++)
             for (int c = 0; c < 16; c++)
-                for (int o = 0; o < 32; o++)
-                    bf(P_W2)[(((k2 * 3 + k1) * 2 + c / 8) * 32 + o) * 8 + c % 8] = f2bf(w2(k1, k2, c, o));
-    // W3: [k2][k1][m (2)][chunk (2)][o (64)][8], channel c = 16 m + 8 chunk + j
-    for (int k2 = 0; k2 < 6; k2++)
-        for (int k1 = 0; k1 < 6; k1++)
-            for (int c = 0; c < 32; c++)
-                for (int o = 0; o < 64; o++)
-                    bf(P_W3)[((((k2 * 6 + k1) * 2 + c / 16) * 2 + (c / 8) % 2) * 64 + o) * 8 + c % 8] = f2bf(w3(k1, k2, c, o));
-    // W3 for engine 16: 36 blocks (j, k1, m) of 128 stacked rows x 16 channels, canonical K-major core matrices:
+                for (int o = 0; o < 32; o++) {
+                    const size_t i = (((k2 * 3 + k1) * 2 + c / 8) * 32 + o) * 8 + c % 8;
+                    bf(P_W2)[i] = f2bf(w2(k1, k2, c, o));
+                    for (int part = 0; part < 2; part++) bf(P_S_W2)[(size_t)part * 4608 + i] = f2h_part(w2(k1, k2, c, o), part);
+                }
+    // W3: 36 blocks (j, k1, m) of 128 stacked rows x 16 channels, canonical K-major core matrices:
     // row R = 64 h + o carries kernel row k2 = 2 j + h; [K chunk (2)][row group (16)][row (8)][8 channels]
     for (int j = 0; j < 3; j++)
         for (int k1 = 0; k1 < 6; k1++)
             for (int m = 0; m < 2; m++)
                 for (int R = 0; R < 128; R++)
-                    for (int kk = 0; kk < 16; kk++)
-                        bf(P_W3B)[(size_t)((j * 6 + k1) * 2 + m) * 2048 + (((kk / 8) * 16 + R / 8) * 8 + R % 8) * 8 + kk % 8] =
-                            f2bf(w3(k1, 2 * j + R / 64, 16 * m + kk, R % 64));
+                    for (int kk = 0; kk < 16; kk++) {
+                        const size_t i = (size_t)((j * 6 + k1) * 2 + m) * 2048 + (((kk / 8) * 16 + R / 8) * 8 + R % 8) * 8 + kk % 8;
+                        const float w = w3(k1, 2 * j + R / 64, 16 * m + kk, R % 64);
+                        bf(P_W3B)[i] = f2bf(w);
+                        for (int part = 0; part < 2; part++) bf(P_S_W3)[(size_t)part * 36 * 2048 + i] = f2h_part(w, part);
+                    }
     float *bias = reinterpret_cast<float *>(blob.data() + P_BIAS);
     memcpy(bias, b1, 64); memcpy(bias + 16, b2, 128); memcpy(bias + 48, b3, 256);
     // W4 (64,1600) column-major, Flux flatten index kF = x + 5 y + 25 c  ->  [n][k' = (y*5 + x)*64 + c]
     for (int n = 0; n < 64; n++)
         for (int c = 0; c < 64; c++)
             for (int y = 0; y < 5; y++)
-                for (int x = 0; x < 5; x++)
-                    bf(P_W4)[(size_t)n * 1600 + (y * 5 + x) * 64 + c] = f2bf(W4[n + 64 * (x + 5 * y + 25 * c)]);
+                for (int x = 0; x < 5; x++) {
+                    const float w = W4[n + 64 * (x + 5 * y + 25 * c)];
+                    const size_t k = (size_t)(y * 5 + x) * 64 + c;
+                    bf(P_W4)[(size_t)n * 1600 + k] = f2bf(w);
+                    for (int part = 0; part < 2; part++) bf(P_S_W4)[(size_t)n * 3200 + part * 1600 + k] = f2h_part(w, part);
+                }
     memcpy(blob.data() + P_B4, b4, 256);
     memcpy(blob.data() + P_W5, W5, 768);          // (3,64) column-major: W5[a + 3 c]
     memcpy(blob.data() + P_B5, b5, 12);
@@ -1285,17 +1137,17 @@ static int tensor_map_encoder(EncodeTiledFn *out) {
     *out = enc;
     return SNK_OK;
 }
-static int make_map_bf16(CUtensorMap *m, const void *base, long long rows, long long cols, int box_rows, int box_cols) {
-    EncodeTiledFn enc;
+static int make_map_16bit(CUtensorMap *m, bool fp16, const void *base, long long rows, long long cols, int box_rows, int box_cols) {
+    EncodeTiledFn enc = nullptr;
     int rc = tensor_map_encoder(&enc);
     if (rc != SNK_OK) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SNK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return SNK_OK;
 }
@@ -1306,45 +1158,54 @@ using namespace snk;
 using namespace snk::qnet;
 
 struct snk_qnet_s {
-    __half2 w1h[144], b1h[8];
+    __half2 w1h[144], b1h[8];    // conv1 weights of the bf16 mode (kernel parameters)
+    float w1f[288], b1f[16];     // the same in FP32 for the Float32-faithful mode
     long long *timing;
     int device;
+    int precision;               // SNK_QNET_BF16 | SNK_QNET_F32
     uint8_t *params;
-    __nv_bfloat16 *out3;
-    long long out3_cap;
+    void *out3;                  // conv3 activations: bf16 [cap][1600] or fp16 [2 cap][1600]
+    long long out3_cap;          // in samples
+    int *d_overflow;             // SNK_QNET_F32: an activation left the fp16 range
     int sms;
-    int engine;                  // SNK_QNET_ENGINE: 17 (default) conv3 weights stationary in tensor memory, tile-by-tile conv3;
-                                 // 16: stacked-tap conv3 with streamed weights; 12: the first engine
 };
 
 extern "C" {
 
-int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device) {
+int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, int device, int precision) {
     SNK_REQUIRE(out != nullptr && theta_host != nullptr, "null argument");
     SNK_REQUIRE(n_params == 181395, "theta must be Flux.destructure of the two-frame Q-net (181,395 parameters, structs.jl:127-139)");
+    SNK_REQUIRE(precision == SNK_QNET_BF16 || precision == SNK_QNET_F32, "precision must be SNK_QNET_BF16 or SNK_QNET_F32");
     *out = nullptr;
-    SNK_CUDA(cudaSetDevice(device));
+    if (precision == SNK_QNET_F32)
+        for (int64_t i = 0; i < n_params; i++)
+            if (!(fabsf(theta_host[i]) <= 65504.0f))
+                return fail(SNK_ERR_UNSUPPORTED, "snk_qnet_create: parameter %lld = %g is outside the fp16 range of the split operands",
+                            (long long)i, (double)theta_host[i]);
+    DeviceGuard guard(device);
+    SNK_CUDA(cudaGetLastError());
     std::vector<uint8_t> blob;
     pack_params(theta_host, blob);
     snk_qnet_s *q = new (std::nothrow) snk_qnet_s();      // value-initialised: every member zero
     if (q == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
     q->device = device;
+    q->precision = precision;
     {
         const float *w1f = reinterpret_cast<const float *>(blob.data() + P_W1);
         const float *b1f = reinterpret_cast<const float *>(blob.data() + P_BIAS);
         for (int i = 0; i < 144; i++) q->w1h[i] = __floats2half2_rn(w1f[2 * i], w1f[2 * i + 1]);
         for (int i = 0; i < 8; i++) q->b1h[i] = __floats2half2_rn(b1f[2 * i], b1f[2 * i + 1]);
+        memcpy(q->w1f, w1f, sizeof(q->w1f));
+        memcpy(q->b1f, b1f, sizeof(q->b1f));
     }
     cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
-    {
-        const char *e = getenv("SNK_QNET_ENGINE");
-        const int v = e != nullptr ? atoi(e) : 0;
-        q->engine = (v == 12 || v == 16) ? v : 17;
-    }
     cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&q->d_overflow, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(q->d_overflow, 0, sizeof(int));
     if (e != cudaSuccess) {
         if (q->params) cudaFree(q->params);
+        if (q->d_overflow) cudaFree(q->d_overflow);
         delete q;
         return fail(SNK_ERR_CUDA, "snk_qnet_create: %s", cudaGetErrorString(e));
     }
@@ -1354,14 +1215,31 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
 
 int snk_qnet_destroy(snk_qnet q) {
     if (q == nullptr) return SNK_OK;
-    cudaSetDevice(q->device);
+    DeviceGuard guard(q->device);
     if (q->params) cudaFree(q->params);
     if (q->out3) cudaFree(q->out3);
+    if (q->d_overflow) cudaFree(q->d_overflow);
     delete q;
     return SNK_OK;
 }
 
-// debug: device buffer (8 x iterations of block 0 x int64) receiving clock64 stamps of the conv phases; NULL = off
+int snk_qnet_precision(snk_qnet q, int *precision) {
+    SNK_REQUIRE(q != nullptr && precision != nullptr, "null argument");
+    *precision = q->precision;
+    return SNK_OK;
+}
+
+// SNK_QNET_F32: 1 if any forward since the last call produced an activation outside the fp16 range (then its Q-values are
+// not valid); reads and clears the flag (synchronises the device)
+int snk_qnet_overflow_host(snk_qnet q, int *flag) {
+    SNK_REQUIRE(q != nullptr && flag != nullptr, "null argument");
+    DeviceGuard guard(q->device);
+    SNK_CUDA(cudaMemcpy(flag, q->d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*flag) SNK_CUDA(cudaMemset(q->d_overflow, 0, sizeof(int)));
+    return SNK_OK;
+}
+
+// debug (bf16 mode): device buffer of 512 int64 receiving clock64 stamps of the conv phases of CTA 0; NULL = off
 int snk_qnet_debug_timing(snk_qnet q, long long *device_buf) {
     SNK_REQUIRE(q != nullptr, "null qnet");
     q->timing = device_buf;
@@ -1370,47 +1248,55 @@ int snk_qnet_debug_timing(snk_qnet q, long long *device_buf) {
 
 int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3xN, void *cuda_stream) {
     SNK_REQUIRE(q != nullptr && obs_f32 != nullptr && q_out_3xN != nullptr && N > 0, "bad argument");
-    SNK_CUDA(cudaSetDevice(q->device));
+    DeviceGuard guard(q->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool f32 = q->precision == SNK_QNET_F32;
+    const size_t row_bytes = f32 ? 2 * 1600 * 2 : 1600 * 2;             // per sample
     if (q->out3_cap < N) {
-        if (q->out3) { SNK_CUDA(cudaStreamSynchronize(st)); SNK_CUDA(cudaFree(q->out3)); q->out3 = nullptr; }
+        if (q->out3) { SNK_CUDA(cudaStreamSynchronize(st)); SNK_CUDA(cudaFree(q->out3)); q->out3 = nullptr; q->out3_cap = 0; }
         long long cap = (N + 127) / 128 * 128;
-        SNK_CUDA(cudaMalloc((void **)&q->out3, (size_t)cap * 1600 * 2));
-        SNK_CUDA(cudaMemsetAsync(q->out3, 0, (size_t)cap * 1600 * 2, st));
+        SNK_CUDA(cudaMalloc(&q->out3, (size_t)cap * row_bytes));
+        SNK_CUDA(cudaMemsetAsync(q->out3, 0, (size_t)cap * row_bytes, st));
         q->out3_cap = cap;
     }
-    ConvArgs ca;
-    ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = q->out3; ca.timing = q->timing;
-    for (int i = 0; i < 144; i++) ca.w1h[i] = q->w1h[i];
-    for (int i = 0; i < 8; i++) ca.b1h[i] = q->b1h[i];
-    int grid;
-    if (q->engine == 17) {
+    int grid, rc;
+    CUtensorMap mx, mw;
+    if (f32) {
+        SplitArgs sa;
+        sa.obs = obs_f32; sa.n = N; sa.params = q->params; sa.out3 = (__half *)q->out3; sa.overflow = q->d_overflow;
+        memcpy(sa.w1f, q->w1f, sizeof(sa.w1f));
+        memcpy(sa.b1f, q->b1f, sizeof(sa.b1f));
+        const long long n_iter = (N + split::SR - 1) / split::SR;
+        grid = (int)(n_iter < q->sms ? n_iter : q->sms);
+        SNK_CUDA(cudaFuncSetAttribute(split::k_qnet_convs_split, cudaFuncAttributeMaxDynamicSharedMemorySize, split::SMEM));
+        split::k_qnet_convs_split<<<grid, THREADS, split::SMEM, st>>>(sa);
+        SNK_CUDA(cudaGetLastError());
+        if ((rc = make_map_16bit(&mx, true, q->out3, 2 * q->out3_cap, 1600, HB_M, HB_K)) != SNK_OK) return rc;
+        if ((rc = make_map_16bit(&mw, true, q->params + P_S_W4, 64, 3200, 64, HB_K)) != SNK_OK) return rc;
+    } else {
+        ConvArgs ca;
+        ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = (__nv_bfloat16 *)q->out3; ca.timing = q->timing;
+        for (int i = 0; i < 144; i++) ca.w1h[i] = q->w1h[i];
+        for (int i = 0; i < 8; i++) ca.b1h[i] = q->b1h[i];
         const long long n_iter = (N + e17::S - 1) / e17::S;
         grid = (int)(n_iter < q->sms ? n_iter : q->sms);
         SNK_CUDA(cudaFuncSetAttribute(e17::k_qnet_convs17, cudaFuncAttributeMaxDynamicSharedMemorySize, e17::SMEM));
         e17::k_qnet_convs17<<<grid, e17::NTHREADS, e17::SMEM, st>>>(ca);
-    } else if (q->engine == 16) {
-        const long long n_iter = (N + e16::S - 1) / e16::S;
-        grid = (int)(n_iter < q->sms ? n_iter : q->sms);
-        SNK_CUDA(cudaFuncSetAttribute(e16::k_qnet_convs16, cudaFuncAttributeMaxDynamicSharedMemorySize, e16::SMEM));
-        e16::k_qnet_convs16<<<grid, THREADS, e16::SMEM, st>>>(ca);
-    } else {
-        const long long n_iter = (N + S - 1) / S;
-        grid = (int)(n_iter < q->sms ? n_iter : q->sms);
-        SNK_CUDA(cudaFuncSetAttribute(k_qnet_convs, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_A));
-        k_qnet_convs<<<grid, THREADS, SMEM_A, st>>>(ca);
+        SNK_CUDA(cudaGetLastError());
+        if ((rc = make_map_16bit(&mx, false, q->out3, q->out3_cap, 1600, HB_M, HB_K)) != SNK_OK) return rc;
+        if ((rc = make_map_16bit(&mw, false, q->params + P_W4, 64, 1600, 64, HB_K)) != SNK_OK) return rc;
     }
-    SNK_CUDA(cudaGetLastError());
-    CUtensorMap mx, mw;
-    int rc;
-    if ((rc = make_map_bf16(&mx, q->out3, q->out3_cap, 1600, HB_M, HB_K)) != SNK_OK) return rc;
-    if ((rc = make_map_bf16(&mw, q->params + P_W4, 64, 1600, 64, HB_K)) != SNK_OK) return rc;
     HeadArgs ha;
     ha.params = q->params; ha.q_out = q_out_3xN; ha.n = N;
-    const long long n_tiles = (N + HB_M - 1) / HB_M;
+    const long long n_tiles = ((f32 ? 2 * N : N) + HB_M - 1) / HB_M;
     grid = (int)(n_tiles < q->sms ? n_tiles : q->sms);
-    SNK_CUDA(cudaFuncSetAttribute(k_qnet_head, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM));
-    k_qnet_head<<<grid, HB_THREADS, HB_SMEM, st>>>(mx, mw, ha);
+    if (f32) {
+        SNK_CUDA(cudaFuncSetAttribute(k_qnet_head<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM));
+        k_qnet_head<true><<<grid, HB_THREADS, HB_SMEM, st>>>(mx, mw, ha);
+    } else {
+        SNK_CUDA(cudaFuncSetAttribute(k_qnet_head<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM));
+        k_qnet_head<false><<<grid, HB_THREADS, HB_SMEM, st>>>(mx, mw, ha);
+    }
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }

@@ -630,6 +630,46 @@ __global__ void __launch_bounds__(TPB) k_state(EnvState s, long long n, void *ob
     expand_obs<OBS>(obs, env0, n_local, s_planes, s_tb, tid);
 }
 
+// assemble_state! for the envs the last step re-initialised (auto-reset): rows of `obs` whose done flag is set are
+// overwritten with the constructor state (init, init) (structs.jl:53-55), all other rows are left alone.  Turns the
+// next_state output of one fused step into the acting state of the next one without re-expanding all N envs.
+template <int OBS>
+__global__ void __launch_bounds__(TPB) k_patch_reset(long long n, const uint8_t *__restrict__ done, void *obs) {
+    __shared__ __align__(16) uint32_t s_pl[8];
+    __shared__ ObsTables s_tb;
+    __shared__ int s_list[TPB];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x;
+    const long long env0 = (long long)blockIdx.x * TPB;
+    fill_tables<OBS>(s_tb, tid);
+    if (tid == 0) {
+        s_cnt = 0;
+        board_planes(INIT_OCC, 3, 4, false, 0, 0, s_pl);
+    }
+    __syncthreads();
+    if (env0 + tid < n && done[env0 + tid] != 0) s_list[atomicAdd(&s_cnt, 1)] = tid;
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (OBS == SNK_OBS_I64) {
+        for (int j = tid; j < cnt * 100; j += TPB) {
+            const int e = j / 100, p = j - e * 100, k = 2 * (p % 50);
+            longlong2 v;
+            v.x = code_value(cell_code(s_pl, k));
+            v.y = code_value(cell_code(s_pl, k + 1));
+            reinterpret_cast<longlong2 *>(obs)[(env0 + s_list[e]) * 100 + p] = v;
+        }
+    } else {
+        for (int j = tid; j < cnt * 50; j += TPB) {
+            const int e = j / 50, qq = j - e * 50;
+            const uint32_t idx = reinterpret_cast<const uint8_t *>(s_pl)[qq % 25];
+            const long long o = (env0 + s_list[e]) * 50 + qq;
+            if (OBS == SNK_OBS_F32) reinterpret_cast<float4 *>(obs)[o] = s_tb.f32[idx];
+            else if (OBS == SNK_OBS_I8) reinterpret_cast<uint32_t *>(obs)[o] = reinterpret_cast<const uint32_t *>(s_tb.f32)[idx];
+            else reinterpret_cast<uint8_t *>(obs)[o] = reinterpret_cast<const uint8_t *>(s_tb.f32)[idx];
+        }
+    }
+}
+
 __global__ void k_reset(EnvState s, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -811,7 +851,7 @@ struct snk_env {
     FoodTable food;            // active list
     cudaStream_t own_stream, stream;
     cudaStream_t copy_stream[2];
-    cudaEvent_t ev_in, ev_chunk[64], ev_done;
+    cudaEvent_t ev_in, ev_chunk[64], ev_up[64], ev_done;
     u64 seed, step_counter;
     unsigned long long *d_count;
     // staging for the _host entry points (allocated on first use)
@@ -844,8 +884,8 @@ static inline unsigned nblocks(long long n, int tpb) { return (unsigned)((n + tp
 #define SNK_CHECK_HANDLE(h)                                                  \
     do {                                                                     \
         if ((h) == nullptr) return fail(SNK_ERR_INVALID, "%s: null handle", __func__); \
-        SNK_CUDA(cudaSetDevice((h)->device));                                \
-    } while (0)
+    } while (0);                                                             \
+    snk::DeviceGuard guard__((h)->device)
 
 template <typename T>
 static cudaError_t ensure(T **p, size_t bytes) {
@@ -879,7 +919,7 @@ int snk_create(snk_handle *out, int64_t n_envs, int device, uint32_t flags) {
     if (prop.major != 10)
         return fail(SNK_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
                     prop.minor);
-    SNK_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     snk_env *h = new (std::nothrow) snk_env();
     if (h == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
     memset(h, 0, sizeof(*h));
@@ -896,6 +936,7 @@ int snk_create(snk_handle *out, int64_t n_envs, int device, uint32_t flags) {
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
     for (int i = 0; i < 64 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming);
+    for (int i = 0; i < 64 && ce == cudaSuccess; i++) ce = cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming);
     if (ce != cudaSuccess) {
         int rc = fail(SNK_ERR_CUDA, "snk_create: %s", cudaGetErrorString(ce));
         snk_destroy(h);
@@ -910,7 +951,7 @@ int snk_create(snk_handle *out, int64_t n_envs, int device, uint32_t flags) {
 
 int snk_destroy(snk_handle h) {
     if (h == nullptr) return SNK_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     void *ptrs[] = {h->s.occ, h->s.pocc, h->s.clo, h->s.chi, h->s.cons, h->s.misc, h->s.ret, h->d_count, h->d_q, h->d_u,
                     h->d_reward, h->d_ep_return, h->d_ridx, h->d_act, h->d_done, h->d_mask, h->d_ep_score, h->d_obs};
@@ -919,6 +960,7 @@ int snk_destroy(snk_handle h) {
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     for (int i = 0; i < 64; i++) if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+    for (int i = 0; i < 64; i++) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return SNK_OK;
@@ -1106,69 +1148,23 @@ int snk_host_free(void *p) {
     return SNK_OK;
 }
 
+struct snk_replay_s;
+static int step_fused_host_impl(snk_handle h, snk_replay_s *r, const float *q, float eps, const float *u, const uint8_t *ridx,
+                                uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask,
+                                float *ep_return, int32_t *ep_score);
+
 int snk_step_fused_host(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx, uint8_t *act_idx,
                         float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask, float *ep_return,
                         int32_t *ep_score) {
-    SNK_CHECK_HANDLE(h);
-    SNK_REQUIRE(q != nullptr || act_idx != nullptr, "need q (select) or act_idx (input)");
-    SNK_REQUIRE(obs_fmt == SNK_OBS_NONE || obs != nullptr, "obs_fmt given without an obs buffer");
-    const size_t n = (size_t)h->n;
-    const size_t opb = obs ? obs_bytes_per_env(obs_fmt) : 0;
-    if (obs && opb == 0) return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
-    // device staging
-    SNK_CUDA(ensure(&h->d_act, n));
-    if (q) { SNK_CUDA(ensure(&h->d_q, 12 * n)); }
-    if (u) { SNK_CUDA(ensure(&h->d_u, 4 * n)); }
-    if (ridx) { SNK_CUDA(ensure(&h->d_ridx, n)); }
-    if (reward) { SNK_CUDA(ensure(&h->d_reward, 4 * n)); }
-    if (done) { SNK_CUDA(ensure(&h->d_done, n)); }
-    if (mask) { SNK_CUDA(ensure(&h->d_mask, 3 * n)); }
-    if (ep_return) { SNK_CUDA(ensure(&h->d_ep_return, 4 * n)); }
-    if (ep_score) { SNK_CUDA(ensure(&h->d_ep_score, 4 * n)); }
-    if (opb && h->d_obs_bytes < opb * n) {
-        if (h->d_obs) { SNK_CUDA(cudaStreamSynchronize(h->stream)); SNK_CUDA(cudaFree(h->d_obs)); h->d_obs = nullptr; }
-        SNK_CUDA(cudaMalloc(&h->d_obs, opb * n));
-        h->d_obs_bytes = opb * n;
-    }
-    cudaStream_t st = h->stream, c0 = h->copy_stream[0];
-    // inputs up (small: <= 17 B/env) on the compute stream
-    if (q) SNK_CUDA(cudaMemcpyAsync(h->d_q, q, 12 * n, cudaMemcpyHostToDevice, st));
-    if (u) SNK_CUDA(cudaMemcpyAsync(h->d_u, u, 4 * n, cudaMemcpyHostToDevice, st));
-    if (ridx) SNK_CUDA(cudaMemcpyAsync(h->d_ridx, ridx, n, cudaMemcpyHostToDevice, st));
-    if (!q) SNK_CUDA(cudaMemcpyAsync(h->d_act, act_idx, n, cudaMemcpyHostToDevice, st));
-    StepArgs a;
-    base_args(h, a);
-    a.q = q ? h->d_q : nullptr; a.eps = eps; a.u = u ? h->d_u : nullptr; a.ridx = ridx ? h->d_ridx : nullptr;
-    if (q) a.act_out = act_idx ? h->d_act : nullptr; else a.act = h->d_act;
-    a.reward = reward ? h->d_reward : nullptr; a.done = done ? h->d_done : nullptr; a.obs = opb ? h->d_obs : nullptr;
-    a.mask = mask ? h->d_mask : nullptr; a.ep_return = ep_return ? h->d_ep_return : nullptr;
-    a.ep_score = ep_score ? h->d_ep_score : nullptr;
-    // env chunks: kernel of chunk c+1 overlaps the device->host copy of chunk c
-    const long long align = TPB * 8;
-    int n_chunks = (int)((h->n + (1 << 16) - 1) >> 16);
-    if (n_chunks < 1) n_chunks = 1;
-    if (n_chunks > 16) n_chunks = 16;
-    long long per = ((h->n + n_chunks - 1) / n_chunks + align - 1) / align * align;
-    int ci = 0;
-    for (long long b = 0; b < h->n; b += per, ci++) {
-        long long e = b + per < h->n ? b + per : h->n;
-        int rc = launch_step(h, a, opb ? obs_fmt : SNK_OBS_NONE, q != nullptr, b, e, st);
-        if (rc != SNK_OK) return rc;
-        SNK_CUDA(cudaEventRecord(h->ev_chunk[ci], st));
-        SNK_CUDA(cudaStreamWaitEvent(c0, h->ev_chunk[ci], 0));
-        size_t nb = (size_t)(e - b);
-        if (opb) SNK_CUDA(cudaMemcpyAsync((char *)obs + opb * b, (char *)h->d_obs + opb * b, opb * nb, cudaMemcpyDeviceToHost, c0));
-        if (mask) SNK_CUDA(cudaMemcpyAsync(mask + 3 * b, h->d_mask + 3 * b, 3 * nb, cudaMemcpyDeviceToHost, c0));
-        if (reward) SNK_CUDA(cudaMemcpyAsync(reward + b, h->d_reward + b, 4 * nb, cudaMemcpyDeviceToHost, c0));
-        if (done) SNK_CUDA(cudaMemcpyAsync(done + b, h->d_done + b, nb, cudaMemcpyDeviceToHost, c0));
-        if (ep_return) SNK_CUDA(cudaMemcpyAsync(ep_return + b, h->d_ep_return + b, 4 * nb, cudaMemcpyDeviceToHost, c0));
-        if (ep_score) SNK_CUDA(cudaMemcpyAsync(ep_score + b, h->d_ep_score + b, 4 * nb, cudaMemcpyDeviceToHost, c0));
-        if (q && act_idx) SNK_CUDA(cudaMemcpyAsync(act_idx + b, h->d_act + b, nb, cudaMemcpyDeviceToHost, c0));
-    }
-    h->step_counter++;
-    // make the handle's stream wait for the copies, so snk_sync() covers the whole call
-    SNK_CUDA(cudaEventRecord(h->ev_done, c0));
-    SNK_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+    return step_fused_host_impl(h, nullptr, q, eps, u, ridx, act_idx, reward, done, obs, obs_fmt, mask, ep_return, ep_score);
+}
+
+// device staging buffer of the host getters (grown on demand)
+static int ensure_obs_staging(snk_handle h, size_t bytes) {
+    if (h->d_obs_bytes >= bytes) return SNK_OK;
+    if (h->d_obs) { SNK_CUDA(cudaStreamSynchronize(h->stream)); SNK_CUDA(cudaFree(h->d_obs)); h->d_obs = nullptr; h->d_obs_bytes = 0; }
+    SNK_CUDA(cudaMalloc(&h->d_obs, bytes));
+    h->d_obs_bytes = bytes;
     return SNK_OK;
 }
 
@@ -1182,6 +1178,23 @@ int snk_state(snk_handle h, void *obs, int obs_fmt) {
         case SNK_OBS_I8: k_state<SNK_OBS_I8><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
         case SNK_OBS_I64: k_state<SNK_OBS_I64><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
         case SNK_OBS_PACKED2: k_state<SNK_OBS_PACKED2><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
+        default: return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
+    }
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+int snk_patch_reset_obs(snk_handle h, const uint8_t *done, void *obs, int obs_fmt) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(done != nullptr && obs != nullptr, "null argument");
+    SNK_REQUIRE(((uintptr_t)obs & 15u) == 0, "obs must be 16-byte aligned");
+    if (!(h->flags & SNK_AUTO_RESET)) return SNK_OK;          // frozen envs keep their terminal state
+    unsigned grid = nblocks(h->n, TPB);
+    switch (obs_fmt) {
+        case SNK_OBS_F32: k_patch_reset<SNK_OBS_F32><<<grid, TPB, 0, h->stream>>>(h->n, done, obs); break;
+        case SNK_OBS_I8: k_patch_reset<SNK_OBS_I8><<<grid, TPB, 0, h->stream>>>(h->n, done, obs); break;
+        case SNK_OBS_I64: k_patch_reset<SNK_OBS_I64><<<grid, TPB, 0, h->stream>>>(h->n, done, obs); break;
+        case SNK_OBS_PACKED2: k_patch_reset<SNK_OBS_PACKED2><<<grid, TPB, 0, h->stream>>>(h->n, done, obs); break;
         default: return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
     }
     SNK_CUDA(cudaGetLastError());
@@ -1251,13 +1264,15 @@ struct snk_replay_s {
     long long total;         // transitions ever stored since the last clear
     u64 draws;               // sample calls so far (counter of the keyed permutation)
     int *d_bad;
+    uint8_t *stage;          // device staging of snk_replay_gather_host
+    size_t stage_bytes;
 };
 
 int snk_replay_create(snk_replay *out, int64_t capacity, int device) {
     SNK_REQUIRE(out != nullptr, "null out");
     SNK_REQUIRE(capacity >= 64, "batch_size (64) cannot be greater than the capacity of the buffer");   // structs.jl:113
     *out = nullptr;
-    SNK_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     snk_replay_s *r = new (std::nothrow) snk_replay_s();
     if (r == nullptr) return fail(SNK_ERR_INVALID, "out of host memory");
     memset(r, 0, sizeof(*r));
@@ -1275,9 +1290,10 @@ int snk_replay_create(snk_replay *out, int64_t capacity, int device) {
 }
 int snk_replay_destroy(snk_replay r) {
     if (r == nullptr) return SNK_OK;
-    cudaSetDevice(r->device);
+    DeviceGuard guard(r->device);
     cudaFree(r->ring);
     cudaFree(r->d_bad);
+    if (r->stage) cudaFree(r->stage);
     delete r;
     return SNK_OK;
 }
@@ -1322,7 +1338,7 @@ int snk_replay_gather(snk_replay r, const int64_t *idx, int64_t B, float *states
     SNK_REQUIRE(r != nullptr && idx != nullptr && B >= 0, "bad argument");
     SNK_REQUIRE((((uintptr_t)states | (uintptr_t)next_states) & 15u) == 0, "state buffers must be 16-byte aligned");
     if (B == 0) return SNK_OK;
-    SNK_CUDA(cudaSetDevice(r->device));
+    DeviceGuard guard(r->device);
     k_replay_gather<<<nblocks(B, GATHER_S), 128, 0, (cudaStream_t)cuda_stream>>>(
         r->ring, r->capacity, (const long long *)idx, B, states, next_states, actions, rewards, dones, mask, ep_return,
         score, r->d_bad);
@@ -1336,7 +1352,7 @@ int snk_replay_sample_indices(snk_replay r, uint64_t seed, int64_t B, int64_t *i
     // sample(rpb): min(batch, length) distinct transitions (utils.jl:280-287)
     SNK_REQUIRE(B >= 0 && B <= n, "cannot sample more distinct transitions than the buffer holds");
     if (B == 0) return SNK_OK;
-    SNK_CUDA(cudaSetDevice(r->device));
+    DeviceGuard guard(r->device);
     const u64 key = splitmix64(seed ^ splitmix64(r->draws++));
     k_replay_sample<<<nblocks(B, 256), 256, 0, (cudaStream_t)cuda_stream>>>(n, B, key, (long long *)idx_out);
     SNK_CUDA(cudaGetLastError());
@@ -1345,8 +1361,175 @@ int snk_replay_sample_indices(snk_replay r, uint64_t seed, int64_t B, int64_t *i
 
 int snk_replay_bad_index_host(snk_replay r, int *flag) {
     SNK_REQUIRE(r != nullptr && flag != nullptr, "bad argument");
-    SNK_CUDA(cudaSetDevice(r->device));
+    DeviceGuard guard(r->device);
     SNK_CUDA(cudaMemcpy(flag, r->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    return SNK_OK;
+}
+
+// ---- host-buffer forms ------------------------------------------------------------------------------------
+// The fused step with HOST buffers: env chunks are pipelined three deep — the inputs of chunk c+1 go up on one copy
+// stream while the kernel of chunk c runs and the outputs of chunk c-1 come down on the other (PCIe is full duplex).
+// With a replay ring the same kernels also store! every transition into it (utils.jl:267-277).
+static int step_fused_host_impl(snk_handle h, snk_replay_s *r, const float *q, float eps, const float *u, const uint8_t *ridx,
+                                uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask,
+                                float *ep_return, int32_t *ep_score) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(q != nullptr || act_idx != nullptr, "need q (select) or act_idx (input)");
+    SNK_REQUIRE(obs_fmt == SNK_OBS_NONE || obs != nullptr, "obs_fmt given without an obs buffer");
+    if (r != nullptr) {
+        SNK_REQUIRE(r->device == h->device, "replay ring and env live on different devices");
+        if (!(h->flags & SNK_AUTO_RESET))
+            return fail(SNK_ERR_UNSUPPORTED, "storing transitions needs an env created with SNK_AUTO_RESET (every env must step)");
+    }
+    const size_t n = (size_t)h->n;
+    const size_t opb = obs ? obs_bytes_per_env(obs_fmt) : 0;
+    if (obs && opb == 0) return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
+    // device staging
+    SNK_CUDA(ensure(&h->d_act, n));
+    if (q) { SNK_CUDA(ensure(&h->d_q, 12 * n)); }
+    if (u) { SNK_CUDA(ensure(&h->d_u, 4 * n)); }
+    if (ridx) { SNK_CUDA(ensure(&h->d_ridx, n)); }
+    if (reward) { SNK_CUDA(ensure(&h->d_reward, 4 * n)); }
+    if (done) { SNK_CUDA(ensure(&h->d_done, n)); }
+    if (mask) { SNK_CUDA(ensure(&h->d_mask, 3 * n)); }
+    if (ep_return) { SNK_CUDA(ensure(&h->d_ep_return, 4 * n)); }
+    if (ep_score) { SNK_CUDA(ensure(&h->d_ep_score, 4 * n)); }
+    if (opb) { int rc = ensure_obs_staging(h, opb * n); if (rc != SNK_OK) return rc; }
+    cudaStream_t st = h->stream, down = h->copy_stream[0], up = h->copy_stream[1];
+    StepArgs a;
+    base_args(h, a);
+    a.q = q ? h->d_q : nullptr; a.eps = eps; a.u = u ? h->d_u : nullptr; a.ridx = ridx ? h->d_ridx : nullptr;
+    if (q) a.act_out = act_idx ? h->d_act : nullptr; else a.act = h->d_act;
+    a.reward = reward ? h->d_reward : nullptr; a.done = done ? h->d_done : nullptr; a.obs = opb ? h->d_obs : nullptr;
+    a.mask = mask ? h->d_mask : nullptr; a.ep_return = ep_return ? h->d_ep_return : nullptr;
+    a.ep_score = ep_score ? h->d_ep_score : nullptr;
+    if (r != nullptr) { a.sink = r->ring; a.sink_base = r->total; a.sink_cap = r->capacity; a.sink_n = h->n; }
+    const long long align = TPB * 8;
+    int n_chunks = (int)((h->n + (1 << 16) - 1) >> 16);
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 16) n_chunks = 16;
+    const long long per = ((h->n + n_chunks - 1) / n_chunks + align - 1) / align * align;
+    // the staging buffers may still be read by earlier work on the handle's stream
+    SNK_CUDA(cudaEventRecord(h->ev_in, st));
+    SNK_CUDA(cudaStreamWaitEvent(up, h->ev_in, 0));
+    int ci = 0;
+    for (long long b = 0; b < h->n; b += per, ci++) {
+        const long long e = b + per < h->n ? b + per : h->n;
+        const size_t nb = (size_t)(e - b);
+        if (q) SNK_CUDA(cudaMemcpyAsync(h->d_q + 3 * b, q + 3 * b, 12 * nb, cudaMemcpyHostToDevice, up));
+        if (u) SNK_CUDA(cudaMemcpyAsync(h->d_u + b, u + b, 4 * nb, cudaMemcpyHostToDevice, up));
+        if (ridx) SNK_CUDA(cudaMemcpyAsync(h->d_ridx + b, ridx + b, nb, cudaMemcpyHostToDevice, up));
+        if (!q) SNK_CUDA(cudaMemcpyAsync(h->d_act + b, act_idx + b, nb, cudaMemcpyHostToDevice, up));
+        SNK_CUDA(cudaEventRecord(h->ev_up[ci], up));
+        SNK_CUDA(cudaStreamWaitEvent(st, h->ev_up[ci], 0));
+        int rc = launch_step(h, a, opb ? obs_fmt : SNK_OBS_NONE, q != nullptr, b, e, st);
+        if (rc != SNK_OK) return rc;
+        SNK_CUDA(cudaEventRecord(h->ev_chunk[ci], st));
+        SNK_CUDA(cudaStreamWaitEvent(down, h->ev_chunk[ci], 0));
+        if (opb) SNK_CUDA(cudaMemcpyAsync((char *)obs + opb * b, (char *)h->d_obs + opb * b, opb * nb, cudaMemcpyDeviceToHost, down));
+        if (mask) SNK_CUDA(cudaMemcpyAsync(mask + 3 * b, h->d_mask + 3 * b, 3 * nb, cudaMemcpyDeviceToHost, down));
+        if (reward) SNK_CUDA(cudaMemcpyAsync(reward + b, h->d_reward + b, 4 * nb, cudaMemcpyDeviceToHost, down));
+        if (done) SNK_CUDA(cudaMemcpyAsync(done + b, h->d_done + b, nb, cudaMemcpyDeviceToHost, down));
+        if (ep_return) SNK_CUDA(cudaMemcpyAsync(ep_return + b, h->d_ep_return + b, 4 * nb, cudaMemcpyDeviceToHost, down));
+        if (ep_score) SNK_CUDA(cudaMemcpyAsync(ep_score + b, h->d_ep_score + b, 4 * nb, cudaMemcpyDeviceToHost, down));
+        if (q && act_idx) SNK_CUDA(cudaMemcpyAsync(act_idx + b, h->d_act + b, nb, cudaMemcpyDeviceToHost, down));
+    }
+    h->step_counter++;
+    if (r != nullptr) r->total += h->n;
+    // make the handle's stream wait for the copies, so snk_sync() covers the whole call
+    SNK_CUDA(cudaEventRecord(h->ev_done, down));
+    SNK_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+    return SNK_OK;
+}
+
+int snk_step_fused_store_host(snk_handle h, snk_replay r, const float *q, float eps, const float *u, const uint8_t *ridx,
+                              uint8_t *act_idx, float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask,
+                              float *ep_return, int32_t *ep_score) {
+    SNK_REQUIRE(r != nullptr, "null replay");
+    return step_fused_host_impl(h, r, q, eps, u, ridx, act_idx, reward, done, obs, obs_fmt, mask, ep_return, ep_score);
+}
+
+// Per-call getters with HOST outputs (any host memory; pinned is faster).  Unlike the enqueue-and-return entry points these
+// return when the data has arrived: they are what a Julia host calls where the reference reads a field of `game`.
+static int to_host(snk_handle h, void *dst_host, const void *src_dev, size_t bytes) {
+    SNK_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    SNK_CUDA(cudaStreamSynchronize(h->stream));
+    return SNK_OK;
+}
+
+int snk_state_host(snk_handle h, void *obs_host, int obs_fmt) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(obs_host != nullptr, "null out");
+    const size_t opb = obs_bytes_per_env(obs_fmt);
+    if (opb == 0) return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
+    int rc = ensure_obs_staging(h, opb * (size_t)h->n);
+    if (rc != SNK_OK) return rc;
+    if ((rc = snk_state(h, h->d_obs, obs_fmt)) != SNK_OK) return rc;
+    return to_host(h, obs_host, h->d_obs, opb * (size_t)h->n);
+}
+
+int snk_losing_mask_host(snk_handle h, uint8_t *mask_3xN_host) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(mask_3xN_host != nullptr, "null out");
+    SNK_CUDA(ensure(&h->d_mask, 3 * (size_t)h->n));
+    int rc = snk_losing_mask(h, h->d_mask);
+    if (rc != SNK_OK) return rc;
+    return to_host(h, mask_3xN_host, h->d_mask, 3 * (size_t)h->n);
+}
+
+int snk_available_actions_host(snk_handle h, uint8_t *dirs_3xN_host) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(dirs_3xN_host != nullptr, "null out");
+    SNK_CUDA(ensure(&h->d_mask, 3 * (size_t)h->n));
+    int rc = snk_available_actions(h, h->d_mask);
+    if (rc != SNK_OK) return rc;
+    return to_host(h, dirs_3xN_host, h->d_mask, 3 * (size_t)h->n);
+}
+
+static int scalars_host(snk_handle h, int which, void *out_host, size_t elem) {
+    SNK_CHECK_HANDLE(h);
+    SNK_REQUIRE(out_host != nullptr, "null out");
+    SNK_CUDA(ensure(&h->d_ep_score, 4 * (size_t)h->n));          // 4 bytes per env covers the u8 and the i32 scalars
+    int rc = scalars(h, which, h->d_ep_score);
+    if (rc != SNK_OK) return rc;
+    return to_host(h, out_host, h->d_ep_score, elem * (size_t)h->n);
+}
+int snk_get_score_host(snk_handle h, int32_t *score_host) { return scalars_host(h, 0, score_host, 4); }
+int snk_get_done_host(snk_handle h, uint8_t *done_host) { return scalars_host(h, 1, done_host, 1); }
+int snk_get_error_flags_host(snk_handle h, uint8_t *flags_host) { return scalars_host(h, 2, flags_host, 1); }
+int snk_get_steps_host(snk_handle h, int32_t *steps_host) { return scalars_host(h, 3, steps_host, 4); }
+
+// stack_exp (utils.jl:343-383) with HOST outputs for idx_host[0..B) (0-based slots): the sampled transitions are expanded to
+// Float32 on the device and copied down (2 x 800 B + 13 B per sample); returns when the data has arrived.
+int snk_replay_gather_host(snk_replay r, const int64_t *idx_host, int64_t B, float *states, float *next_states, uint8_t *actions,
+                           float *rewards, uint8_t *dones, uint8_t *mask, void *cuda_stream) {
+    SNK_REQUIRE(r != nullptr && idx_host != nullptr && B >= 0, "bad argument");
+    if (B == 0) return SNK_OK;
+    DeviceGuard guard(r->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t need = (size_t)B * 1632 + 256;     // 2 x 800 B of states + 8 idx + 4 + 1 + 1 + 3 per sample
+    if (r->stage_bytes < need) {
+        if (r->stage) { SNK_CUDA(cudaStreamSynchronize(st)); SNK_CUDA(cudaFree(r->stage)); r->stage = nullptr; r->stage_bytes = 0; }
+        SNK_CUDA(cudaMalloc((void **)&r->stage, need));
+        r->stage_bytes = need;
+    }
+    // staging layout: states | next_states | idx | rewards | actions | dones | mask
+    uint8_t *base = r->stage;
+    float *d_s = (float *)base, *d_ns = d_s + 200 * B;
+    int64_t *d_idx = (int64_t *)(d_ns + 200 * B);
+    float *d_rw = (float *)(d_idx + B);
+    uint8_t *d_act = (uint8_t *)(d_rw + B), *d_dn = d_act + B, *d_mk = d_dn + B;
+    SNK_CUDA(cudaMemcpyAsync(d_idx, idx_host, 8 * (size_t)B, cudaMemcpyHostToDevice, st));
+    int rc = snk_replay_gather(r, d_idx, B, states ? d_s : nullptr, next_states ? d_ns : nullptr, actions ? d_act : nullptr,
+                               rewards ? d_rw : nullptr, dones ? d_dn : nullptr, mask ? d_mk : nullptr, nullptr, nullptr, cuda_stream);
+    if (rc != SNK_OK) return rc;
+    if (states) SNK_CUDA(cudaMemcpyAsync(states, d_s, 800 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (next_states) SNK_CUDA(cudaMemcpyAsync(next_states, d_ns, 800 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (rewards) SNK_CUDA(cudaMemcpyAsync(rewards, d_rw, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (actions) SNK_CUDA(cudaMemcpyAsync(actions, d_act, (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (dones) SNK_CUDA(cudaMemcpyAsync(dones, d_dn, (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (mask) SNK_CUDA(cudaMemcpyAsync(mask, d_mk, 3 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    SNK_CUDA(cudaStreamSynchronize(st));
     return SNK_OK;
 }
 

@@ -22,6 +22,7 @@ const lib = get(ENV, "SNAKE_B200_LIB", joinpath(@__DIR__, "..", "libsnake_b200.s
 
 const OBS_F32, OBS_I8, OBS_I64, OBS_PACKED2 = Cint(1), Cint(2), Cint(3), Cint(4)
 const AUTO_RESET = UInt32(1)
+const QNET_BF16, QNET_F32 = Cint(0), Cint(1)
 # utils.jl:8 order
 const DIRS = (CartesianIndex(-1, 0), CartesianIndex(1, 0), CartesianIndex(0, -1), CartesianIndex(0, 1))
 
@@ -196,9 +197,11 @@ stack_exp(r::DeviceReplayBuffer, d_idx::Ptr{Int64}, B::Integer, d_states::Ptr{Fl
 # ---- Q-net forward (structs.jl:127-139) from Flux.destructure(q_net) ------------------------------------------
 mutable struct DeviceQNet
     handle::Ptr{Cvoid}
-    function DeviceQNet(theta::Vector{Float32}; device::Integer = 0)     # theta, _ = Flux.destructure(model.q_net)
+    # theta, _ = Flux.destructure(model.q_net); precision = :f32 (Float32-faithful, the default) or :bf16 (fast, ~1e-2)
+    function DeviceQNet(theta::Vector{Float32}; device::Integer = 0, precision::Symbol = :f32)
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:snk_qnet_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ptr{Float32}, Int64, Cint), h, theta, length(theta), device))
+        check(ccall((:snk_qnet_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ptr{Float32}, Int64, Cint, Cint), h, theta, length(theta), device,
+                    precision == :bf16 ? QNET_BF16 : QNET_F32))
         q = new(h[])
         finalizer(x -> ccall((:snk_qnet_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), q)
         return q

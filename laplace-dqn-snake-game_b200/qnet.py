@@ -1,23 +1,29 @@
-"""The reference's Q-network (structs.jl:127-139) on the device.
+"""The reference's Q-network (structs.jl:127-139) on the device — native kernels only.
 
     Conv((3,3), 2=>16, relu; pad=1) -> Conv((3,3), 16=>32, relu; pad=1) -> Conv((6,6), 32=>64, relu) ->
     Flux.flatten -> Dense(1600, 64, relu) -> Dense(64, 3)
 
-`QNet` holds the parameters in torch layout (converted from Flux's with bson_io.conv_weight_to_torch) and runs
-the forward pass.  backend="torch" is a LIBRARY path (cuDNN / cuBLAS through torch), kept as the reference
-implementation the native kernel is checked against; it is labelled as such wherever it is timed.
+`QNet` hands Flux.destructure(q_net) to snk_qnet_create and runs snk_qnet_forward (tcgen05 implicit-GEMM convolutions,
+csrc/qnet.cu).  precision="f32" (default) is the Float32-faithful mode the reference's Float32 network needs for
+identical greedy actions; precision="bf16" is the fast, lower-precision mode.  There is no library (cuDNN) path in the
+product: the torch restatement used as a timing baseline and cross-check lives in tools/torch_qnet.py.
 """
 import ctypes as C
 import math
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import bson_io
 
 SHAPES = [("conv", (3, 3, 2, 16), 1), ("conv", (3, 3, 16, 32), 1), ("conv", (6, 6, 32, 64), 0),
           ("dense", (64, 1600), None), ("dense", (3, 64), None)]
+N_PARAMS = 181395
+PRECISIONS = {"bf16": 0, "f32": 1}            # SNK_QNET_BF16, SNK_QNET_F32 (include/snake_b200.h)
+PRECISION_NOTES = {
+    "f32": "Float32-faithful: fp16 (hi, lo) split operands, four partial products on tcgen05, FP32 accumulation",
+    "bf16": "bf16 operands on tcgen05, FP32 accumulation: ~1.5e-2 of max|Q|, NOT the reference's Float32 fidelity",
+}
 
 
 def glorot_layers(seed=0, in_frames=2):
@@ -44,39 +50,25 @@ def glorot_layers(seed=0, in_frames=2):
     return layers
 
 
-BACKEND_NOTES = {
-    "torch": "LIBRARY path: torch conv2d/linear (cuDNN/cuBLAS), fp32 — the baseline, not a kernel of this repo",
-    "torch_bf16": "LIBRARY path: torch conv2d/linear in bf16 channels_last (cuDNN/cuBLAS)",
-    "native": "this repo: tcgen05 implicit-GEMM convolutions + TMA/tcgen05 dense head (snk_qnet_forward), bf16 operands, fp32 accumulate",
-}
-
-
-def available_backends():
-    return ["native", "torch_bf16", "torch"]
-
-
 class QNet:
-    def __init__(self, layers, device, dtype=torch.float32, backend="torch"):
-        self.backend = backend
-        if backend == "torch_bf16":
-            dtype = torch.bfloat16
-        self.device, self.dtype = torch.device(device), dtype
-        self.params = []
-        for kind, p in layers:
-            if kind == "conv":
-                w = torch.from_numpy(bson_io.conv_weight_to_torch(p["W"])).to(self.device, dtype)
-                self.params.append(("conv", w, torch.from_numpy(p["b"]).to(self.device, dtype), int(p["pad"][0])))
-            elif kind == "dense":
-                self.params.append(("dense", torch.from_numpy(np.ascontiguousarray(p["W"])).to(self.device, dtype),
-                                    torch.from_numpy(p["b"]).to(self.device, dtype), None))
-        self.n_params = sum(w.numel() + b.numel() for _, w, b, _ in self.params)
-        self._q = None
-        if backend == "native":
-            from . import _check, lib
-            theta = np.ascontiguousarray(bson_io.destructure(layers), dtype=np.float32)
-            self._q = C.c_void_p()
-            _check(lib().snk_qnet_create(C.byref(self._q), theta.ctypes.data_as(C.c_void_p), theta.size,
-                                         self.device.index or 0))
+    """q_net / t_net of DQNModel (structs.jl:120-147) as a callable: obs (N,2,10,10) f32 [= Julia (10,10,2,N)] -> Q (N,3)."""
+
+    def __init__(self, layers, device, precision="f32"):
+        from . import _check, lib
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be 'f32' or 'bf16'")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("QNet runs on a CUDA device only (no CPU fallback)")
+        self.precision = precision
+        self.theta = np.ascontiguousarray(bson_io.destructure(layers), dtype=np.float32)
+        if self.theta.size != N_PARAMS:
+            raise ValueError("the native Q-net is the two-frame network of structs.jl:127-139 (%d parameters), got %d"
+                             % (N_PARAMS, self.theta.size))
+        self.n_params = int(self.theta.size)
+        self._q = C.c_void_p()
+        _check(lib().snk_qnet_create(C.byref(self._q), self.theta.ctypes.data_as(C.c_void_p), self.theta.size,
+                                     self.device.index or 0, PRECISIONS[precision]))
 
     def close(self):
         if getattr(self, "_q", None):
@@ -89,33 +81,28 @@ class QNet:
 
     __del__ = close
 
-    def forward_native(self, obs):
-        """snk_qnet_forward: obs (N,2,10,10) float32 contiguous -> Q (N,3) float32"""
+    @classmethod
+    def from_trainer_bson(cls, path, device, which="q_net", precision="f32"):
+        """q_net / t_net of ./trainers/<name>.bson (load_trainer, utils.jl:413-418)"""
+        q, t = bson_io.load_trainer_nets(path)
+        return cls(q if which == "q_net" else t, device, precision)
+
+    def forward(self, obs, out=None):
+        """snk_qnet_forward: obs (N,2,10,10) float32 contiguous -> Q (N,3) float32 [= Julia (3,N)]"""
         from . import _check, _ptr, lib
         n = obs.shape[0]
-        out = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(n, 3, dtype=torch.float32, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _check(lib().snk_qnet_forward(self._q, _ptr(obs, torch.float32, n * 200, self.device), n, _ptr(out), st))
+        _check(lib().snk_qnet_forward(self._q, _ptr(obs, torch.float32, n * 200, self.device), n,
+                                      _ptr(out, torch.float32, 3 * n, self.device), st))
         return out
 
-    @classmethod
-    def from_trainer_bson(cls, path, device, which="q_net", dtype=torch.float32):
-        q, t = bson_io.load_trainer_nets(path)
-        return cls(q if which == "q_net" else t, device, dtype)
+    __call__ = forward
 
-    def forward_torch(self, obs):
-        """obs: (N, C, 10, 10) = Julia (10,10,C,N).  Returns Q (N, 3) float32 [= Julia (3, N)]."""
-        x = obs.to(self.dtype)
-        if self.backend == "torch_bf16":
-            x = x.contiguous(memory_format=torch.channels_last)
-        convs = [p for p in self.params if p[0] == "conv"]
-        denses = [p for p in self.params if p[0] == "dense"]
-        for _, w, b, pad in convs:
-            x = F.relu(F.conv2d(x, w, b, padding=pad))
-        x = x.flatten(1)
-        x = F.relu(F.linear(x, denses[0][1], denses[0][2]))
-        x = F.linear(x, denses[1][1], denses[1][2])
-        return x.float().contiguous()
-
-    def __call__(self, obs):
-        return self.forward_native(obs) if self.backend == "native" else self.forward_torch(obs)
+    def overflow(self):
+        """f32 mode: True if an activation left the fp16 range of the split operands since the last call (synchronises)."""
+        from . import _check, lib
+        f = C.c_int(0)
+        _check(lib().snk_qnet_overflow_host(self._q, C.byref(f)))
+        return bool(f.value)

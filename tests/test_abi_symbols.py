@@ -49,7 +49,7 @@ def test_library_exports_every_declared_symbol(built):
     L = S.lib()
     for n in declared_symbols():
         assert hasattr(L, n)
-    assert L.snk_version() == 100
+    assert L.snk_version() == 200
 
 
 def test_library_is_sm100a_native_and_has_no_oracle_dependency(built):

@@ -156,6 +156,7 @@ def test_flux_to_torch_layout_matches_the_true_convolution_oracle():
     state_julia = rng.integers(-1, 3, (10, 10, 2, N)).astype(np.float64)        # (10,10,2,N) WHCN
     want = QO.forward(layers, state_julia)                                       # (3, N)
     obs_torch = torch.from_numpy(np.ascontiguousarray(state_julia.transpose(3, 2, 1, 0)))   # same bytes as col-major
-    net = qnet.QNet(layers, "cpu", dtype=torch.float64)
-    got = net.forward_torch(obs_torch).numpy().T
+    from tools.torch_qnet import TorchQNet
+    net = TorchQNet(layers, "cpu", dtype=torch.float64)
+    got = net(obs_torch).numpy().T
     assert np.allclose(got, want, rtol=1e-5, atol=1e-6)

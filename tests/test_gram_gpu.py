@@ -146,5 +146,5 @@ def test_sample_model_weights_matches_numpy():
     got = S.laplace.sample_model_weights(t(mean), t(var), t(D), t(z1), t(z2)).cpu().numpy()
     assert np.max(np.abs(got - want)) < 1e-13 * np.max(np.abs(want)) + 1e-15
     # the sampled weights are a valid Q-net
-    net = S.qnet.QNet(S.qnet.glorot_layers(0), "cuda:0", backend="native")
+    net = S.qnet.QNet(S.qnet.glorot_layers(0), "cuda:0", precision="f32")
     assert got.shape == (net.n_params,)

@@ -12,7 +12,7 @@ S = graft.load_package()
 n = 65536
 env = S.SnakeGame(n, auto_reset=True)
 obs = env.assemble_state("f32")
-net = S.qnet.QNet(S.qnet.glorot_layers(0), env.device, backend="native")
+net = S.qnet.QNet(S.qnet.glorot_layers(0), env.device, precision="bf16")
 for _ in range(3):
     q = net(obs)
 torch.cuda.synchronize()

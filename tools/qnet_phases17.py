@@ -19,7 +19,7 @@ S = graft.load_package()
 n = 65536
 env = S.SnakeGame(n, auto_reset=True)
 obs = env.assemble_state("f32")
-net = S.qnet.QNet(S.qnet.glorot_layers(0), env.device, backend="native")
+net = S.qnet.QNet(S.qnet.glorot_layers(0), env.device, precision="bf16")
 buf = torch.zeros(8 * 64, dtype=torch.int64, device="cuda")
 L = S.lib()
 L.snk_qnet_debug_timing.argtypes = [C.c_void_p, C.c_void_p]
