@@ -241,6 +241,17 @@ SNK_API int snk_qnet_precision(snk_qnet q, int *precision);
 /* SNK_QNET_F32: *flag = 1 if a forward since the last call produced an activation outside the fp16 range (its Q-values are
  * then not valid); reads and clears the flag, synchronises the device */
 SNK_API int snk_qnet_overflow_host(snk_qnet q, int *flag);
+/* ---- per-sample gradients of the DQN loss  utils.jl:452-466 (Flux.huber_loss(q_net(s)[a], y), delta = 1) ------------
+ * Row i of J = d huber(q_net(s_i)[a_i], y_i) / d theta, theta in Flux.destructure order (181,395 columns) — the per-sample
+ * term of the batch loss, without its 1/B.  BASELINE config 5b takes the Gram of these rows over the replay buffer.
+ * states (10,10,2,B) f32 and actions (B) u8 0-based as snk_replay_gather returns them, targets (B) Float64 as
+ * snk_masked_target returns them.  Outputs (each optional): the bf16 planes hi / lo2 = 2 (v - hi) with a row pitch of
+ * pitch_elems (exactly what snk_gram_block / snk_gram_shard_run(A_rows = NULL) consume: snk_gram_shard_planes,
+ * snk_gram_planes_layout), J_f32 (B x ldJ) Float32, loss (B) Float32.  Computed in FP32 from the Float32 weights whatever
+ * the handle's forward precision is. */
+SNK_API int snk_qnet_sample_grads(snk_qnet q, const float *states, const uint8_t *actions, const double *targets, int64_t B,
+                                  void *hi, void *lo2, int64_t pitch_elems, float *J_f32, int64_t ldJ, float *loss,
+                                  void *cuda_stream);
 /* profiling aid (SNK_QNET_BF16): device buffer of 512 int64 that receives clock64 stamps of the conv phases of CTA 0 on every
  * later forward (64 slots for each of its first 8 iterations, tools/qnet_phases17.py); NULL switches it off */
 SNK_API int snk_qnet_debug_timing(snk_qnet q, long long *device_buf);
@@ -289,6 +300,35 @@ SNK_API int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, c
                            int terms, int block_k, int splits, void *scratch, float *Y, int64_t ldY, void *cuda_stream);
 SNK_API int snk_gram_symmetrize_block(const float *Y, int64_t ldY, const float *YT, int64_t ldYT, int64_t rows_a,
                                       int64_t rows_b, float *G, int64_t ldG, void *cuda_stream);
+/* ---- the row-sharded Gram as ONE call per rank (one process per GPU; SURVEY 8b `snk_gram(..., comm)`, BASELINE config 5b)
+ * rows_all[world]: rows of A owned by every rank; this rank owns rows_all[rank] rows x P.  Set-up, once:
+ *   create -> export_host (192 bytes) -> [the host language moves the 192 bytes of every rank to every rank: MPI,
+ *   Distributed.jl, torch.distributed, a file ...] -> connect_host(all handles, world x 192 bytes, own entry ignored).
+ * snk_gram_shard_run(g, A_rows, ...) then enqueues the whole Gram on `cuda_stream`: pack -> planes ring over NVLink peer
+ * memory under the tcgen05 main loop -> (Y + Y^T)/2 with the transposed blocks read from the peers' memory; the phases are
+ * separated by a device-side barrier over peer memory (no host synchronisation, no communicator).  Every rank must call
+ * it the same number of times.  G_rows: (rows x K_total) Float32, leading dimension ldG >= K_total.  A_rows == NULL: the
+ * planes (snk_gram_shard_planes) were already written by a producer (snk_qnet_sample_grads).
+ * pack / ring / symmetrize / barrier are the phases on their own; connect_local wires shards of ONE process together
+ * (virtual ranks on one GPU, used by the tests) — there the caller orders the phases itself. */
+#define SNK_GRAM_SHARD_HANDLE_BYTES 192
+typedef struct snk_gram_shard_s *snk_gram_shard;
+SNK_API int snk_gram_shard_create(snk_gram_shard *out, const int64_t *rows_all, int world, int rank, int64_t P, int splits,
+                                  int device);
+SNK_API int snk_gram_shard_destroy(snk_gram_shard g);
+SNK_API int snk_gram_shard_export_host(snk_gram_shard g, uint8_t *handle192);
+SNK_API int snk_gram_shard_connect_host(snk_gram_shard g, const uint8_t *handles_world_x_192);
+SNK_API int snk_gram_shard_connect_local(snk_gram_shard g, const snk_gram_shard *peers);
+SNK_API int snk_gram_shard_run(snk_gram_shard g, const void *A_rows, int a_dtype, int terms, int block_k, float *G_rows,
+                               int64_t ldG, void *cuda_stream);
+SNK_API int snk_gram_shard_pack(snk_gram_shard g, const void *A_rows, int a_dtype, void *cuda_stream);
+SNK_API int snk_gram_shard_ring(snk_gram_shard g, int terms, int block_k, void *cuda_stream);
+SNK_API int snk_gram_shard_symmetrize(snk_gram_shard g, int terms, float *G_rows, int64_t ldG, void *cuda_stream);
+SNK_API int snk_gram_shard_barrier(snk_gram_shard g, void *cuda_stream);
+SNK_API int snk_gram_shard_planes(snk_gram_shard g, void **hi, void **lo2, int64_t *pitch_elems);
+/* SNK_ERR_TIMEOUT if a barrier gave up waiting for a peer (synchronises) */
+SNK_API int snk_gram_shard_status_host(snk_gram_shard g, int *timed_out);
+
 /* device memory that other ranks of the box can map (cudaIpc*): allocate, export a 64-byte handle, import a
  * peer's handle, copy (works on peer-mapped pointers: the planes ring of the sharded Gram) */
 SNK_API int snk_ipc_alloc(void **p, size_t bytes);

@@ -85,6 +85,7 @@ def lib():
         "snk_qnet_create": [C.POINTER(vp), vp, i64, i32, i32], "snk_qnet_destroy": [vp],
         "snk_qnet_forward": [vp, vp, i64, vp, vp], "snk_qnet_precision": [vp, C.POINTER(i32)],
         "snk_qnet_overflow_host": [vp, C.POINTER(i32)], "snk_qnet_debug_timing": [vp, vp],
+        "snk_qnet_sample_grads": [vp, vp, vp, vp, i64, vp, vp, i64, vp, i64, vp, vp],
         "snk_gram_workspace_bytes": [i64, i64, i32, C.POINTER(C.c_size_t)],
         "snk_gram_pack": [vp, i32, i64, i64, vp, vp],
         "snk_gram": [vp, i64, i64, i32, i32, i32, vp, vp],
@@ -94,6 +95,14 @@ def lib():
         "snk_gram_block_scratch_bytes": [i64, i64, i64, i32, C.POINTER(C.c_size_t)],
         "snk_gram_block": [vp, i64, vp, vp, i64, i64, i32, i32, i32, vp, vp, i64, vp],
         "snk_gram_symmetrize_block": [vp, i64, vp, i64, i64, i64, vp, i64, vp],
+        "snk_gram_shard_create": [C.POINTER(vp), vp, i32, i32, i64, i32, i32], "snk_gram_shard_destroy": [vp],
+        "snk_gram_shard_export_host": [vp, vp], "snk_gram_shard_connect_host": [vp, vp],
+        "snk_gram_shard_connect_local": [vp, vp],
+        "snk_gram_shard_run": [vp, vp, i32, i32, i32, vp, i64, vp],
+        "snk_gram_shard_pack": [vp, vp, i32, vp], "snk_gram_shard_ring": [vp, i32, i32, vp],
+        "snk_gram_shard_symmetrize": [vp, i32, vp, i64, vp], "snk_gram_shard_barrier": [vp, vp],
+        "snk_gram_shard_planes": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)],
+        "snk_gram_shard_status_host": [vp, C.POINTER(i32)],
         "snk_ipc_alloc": [C.POINTER(vp), C.c_size_t], "snk_ipc_free": [vp],
         "snk_ipc_export": [vp, vp], "snk_ipc_import": [vp, C.POINTER(vp)], "snk_ipc_close": [vp],
         "snk_copy_async": [vp, vp, C.c_size_t, vp],
@@ -440,6 +449,13 @@ class GramPlan:
         with torch.cuda.device(self.device):
             _check(lib().snk_gram_pack(_ptr(A, device=self.device), dt, self.P, self.K, _ptr(self.ws), self._stream()))
         return self
+
+    def planes(self):
+        """(hi pointer, lo2 pointer, pitch in elements) of the bf16 planes inside the workspace: a producer
+        (QNet.sample_grads) can write them instead of pack()"""
+        pb, pitch = C.c_size_t(0), C.c_int64(0)
+        _check(lib().snk_gram_planes_layout(self.K, self.P, C.byref(pb), C.byref(pitch)))
+        return self.ws.data_ptr(), self.ws.data_ptr() + pb.value, pitch.value
 
     def gram(self, terms=3, block_k=0, out=None):
         G = out if out is not None else torch.empty(self.K, self.K, dtype=torch.float32, device=self.device)

@@ -43,6 +43,10 @@
 #include "common.h"
 
 namespace snk {
+namespace qgrad {       // qnet_grads.cu
+int launch_sample_grads(const float *theta_dev, const float *states, const uint8_t *actions, const double *targets, long long B,
+                        void *hi, void *lo2, long long pitch, float *J, long long ldJ, float *loss, int sms, cudaStream_t st);
+}
 namespace qnet {
 
 constexpr int THREADS = 512;                  // split engine: warps 0,1 MMA issuers, warp 2 weight producer, warps 4..15 = 3 epilogue groups
@@ -1164,6 +1168,7 @@ struct snk_qnet_s {
     int device;
     int precision;               // SNK_QNET_BF16 | SNK_QNET_F32
     uint8_t *params;
+    float *theta;                // Flux.destructure(q_net) as given, Float32 on the device (per-sample gradients)
     void *out3;                  // conv3 activations: bf16 [cap][1600] or fp16 [2 cap][1600]
     long long out3_cap;          // in samples
     int *d_overflow;             // SNK_QNET_F32: an activation left the fp16 range
@@ -1201,10 +1206,13 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
     cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&q->theta, (size_t)n_params * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(q->theta, theta_host, (size_t)n_params * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void **)&q->d_overflow, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(q->d_overflow, 0, sizeof(int));
     if (e != cudaSuccess) {
         if (q->params) cudaFree(q->params);
+        if (q->theta) cudaFree(q->theta);
         if (q->d_overflow) cudaFree(q->d_overflow);
         delete q;
         return fail(SNK_ERR_CUDA, "snk_qnet_create: %s", cudaGetErrorString(e));
@@ -1217,10 +1225,26 @@ int snk_qnet_destroy(snk_qnet q) {
     if (q == nullptr) return SNK_OK;
     DeviceGuard guard(q->device);
     if (q->params) cudaFree(q->params);
+    if (q->theta) cudaFree(q->theta);
     if (q->out3) cudaFree(q->out3);
     if (q->d_overflow) cudaFree(q->d_overflow);
     delete q;
     return SNK_OK;
+}
+
+// per-sample gradients of huber(q_net(s_i)[a_i], y_i) (utils.jl:452-466), always from the Float32 weights: csrc/qnet_grads.cu
+int snk_qnet_sample_grads(snk_qnet q, const float *states, const uint8_t *actions, const double *targets, int64_t B, void *hi,
+                          void *lo2, int64_t pitch_elems, float *J_f32, int64_t ldJ, float *loss, void *cuda_stream) {
+    SNK_REQUIRE(q != nullptr && states != nullptr && actions != nullptr && targets != nullptr && B >= 0, "bad argument");
+    SNK_REQUIRE((hi == nullptr) == (lo2 == nullptr), "hi and lo2 planes come together");
+    SNK_REQUIRE(hi != nullptr || J_f32 != nullptr || loss != nullptr, "no output requested");
+    SNK_REQUIRE(hi == nullptr || (pitch_elems >= 181395 && pitch_elems % 8 == 0 && (((uintptr_t)hi | (uintptr_t)lo2) & 15u) == 0),
+                "planes need a pitch >= 181395 that is a multiple of 8 elements and 16-byte aligned bases");
+    SNK_REQUIRE(J_f32 == nullptr || ldJ >= 181395, "ldJ too small");
+    if (B == 0) return SNK_OK;
+    DeviceGuard guard(q->device);
+    return qgrad::launch_sample_grads(q->theta, states, actions, targets, B, hi, lo2, pitch_elems, J_f32, ldJ, loss, q->sms,
+                                      (cudaStream_t)cuda_stream);
 }
 
 int snk_qnet_precision(snk_qnet q, int *precision) {

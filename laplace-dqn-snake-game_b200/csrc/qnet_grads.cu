@@ -1,0 +1,348 @@
+// qnet_grads.cu — per-sample gradients of the DQN loss, the rows of the matrix J whose Gram BASELINE config 5b names
+// ("Gram/D matrix of per-sample gradients ... over a 50k-transition buffer").
+//
+// Reference: the loss of train! (utils.jl:452-466; dup compute_D.jl:102-116, la_utils.jl:193-207)
+//     q_pred = q_net(states);  q_sel = q_pred[a_i, i];  Flux.huber_loss(q_sel, q_target)         (delta = 1)
+// through the network of structs.jl:127-139.  Row i of J is d huber(q_net(s_i)[a_i], y_i) / d theta with theta in
+// Flux.destructure order (W1 b1 W2 b2 W3 b3 W4 b4 W5 b5, column-major) — the per-sample term, without the 1/B of the batch
+// mean.  The reference itself never forms per-sample gradients (Zygote returns their mean); the oracle is a Float64
+// torch.func evaluation of the same expression (tests/test_sample_grads_gpu.py) — parity unpinned by the reference.
+//
+// One CTA per sample, all activations and back-propagated signals of the sample in shared memory, plain FP32 FMAs: per
+// sample the contractions are 25..2304 deep — CUDA-core work; the kernel is bound by FP32 issue (14.6 MFLOP per sample) and
+// by the 725 KB (two bf16 planes) it writes per sample.  The row goes STRAIGHT into the bf16 hi / 2 lo planes the Gram
+// kernel consumes (hi = bf16(v), lo2 = bf16(2 (v - hi)): the same split as k_gram_pack), optionally also as Float32.
+// Weights are read from global memory (L2-resident, 726 KB) through warp-uniform loads: a warp owns an output channel (or
+// a pair), its lanes the output positions.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace snk {
+namespace qgrad {
+
+constexpr int NT = 256, NW = NT / 32;
+// Flux.destructure offsets
+constexpr int O_W1 = 0, O_B1 = 288, O_W2 = 304, O_B2 = 4912, O_W3 = 4944, O_B3 = 78672, O_W4 = 78736, O_B4 = 181136,
+              O_W5 = 181200, O_B5 = 181392, NP = 181395;
+// shared memory map (floats)
+constexpr int S_XIN = 0;                       // [2][12][12]   input, zero padded by 1
+constexpr int S_A1 = S_XIN + 2 * 144;          // [16][12][12]  relu(conv1), zero padded by 1
+constexpr int S_A2 = S_A1 + 16 * 144;          // [32][10][10]  relu(conv2)
+constexpr int S_A3 = S_A2 + 3200;              // [64][5][5]    relu(conv3) = Flux.flatten order x + 5 y + 25 c
+constexpr int S_HID = S_A3 + 1600;             // [64]          relu(dense1)
+constexpr int S_GH = S_HID + 64;               // [64]          d loss / d (dense1 pre-activation)
+constexpr int S_Q = S_GH + 64;                 // [4]           q-values, [3] = d loss / d q[a]
+constexpr int S_RED = S_Q + 4;                 // [256]         reduction scratch
+constexpr int S_G3 = S_RED + 256;              // [64][15][15]  d loss / d (conv3 pre-activation), zero padded by 5
+constexpr int S_G2 = S_G3 + 64 * 225;          // [32][12][12]  d loss / d (conv2 pre-activation), zero padded by 1
+constexpr int S_G1 = S_G2 + 32 * 144;          // [16][10][10]  d loss / d (conv1 pre-activation)
+constexpr int S_END = S_G1 + 1600;
+constexpr int SMEM_BYTES = S_END * 4;
+
+struct GradArgs {
+    const float *theta;          // 181,395 Float32, Flux.destructure order
+    const float *states;         // (10,10,2,B) f32
+    const uint8_t *actions;      // (B) 0-based index into available_actions
+    const double *targets;       // (B) Float64 (what snk_masked_target returns)
+    long long B;
+    __nv_bfloat16 *hi, *lo2;     // planes [B][pitch] or NULL
+    long long pitch;
+    float *J;                    // [B][ldJ] Float32 or NULL
+    long long ldJ;
+    float *loss;                 // (B) or NULL
+};
+
+struct Row {
+    __nv_bfloat16 *hi, *lo;
+    float *J;
+};
+__device__ __forceinline__ uint32_t split2(float v0, float v1, uint32_t &lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(2.0f * (v0 - __bfloat162float(h0)));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(2.0f * (v1 - __bfloat162float(h1)));
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    return (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+}
+__device__ __forceinline__ void emit1(const Row &r, int idx, float v) {
+    if (r.hi != nullptr) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        r.hi[idx] = h;
+        r.lo[idx] = __float2bfloat16_rn(2.0f * (v - __bfloat162float(h)));
+    }
+    if (r.J != nullptr) r.J[idx] = v;
+}
+template <int N>      // N = 4 or 8 consecutive values, idx a multiple of N
+__device__ __forceinline__ void emitv(const Row &r, int idx, const float (&v)[N]) {
+    if (r.hi != nullptr) {
+        uint32_t h[N / 2], l[N / 2];
+#pragma unroll
+        for (int j = 0; j < N / 2; j++) h[j] = split2(v[2 * j], v[2 * j + 1], l[j]);
+        if (N == 8) {
+            *reinterpret_cast<uint4 *>(r.hi + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(r.lo + idx) = make_uint4(l[0], l[1], l[2], l[3]);
+        } else {
+            *reinterpret_cast<uint2 *>(r.hi + idx) = make_uint2(h[0], h[1]);
+            *reinterpret_cast<uint2 *>(r.lo + idx) = make_uint2(l[0], l[1]);
+        }
+    }
+    if (r.J != nullptr) {
+#pragma unroll
+        for (int j = 0; j < N; j++) r.J[idx + j] = v[j];
+    }
+}
+
+// out(x, y, o) = relu(b[o] + sum_{c,a2,a1} W[a1 + K (a2 + K (c + CIN o))] * in[c][y + K-1-a2][x + K-1-a1])   (true convolution;
+// `in` is the zero-padded input plane, row pitch IP, channel stride IC).  A warp owns an output channel, its lanes up to PPL
+// output positions each; the weight is a warp-uniform load.
+template <int K, int CIN, int COUT, int OW, int IP, int IC, int PPL>
+__device__ __forceinline__ void conv_forward(const float *__restrict__ W, const float *__restrict__ b, const float *in, float *out,
+                                             int out_pitch, int out_cs, int out_off, int warp, int lane) {
+    for (int o = warp; o < COUT; o += NW) {
+        float acc[PPL];
+        int base[PPL];
+        bool live[PPL];
+#pragma unroll
+        for (int j = 0; j < PPL; j++) {
+            const int p = lane + 32 * j;
+            live[j] = p < OW * OW;
+            const int y = live[j] ? p / OW : 0, x = live[j] ? p - OW * (p / OW) : 0;
+            base[j] = (y + K - 1) * IP + (x + K - 1);
+            acc[j] = __ldg(b + o);
+        }
+        const float *w = W + (size_t)K * K * CIN * o;
+        for (int c = 0; c < CIN; c++)
+#pragma unroll
+            for (int a2 = 0; a2 < K; a2++)
+#pragma unroll
+                for (int a1 = 0; a1 < K; a1++) {
+                    const float wv = __ldg(w + a1 + K * (a2 + K * c));
+#pragma unroll
+                    for (int j = 0; j < PPL; j++) acc[j] = fmaf(wv, in[c * IC + base[j] - a2 * IP - a1], acc[j]);
+                }
+#pragma unroll
+        for (int j = 0; j < PPL; j++)
+            if (live[j]) {
+                const int p = lane + 32 * j, y = p / OW, x = p - OW * y;
+                out[o * out_cs + y * out_pitch + x + out_off] = fmaxf(acc[j], 0.f);
+            }
+    }
+}
+
+// d loss / d in(u, v, c) = sum_{o,a2,a1} W[a1 + K (a2 + K (c + CIN o))] * gp[o][v + a2][u + a1], gp = the gradient at the layer's
+// pre-activation zero-padded by K-1-pad on each side (row pitch GP, channel stride GC); masked by relu'(in) and stored.
+// A warp owns an input channel c, its lanes up to PPL input positions each.
+template <int K, int CIN, int COUT, int IW, int GP, int GC, int PPL>
+__device__ __forceinline__ void conv_backward_data(const float *__restrict__ W, const float *gp, const float *act, int act_pitch,
+                                                   int act_cs, int act_off, float *out, int out_pitch, int out_cs, int out_off,
+                                                   int warp, int lane) {
+    for (int c = warp; c < CIN; c += NW) {
+        float acc[PPL];
+        int base[PPL];
+        bool live[PPL];
+#pragma unroll
+        for (int j = 0; j < PPL; j++) {
+            const int p = lane + 32 * j;
+            live[j] = p < IW * IW;
+            const int v = live[j] ? p / IW : 0, u = live[j] ? p - IW * (p / IW) : 0;
+            base[j] = v * GP + u;
+            acc[j] = 0.f;
+        }
+        for (int o = 0; o < COUT; o++) {
+            const float *w = W + (size_t)K * K * (c + CIN * o);
+#pragma unroll
+            for (int a2 = 0; a2 < K; a2++)
+#pragma unroll
+                for (int a1 = 0; a1 < K; a1++) {
+                    const float wv = __ldg(w + a1 + K * a2);
+#pragma unroll
+                    for (int j = 0; j < PPL; j++) acc[j] = fmaf(wv, gp[o * GC + base[j] + a2 * GP + a1], acc[j]);
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < PPL; j++)
+            if (live[j]) {
+                const int p = lane + 32 * j, v = p / IW, u = p - IW * v;
+                const float a = act[c * act_cs + v * act_pitch + u + act_off];
+                out[c * out_cs + v * out_pitch + u + out_off] = a > 0.f ? acc[j] : 0.f;
+            }
+    }
+}
+
+// d loss / d W[a1 + K (a2 + K (c + CIN o))] = sum_{x,y} g(x, y, o) * in[c][y + K-1-a2][x + K-1-a1]; g read from its padded
+// array (gp + g_off = position (0,0)).  One task = (input channel c, NO consecutive output channels): K*K*NO accumulators in
+// registers; lanes of a warp differ in o, so the input reads are broadcasts.
+template <int K, int CIN, int COUT, int OW, int IP, int IC, int GP, int GC, int NO>
+__device__ __forceinline__ void conv_backward_weights(const float *gp, int g_off, const float *in, const Row &row, int w_off, int tid) {
+    constexpr int OG = COUT / NO;
+    for (int task = tid; task < CIN * OG; task += NT) {
+        const int og = task % OG, c = task / OG;
+        float acc[NO][K * K];
+#pragma unroll
+        for (int n = 0; n < NO; n++)
+#pragma unroll
+            for (int t = 0; t < K * K; t++) acc[n][t] = 0.f;
+        for (int y = 0; y < OW; y++)
+            for (int x = 0; x < OW; x++) {
+                float g[NO];
+#pragma unroll
+                for (int n = 0; n < NO; n++) g[n] = gp[(og * NO + n) * GC + g_off + y * GP + x];
+                const float *ip = in + c * IC + (y + K - 1) * IP + (x + K - 1);
+#pragma unroll
+                for (int a2 = 0; a2 < K; a2++)
+#pragma unroll
+                    for (int a1 = 0; a1 < K; a1++) {
+                        const float v = ip[-a2 * IP - a1];
+#pragma unroll
+                        for (int n = 0; n < NO; n++) acc[n][a2 * K + a1] = fmaf(g[n], v, acc[n][a2 * K + a1]);
+                    }
+            }
+#pragma unroll
+        for (int n = 0; n < NO; n++) {
+            const int idx = w_off + K * K * (c + CIN * (og * NO + n));
+            if ((K * K) % 4 == 0) {
+#pragma unroll
+                for (int t = 0; t < K * K; t += 4) {
+                    const float v4[4] = {acc[n][t], acc[n][t + 1], acc[n][t + 2], acc[n][t + 3]};
+                    emitv<4>(row, idx + t, v4);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < K * K; t++) emit1(row, idx + t, acc[n][t]);
+            }
+        }
+    }
+}
+
+// bias gradient: sum over the positions of one channel of a (padded) gradient array
+template <int C, int OW, int GP, int GC>
+__device__ __forceinline__ void bias_grad(const float *gp, int g_off, const Row &row, int b_off, int warp, int lane) {
+    for (int o = warp; o < C; o += NW) {
+        float s = 0.f;
+        for (int p = lane; p < OW * OW; p += 32) s += gp[o * GC + g_off + (p / OW) * GP + (p % OW)];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) emit1(row, b_off + o, s);
+    }
+}
+
+__global__ void __launch_bounds__(NT) k_sample_grads(const GradArgs a) {
+    extern __shared__ float sm[];
+    float *xin = sm + S_XIN, *a1p = sm + S_A1, *a2s = sm + S_A2, *a3s = sm + S_A3, *hid = sm + S_HID, *gh = sm + S_GH;
+    float *qv = sm + S_Q, *red = sm + S_RED, *g3p = sm + S_G3, *g2p = sm + S_G2, *g1s = sm + S_G1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float *th = a.theta;
+    for (int i = tid; i < S_END; i += NT) sm[i] = 0.f;            // the zero borders of the padded arrays stay zero
+    for (long long s = blockIdx.x; s < a.B; s += gridDim.x) {
+        __syncthreads();
+        Row row;
+        row.hi = a.hi != nullptr ? a.hi + s * a.pitch : nullptr;
+        row.lo = a.lo2 != nullptr ? a.lo2 + s * a.pitch : nullptr;
+        row.J = a.J != nullptr ? a.J + s * a.ldJ : nullptr;
+        // ---------------- forward (structs.jl:127-139) ----------------
+        for (int i = tid; i < 200; i += NT) {
+            const int c = i / 100, p = i - 100 * c, y = p / 10, x = p - 10 * y;
+            xin[c * 144 + (y + 1) * 12 + (x + 1)] = a.states[s * 200 + i];
+        }
+        __syncthreads();
+        conv_forward<3, 2, 16, 10, 12, 144, 4>(th + O_W1, th + O_B1, xin, a1p, 12, 144, 13, warp, lane);
+        __syncthreads();
+        conv_forward<3, 16, 32, 10, 12, 144, 4>(th + O_W2, th + O_B2, a1p, a2s, 10, 100, 0, warp, lane);
+        __syncthreads();
+        conv_forward<6, 32, 64, 5, 10, 100, 1>(th + O_W3, th + O_B3, a2s, a3s, 5, 25, 0, warp, lane);
+        __syncthreads();
+        {   // Dense(1600, 64, relu): thread = (n, quarter of k)
+            const int n = tid & 63, part = tid >> 6;
+            float acc = 0.f;
+            for (int k = part * 400; k < part * 400 + 400; k++) acc = fmaf(__ldg(th + O_W4 + n + 64 * k), a3s[k], acc);
+            red[tid] = acc;
+            __syncthreads();
+            if (tid < 64) hid[tid] = fmaxf(red[tid] + red[tid + 64] + red[tid + 128] + red[tid + 192] + __ldg(th + O_B4 + tid), 0.f);
+            __syncthreads();
+        }
+        const int act = a.actions[s] < 3 ? a.actions[s] : 0;
+        if (warp == 0) {   // Dense(64, 3), Huber loss (delta = 1) on the selected action (utils.jl:452-458)
+            float q3[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float p = fmaf(__ldg(th + O_W5 + k + 3 * lane), hid[lane], 0.f) + fmaf(__ldg(th + O_W5 + k + 3 * (lane + 32)), hid[lane + 32], 0.f);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) p += __shfl_xor_sync(0xffffffffu, p, d);
+                q3[k] = p + __ldg(th + O_B5 + k);
+            }
+            if (lane == 0) {
+                // q_target is Float64 in the reference (the 0.97 literal promotes, utils.jl:451), so the loss is evaluated in
+                // Float64 and its gradient projected back to the Float32 of q_pred
+                const double d = (double)q3[act] - a.targets[s];
+                const double ad = fabs(d);
+                qv[0] = q3[0]; qv[1] = q3[1]; qv[2] = q3[2];
+                qv[3] = (float)(ad < 1.0 ? d : copysign(1.0, d));          // d huber / d q_sel
+                if (a.loss != nullptr) a.loss[s] = (float)(ad < 1.0 ? 0.5 * d * d : ad - 0.5);
+            }
+        }
+        __syncthreads();
+        // ---------------- backward ----------------
+        const float g = qv[3];
+        if (tid < 192) emit1(row, O_W5 + tid, (tid % 3) == act ? g * hid[tid / 3] : 0.f);       // W5 is (3,64) column-major
+        if (tid < 3) emit1(row, O_B5 + tid, tid == act ? g : 0.f);
+        if (tid >= 192 && tid < 192 + 45 && NP + (tid - 192) < a.pitch && row.hi != nullptr) {   // padding columns of the planes
+            row.hi[NP + tid - 192] = __float2bfloat16_rn(0.f);
+            row.lo[NP + tid - 192] = __float2bfloat16_rn(0.f);
+        }
+        if (tid < 64) {
+            const float v = hid[tid] > 0.f ? __ldg(th + O_W5 + act + 3 * tid) * g : 0.f;
+            gh[tid] = v;
+            emit1(row, O_B4 + tid, v);
+        }
+        __syncthreads();
+        // grad W4[n + 64 k] = gh[n] a3[k]: 8 consecutive n per store
+        for (int i = tid; i < 1600 * 8; i += NT) {
+            const int k = i >> 3, n0 = (i & 7) * 8;
+            const float ak = a3s[k];
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v8[j] = gh[n0 + j] * ak;
+            emitv<8>(row, O_W4 + n0 + 64 * k, v8);
+        }
+        // d loss / d a3[k] = sum_n W4[n + 64 k] gh[n], through relu, into the padded conv3 gradient
+        for (int k = tid; k < 1600; k += NT) {
+            const float4 *w4 = reinterpret_cast<const float4 *>(th + O_W4 + 64 * k);
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const float4 w = __ldg(w4 + j);
+                acc = fmaf(w.x, gh[4 * j], acc); acc = fmaf(w.y, gh[4 * j + 1], acc);
+                acc = fmaf(w.z, gh[4 * j + 2], acc); acc = fmaf(w.w, gh[4 * j + 3], acc);
+            }
+            const int o = k / 25, p = k - 25 * o, y = p / 5, x = p - 5 * y;
+            g3p[o * 225 + (y + 5) * 15 + (x + 5)] = a3s[k] > 0.f ? acc : 0.f;
+        }
+        __syncthreads();
+        bias_grad<64, 5, 15, 225>(g3p, 5 * 15 + 5, row, O_B3, warp, lane);
+        conv_backward_weights<6, 32, 64, 5, 10, 100, 15, 225, 2>(g3p, 5 * 15 + 5, a2s, row, O_W3, tid);
+        conv_backward_data<6, 32, 64, 10, 15, 225, 4>(th + O_W3, g3p, a2s, 10, 100, 0, g2p, 12, 144, 13, warp, lane);
+        __syncthreads();
+        bias_grad<32, 10, 12, 144>(g2p, 13, row, O_B2, warp, lane);
+        conv_backward_weights<3, 16, 32, 10, 12, 144, 12, 144, 1>(g2p, 13, a1p, row, O_W2, tid);
+        conv_backward_data<3, 16, 32, 10, 12, 144, 4>(th + O_W2, g2p, a1p, 12, 144, 13, g1s, 10, 100, 0, warp, lane);
+        __syncthreads();
+        bias_grad<16, 10, 10, 100>(g1s, 0, row, O_B1, warp, lane);
+        conv_backward_weights<3, 2, 16, 10, 12, 144, 10, 100, 1>(g1s, 0, xin, row, O_W1, tid);
+    }
+}
+
+int launch_sample_grads(const float *theta_dev, const float *states, const uint8_t *actions, const double *targets, long long B,
+                        void *hi, void *lo2, long long pitch, float *J, long long ldJ, float *loss, int sms, cudaStream_t st) {
+    GradArgs a;
+    a.theta = theta_dev; a.states = states; a.actions = actions; a.targets = targets; a.B = B;
+    a.hi = (__nv_bfloat16 *)hi; a.lo2 = (__nv_bfloat16 *)lo2; a.pitch = pitch; a.J = J; a.ldJ = ldJ; a.loss = loss;
+    SNK_CUDA(cudaFuncSetAttribute(k_sample_grads, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const long long max_grid = 2ll * sms;                    // 2 CTAs of 111 KB per SM
+    const int grid = (int)(B < max_grid ? B : max_grid);
+    k_sample_grads<<<grid, NT, SMEM_BYTES, st>>>(a);
+    SNK_CUDA(cudaGetLastError());
+    return SNK_OK;
+}
+
+}  // namespace qgrad
+}  // namespace snk

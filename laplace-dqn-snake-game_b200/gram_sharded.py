@@ -13,9 +13,10 @@ place on the path with a real exchange step:
      the transposed block Y[rows_p, rows_g] straight out of rank p's memory (peer loads over NVLink) —
      the transpose "all-to-all" is fused into that kernel.
 
-torch.distributed is only plumbing here (IPC-handle exchange, barriers); it works with gloo as well, which
-is how the CPU test drives the schedule.  `LocalPeers` emulates R ranks inside one process on one GPU with
-the same kernels (tests on a single B200).
+The orchestration lives in the C library (csrc/gram_shard.cu: snk_gram_shard_*, one call per rank and Gram, device-side
+barriers over peer memory); this module is the thin Python caller.  torch.distributed only carries the 192-byte IPC
+handles at set-up.  `LocalPeers` emulates R ranks inside one process on one GPU with the same kernels (tests on a
+single B200); `AllGatherGram` is the library-collective (NCCL) baseline the planes ring is measured against.
 """
 import ctypes as C
 
@@ -31,134 +32,99 @@ def ring_schedule(rank, world):
     return [(rank + i) % world for i in range(world)]
 
 
-class _Buf:
-    """cudaMalloc'ed (IPC-exportable) device buffer."""
-
-    def __init__(self, nbytes):
-        self.ptr = C.c_void_p()
-        self.nbytes = int(nbytes)
-        _check(lib().snk_ipc_alloc(C.byref(self.ptr), max(self.nbytes, 256)))
-
-    def handle(self):
-        h = (C.c_uint8 * 64)()
-        _check(lib().snk_ipc_export(self.ptr, h))
-        return bytes(h)
-
-    def free(self):
-        if self.ptr:
-            lib().snk_ipc_free(self.ptr)
-            self.ptr = C.c_void_p()
+HANDLE_BYTES = 192            # SNK_GRAM_SHARD_HANDLE_BYTES
 
 
 class GramShard:
-    """One rank's state: planes of its own rows, a double buffer for peers' planes, its Y and G row blocks."""
+    """One rank's snk_gram_shard: planes of its own rows, a double buffer for peers' planes, its Y row block — all owned
+    by the C library (csrc/gram_shard.cu).  Python only carries the IPC handles between the processes."""
 
     def __init__(self, rows_all, rank, P, device, splits=0):
-        self.rows_all = list(rows_all)                     # rows owned by every rank
-        self.rank, self.world, self.P = rank, len(rows_all), int(P)
-        self.rows = self.rows_all[rank]
-        self.K = sum(self.rows_all)
+        self.rows_all = [int(r) for r in rows_all]
+        self.rank, self.world, self.P = int(rank), len(rows_all), int(P)
+        self.rows, self.K = self.rows_all[rank], sum(self.rows_all)
         self.col0 = [sum(self.rows_all[:r]) for r in range(self.world)]
         self.device = torch.device(device)
-        self.splits = splits
-        max_rows = max(self.rows_all)
-        pb, pitch = C.c_size_t(0), C.c_int64(0)
-        _check(lib().snk_gram_planes_layout(max_rows, self.P, C.byref(pb), C.byref(pitch)))
-        self.plane_bytes, self.pitch = pb.value, pitch.value
-        with torch.cuda.device(self.device):
-            self.planes = _Buf(2 * self.plane_bytes)                       # [hi | lo2] of my rows (exported)
-            self.stage = [_Buf(2 * self.plane_bytes) for _ in range(2)]    # peers' planes, double buffered
-            self.Y = _Buf(self.rows * self.K * 4)                          # my row block of Y (exported)
-            sb = C.c_size_t(0)
-            _check(lib().snk_gram_block_scratch_bytes(self.rows, max_rows, self.P, splits, C.byref(sb)))
-            self.scratch = _Buf(sb.value)
+        arr = (C.c_int64 * self.world)(*self.rows_all)
+        self._g = C.c_void_p()
+        _check(lib().snk_gram_shard_create(C.byref(self._g), arr, self.world, self.rank, self.P, int(splits),
+                                           self.device.index or 0))
         self.G = torch.empty(self.rows, self.K, dtype=torch.float32, device=self.device)
-        self.compute = torch.cuda.current_stream(self.device)
-        self.copy = torch.cuda.Stream(self.device)
 
-    def _p(self, buf, off=0):
-        return C.c_void_p(buf.ptr.value + off)
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def pack(self, A_rows):
+    def handle(self):
+        h = (C.c_uint8 * HANDLE_BYTES)()
+        _check(lib().snk_gram_shard_export_host(self._g, h))
+        return bytes(h)
+
+    def connect(self, handles):
+        """handles: list of every rank's 192-byte handle (own entry ignored)"""
+        blob = b"".join(handles)
+        _check(lib().snk_gram_shard_connect_host(self._g, (C.c_uint8 * len(blob)).from_buffer_copy(blob)))
+
+    def planes(self):
+        """(hi pointer, lo2 pointer, pitch in elements) of this rank's bf16 planes, for a producer that writes them directly"""
+        hi, lo, pitch = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _check(lib().snk_gram_shard_planes(self._g, C.byref(hi), C.byref(lo), C.byref(pitch)))
+        return hi.value, lo.value, pitch.value
+
+    def _a(self, A_rows):
+        if A_rows is None:
+            return None, 0
         assert tuple(A_rows.shape) == (self.rows, self.P)
-        dt = {torch.float64: DTYPE_F64, torch.float32: DTYPE_F32}[A_rows.dtype]
-        with torch.cuda.device(self.device):
-            _check(lib().snk_gram_pack_planes(_ptr(A_rows, device=self.device), dt, self.P, self.rows, self.planes.ptr,
-                                              self._p(self.planes, self.plane_bytes),
-                                              C.c_void_p(self.compute.cuda_stream)))
+        return _ptr(A_rows, device=self.device), {torch.float64: DTYPE_F64, torch.float32: DTYPE_F32}[A_rows.dtype]
+
+    def run(self, A_rows, terms=3, block_k=0):
+        """the whole sharded Gram for this rank, enqueued on the current stream: G[rows_rank, :] (an internal buffer, valid
+        until the next run).  A_rows None = the planes were written by a producer."""
+        a, dt = self._a(A_rows)
+        _check(lib().snk_gram_shard_run(self._g, a, dt, int(terms), int(block_k), _ptr(self.G), self.K, self._stream()))
+        return self.G
+
+    # the phases on their own (virtual ranks in one process order them themselves)
+    def pack(self, A_rows):
+        a, dt = self._a(A_rows)
+        _check(lib().snk_gram_shard_pack(self._g, a, dt, self._stream()))
+
+    def ring(self, terms=3, block_k=0):
+        _check(lib().snk_gram_shard_ring(self._g, int(terms), int(block_k), self._stream()))
+
+    def symmetrize(self, terms=3):
+        _check(lib().snk_gram_shard_symmetrize(self._g, int(terms), _ptr(self.G), self.K, self._stream()))
+        return self.G
+
+    def check(self):
+        t = C.c_int(0)
+        _check(lib().snk_gram_shard_status_host(self._g, C.byref(t)))
 
     def free(self):
-        for b in [self.planes, self.Y, self.scratch] + self.stage:
-            b.free()
-
-
-def run_ring(shard, peer_planes, terms=3, block_k=0):
-    """Steps 2 of the module docstring for one rank.  peer_planes[r] = device pointer (int) to rank r's
-    [hi | lo2] planes as visible from this process (own pointer for r == rank)."""
-    L = lib()
-    sched = ring_schedule(shard.rank, shard.world)
-    cs, ks = shard.copy, shard.compute
-    ev_copied = [torch.cuda.Event() for _ in sched]
-    ev_used = [torch.cuda.Event() for _ in sched]
-    with torch.cuda.device(shard.device):
-        for i, p in enumerate(sched):
-            # prefetch the NEXT peer's planes into the other staging buffer while this step computes
-            if i + 1 < len(sched):
-                nxt = sched[i + 1]
-                if i >= 1:
-                    cs.wait_event(ev_used[i - 1])          # that buffer was the B operand of step i-1
-                nbytes = shard.plane_bytes + shard.rows_all[nxt] * shard.pitch * 2
-                _check(L.snk_copy_async(shard.stage[(i + 1) % 2].ptr, C.c_void_p(peer_planes[nxt]), nbytes,
-                                        C.c_void_p(cs.cuda_stream)))
-                ev_copied[i + 1].record(cs)
-            if i == 0:
-                b_hi = shard.planes.ptr.value
-            else:
-                ks.wait_event(ev_copied[i])
-                b_hi = shard.stage[i % 2].ptr.value
-            b_lo = b_hi + shard.plane_bytes
-            ycol = C.c_void_p(shard.Y.ptr.value + 4 * shard.col0[p])
-            _check(L.snk_gram_block(shard.planes.ptr, shard.rows, C.c_void_p(b_hi), C.c_void_p(b_lo), shard.rows_all[p],
-                                    shard.P, terms, block_k, shard.splits, shard.scratch.ptr, ycol, shard.K,
-                                    C.c_void_p(ks.cuda_stream)))
-            ev_used[i].record(ks)
-
-
-def run_symmetrize(shard, peer_Y, terms=3):
-    """Step 3: G[rows_g, rows_p] = (Y[rows_g, rows_p] + Y_p[rows_p, rows_g]^T)/2, Y_p read from peer memory."""
-    L = lib()
-    g = shard
-    with torch.cuda.device(g.device):
-        st = C.c_void_p(g.compute.cuda_stream)
-        for p in range(g.world):
-            y = C.c_void_p(g.Y.ptr.value + 4 * g.col0[p])
-            out = C.c_void_p(g.G.data_ptr() + 4 * g.col0[p])
-            if terms == 1:
-                _check(L.snk_copy_async(C.c_void_p(g.G.data_ptr()), g.Y.ptr, g.rows * g.K * 4, st))
-                break
-            yt = C.c_void_p(peer_Y[p] + 4 * g.col0[g.rank])       # rank p's block (rows_p x rows_g), ld K
-            _check(L.snk_gram_symmetrize_block(y, g.K, yt, g.K, g.rows, g.rows_all[p], out, g.K, st))
-    return g.G
+        if getattr(self, "_g", None) and self._g.value:
+            lib().snk_gram_shard_destroy(self._g)
+            self._g = C.c_void_p()
 
 
 class LocalPeers:
-    """R virtual ranks in ONE process on ONE GPU — same kernels, local pointers.  For tests on a single B200."""
+    """R virtual ranks in ONE process on ONE GPU — same kernels, local pointers (snk_gram_shard_connect_local); the phases
+    are ordered by the host here because the virtual ranks share one stream.  For tests on a single B200."""
 
     def __init__(self, K_total, P, world, device, splits=0):
         rows = [shard_range(K_total, r, world)[1] - shard_range(K_total, r, world)[0] for r in range(world)]
         self.shards = [GramShard(rows, r, P, device, splits) for r in range(world)]
+        arr = (C.c_void_p * world)(*[s._g.value for s in self.shards])
+        for s in self.shards:
+            _check(lib().snk_gram_shard_connect_local(s._g, arr))
 
     def gram(self, A, terms=3, block_k=0):
         for s in self.shards:
             lo = s.col0[s.rank]
             s.pack(A[lo:lo + s.rows].contiguous())
-        planes = [s.planes.ptr.value for s in self.shards]
-        Ys = [s.Y.ptr.value for s in self.shards]
         torch.cuda.synchronize()                  # "barrier": every virtual rank's planes are packed
         for s in self.shards:
-            run_ring(s, planes, terms, block_k)
+            s.ring(terms, block_k)
         torch.cuda.synchronize()
-        out = [run_symmetrize(s, Ys, terms) for s in self.shards]
+        out = [s.symmetrize(terms) for s in self.shards]
         torch.cuda.synchronize()
         return torch.cat(out, 0)
 
@@ -168,8 +134,9 @@ class LocalPeers:
 
 
 class DistributedGram:
-    """Persistent multi-process sharded Gram (one process per GPU): buffers and peer mappings are set up once
-    (cudaMalloc + cudaIpc handle exchange through torch.distributed), run() can then be called repeatedly."""
+    """Persistent multi-process sharded Gram (one process per GPU): buffers and peer mappings are set up once (the 192-byte
+    IPC handles travel through torch.distributed — the only thing it is used for), run() is then ONE library call per rank:
+    no host synchronisation, the phases are separated by device-side barriers over peer memory."""
 
     def __init__(self, rows_all, P, device, splits=0, group=None):
         self.group = group
@@ -177,40 +144,17 @@ class DistributedGram:
         self.device = torch.device(device)
         self.shard = GramShard(rows_all, self.rank, P, self.device, splits)
         handles = [None] * self.world
-        dist.all_gather_object(handles, (self.shard.planes.handle(), self.shard.Y.handle()), group=group)
-        self.planes, self.Ys, self._opened = [], [], []
-        for r, (hp, hy) in enumerate(handles):
-            if r == self.rank:
-                self.planes.append(self.shard.planes.ptr.value)
-                self.Ys.append(self.shard.Y.ptr.value)
-                continue
-            pp, py = C.c_void_p(), C.c_void_p()
-            with torch.cuda.device(self.device):
-                _check(lib().snk_ipc_import((C.c_uint8 * 64).from_buffer_copy(hp), C.byref(pp)))
-                _check(lib().snk_ipc_import((C.c_uint8 * 64).from_buffer_copy(hy), C.byref(py)))
-            self._opened += [pp, py]
-            self.planes.append(pp.value)
-            self.Ys.append(py.value)
-
-    def _barrier(self):
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
+        dist.all_gather_object(handles, self.shard.handle(), group=group)
+        self.shard.connect(handles)
 
     def run(self, A_rows, terms=3, block_k=0):
         """G[rows_rank, :] (a view of an internal buffer, valid until the next run)."""
-        self.shard.pack(A_rows)
-        self._barrier()                           # every rank's planes are packed
-        run_ring(self.shard, self.planes, terms, block_k)
-        self._barrier()                           # every rank's Y row block is complete
-        G = run_symmetrize(self.shard, self.Ys, terms)
-        self._barrier()                           # nobody still reads my Y / planes
-        return G
+        return self.shard.run(A_rows, terms, block_k)
 
     def close(self):
-        self._barrier()
-        for p in self._opened:
-            lib().snk_ipc_close(p)
-        self._opened = []
+        torch.cuda.synchronize(self.device)
+        self.shard.check()
+        dist.barrier(group=self.group)
         self.shard.free()
 
 

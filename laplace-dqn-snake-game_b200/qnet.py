@@ -100,6 +100,26 @@ class QNet:
 
     __call__ = forward
 
+    def sample_grads(self, states, actions, targets, planes=None, want_J=False, want_loss=True):
+        """Per-sample gradients of huber(q_net(s_i)[a_i], y_i) (utils.jl:452-466), FP32, Flux.destructure order.
+        states (B,2,10,10) f32, actions (B) u8 (0-based), targets (B) f64 — as ReplayBuffer.stack_exp / masked_target give.
+        planes: (hi_ptr, lo2_ptr, pitch) of bf16 Gram planes to fill (GramShard.planes(), GramPlan.planes()) or None.
+        Returns dict(J (B, 181395) f32 if want_J, loss (B) f32 if want_loss)."""
+        from . import _check, _ptr, lib
+        B = states.shape[0]
+        dev = self.device
+        out = {}
+        if want_J:
+            out["J"] = torch.empty(B, N_PARAMS, dtype=torch.float32, device=dev)
+        if want_loss:
+            out["loss"] = torch.empty(B, dtype=torch.float32, device=dev)
+        hi, lo, pitch = (C.c_void_p(planes[0]), C.c_void_p(planes[1]), int(planes[2])) if planes is not None else (None, None, 0)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _check(lib().snk_qnet_sample_grads(self._q, _ptr(states, torch.float32, B * 200, dev), _ptr(actions, torch.uint8, B, dev),
+                                           _ptr(targets, torch.float64, B, dev), B, hi, lo, pitch, _ptr(out.get("J")), N_PARAMS,
+                                           _ptr(out.get("loss")), st))
+        return out
+
     def overflow(self):
         """f32 mode: True if an activation left the fp16 range of the split operands since the last call (synchronises)."""
         from . import _check, lib

@@ -85,6 +85,35 @@ def test_row_sharded_gram_with_virtual_ranks(world, K, P, terms):
     assert _rel_fro(G, single.astype(np.float64)) < 2e-6       # same arithmetic up to split-K summation order
 
 
+def test_sharded_run_with_device_barriers_two_virtual_ranks_on_two_streams():
+    """snk_gram_shard_run — pack, planes ring, symmetrise separated by the device-side peer barrier — for two virtual ranks of
+    one process, each on its own stream: rank 0's barrier kernel spins until rank 1's stream reaches its barrier.  Run twice
+    (the barrier epochs keep counting)."""
+    S = pkg()
+    from snake_b200 import gram_sharded as GS
+    K, P = 600, 4099
+    rng = np.random.default_rng(3)
+    A = rng.normal(0, 1, (K, P))
+    ref = GO.gram(A)
+    dev = torch.device("cuda", 0)
+    peers = GS.LocalPeers(K, P, 2, dev)
+    dA = torch.from_numpy(A).cuda()
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(2):
+        outs = []
+        for s, st in zip(peers.shards, streams):
+            with torch.cuda.stream(st):
+                lo = s.col0[s.rank]
+                outs.append(s.run(dA[lo:lo + s.rows].contiguous(), terms=3))
+        torch.cuda.synchronize()
+        for s in peers.shards:
+            s.check()                                    # no barrier timed out
+        G = torch.cat(outs, 0).cpu().numpy()
+        assert _rel_fro(G, ref) < 1e-5, rep
+    peers.free()
+
+
 def test_plot_traj_numeric_path_matches_numpy_svd():
     """compute_D.jl + plot_traj.jl end to end: snapshots -> D -> centring -> spectrum S.^2/(K-1), the 99 % column
     count and the two-direction trajectory U[:, 1:2]' D, against numpy's SVD of the centred Float64 D."""

@@ -152,12 +152,12 @@ def test_f32_mode_flags_activations_outside_the_fp16_range():
     ok = S.qnet.QNet(layers, obs.device, precision="f32")
     ok(obs)
     assert not ok.overflow()
-    big = [(k, dict(p)) for k, p in layers]
-    big[0][1]["W"] = (layers[0][1]["W"] * 3.0e4).astype(np.float32)       # conv1 outputs ~1e5 > 65504
-    net = S.qnet.QNet(big, obs.device, precision="f32")
-    net(obs)
+    net = S.qnet.QNet(layers, obs.device, precision="f32")
+    net(torch.full((64, 2, 10, 10), 1.0e6, device=obs.device))            # conv1 outputs ~5e5 > 65504
     assert net.overflow()
     assert not net.overflow()                                              # reading clears the flag
+    net(obs)
+    assert not net.overflow()
     huge = [(k, dict(p)) for k, p in layers]
     huge[1][1]["W"] = (layers[1][1]["W"] * 1e7).astype(np.float32)
     with pytest.raises(S.SnakeB200Error):                                  # a weight outside the fp16 range is refused at create
