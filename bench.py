@@ -7,8 +7,11 @@ Workload (config.workload): BASELINE config 3 — E = 1,048,576 batched envs PER
 independent, each rank owns its own shard, no collective on the step path), every step = ONE fused kernel
 doing epsilon-greedy selection (eps = 0.05, injected Q (3,E) f32 + u f32 + ridx u8) + step! + losing mask +
 Float32 two-frame observation.  Inputs are synthetic, generated on the device before the timed region.
-`value` times that kernel with everything resident in HBM; `e2e` times the same step through the host-buffer
-C-ABI entry point (snk_step_fused_host) with pinned host tensors, H2D + D2H inside the timed region.
+`value` times that kernel with everything resident in HBM; `e2e` times one iteration of a HOST trainer's data path
+(utils.jl:436-443) through the host-buffer C-ABI entry points with pinned host tensors, H2D + D2H inside the timed region:
+snk_step_fused_store_host (q, u, ridx up; lossless 2-bit packed next_state, reward, done, mask, action down; every transition
+store!d into the device replay ring) + snk_replay_gather_host (stack_exp of 64 sampled transitions expanded to Float32 — where
+the reference casts, utils.jl:361-362).  The full-Float32 and int8 observation forms of the same call are secondary keys.
 `config2_4096_envs` reports BASELINE config 2 (4,096 envs, given actions) as a CUDA-graph of steps.
 
 --impl reference: the reference's CPU implementation of the same path.  Julia is not in the image, so this is
@@ -28,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 BYTES_PER_STEP_CONFIG3 = 876   # 50 state + 1 action + 4 reward + 1 done + 3 mask + 800 obs + 12 q + 4 u + 1 ridx
 BYTES_PER_STEP_CONFIG2 = 859
+REF_SAMPLE_ENVS = 32768        # env count of the CPU arm's bounded sample (independent of the host's thread count)
 METRIC = "snake_env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -112,7 +116,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = host_threads()
-    n_envs, n_steps = 4096 * max(1, threads // 2), 200
+    n_envs, n_steps = REF_SAMPLE_ENVS, 200                       # fixed sample: comparable across boxes
     cpu_reference_run(min(n_envs, 1024), 20, threads)            # warm the allocator / page in the library
     vals = []
     for _ in range(max(1, args.warmup)):
@@ -130,8 +134,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / len(vals), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "config3: batched envs, fused select+step+mask+f32 obs (CPU arm: bounded sample, given random actions)",
-                   "envs_per_bench_step": n_envs, "steps_per_bench_step": n_steps},
+        "config": {"workload": "config3: batched envs, step! + losing mask + f32 two-frame obs per env-step (CPU arm: bounded sample)",
+                   "envs_per_bench_step": n_envs, "steps_per_bench_step": n_steps, "host_threads": threads,
+                   "differences_from_the_gpu_arm": ["%d envs instead of 1,048,576 per GPU (bounded sample)" % n_envs,
+                                                    "given uniform random actions: no epsilon-greedy select from Q",
+                                                    "reference-shaped oracle (keep_history: board copy per step, 3 whole-game deep copies per step)"]},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the Julia reference (Julia is not installed); reference-shaped mode: "
                                  "Int64 boards, board copy per step, 3 whole-game deep copies per step"},
@@ -204,14 +211,22 @@ def run_ours(args):
         j = i % R
         env.step_fused(q=qs[j], eps=eps, u=us[j], ridx=rs[j], out=out)
 
+    # clocks are sampled from BEFORE the warm-up to the end of the timed region (a 20-step region lasts 3 ms, one
+    # nvidia-smi period is 20 ms): the warm-up is stretched with extra untimed steps until the sampler has delivered
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(W):
         one_step(i)
+    extra, t_w = 0, time.perf_counter()
+    while rank == 0 and len(sampler.rows) < 8 and time.perf_counter() - t_w < 1.5 and sampler.proc is not None:
+        for i in range(50):
+            one_step(W + extra + i)
+        torch.cuda.synchronize()
+        extra += 50
     barrier()
-    sampler = ClockSampler(local)
     use_graph = E < 400_000       # a shard this small takes < 60 us per step: launch through a CUDA graph of R steps
     if not use_graph:
-        if rank == 0:
-            sampler.start()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
         ev[0].record()
         for i in range(K):
@@ -234,8 +249,6 @@ def run_ours(args):
             graph.replay()
             st.synchronize()
             barrier()
-            if rank == 0:
-                sampler.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
             for _ in range(K // R):
@@ -276,42 +289,52 @@ def run_ours(args):
                             "and no observation at all (reward / done / mask only): the smaller the output, the more the kernel is "
                             "bound by its per-env arithmetic and latency instead of HBM")
 
-    # ---- e2e: the host-buffer C-ABI call, pinned host tensors, copies inside the timed region
+    # ---- e2e: one iteration of a host trainer's data path through the host-buffer C ABI, copies inside the timed region
     Ke = max(2, min(K, args.e2e_steps))
-    host = {"obs_fmt": "f32", "q": S.pinned_empty((E, 3), torch.float32), "u": S.pinned_empty((E,), torch.float32),
+    ring = S.ReplayBuffer(capacity=50000, device=local, batch_size=64)
+    host = {"q": S.pinned_empty((E, 3), torch.float32), "u": S.pinned_empty((E,), torch.float32),
             "ridx": S.pinned_empty((E,), torch.uint8), "act_idx": S.pinned_empty((E,), torch.uint8),
             "reward": S.pinned_empty((E,), torch.float32), "done": S.pinned_empty((E,), torch.uint8),
-            "obs": S.pinned_empty((E, 2, 10, 10), torch.float32), "mask": S.pinned_empty((E, 3), torch.uint8)}
+            "mask": S.pinned_empty((E, 3), torch.uint8)}
     host["q"].copy_(qs[0]); host["u"].copy_(us[0]); host["ridx"].copy_(rs[0])
-    h2d = E * (12 + 4 + 1)
-    d2h = E * (800 + 3 + 4 + 1 + 1)
-    for _ in range(2):
-        env.step_fused_host(host, q=True, eps=eps)
-    env.sync()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(Ke):
-        env.step_fused_host(host, q=True, eps=eps)
-    e1.record()
-    env.sync()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    batch_host = {"states": S.pinned_empty((64, 2, 10, 10), torch.float32), "next_states": S.pinned_empty((64, 2, 10, 10), torch.float32),
+                  "actions": S.pinned_empty((64,), torch.uint8), "rewards": S.pinned_empty((64,), torch.float32),
+                  "dones": S.pinned_empty((64,), torch.uint8), "mask": S.pinned_empty((64, 3), torch.uint8)}
+    idx_rng = torch.Generator().manual_seed(7 + rank)
+
+    def e2e_run(fmt, dtype, per_env, store):
+        host["obs"] = S.pinned_empty((E, 2, 10, 10) if per_env == 200 else (E, per_env), dtype)
+        host["obs_fmt"] = fmt
+
+        def it():
+            env.step_fused_host(host, q=True, eps=eps, replay=ring if store else None)
+            env.sync()                                            # outputs are in host memory
+            if store:                                             # sample(rpb) + stack_exp (utils.jl:442-443): 64 transitions as Float32
+                idx = torch.randint(0, len(ring), (64,), generator=idx_rng, dtype=torch.int64)
+                ring.stack_exp_host(idx, out=batch_host)
+
+        for _ in range(2):
+            it()
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(Ke):
+            it()
+        t1.record()
+        env.sync()
+        barrier()
+        return max_over_ranks(t0.elapsed_time(t1))
+
+    e2e_ms = e2e_run("packed2", torch.uint8, 50, True)
     e2e_value = world * E * Ke / (e2e_ms * 1e-3)
-    # same call with the int8 observation format (the reference's game.state is an integer array; 200 B/env)
-    host["obs"] = S.pinned_empty((E, 2, 10, 10), torch.int8)
-    host["obs_fmt"] = "i8"
-    for _ in range(2):
-        env.step_fused_host(host, q=True, eps=eps)
-    env.sync()
-    barrier()
-    e0.record()
-    for _ in range(Ke):
-        env.step_fused_host(host, q=True, eps=eps)
-    e1.record()
-    env.sync()
-    barrier()
-    e2e_i8_ms = max_over_ranks(e0.elapsed_time(e1))
+    h2d = E * (12 + 4 + 1) + 64 * 8
+    d2h = E * (50 + 3 + 4 + 1 + 1) + 64 * 1613
+    e2e_f32_ms = e2e_i8_ms = None
+    if not args.skip_variants:
+        e2e_f32_ms = e2e_run("f32", torch.float32, 200, False)
+        e2e_i8_ms = e2e_run("i8", torch.int8, 200, False)
+    del host["obs"]
+    ring.close()
 
     # ---- BASELINE config 2 (4,096 envs, given actions) as a CUDA graph of steps: launch-latency regime
     cfg2 = None
@@ -375,13 +398,13 @@ def run_ours(args):
     # ---- BASELINE config 5b shape: row-sharded Gram across the ranks (6,250 rows of J per GPU, P = 181,395)
     gram_sh = None
     if world > 1 and not args.skip_gram:
-        gram_sh = bench_gram_sharded(S, dev, rank, world, local, max_over_ranks)
+        gram_sh = bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=args.gram_rows)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         threads = host_threads()
-        n_c = 4096 * max(1, threads // 2)
+        n_c = REF_SAMPLE_ENVS
         cpu_reference_run(1024, 20, threads)
         v_mt, dt_mt = cpu_reference_run(n_c, 200, threads)
         v_1t, dt_1t = cpu_reference_run(4096, 100, 1)
@@ -407,12 +430,21 @@ def run_ours(args):
                          "traffic": None, "peak_source": peak_src, "kernel": "k_step<F32,select>",
                          "bytes_per_env_step": BYTES_PER_STEP_CONFIG3, "kernel_ms": kern_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": e2e_ms / Ke, "api": "snk_step_fused_host (pinned host buffers), f32 observations",
-                    "host_affinity_rank0": affinity,
-                    "int8_obs_variant": {"value": world * E * Ke / (e2e_i8_ms * 1e-3), "d2h_bytes_per_step": E * 209}},
+                    "steps": Ke, "ms_per_step": e2e_ms / Ke,
+                    "api": "snk_step_fused_store_host (pinned host buffers: q/u/ridx up; 2-bit packed next_state (50 B/env, lossless) + "
+                           "reward/done/mask/action down; every transition store!d into the device replay ring) + snk_sync + "
+                           "snk_replay_gather_host (stack_exp of 64 sampled transitions as Float32, utils.jl:343-383) per step",
+                    "obs_format": "packed2 (SNK_OBS_PACKED2); Float32 only for the 64 sampled transitions, as the reference casts (utils.jl:361-362)",
+                    "host_affinity_rank0": affinity},
             "gpu_launches": K * world,
             "clocks": clocks,
+            "warmup_extra_untimed_steps": extra,
         }
+        if e2e_f32_ms is not None:
+            line["e2e"]["full_f32_obs_variant"] = {"value": world * E * Ke / (e2e_f32_ms * 1e-3), "d2h_bytes_per_step": E * 809,
+                                                   "api": "snk_step_fused_host, Float32 next_state for every env (round-1 headline form)"}
+            line["e2e"]["int8_obs_variant"] = {"value": world * E * Ke / (e2e_i8_ms * 1e-3), "d2h_bytes_per_step": E * 209,
+                                               "api": "snk_step_fused_host, int8 next_state for every env"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if variants:
@@ -436,14 +468,23 @@ def run_ours(args):
 def bench_config4(S, dev, local, n=65536, steps=20):
     """One rollout step = q_net(state) -> fused eps-greedy/step!/virtual_step/obs/store! -> t_net(next_state) ->
     masked max-Q target (utils.jl:203-208, 448-451).  Q-net = seeded Glorot init of structs.jl:127-139 (the
-    two-frame checkpoints BASELINE names are missing from the reference mount)."""
+    two-frame checkpoints BASELINE names are missing from the reference mount).  Native kernels in both precisions
+    ("f32" = Float32-faithful, the like-for-like number; "bf16" = fast mode); the torch/cuDNN timings are LIBRARY baselines."""
     import torch
+    from tools.torch_qnet import TorchQNet
     env = S.SnakeGame(n, device=local, auto_reset=True)
     rb = S.ReplayBuffer(capacity=50000, device=local)
     layers = S.qnet.glorot_layers(seed=0)
     out = {"workload": "config4: %d envs, eps=0.05, Glorot-init Q-net (synthetic weights), 50k replay ring" % n}
-    for backend in S.qnet.available_backends():
-        qn = S.qnet.QNet(layers, dev, backend=backend)
+    peak = bf16_peak_tflops()
+    nets = [("native_f32", S.qnet.QNet(layers, dev, "f32"), S.qnet.PRECISION_NOTES["f32"]),
+            ("native_bf16", S.qnet.QNet(layers, dev, "bf16"), S.qnet.PRECISION_NOTES["bf16"])]
+    if not os.environ.get("SNK_BENCH_SKIP_LIBRARY"):
+        nets += [("library_cudnn_fp32", TorchQNet(layers, dev, dtype=torch.float32), "LIBRARY baseline: torch conv2d/linear, fp32 with TF32 off"),
+                 ("library_cudnn_tf32", TorchQNet(layers, dev, dtype=torch.float32, allow_tf32=True), "LIBRARY baseline: torch default (TF32 convolutions)"),
+                 ("library_cudnn_bf16", TorchQNet(layers, dev, dtype=torch.bfloat16, channels_last=True), "LIBRARY baseline: torch bf16 channels_last")]
+    ref64 = TorchQNet(layers, dev, dtype=torch.float64)
+    for name, qn, note in nets:
         ro = S.rollout.Rollout(env, qn, qn, rb, epsilon=0.05)
         for _ in range(3):
             ro.step()
@@ -455,8 +496,7 @@ def bench_config4(S, dev, local, n=65536, steps=20):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        # the two network forwards alone
-        x = ro.state
+        x = ro.state                                              # the network forward alone
         for _ in range(2):
             qn(x)
         e0.record()
@@ -465,62 +505,114 @@ def bench_config4(S, dev, local, n=65536, steps=20):
         e1.record()
         torch.cuda.synchronize()
         fwd = e0.elapsed_time(e1) / steps
+        want = ref64(x[:4096].double())
+        err = float(((qn(x[:4096]).double() - want).abs().max() / want.abs().max()).item())
         tflops = 4870784.0 * n / (fwd * 1e-3) / 1e12            # 4,870,784 FLOP per sample (useful)
-        out[backend] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "qnet_forward_ms": fwd,
-                        "qnet_tflops": tflops, "note": S.qnet.BACKEND_NOTES[backend]}
-        if backend == "native":
-            peak = bf16_peak_tflops()
-            out[backend]["roofline"] = {
-                "bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
-                "note": "useful FLOP of the five layers / time of snk_qnet_forward (conv kernel + dense head); ncu of the conv "
-                        "kernel: profiles/r01_ncu_qnet_full.csv (tensor pipe % of active cycles)"}
+        out[name] = {"env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "qnet_forward_ms": fwd, "qnet_useful_tflops": tflops,
+                     "max_err_vs_float64_of_maxQ": err, "note": note}
+        if name.startswith("native"):
+            mma_x = 4.0 if name == "native_f32" else 1.0        # the split issues every MMA for (hi, lo) x (hi, lo)
+            out[name]["roofline"] = {
+                "bound": "tensor", "achieved": tflops * mma_x, "peak": peak, "unit": "TFLOP/s", "frac": tflops * mma_x / peak,
+                "frac_algorithmic": tflops / peak, "traffic": None,
+                "note": "achieved = executed MMA FLOP (useful x %.0f) / time of snk_qnet_forward; frac_algorithmic = useful FLOP "
+                        "(4,870,784 per sample) / time / peak; ncu tensor-pipe %% in profiles/r02_ncu_qnet_*.csv" % mma_x}
+    out["like_for_like"] = "native_f32 (the reference network is Float32; bf16 and TF32 give different greedy actions)"
     out["replay_len"] = len(rb)
     env.close()
     rb.close()
     return out
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum per k_step launch, from the committed ncu --set full capture
-    of this same workload (profiles/r01_ncu_k_step_full.csv); None if the file is absent."""
+def ncu_csv_traffic(pattern, kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of kernels whose name starts with kernel_prefix, from the newest
+    committed ncu --set full capture profiles/r??_<pattern>.csv (raw page export); (bytes, file) or (None, None)."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01_ncu_k_step_full.csv")
-    if not os.path.exists(p):
-        return None
-    rows = list(csv.reader(open(p)))
-    hdr = rows[0]
-    r, w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-    vals = [(float(x[r]) + float(x[w])) * 1e6 for x in rows[2:] if len(x) > w and x[0].startswith("void k_step")]
-    return sum(vals) / len(vals) if vals else None
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r??_" + pattern + ".csv")))
+    for path in reversed(files):
+        rows = list(csv.reader(open(path)))
+        if not rows or "dram__bytes_read.sum" not in rows[0]:
+            continue
+        hdr, units = rows[0], rows[1]
+        r, w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        name_col = hdr.index("Kernel Name") if "Kernel Name" in hdr else 0
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(x[r]) * scale.get(units[r], 1e6) + float(x[w]) * scale.get(units[w], 1e6)
+                for x in rows[2:] if len(x) > max(r, w) and kernel_prefix in x[name_col]]
+        if vals:
+            return sum(vals) / len(vals), os.path.relpath(path, ROOT)
+    return None, None
+
+
+def ncu_traffic_bytes():
+    """per k_step launch, from the newest committed capture of this same workload (profiles/r??_ncu_k_step_full.csv)"""
+    return ncu_csv_traffic("ncu_k_step_full", "k_step")[0]
 
 
 def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181395, iters=3):
-    """Every rank owns R rows of a synthetic J (N(0,1) Float32); G[rows_rank, :] over all ranks through the
-    planes ring (NVLink peer copies under the tcgen05 main loop) and the peer-read symmetrise kernel."""
+    """BASELINE config 5b: the Gram of per-sample gradients of the DQN loss over the replay buffer, row-sharded.
+    Every rank fills its own device replay ring by acting with the Float32-faithful Q-net, draws R transitions, and
+      timed: snk_qnet_sample_grads (rows of J straight into this rank's bf16 planes) + snk_gram_shard_run (planes ring over
+             NVLink peer memory under the tcgen05 main loop, device-side barriers, peer-read symmetrise) -> G[rows_rank, :].
+    Verified on EVERY rank against Float64 dot products of Float32 J rows (>= 1000 off-diagonal entries), and against the
+    NCCL all-gather + all-to-all form of the same Gram (bit-identical)."""
     import torch
     import torch.distributed as dist
     from snake_b200 import gram_sharded as GS
+    n_env = 16384
+    env = S.SnakeGame(n_env, device=local, auto_reset=True)
+    ring = S.ReplayBuffer(capacity=50000, device=local, seed=1000 + rank)
+    q_net = S.qnet.QNet(S.qnet.glorot_layers(seed=0), dev, "f32")
+    t_net = S.qnet.QNet(S.qnet.glorot_layers(seed=1), dev, "f32")
+    ro = S.rollout.Rollout(env, q_net, t_net, ring, epsilon=0.3)
     g = torch.Generator(device=dev)
     g.manual_seed(100 + rank)
-    J = torch.randn(R, P, device=dev, dtype=torch.float32, generator=g)
+    for _ in range(8):                                           # 131,072 transitions through a 50,000-slot ring
+        ro.step(u=torch.rand(n_env, device=dev, generator=g), ridx=torch.randint(0, 3, (n_env,), device=dev, generator=g, dtype=torch.uint8))
+    batch = ring.stack_exp(ring.sample_indices(R))               # sample(rpb) + stack_exp, R distinct transitions
+    y = S.masked_target(t_net(batch["next_states"]), batch["mask"], batch["rewards"], batch["dones"])
     dg = GS.DistributedGram([R] * world, P, dev)
-    times = []
+    planes = dg.shard.planes()
+    times, t_prod = [], []
     for it in range(iters + 1):
         torch.cuda.synchronize()
         dist.barrier(device_ids=[local])
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        G = dg.run(J, terms=3)
+        q_net.sample_grads(batch["states"], batch["actions"], y, planes=planes, want_loss=False)
         e1.record()
+        G = dg.run(None, terms=3)
+        e2.record()
         torch.cuda.synchronize()
-        t = max_over_ranks(e0.elapsed_time(e1))
+        t = max_over_ranks(e0.elapsed_time(e2))
+        tp = max_over_ranks(e0.elapsed_time(e1))
         if it > 0:
             times.append(t)
-    want = float((J[0].double() ** 2).sum().item())
-    got = float(G[0, rank * R].item())
+            t_prod.append(tp)
+    dg.shard.check()
+    # ---- verification on every rank: 128 random local rows x (8 probe rows of every rank), Float64 dot products of FP32 J rows
+    gi = torch.Generator(device="cpu").manual_seed(5 + rank)
+    rows_i = torch.randperm(R, generator=gi)[:128].to(dev)
+    sub = torch.cat([rows_i, torch.arange(8, device=dev)])
+    Jsub = q_net.sample_grads(batch["states"][sub].contiguous(), batch["actions"][sub].contiguous(), y[sub].contiguous(),
+                              want_J=True, want_loss=False)["J"]
+    probes = [torch.empty(8, P, dtype=torch.float32, device=dev) for _ in range(world)]
+    dist.all_gather(probes, Jsub[128:].contiguous())
+    Jp = torch.cat(probes, 0).double()                           # (8 world, P): rows 0..7 of every rank
+    want = Jsub[:128].double() @ Jp.T                            # (128, 8 world)
+    cols = torch.tensor([r * R + k for r in range(world) for k in range(8)], device=dev)
+    got = G[rows_i][:, cols].double()
+    offdiag = (rows_i[:, None] + rank * R) != cols[None, :]
+    scale = torch.sqrt(torch.diagonal(Jsub[:128].double() @ Jsub[:128].double().T))[:, None] * torch.sqrt((Jp * Jp).sum(1))[None, :]
+    err = float(((got - want).abs() / scale)[offdiag].max().item())
+    errs = [None] * world
+    dist.all_gather_object(errs, err)
+    n_checked = int(offdiag.sum().item())
     Gring = G.clone()
     dg.close()
-    # baseline: the same block Grams behind library collectives (NCCL all-gather of the planes, all-to-all of Y^T blocks)
+    # ---- baseline: the same block Grams behind library collectives (NCCL all-gather of the planes, all-to-all of Y^T blocks)
+    J = q_net.sample_grads(batch["states"], batch["actions"], y, want_J=True, want_loss=False)["J"]
     ag = GS.AllGatherGram([R] * world, P, dev)
     times_ag = []
     for it in range(iters + 1):
@@ -536,17 +628,31 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
             times_ag.append(t)
     same = bool(torch.equal(Ga, Gring))
     ag.close()
+    del J
+    env.close()
+    ring.close()
     ms = sorted(times)[len(times) // 2]
+    ms_prod = sorted(t_prod)[len(t_prod) // 2]
     Kt = R * world
     useful = 2.0 * Kt * Kt * P
-    return {"workload": "config5b shape: Gram of J (%d rows per GPU x %d), row-sharded over %d GPUs, hi/lo bf16 split" % (R, P, world),
-            "K_total": Kt, "ms": ms, "useful_tflops_total": useful / (ms * 1e-3) / 1e12,
-            "mma_tflops_per_gpu": 2 * useful / world / (ms * 1e-3) / 1e12,
-            "diag_rel_err_sample": abs(got - want) / want,
+    mma = 2 * useful / world / ((ms - ms_prod) * 1e-3) / 1e12
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1421.8)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1421.8
+    return {"workload": "config5b: Gram of per-sample DQN-loss gradients J (%d transitions per GPU out of each rank's 50,000-slot replay ring "
+                        "x %d parameters), row-sharded over %d GPUs, hi/lo bf16 split" % (R, P, world),
+            "data": "real J: rollout with the Float32-faithful Q-net (Glorot-init synthetic weights) -> replay ring -> sample -> "
+                    "masked max-Q targets -> per-sample gradients",
+            "K_total": Kt, "ms": ms, "producer_ms": ms_prod, "gram_ms": ms - ms_prod,
+            "useful_tflops_total": useful / ((ms - ms_prod) * 1e-3) / 1e12, "mma_tflops_per_gpu": mma,
+            "roofline": {"bound": "tensor", "achieved": mma, "peak": peak, "unit": "TFLOP/s", "frac": mma / peak,
+                         "frac_algorithmic": mma / 2 / peak, "traffic": None,
+                         "note": "per GPU, Gram phase only; peak = sustained bf16 (a %.0f ms region); executed MMA FLOP = 2 x algorithmic (hi/lo split)" % ms},
+            "verify_per_rank": {"entries_per_rank": n_checked, "max_err_over_sqrt_GiiGjj": errs,
+                                "how": "128 random local rows x rows 0..7 of every rank (off-diagonal), Float64 dot products of FP32 J rows"},
             "nccl_allgather_baseline_ms": sorted(times_ag)[len(times_ag) // 2], "nccl_allgather_same_bits_rank0": same,
-            "exchange": "planes ring: cudaMemcpyAsync from peer-mapped (cudaIpc) memory on a copy stream under the MMA main loop; "
-                        "transpose exchange: peer loads inside the symmetrise kernel; torch.distributed only for handles/barriers",
-            "timed": "pack + barriers + ring + block Grams + symmetrise; buffers and IPC mappings set up once"}
+            "exchange": "snk_gram_shard_run: cudaMemcpyAsync from peer-mapped (cudaIpc) memory on a copy stream under the MMA main loop; "
+                        "device-side barriers over peer memory; transpose exchange by peer loads inside the symmetrise kernel; "
+                        "torch.distributed only carries the IPC handles at set-up",
+            "timed": "per-sample gradients into the planes + one snk_gram_shard_run per rank; buffers and IPC mappings set up once"}
 
 
 def bench_gram(S, dev, K=1000, P=181395, iters=10):
@@ -577,6 +683,11 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10):
         return ts[len(ts) // 2]
 
     out["pack_ms"] = timed(lambda: plan.pack(A))
+    out["pack_hbm_frac"] = 12.0 * K * P / (out["pack_ms"] * 1e-3) / 1e9 / peaks()[0]
+    A32 = A.float()
+    out["pack_f32_ms"] = timed(lambda: plan.pack(A32))
+    out["pack_f32_hbm_frac"] = 8.0 * K * P / (out["pack_f32_ms"] * 1e-3) / 1e9 / peaks()[0]
+    plan.pack(A)
     Dc = A.clone()
     out["center_ms"] = timed(lambda: S.center_columns(Dc))       # Welford + centring of the Float64 D (3 passes over 1.45 GB)
     out["center_hbm_frac"] = 3 * 8.0 * K * P / (out["center_ms"] * 1e-3) / 1e9 / peaks()[0]
@@ -586,12 +697,17 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10):
         ms = timed(lambda: plan.gram(terms, 0, out=G))
         err = float((G.double() - ref).norm() / ref.norm())
         mma = (2 if terms == 3 else 1) * 2.0 * K * K * P / (ms * 1e-3) / 1e12
-        out["terms%d" % terms] = {"ms": ms, "useful_tflops": 2.0 * K * K * P / (ms * 1e-3) / 1e12, "mma_tflops": mma,
+        useful = 2.0 * K * K * P / (ms * 1e-3) / 1e12
+        traffic, src = ncu_csv_traffic("ncu_gram_5a_terms%d_full" % terms, "k_gram")
+        out["terms%d" % terms] = {"ms": ms, "useful_tflops": useful, "mma_tflops": mma,
                                   "frac_of_measured_bf16_peak": mma / peak, "rel_fro_err_vs_fp64": err,
                                   "roofline": {"bound": "tensor", "achieved": mma, "peak": peak, "unit": "TFLOP/s",
-                                               "frac": mma / peak, "traffic": 726.4e6 if terms == 3 else 363.2e6,
-                                               "note": "time covers k_gram + the split-K/symmetrise pass; traffic = ncu dram bytes of "
-                                                       "k_gram (profiles/r01_ncu_gram_5a_*.csv): the bf16 planes read once"}}
+                                               "frac": mma / peak, "frac_algorithmic": useful / peak, "traffic": traffic,
+                                               "algorithmic_bytes": (2 if terms == 3 else 1) * 2.0 * K * ((P + 63) // 64 * 64),
+                                               "traffic_source": src,
+                                               "note": "achieved = executed MMA FLOP (the hi/lo split runs 2 products per k-step); frac_algorithmic = "
+                                                       "SURVEY 8(d)'s 2 K^2 P / time / peak; time covers the tile kernel + the split-K/symmetrise pass; "
+                                                       "traffic = ncu dram bytes of the tile kernel actually run, algorithmic_bytes = the bf16 planes read once"}}
     Ab = A.to(torch.bfloat16)
     ms = timed(lambda: torch.matmul(Ab, Ab.T))
     out["cublas_bf16_same_shape_ms"] = ms
@@ -611,6 +727,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-config2", action="store_true")
     ap.add_argument("--skip-gram", action="store_true")
+    ap.add_argument("--gram-rows", type=int, default=6250, help="rows of J per GPU in the row-sharded Gram (config 5b: 6,250)")
     ap.add_argument("--skip-config4", action="store_true")
     ap.add_argument("--skip-variants", action="store_true", help="skip the int8-observation / no-observation timings")
     args = ap.parse_args()

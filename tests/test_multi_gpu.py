@@ -31,6 +31,20 @@ def test_row_sharded_gram_over_nvlink_matches_fp64():
 
 
 @needs2
+def test_sharded_gram_of_real_per_sample_gradients_two_gpus():
+    """config 5b end to end on 2 GPUs at a small shard size: rollout -> replay ring -> per-sample gradients -> one
+    snk_gram_shard_run per rank; every rank checks >= 1000 off-diagonal entries against Float64 dot products"""
+    lines = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "20", "--warmup", "3", "--envs", "65536", "--skip-config2",
+                      "--skip-config4", "--skip-variants", "--e2e-steps", "2", "--gram-rows", "640")
+    assert len(lines) == 1
+    g = json.loads(lines[0])["gram_5b_sharded"]
+    assert g["K_total"] == 1280 and g["nccl_allgather_same_bits_rank0"] is True
+    v = g["verify_per_rank"]
+    assert v["entries_per_rank"] >= 1000 and len(v["max_err_over_sqrt_GiiGjj"]) == 2
+    assert max(v["max_err_over_sqrt_GiiGjj"]) < 1e-5
+
+
+@needs2
 def test_env_sharded_bench_line_two_gpus():
     lines = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "50", "--warmup", "5", "--envs", "65536", "--skip-gram",
                       "--skip-config2", "--skip-config4", "--e2e-steps", "2")
