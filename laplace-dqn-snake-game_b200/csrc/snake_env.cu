@@ -556,11 +556,11 @@ struct RolloutArgs {
 #ifndef SNK_RTPB
 #define SNK_RTPB 128
 #endif
-#ifndef SNK_REPB
-#define SNK_REPB 16            // measured at 4,096 envs: 16 -> 1.67 us per step, 32 -> 1.86, 64 -> 2.25
+#ifndef SNK_WS_EPB
+#define SNK_WS_EPB 8
 #endif
+constexpr int WS_EPB = SNK_WS_EPB; // envs per CTA of the warp-specialised small-batch rollout kernel
 constexpr int RTPB = SNK_RTPB;    // threads per CTA of the rollout kernel (latency-bound: tuned separately from k_step)
-constexpr int REPB = SNK_REPB;    // envs per CTA of the rollout kernel for small batches
 template <int OBS, int EPB>
 __global__ void __launch_bounds__(RTPB) k_rollout(const __grid_constant__ RolloutArgs a) {
     __shared__ __align__(16) uint32_t s_planes[EPB * PLANE_WORDS];
@@ -607,6 +607,103 @@ __global__ void __launch_bounds__(RTPB) k_rollout(const __grid_constant__ Rollou
         }
     }
     if (mine) env_store(e, a.s, env);
+}
+
+// ---- small batches: warp-specialised multi-step rollout -------------------------------------------------------------
+// At 4,096 envs (BASELINE config 2) a step moves 3.5 MB: the time per step is the serial instruction chain of ONE env-step,
+// not memory.  So the chain is cut to the bone and everything else runs beside it: warp 0 of a CTA (EPB envs, one per lane)
+// only advances the envs and drops a 32-byte record per env into a double-buffered hand-over slot; warps 1..3 turn the
+// records into the outputs — scalars, the two boards as unit bytes, the expanded observation — while warp 0 is already in
+// the next step.  Actions are prefetched two steps ahead.  Named barriers: FULL[b] (warp 0 arrives, expanders wait),
+// EMPTY[b] (expanders arrive, warp 0 waits two steps later), and one among the expanders.
+struct __align__(16) Handoff {
+    u64 occ, pocc;
+    uint32_t pk;             // hr hc fr fc pfr pfc (4 bits each) | done << 24 | mask bits << 25
+    float reward, ret;
+    int score;
+};
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int OBS, int EPB>
+__global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ RolloutArgs a) {
+    static_assert(EPB <= 32, "one env per lane of the logic warp");
+    __shared__ Handoff s_hand[2][EPB];
+    __shared__ __align__(16) uint32_t s_planes[EPB * PLANE_WORDS];
+    __shared__ ObsTables s_tb;
+    __shared__ uint8_t s_food_bit[MAX_FOOD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long env0 = (long long)blockIdx.x * EPB;
+    const long long rem = a.n - env0;
+    const int n_local = rem < EPB ? (int)rem : EPB;
+    if (tid < MAX_FOOD) s_food_bit[tid] = a.food.bit[tid];
+    if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid, 128);
+    __syncthreads();
+    constexpr int FULL = 1, EMPTY = 3, XB = 5;              // barrier ids: FULL+b, EMPTY+b, expanders
+    if (warp == 0) {
+        const bool mine = lane < n_local;
+        const long long env = env0 + (mine ? lane : 0);
+        const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
+        Env e;
+        env_load(e, a.s, env);
+        int a0 = a.steps > 0 ? a.act[env] : 0, a1 = a.steps > 1 ? a.act[a.n + env] : 0;
+        for (int t = 0; t < a.steps; t++) {
+            const int a2 = t + 2 < a.steps ? a.act[(long long)(t + 2) * a.n + env] : 0;      // in flight during two steps
+            const int b = t & 1;
+            if (t >= 2) nbar_sync(EMPTY + b, 128);           // the expanders have consumed slot b (step t-2)
+            int aidx = a0;
+            float reward = 0.0f;
+            uint32_t m3 = 7u;
+            if (!e.dn) reward = env_advance(e, aidx, a.is_abs, list_mask, s_food_bit, m3);
+            if (mine) {
+                Handoff h;
+                h.occ = e.occ; h.pocc = e.pocc;
+                h.pk = (uint32_t)e.hr | ((uint32_t)e.hc << 4) | ((uint32_t)e.fr << 8) | ((uint32_t)e.fc << 12) |
+                       ((uint32_t)e.pfr << 16) | ((uint32_t)e.pfc << 20) | ((uint32_t)e.dn << 24) | (m3 << 25);
+                h.reward = reward; h.ret = e.ret; h.score = e.len - 2;
+                s_hand[b][lane] = h;
+            }
+            if (e.dn && a.auto_reset) env_reset(e);
+            __syncwarp();
+            nbar_arrive(FULL + b, 128);
+            a0 = a1; a1 = a2;
+        }
+        if (mine) env_store(e, a.s, env);
+    } else {
+        const int et = tid - 32;                             // 0..95
+        const size_t obs_step = (size_t)a.n * (OBS == SNK_OBS_F32 ? 800 : OBS == SNK_OBS_I8 ? 200 : OBS == SNK_OBS_I64 ? 1600 : 50);
+        for (int t = 0; t < a.steps; t++) {
+            const int b = t & 1;
+            nbar_sync(FULL + b, 128);
+            // threads 0..EPB-1: scalars + the older board; threads 32..32+EPB-1: the newer board
+            const int j = et & 31, role = et >> 5;
+            if (j < n_local && role < 2) {
+                const Handoff h = s_hand[b][j];
+                if (role == 0) {
+                    const long long o = (long long)t * a.n + env0 + j;
+                    if (a.reward != nullptr) a.reward[o] = h.reward;
+                    if (a.done != nullptr) a.done[o] = (uint8_t)((h.pk >> 24) & 1u);
+                    if (a.mask != nullptr) {
+                        uint8_t *m = a.mask + 3 * o;
+                        m[0] = (uint8_t)((h.pk >> 25) & 1u); m[1] = (uint8_t)((h.pk >> 26) & 1u); m[2] = (uint8_t)((h.pk >> 27) & 1u);
+                    }
+                    if (a.ep_return != nullptr) a.ep_return[o] = h.ret;
+                    if (a.ep_score != nullptr) a.ep_score[o] = h.score;
+                    if (OBS != SNK_OBS_NONE)
+                        board_planes(h.pocc, (int)(h.pk >> 16) & 15, (int)(h.pk >> 20) & 15, false, 0, 0, s_planes + j * PLANE_WORDS);
+                } else if (OBS != SNK_OBS_NONE) {
+                    board_planes(h.occ, (int)(h.pk >> 8) & 15, (int)(h.pk >> 12) & 15, true, (int)h.pk & 15, (int)(h.pk >> 4) & 15,
+                                 s_planes + j * PLANE_WORDS + 8);
+                }
+            }
+            if (t + 2 < a.steps) nbar_arrive(EMPTY + b, 128);       // the record has been read: warp 0 may overwrite it at step t+2
+            if (OBS != SNK_OBS_NONE) {
+                nbar_sync(XB, 96);
+                expand_obs<OBS, 96, 5, true>((uint8_t *)a.obs + (size_t)t * obs_step, env0, n_local, s_planes, s_tb, et);
+                nbar_sync(XB, 96);
+            }
+        }
+    }
 }
 
 // ---- stand-alone views of the state ------------------------------------------------------------
@@ -1107,11 +1204,11 @@ int snk_rollout_fused(snk_handle h, const uint8_t *act_TxN, int64_t T, int is_ab
     a.ep_return = ep_return; a.ep_score = ep_score; a.n = h->n; a.steps = (int)T; a.is_abs = is_abs;
     a.auto_reset = (h->flags & SNK_AUTO_RESET) ? 1 : 0;
     const int fmt = obs ? obs_fmt : SNK_OBS_NONE;
-    // small batches: 32 envs per CTA so that the observation expansion of one env is spread over 4 threads
+    // small batches: the warp-specialised kernel, WS_EPB envs per CTA (4,096 envs -> 512 CTAs over the 148 SMs)
     const bool small = h->n <= 32 * 1024;
 #define SNK_RO(FMT)                                                                                       \
     do {                                                                                                  \
-        if (small) k_rollout<FMT, REPB><<<nblocks(h->n, REPB), RTPB, 0, h->stream>>>(a);                      \
+        if (small) k_rollout_ws<FMT, WS_EPB><<<nblocks(h->n, WS_EPB), 128, 0, h->stream>>>(a);               \
         else k_rollout<FMT, RTPB><<<nblocks(h->n, RTPB), RTPB, 0, h->stream>>>(a);                        \
     } while (0)
     switch (fmt) {

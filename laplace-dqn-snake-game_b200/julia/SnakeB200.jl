@@ -12,8 +12,9 @@ module SnakeB200
 
 export BatchedSnakeGame, available_actions, step!, step_fused!, virtual_step, assemble_state!,
        epsilon_greedy, masked_target, center_columns!, reset!, set_food_list!, score, lost,
-       DeviceReplayBuffer, store_step!, stack_exp, sample_indices, DeviceQNet, forward!, store_snapshot!,
-       gram!, sample_model_weights!, empty_buffer!,
+       DeviceReplayBuffer, store_step!, store_step_host!, stack_exp, sample_indices, DeviceQNet, forward!, overflowed,
+       sample_grads!, store_snapshot!, gram!, sample_model_weights!, empty_buffer!, patch_reset_obs!,
+       GramShard, export_handle, connect!, run!, planes,
        step_device!, step_abs_device!, step_fused_device!, rollout_device!, state_device!, losing_mask_device!,
        lost_device!, steps_device!, error_flags_device!, count_errors, seed!, set_stream!, num_envs, library_version,
        default_food_list
@@ -59,7 +60,14 @@ mutable struct BatchedSnakeGame
     end
 end
 
-reset!(g::BatchedSnakeGame) = check(ccall((:snk_reset, lib), Cint, (Ptr{Cvoid},), g.handle))
+"""every game back to `SnakeGame()` (structs.jl:33-99); the host mirrors are refreshed from the device"""
+function reset!(g::BatchedSnakeGame)
+    check(ccall((:snk_reset, lib), Cint, (Ptr{Cvoid},), g.handle))
+    fill!(g.reward, 0f0); fill!(g.lost, 0x00)
+    virtual_step(g)
+    assemble_state!(g)
+    return g
+end
 
 """food_list injection (structs.jl:70): vector of CartesianIndex{2} in 2:9 × 2:9."""
 function set_food_list!(g::BatchedSnakeGame, cells::Vector{CartesianIndex{2}})
@@ -107,37 +115,54 @@ function step_fused!(g::BatchedSnakeGame, q::Matrix{Float32}, epsilon::Float32;
     return g
 end
 
-# The reference's per-call API, for code that wants the individual pieces ------------------------------
-# (these go through small device buffers owned by the caller when CUDA.jl is present; the host versions
-#  below round-trip through step_fused! outputs)
+# The reference's per-call API on HOST arrays: every function asks the library (the `_host` entry points copy the
+# answer down and return when it has arrived), nothing is reconstructed on the Julia side -------------------------------
 
 """utils.jl:100-109 for all N games; `actions` are indices 1:3 into available_actions(g)."""
 step!(g::BatchedSnakeGame, actions::AbstractVector{<:Integer}) = step_fused!(g, actions)
 
-"""utils.jl:112-132: `next_is_suicidal` (3,N) of the current states (filled by the last step)."""
-virtual_step(g::BatchedSnakeGame) = g.next_is_suicidal .!= 0
+"""utils.jl:112-132: `next_is_suicidal` (3,N) of the CURRENT states, `trues(3)` for a lost game."""
+function virtual_step(g::BatchedSnakeGame)
+    check(ccall((:snk_losing_mask_host, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, g.next_is_suicidal))
+    return g.next_is_suicidal .!= 0
+end
 
-"""utils.jl:135-139: (10,10,2,N) Float32 two-frame state."""
+"""utils.jl:135-139: the (10,10,2,N) Float32 two-frame state of every game as it is NOW (also right after `reset!`)."""
 function assemble_state!(g::BatchedSnakeGame)
-    # device -> host through a temporary device buffer is what snk_state + cudaMemcpy do under CUDA.jl;
-    # with plain Arrays the state is refreshed by every step_fused!.  After a reset all envs hold the
-    # constructor state, which is a constant:
-    if all(g.reward .== 0) && all(g.lost .== 0)
-        b = zeros(Float32, 10, 10); b[1, :] .= -1; b[end, :] .= -1; b[:, 1] .= -1; b[:, end] .= -1
-        b[4, 5] = 2; b[8, 2] = 1; b[9, 2] = 1
-        for n in 1:g.n, f in 1:2
-            g.state[:, :, f, n] .= b
-        end
-    end
+    check(ccall((:snk_state_host, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), g.handle, g.state, OBS_F32))
     return g.state
 end
 
+"""utils.jl:7-10 for all N games: (3,N) direction codes 0:3 in the order U, D, L, R (`DIRS[code + 1]` is the CartesianIndex)."""
+function available_actions(g::BatchedSnakeGame)
+    out = Matrix{UInt8}(undef, 3, g.n)
+    check(ccall((:snk_available_actions_host, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, out))
+    return out
+end
+
+"""`game.score` (structs.jl:21) of every game"""
+function score(g::BatchedSnakeGame)
+    out = Vector{Int32}(undef, g.n)
+    check(ccall((:snk_get_score_host, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}), g.handle, out))
+    return out
+end
+"""`game.lost` (structs.jl:28) of every game"""
+function lost(g::BatchedSnakeGame)
+    check(ccall((:snk_get_done_host, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, g.lost))
+    return g.lost .!= 0
+end
+
+# device-pointer forms of the same getters
 score(g::BatchedSnakeGame, d_score::Ptr{Int32}) = check(ccall((:snk_get_score, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}), g.handle, d_score))
-lost(g::BatchedSnakeGame) = g.lost .!= 0
 
 """utils.jl:7-10 on device: fills a (3,N) UInt8 device array with direction codes 0:3 (U,D,L,R)."""
 available_actions(g::BatchedSnakeGame, d_out::Ptr{UInt8}) =
     check(ccall((:snk_available_actions, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, d_out))
+
+"""rows of `d_obs` (a fused step's next_state output) of the games that step re-initialised become (init, init): the
+acting state of the next step without a second expansion of all N states"""
+patch_reset_obs!(g::BatchedSnakeGame, d_done::Ptr{UInt8}, d_obs::Ptr{Cvoid}, obs_fmt::Integer = OBS_F32) =
+    check(ccall((:snk_patch_reset_obs, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Cvoid}, Cint), g.handle, d_done, d_obs, obs_fmt))
 
 """utils.jl:153-172 on device pointers: out[i] = ridx[i] if u[i] < ε else argmax(q[:, i]) - 1."""
 epsilon_greedy(g::BatchedSnakeGame, d_q::Ptr{Float32}, epsilon::Float32, d_u::Ptr{Float32}, d_ridx::Ptr{UInt8},
@@ -181,6 +206,34 @@ store_step!(g::BatchedSnakeGame, r::DeviceReplayBuffer, d_q::Ptr{Float32}, epsil
                  Ptr{Cvoid}, Cint, Ptr{UInt8}, Ptr{Float32}, Ptr{Int32}),
                 g.handle, r.handle, d_q, epsilon, d_u, d_ridx, d_act, d_reward, d_done, d_obs, OBS_F32, d_mask, C_NULL, C_NULL))
 
+"""One iteration's play step for a HOST trainer (utils.jl:436-440): epsilon_greedy + step! + virtual_step, every game's
+Experience store!d into the device ring; down come reward / lost / next_is_suicidal / actions and the lossless 2-bit packed
+next states (50 B per game; Float32 states are produced for the sampled minibatch only, `stack_exp`)."""
+function store_step_host!(g::BatchedSnakeGame, r::DeviceReplayBuffer, q::Matrix{Float32}, epsilon::Float32, packed::Matrix{UInt8};
+                          u::Vector{Float32} = rand(Float32, g.n), ridx::Vector{UInt8} = rand(UInt8(0):UInt8(2), g.n))
+    size(q) == (3, g.n) && size(packed) == (50, g.n) || throw(DimensionMismatch("q must be (3, N), packed (50, N)"))
+    check(ccall((:snk_step_fused_store_host, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float32}, Cfloat, Ptr{Float32}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Float32}, Ptr{UInt8},
+                 Ptr{Cvoid}, Cint, Ptr{UInt8}, Ptr{Float32}, Ptr{Int32}),
+                g.handle, r.handle, q, epsilon, u, ridx, g.actions, g.reward, g.lost, packed, OBS_PACKED2,
+                g.next_is_suicidal, C_NULL, C_NULL))
+    sync(g)
+    return g
+end
+
+"""`stack_exp(sample(rpb))` (utils.jl:343-383) into HOST arrays for the 0-based slots `idx`: (states, actions 1:3, rewards,
+next_states, dones, suicidal_mask) in the reference's order and shapes."""
+function stack_exp(r::DeviceReplayBuffer, idx::Vector{Int64})
+    B = length(idx)
+    states = Array{Float32,4}(undef, 10, 10, 2, B); next_states = similar(states)
+    actions = Vector{UInt8}(undef, B); rewards = Vector{Float32}(undef, B); dones = Vector{UInt8}(undef, B)
+    mask = Matrix{UInt8}(undef, 3, B)
+    check(ccall((:snk_replay_gather_host, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}, Ptr{Float32}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Cvoid}),
+                r.handle, idx, B, states, next_states, actions, rewards, dones, mask, C_NULL))
+    return states, Int.(actions) .+ 1, rewards, next_states, dones .!= 0, mask .!= 0
+end
+
 """`sample(rpb)` indices (0-based slots, distinct) into a device Int64 buffer."""
 sample_indices(r::DeviceReplayBuffer, d_idx::Ptr{Int64}, B::Integer; seed::Integer = 0) =
     check(ccall((:snk_replay_sample_indices, lib), Cint, (Ptr{Cvoid}, UInt64, Int64, Ptr{Int64}, Ptr{Cvoid}),
@@ -210,6 +263,22 @@ end
 """q_net(states): d_obs (10,10,2,N) Float32 -> d_q (3,N) Float32, both on the device."""
 forward!(q::DeviceQNet, d_obs::Ptr{Float32}, N::Integer, d_q::Ptr{Float32}) =
     check(ccall((:snk_qnet_forward, lib), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Float32}, Ptr{Cvoid}), q.handle, d_obs, N, d_q, C_NULL))
+
+"""`true` if a forward since the last call left the fp16 range of the Float32-faithful mode's split operands"""
+function overflowed(q::DeviceQNet)
+    f = Ref{Cint}(0)
+    check(ccall((:snk_qnet_overflow_host, lib), Cint, (Ptr{Cvoid}, Ref{Cint}), q.handle, f))
+    return f[] != 0
+end
+
+"""Per-sample gradients of `Flux.huber_loss(q_net(s)[a], y)` (utils.jl:452-466), rows in Flux.destructure order, written as
+the bf16 planes a Gram consumes (`planes(::GramShard)`) and / or as Float32 rows; device pointers."""
+sample_grads!(q::DeviceQNet, d_states::Ptr{Float32}, d_actions::Ptr{UInt8}, d_targets::Ptr{Float64}, B::Integer,
+              d_hi::Ptr{Cvoid}, d_lo2::Ptr{Cvoid}, pitch::Integer, d_J::Ptr{Float32}, ldJ::Integer, d_loss::Ptr{Float32}) =
+    check(ccall((:snk_qnet_sample_grads, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Float32}, Ptr{UInt8}, Ptr{Float64}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float32}, Int64,
+                 Ptr{Float32}, Ptr{Cvoid}),
+                q.handle, d_states, d_actions, d_targets, B, d_hi, d_lo2, pitch, d_J, ldJ, d_loss, C_NULL))
 
 # ---- Laplace deviation matrix (compute_D.jl, plot_traj.jl, la_utils.jl) ----------------------------------------
 """deviation_matrix[:, position] = Float64.(theta) (compute_D.jl:67-71); position is 1-based like Julia's."""
@@ -299,7 +368,40 @@ function default_food_list()
     return [(Int(cells[1, i]), Int(cells[2, i])) for i in 1:n[]]
 end
 
-# Not bound here: snk_gram_block / snk_gram_symmetrize_block / snk_gram_pack_planes / snk_ipc_* / snk_copy_async — the
-# building blocks of the row-sharded multi-GPU Gram, orchestrated one process per GPU by gram_sharded.py.
+# ---- row-sharded Gram: one process (Distributed.jl worker / MPI rank) per GPU, ONE call per rank and Gram ----------------
+"""This rank's share of G = A A' for A row-sharded over `length(rows_all)` GPUs of one box (BASELINE config 5b)."""
+mutable struct GramShard
+    handle::Ptr{Cvoid}
+    rows::Int
+    K::Int
+    function GramShard(rows_all::Vector{Int64}, rank::Integer, P::Integer; device::Integer = rank, splits::Integer = 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:snk_gram_shard_create, lib), Cint, (Ref{Ptr{Cvoid}}, Ptr{Int64}, Cint, Cint, Int64, Cint, Cint),
+                    h, rows_all, length(rows_all), rank, P, splits, device))
+        g = new(h[], rows_all[rank + 1], sum(rows_all))
+        finalizer(x -> ccall((:snk_gram_shard_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), g)
+        return g
+    end
+end
+"""192 bytes to send to every other rank (e.g. `MPI.Allgather`, or `fetch` from each Distributed.jl worker)"""
+function export_handle(g::GramShard)
+    h = Vector{UInt8}(undef, 192)
+    check(ccall((:snk_gram_shard_export_host, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, h))
+    return h
+end
+"""`handles` = the 192-byte handles of ALL ranks, concatenated in rank order"""
+connect!(g::GramShard, handles::Vector{UInt8}) =
+    check(ccall((:snk_gram_shard_connect_host, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, handles))
+"""G[rows of this rank, :] into the device buffer d_G (rows x K Float32).  d_A: this rank's rows of A on the device (Float64:
+dtype 2, Float32: dtype 1) or C_NULL when the planes were filled by `sample_grads!`.  Enqueued; every rank must call it."""
+run!(g::GramShard, d_A::Ptr{Cvoid}, dtype::Integer, d_G::Ptr{Float32}; terms::Integer = 3) =
+    check(ccall((:snk_gram_shard_run, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Int64, Ptr{Cvoid}),
+                g.handle, d_A, dtype, terms, 0, d_G, g.K, C_NULL))
+"""(hi, lo2, pitch): the bf16 planes of this rank's rows, for a producer that writes them directly"""
+function planes(g::GramShard)
+    hi = Ref{Ptr{Cvoid}}(C_NULL); lo = Ref{Ptr{Cvoid}}(C_NULL); pitch = Ref{Int64}(0)
+    check(ccall((:snk_gram_shard_planes, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}, Ref{Int64}), g.handle, hi, lo, pitch))
+    return hi[], lo[], Int(pitch[])
+end
 
 end # module

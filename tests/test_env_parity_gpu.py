@@ -389,6 +389,41 @@ def test_full_size_1m_envs_replicates_checked_small_run():
     assert big.count_errors() == 0
 
 
+def test_full_size_1m_envs_select_path_replicates_oracle_checked_run():
+    """The path bench.py times — k_step<F32, SELECT>: epsilon_greedy from injected q / u / ridx fused with the step — at the
+    BASELINE config-3 size: env i gets the draws of env (i mod 4096), so the 2^20-env run must reproduce, bit for bit, the
+    4,096-env run, whose selected actions and every other output are checked against the oracle (or_batch_select + step)."""
+    S = pkg()
+    n_small, n_big, steps, eps = 4096, 1 << 20, 120, 0.05
+    small = S.SnakeGame(n_small, auto_reset=True)
+    big = S.SnakeGame(n_big, auto_reset=True)
+    ora = O.OracleBatch(n_small, auto_reset=True)
+    so = small.alloc_outputs(obs="f32", mask=True, ep_stats=True, act=True)
+    bo = big.alloc_outputs(obs="f32", mask=True, ep_stats=True, act=True)
+    rep = n_big // n_small
+    rng = np.random.default_rng(2024)
+    for t in range(steps):
+        q = rng.uniform(-1, 1, (n_small, 3)).astype(np.float32)
+        ties = rng.random(n_small) < 0.05
+        q[ties, 2] = q[ties, 0]                                   # exact ties: Julia's argmax takes the first maximum
+        u = rng.random(n_small, dtype=np.float32)
+        ridx = rng.integers(0, 3, n_small).astype(np.uint8)
+        want_act = ora.select(q, eps, u, ridx)
+        dq, du, dr = torch.from_numpy(q).cuda(), torch.from_numpy(u).cuda(), torch.from_numpy(ridx).cuda()
+        small.step_fused(q=dq, eps=eps, u=du, ridx=dr, out=so)
+        big.step_fused(q=dq.repeat(rep, 1), eps=eps, u=du.repeat(rep), ridx=dr.repeat(rep), out=bo)
+        assert np.array_equal(so["act_idx"].cpu().numpy(), want_act), t
+        ref = ora.step(want_act) if (t % 20 == 0 or t == steps - 1) else ora.step(want_act, obs=())
+        if ref["obs_f32"] is not None:
+            _cmp_step(so, ref, n_small, t)
+        else:
+            assert np.array_equal(bits(so["reward"].cpu().numpy()), bits(ref["reward"])) and np.array_equal(so["done"].cpu().numpy(), ref["done"]), t
+        for k in ("act_idx", "reward", "done", "mask", "ep_return", "ep_score"):
+            assert torch.equal(bo[k].view(rep, *so[k].shape), so[k].unsqueeze(0).expand(rep, *so[k].shape)), (k, t)
+        assert torch.equal(bo["obs"].view(rep, n_small, 200), so["obs"].view(1, n_small, 200).expand(rep, -1, -1)), t
+    assert big.count_errors() == 0
+
+
 def test_two_frame_chaining_and_board_invariants_at_scale():
     """Properties that need no oracle: frame 2 of step t is frame 1 of step t+1 for envs that did not
     reset; walls are intact except the one wall cell a wall death overwrites (R6); one food at most;

@@ -94,3 +94,57 @@ def test_every_ccall_matches_a_header_declaration():
         if ret != want:
             problems.append("%s (line %d): returns %s, bound as %s" % (name, line, rets[name], ret))
     assert not problems, "\n".join(problems)
+
+
+def _julia_definitions(src):
+    """name -> concatenated source text of every method / constructor of that name (block `function` forms up to the matching
+    column-0 `end`, one-line `name(args) = ...` forms up to the next blank line, `mutable struct` blocks incl. inner constructors)"""
+    defs = {}
+    lines = src.split("\n")
+    i = 0
+    while i < len(lines):
+        ln = lines[i]
+        m = re.match(r"(?:mutable\s+)?struct\s+(\w+)", ln) or re.match(r"function\s+(?:Base\.)?(\w+!?)\s*\(", ln)
+        if m:
+            j = i + 1
+            while j < len(lines) and not re.match(r"end\b", lines[j]):
+                j += 1
+            defs[m.group(1)] = defs.get(m.group(1), "") + "\n".join(lines[i:j + 1]) + "\n"
+            i = j + 1
+            continue
+        m = re.match(r"(?:Base\.)?(\w+!?)\(", ln)           # at column 0 a `name(` line is always a short-form definition here
+        if m:
+            j = i
+            while j + 1 < len(lines) and lines[j + 1].startswith((" ", "\t")):
+                j += 1
+            defs[m.group(1)] = defs.get(m.group(1), "") + "\n".join(lines[i:j + 1]) + "\n"
+            i = j + 1
+            continue
+        i += 1
+    return defs
+
+
+def test_every_exported_julia_name_reaches_a_ccall():
+    """no exported function answers from Julia-side bookkeeping alone (round 1's assemble_state! fabricated the board):
+    each exported name has a definition whose body contains a ccall, or calls a function of the module that does"""
+    src = open(WRAPPER).read()
+    exported = re.search(r"^export\s+(.*?)\n\n", src, flags=re.S | re.M).group(1)
+    names = [n.strip() for n in exported.replace("\n", " ").split(",") if n.strip()]
+    assert len(names) >= 40 and "assemble_state!" in names and "virtual_step" in names and "GramShard" in names
+    defs = _julia_definitions(src)
+    missing = [n for n in names if n not in defs]
+    assert not missing, "exported but not defined: %s" % missing
+    reaches = {n for n, body in defs.items() if "ccall(" in body}
+    changed = True
+    while changed:
+        changed = False
+        for n, body in defs.items():
+            if n not in reaches and any(re.search(r"(?<![\w!])%s\(" % re.escape(r), body) for r in reaches):
+                reaches.add(n)
+                changed = True
+    dead = [n for n in names if n not in reaches]
+    assert not dead, "exported names that never reach the library: %s" % dead
+    # the host getters must be the library's, not Julia-side mirrors
+    for fn, sym in (("assemble_state!", "snk_state_host"), ("virtual_step", "snk_losing_mask_host"), ("lost", "snk_get_done_host"),
+                    ("score", "snk_get_score_host"), ("available_actions", "snk_available_actions_host")):
+        assert sym in defs[fn], (fn, sym)
