@@ -387,6 +387,7 @@ __device__ __forceinline__ void env_reset(Env &e) {
 }
 // step!(game, action) + virtual_step for one live env (utils.jl:100-109, 112-132): returns the reward, m3 = the
 // next_is_suicidal bits.  aidx: index into available_actions, or an absolute direction when is_abs.
+template <bool WITH_MASK = true>
 __device__ __forceinline__ float env_advance(Env &e, int &aidx, int is_abs, u64 list_mask, const uint8_t *s_food_bit,
                                              uint32_t &m3) {
     int d;
@@ -439,7 +440,7 @@ __device__ __forceinline__ float env_advance(Env &e, int &aidx, int is_abs, u64 
     e.hr = nr; e.hc = nc; e.pd = d; e.dn = lost;
     e.ret += reward;
     m3 = 7u;
-    if (!lost) m3 = losing_mask3(e.occ, e.cons, e.hr, e.hc, e.tr, e.tc, e.fr, e.fc, e.pd, e.t, list_mask, s_food_bit, e.err);
+    if (WITH_MASK && !lost) m3 = losing_mask3(e.occ, e.cons, e.hr, e.hc, e.tr, e.tc, e.fr, e.fc, e.pd, e.t, list_mask, s_food_bit, e.err);
     return reward;
 }
 
@@ -617,10 +618,11 @@ __global__ void __launch_bounds__(RTPB) k_rollout(const __grid_constant__ Rollou
 // the next step.  Actions are prefetched two steps ahead.  Named barriers: FULL[b] (warp 0 arrives, expanders wait),
 // EMPTY[b] (expanders arrive, warp 0 waits two steps later), and one among the expanders.
 struct __align__(16) Handoff {
-    u64 occ, pocc;
-    uint32_t pk;             // hr hc fr fc pfr pfc (4 bits each) | done << 24 | mask bits << 25
+    u64 occ, pocc, cons;
+    uint32_t pk;             // hr hc fr fc pfr pfc (4 bits each) | done << 24
+    uint32_t pk2;            // tr tc (4 bits each) | prev_dir << 8 | step count << 10
     float reward, ret;
-    int score;
+    int score, pad;
 };
 __device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -632,19 +634,21 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
     __shared__ __align__(16) uint32_t s_planes[EPB * PLANE_WORDS];
     __shared__ ObsTables s_tb;
     __shared__ uint8_t s_food_bit[MAX_FOOD];
+    __shared__ int s_err[EPB];                               // error bits found by the virtual steps (utils.jl:23,37 inside virtual_step)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long env0 = (long long)blockIdx.x * EPB;
     const long long rem = a.n - env0;
     const int n_local = rem < EPB ? (int)rem : EPB;
     if (tid < MAX_FOOD) s_food_bit[tid] = a.food.bit[tid];
+    if (tid < EPB) s_err[tid] = 0;
     if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid, 128);
     __syncthreads();
     constexpr int FULL = 1, EMPTY = 3, XB = 5;              // barrier ids: FULL+b, EMPTY+b, expanders
+    const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
+    Env e;
+    const bool mine = warp == 0 && lane < n_local;
+    const long long env = env0 + (mine ? lane : 0);
     if (warp == 0) {
-        const bool mine = lane < n_local;
-        const long long env = env0 + (mine ? lane : 0);
-        const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
-        Env e;
         env_load(e, a.s, env);
         int a0 = a.steps > 0 ? a.act[env] : 0, a1 = a.steps > 1 ? a.act[a.n + env] : 0;
         for (int t = 0; t < a.steps; t++) {
@@ -653,14 +657,15 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
             if (t >= 2) nbar_sync(EMPTY + b, 128);           // the expanders have consumed slot b (step t-2)
             int aidx = a0;
             float reward = 0.0f;
-            uint32_t m3 = 7u;
-            if (!e.dn) reward = env_advance(e, aidx, a.is_abs, list_mask, s_food_bit, m3);
+            uint32_t m3;
+            if (!e.dn) reward = env_advance<false>(e, aidx, a.is_abs, list_mask, s_food_bit, m3);   // virtual_step is the expanders' job
             if (mine) {
                 Handoff h;
-                h.occ = e.occ; h.pocc = e.pocc;
+                h.occ = e.occ; h.pocc = e.pocc; h.cons = e.cons;
                 h.pk = (uint32_t)e.hr | ((uint32_t)e.hc << 4) | ((uint32_t)e.fr << 8) | ((uint32_t)e.fc << 12) |
-                       ((uint32_t)e.pfr << 16) | ((uint32_t)e.pfc << 20) | ((uint32_t)e.dn << 24) | (m3 << 25);
-                h.reward = reward; h.ret = e.ret; h.score = e.len - 2;
+                       ((uint32_t)e.pfr << 16) | ((uint32_t)e.pfc << 20) | ((uint32_t)e.dn << 24);
+                h.pk2 = (uint32_t)e.tr | ((uint32_t)e.tc << 4) | ((uint32_t)e.pd << 8) | ((uint32_t)e.t << 10);
+                h.reward = reward; h.ret = e.ret; h.score = e.len - 2; h.pad = 0;
                 s_hand[b][lane] = h;
             }
             if (e.dn && a.auto_reset) env_reset(e);
@@ -668,32 +673,39 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
             nbar_arrive(FULL + b, 128);
             a0 = a1; a1 = a2;
         }
-        if (mine) env_store(e, a.s, env);
     } else {
         const int et = tid - 32;                             // 0..95
         const size_t obs_step = (size_t)a.n * (OBS == SNK_OBS_F32 ? 800 : OBS == SNK_OBS_I8 ? 200 : OBS == SNK_OBS_I64 ? 1600 : 50);
         for (int t = 0; t < a.steps; t++) {
             const int b = t & 1;
             nbar_sync(FULL + b, 128);
-            // threads 0..EPB-1: scalars + the older board; threads 32..32+EPB-1: the newer board
+            // threads 0..EPB-1: losing mask + scalars; threads 32..: the older board; threads 64..: the newer board
             const int j = et & 31, role = et >> 5;
-            if (j < n_local && role < 2) {
+            if (j < n_local) {
                 const Handoff h = s_hand[b][j];
+                const int hr = (int)h.pk & 15, hc = (int)(h.pk >> 4) & 15, fr = (int)(h.pk >> 8) & 15, fc = (int)(h.pk >> 12) & 15;
                 if (role == 0) {
+                    const int dn = (int)(h.pk >> 24) & 1;
+                    uint32_t m3 = 7u;
+                    if (!dn) {
+                        int err = 0;
+                        m3 = losing_mask3(h.occ, h.cons, hr, hc, (int)h.pk2 & 15, (int)(h.pk2 >> 4) & 15, fr, fc, (int)(h.pk2 >> 8) & 3,
+                                          (int)(h.pk2 >> 10) & 1023, list_mask, s_food_bit, err);
+                        if (err) s_err[j] |= err;
+                    }
                     const long long o = (long long)t * a.n + env0 + j;
                     if (a.reward != nullptr) a.reward[o] = h.reward;
-                    if (a.done != nullptr) a.done[o] = (uint8_t)((h.pk >> 24) & 1u);
+                    if (a.done != nullptr) a.done[o] = (uint8_t)dn;
                     if (a.mask != nullptr) {
                         uint8_t *m = a.mask + 3 * o;
-                        m[0] = (uint8_t)((h.pk >> 25) & 1u); m[1] = (uint8_t)((h.pk >> 26) & 1u); m[2] = (uint8_t)((h.pk >> 27) & 1u);
+                        m[0] = (uint8_t)(m3 & 1u); m[1] = (uint8_t)((m3 >> 1) & 1u); m[2] = (uint8_t)((m3 >> 2) & 1u);
                     }
                     if (a.ep_return != nullptr) a.ep_return[o] = h.ret;
                     if (a.ep_score != nullptr) a.ep_score[o] = h.score;
-                    if (OBS != SNK_OBS_NONE)
-                        board_planes(h.pocc, (int)(h.pk >> 16) & 15, (int)(h.pk >> 20) & 15, false, 0, 0, s_planes + j * PLANE_WORDS);
+                } else if (OBS != SNK_OBS_NONE && role == 1) {
+                    board_planes(h.pocc, (int)(h.pk >> 16) & 15, (int)(h.pk >> 20) & 15, false, 0, 0, s_planes + j * PLANE_WORDS);
                 } else if (OBS != SNK_OBS_NONE) {
-                    board_planes(h.occ, (int)(h.pk >> 8) & 15, (int)(h.pk >> 12) & 15, true, (int)h.pk & 15, (int)(h.pk >> 4) & 15,
-                                 s_planes + j * PLANE_WORDS + 8);
+                    board_planes(h.occ, fr, fc, true, hr, hc, s_planes + j * PLANE_WORDS + 8);
                 }
             }
             if (t + 2 < a.steps) nbar_arrive(EMPTY + b, 128);       // the record has been read: warp 0 may overwrite it at step t+2
@@ -703,6 +715,11 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
                 nbar_sync(XB, 96);
             }
         }
+    }
+    __syncthreads();
+    if (mine) {
+        e.err |= s_err[lane];
+        env_store(e, a.s, env);
     }
 }
 
@@ -1501,8 +1518,11 @@ static int step_fused_host_impl(snk_handle h, snk_replay_s *r, const float *q, f
     a.mask = mask ? h->d_mask : nullptr; a.ep_return = ep_return ? h->d_ep_return : nullptr;
     a.ep_score = ep_score ? h->d_ep_score : nullptr;
     if (r != nullptr) { a.sink = r->ring; a.sink_base = r->total; a.sink_cap = r->capacity; a.sink_n = h->n; }
+    // Chunking trades copy/kernel overlap against per-copy overhead (~8 us per cudaMemcpyAsync): about 16 MB of traffic per
+    // chunk, at most 16 chunks; only the observation is copied per chunk, the small per-env outputs go down once at the end.
     const long long align = TPB * 8;
-    int n_chunks = (int)((h->n + (1 << 16) - 1) >> 16);
+    const size_t traffic = (opb + 26) * n;
+    int n_chunks = (int)((traffic + (16u << 20) - 1) / (16u << 20));
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > 16) n_chunks = 16;
     const long long per = ((h->n + n_chunks - 1) / n_chunks + align - 1) / align * align;
@@ -1524,13 +1544,14 @@ static int step_fused_host_impl(snk_handle h, snk_replay_s *r, const float *q, f
         SNK_CUDA(cudaEventRecord(h->ev_chunk[ci], st));
         SNK_CUDA(cudaStreamWaitEvent(down, h->ev_chunk[ci], 0));
         if (opb) SNK_CUDA(cudaMemcpyAsync((char *)obs + opb * b, (char *)h->d_obs + opb * b, opb * nb, cudaMemcpyDeviceToHost, down));
-        if (mask) SNK_CUDA(cudaMemcpyAsync(mask + 3 * b, h->d_mask + 3 * b, 3 * nb, cudaMemcpyDeviceToHost, down));
-        if (reward) SNK_CUDA(cudaMemcpyAsync(reward + b, h->d_reward + b, 4 * nb, cudaMemcpyDeviceToHost, down));
-        if (done) SNK_CUDA(cudaMemcpyAsync(done + b, h->d_done + b, nb, cudaMemcpyDeviceToHost, down));
-        if (ep_return) SNK_CUDA(cudaMemcpyAsync(ep_return + b, h->d_ep_return + b, 4 * nb, cudaMemcpyDeviceToHost, down));
-        if (ep_score) SNK_CUDA(cudaMemcpyAsync(ep_score + b, h->d_ep_score + b, 4 * nb, cudaMemcpyDeviceToHost, down));
-        if (q && act_idx) SNK_CUDA(cudaMemcpyAsync(act_idx + b, h->d_act + b, nb, cudaMemcpyDeviceToHost, down));
     }
+    // `down` has waited for the last kernel: every per-env output is complete
+    if (mask) SNK_CUDA(cudaMemcpyAsync(mask, h->d_mask, 3 * n, cudaMemcpyDeviceToHost, down));
+    if (reward) SNK_CUDA(cudaMemcpyAsync(reward, h->d_reward, 4 * n, cudaMemcpyDeviceToHost, down));
+    if (done) SNK_CUDA(cudaMemcpyAsync(done, h->d_done, n, cudaMemcpyDeviceToHost, down));
+    if (ep_return) SNK_CUDA(cudaMemcpyAsync(ep_return, h->d_ep_return, 4 * n, cudaMemcpyDeviceToHost, down));
+    if (ep_score) SNK_CUDA(cudaMemcpyAsync(ep_score, h->d_ep_score, 4 * n, cudaMemcpyDeviceToHost, down));
+    if (q && act_idx) SNK_CUDA(cudaMemcpyAsync(act_idx, h->d_act, n, cudaMemcpyDeviceToHost, down));
     h->step_counter++;
     if (r != nullptr) r->total += h->n;
     // make the handle's stream wait for the copies, so snk_sync() covers the whole call
