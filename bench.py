@@ -308,10 +308,10 @@ def run_ours(args):
 
         def it():
             env.step_fused_host(host, q=True, eps=eps, replay=ring if store else None)
-            env.sync()                                            # outputs are in host memory
-            if store:                                             # sample(rpb) + stack_exp (utils.jl:442-443): 64 transitions as Float32
-                idx = torch.randint(0, len(ring), (64,), generator=idx_rng, dtype=torch.int64)
-                ring.stack_exp_host(idx, out=batch_host)
+            if store:                                             # sample(rpb) + stack_exp (utils.jl:442-443): 64 transitions as Float32;
+                idx = torch.randint(0, len(ring), (64,), generator=idx_rng, dtype=torch.int64)     # ordered behind the step's kernels,
+                ring.stack_exp_host(idx, out=batch_host)                                          # beside its device->host copies
+            env.sync()                                            # every output of the step is in host memory
 
         for _ in range(2):
             it()

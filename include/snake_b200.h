@@ -132,7 +132,9 @@ SNK_API int snk_step_fused(snk_handle h, const float *q, float eps, const float 
                    uint8_t *mask, float *ep_return, int32_t *ep_score);
 /* same call with HOST buffers (pinned memory recommended: snk_host_alloc): env chunks are pipelined three deep — the
  * inputs of chunk c+1 go up while the kernel of chunk c runs and the outputs of chunk c-1 come down.  ASYNCHRONOUS:
- * returns after enqueueing; snk_sync(h) before reading an output or overwriting an input.  obs_fmt SNK_OBS_PACKED2
+ * returns after enqueueing; snk_sync(h) before reading an output or overwriting an input.  The output copies run on a
+ * copy stream of the handle: work enqueued afterwards on the handle's stream (a snk_replay_gather_host of the minibatch,
+ * the Q-net forward of the next step) overlaps them; only snk_sync waits for them.  obs_fmt SNK_OBS_PACKED2
  * (50 B/env, lossless) is the format meant for this entry: the reference casts to Float32 only the 64 transitions a
  * minibatch samples (utils.jl:361-362) — snk_replay_gather_host does that for the device replay ring. */
 SNK_API int snk_step_fused_host(snk_handle h, const float *q, float eps, const float *u, const uint8_t *ridx,
@@ -145,6 +147,10 @@ SNK_API int snk_step_fused_host(snk_handle h, const float *q, float eps, const f
  * obs (T, 10,10,2,N) in obs_fmt, ep_return / ep_score (T,N).  Outputs may be NULL. */
 SNK_API int snk_rollout_fused(snk_handle h, const uint8_t *act_TxN, int64_t T, int is_abs, float *reward, uint8_t *done,
                               void *obs, int obs_fmt, uint8_t *mask, float *ep_return, int32_t *ep_score);
+/* profiling aid: device buffer of 8 int64 that receives cycle counts of CTA 0 of the small-batch rollout kernel on every later
+ * snk_rollout_fused ([0] logic warp total, [1] its wait for the expander warps, [2] expander wait for the logic warp,
+ * [3] losing mask + boards, [4] observation expansion); NULL switches it off */
+SNK_API int snk_debug_rollout_timing(long long *device_buf);
 SNK_API int snk_host_alloc(void **p, size_t bytes);   /* pinned host memory */
 SNK_API int snk_host_free(void *p);
 

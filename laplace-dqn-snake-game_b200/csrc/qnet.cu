@@ -168,6 +168,7 @@ struct SplitArgs {
     const uint8_t *params;
     __half *out3;                // [2 N][1600] fp16: row 2 s = hi, row 2 s + 1 = 2^11 * lo of sample s; k' = (oy*5 + ox)*64 + c
     int *overflow;               // set to 1 when an activation left the fp16 range (|x| > 65504): the result is not valid
+    long long *timing;           // optional (debug): clock64 stamps of block 0, 8 per iteration, first 16 iterations
     float w1f[288];              // conv1 weights [tap*2 + c][o] fp32 (constant-bank FFMA operands)
     float b1f[16];
 };
@@ -269,6 +270,7 @@ __device__ __forceinline__ void conv1_pixmajor(const ConvArgs &a, long long s0, 
 // 18 / 72 / 100 steps of the large terms per layer).  |activation| must stay below 65504 (fp16 range); the kernel
 // raises a flag otherwise (snk_qnet_overflow_host).
 namespace split {
+#define SPLIT_STAMP(k) do { if (a.timing != nullptr && blockIdx.x == 0 && it_local >= 0 && it_local < 16 && lane == 0) a.timing[it_local * 8 + (k)] = clock64(); } while (0)
 constexpr int S = e16::S, SR = 8;             // 16 slots = 8 real samples x (hi, lo)
 constexpr int A1_PLANE = e16::A1_PLANE, A2_PLANE = e16::A2_PLANE, TILES2 = e16::TILES2;
 constexpr int NSLOT = 8;                      // ring of 4 KB conv3 weight blocks
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
     for (long long it = (long long)blockIdx.x - gridDim.x; it < n_iter; it += gridDim.x, it_local++) {
         const bool real = it_local >= 0;
         const long long s0 = it * SR;
+        if (real && warp == 4) SPLIT_STAMP(0);
         if (real && warp == 2 && lane == 0) {
             // weight producer, part 1: fill the ring while conv2 runs
             for (int bi = 0; bi < NSLOT; bi++) {
@@ -482,9 +485,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
             }
         }
         if (real) acc_it += TILES2;
+        if (real && warp == 4) SPLIT_STAMP(1);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        if (real && warp == 4) SPLIT_STAMP(2);
 
         // ================= conv3: 32 -> 64, 6x6, valid; weights are the M operand, 36 lo blocks then 36 hi blocks =================
         if (warp < NISSUE) {
@@ -533,11 +538,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
             if ((warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
                 const int w7 = warp == 3 ? 0 : 2 * ((warp - 4) >> 2) + (warp & 1) + 1;      // 3,6,7,10,11,14,15 -> 0..6
                 conv1_f32_split(a, (it + gridDim.x) * SR, A1, w7 * 32 + lane, 224, amax);
+                if (real && warp == 15) SPLIT_STAMP(6);
             }
             if (real && warp >= 4) {
                 const int grp = (warp - 4) >> 2, q = warp & 3;
                 mbar_wait(c3_full, c3_it & 1);
                 tc_fence_after();
+                if (warp == 4) SPLIT_STAMP(3);
                 float *scratch = reinterpret_cast<float *>(A2);             // [y][column = x*8 + sample][oc]: conv3 no longer reads A2
                 // out[y] = lower lanes of tile y + upper lanes of tile y + 1.  Warp quarter q owns lanes 32q..32q+31, i.e.
                 // output channels (q & 1)*32 + lane of the lower (q < 2) or upper (q >= 2) half.  For even y the upper half
@@ -583,11 +590,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                     }
                 }
                 tc_fence_before();
+                if (warp == 4) SPLIT_STAMP(4);
             }
         }
         if (real) { w3_it += NBLK; c3_it++; }
         fence_proxy_async();
         __syncthreads();                            // conv3 accumulators drained (conv2 reuses the columns), A1/A2 handed over
+        if (real && warp == 4) SPLIT_STAMP(5);
     }
 
     if (amax > 65504.f) *a.overflow = 1;
@@ -1288,6 +1297,7 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
     if (f32) {
         SplitArgs sa;
         sa.obs = obs_f32; sa.n = N; sa.params = q->params; sa.out3 = (__half *)q->out3; sa.overflow = q->d_overflow;
+        sa.timing = q->timing;
         memcpy(sa.w1f, q->w1f, sizeof(sa.w1f));
         memcpy(sa.b1f, q->b1f, sizeof(sa.b1f));
         const long long n_iter = (N + split::SR - 1) / split::SR;

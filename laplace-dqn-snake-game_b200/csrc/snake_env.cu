@@ -552,6 +552,7 @@ struct RolloutArgs {
     int32_t *ep_score;
     long long n;
     int steps, auto_reset, is_abs;
+    long long *prof;         // debug (snk_debug_rollout_timing): cycle counts of CTA 0's logic warp / expander thread 0
     FoodTable food;
 };
 #ifndef SNK_RTPB
@@ -651,10 +652,14 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
     if (warp == 0) {
         env_load(e, a.s, env);
         int a0 = a.steps > 0 ? a.act[env] : 0, a1 = a.steps > 1 ? a.act[a.n + env] : 0;
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && lane == 0;
+        long long p_wait = 0, p_t0 = prof ? clock64() : 0;
         for (int t = 0; t < a.steps; t++) {
             const int a2 = t + 2 < a.steps ? a.act[(long long)(t + 2) * a.n + env] : 0;      // in flight during two steps
             const int b = t & 1;
+            const long long w0 = prof ? clock64() : 0;
             if (t >= 2) nbar_sync(EMPTY + b, 128);           // the expanders have consumed slot b (step t-2)
+            if (prof) p_wait += clock64() - w0;
             int aidx = a0;
             float reward = 0.0f;
             uint32_t m3;
@@ -673,12 +678,17 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
             nbar_arrive(FULL + b, 128);
             a0 = a1; a1 = a2;
         }
+        if (prof) { a.prof[0] = clock64() - p_t0; a.prof[1] = p_wait; }
     } else {
         const int et = tid - 32;                             // 0..95
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && et == 0;
+        long long p_full = 0, p_role = 0, p_exp = 0;
         const size_t obs_step = (size_t)a.n * (OBS == SNK_OBS_F32 ? 800 : OBS == SNK_OBS_I8 ? 200 : OBS == SNK_OBS_I64 ? 1600 : 50);
         for (int t = 0; t < a.steps; t++) {
             const int b = t & 1;
+            long long c0 = prof ? clock64() : 0;
             nbar_sync(FULL + b, 128);
+            if (prof) { const long long c1 = clock64(); p_full += c1 - c0; c0 = c1; }
             // threads 0..EPB-1: losing mask + scalars; threads 32..: the older board; threads 64..: the newer board
             const int j = et & 31, role = et >> 5;
             if (j < n_local) {
@@ -711,10 +721,13 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
             if (t + 2 < a.steps) nbar_arrive(EMPTY + b, 128);       // the record has been read: warp 0 may overwrite it at step t+2
             if (OBS != SNK_OBS_NONE) {
                 nbar_sync(XB, 96);
+                if (prof) { const long long c1 = clock64(); p_role += c1 - c0; c0 = c1; }
                 expand_obs<OBS, 96, 5, true>((uint8_t *)a.obs + (size_t)t * obs_step, env0, n_local, s_planes, s_tb, et);
                 nbar_sync(XB, 96);
+                if (prof) p_exp += clock64() - c0;
             }
         }
+        if (prof) { a.prof[2] = p_full; a.prof[3] = p_role; a.prof[4] = p_exp; }
     }
     __syncthreads();
     if (mine) {
@@ -1007,7 +1020,16 @@ static cudaError_t ensure(T **p, size_t bytes) {
     return cudaMalloc((void **)p, bytes);
 }
 
+static long long *g_rollout_prof = nullptr;
+
 extern "C" {
+
+// profiling aid: device buffer of 8 int64 receiving cycle counts of CTA 0 of the small-batch rollout kernel
+// ([0] logic warp total, [1] its wait for the expanders, [2] expander wait for the logic warp, [3] mask/boards, [4] expansion)
+int snk_debug_rollout_timing(long long *device_buf) {
+    g_rollout_prof = device_buf;
+    return SNK_OK;
+}
 
 int snk_version(void) { return SNK_VERSION; }
 const char *snk_last_error(void) { return err_buf(); }
@@ -1067,6 +1089,7 @@ int snk_destroy(snk_handle h) {
     if (h == nullptr) return SNK_OK;
     DeviceGuard guard(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    for (int i = 0; i < 2; i++) if (h->copy_stream[i]) cudaStreamSynchronize(h->copy_stream[i]);
     void *ptrs[] = {h->s.occ, h->s.pocc, h->s.clo, h->s.chi, h->s.cons, h->s.misc, h->s.ret, h->d_count, h->d_q, h->d_u,
                     h->d_reward, h->d_ep_return, h->d_ridx, h->d_act, h->d_done, h->d_mask, h->d_ep_score, h->d_obs};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -1124,6 +1147,7 @@ int snk_set_seed(snk_handle h, uint64_t seed) {
 int snk_sync(snk_handle h) {
     SNK_CHECK_HANDLE(h);
     SNK_CUDA(cudaStreamSynchronize(h->stream));
+    SNK_CUDA(cudaStreamSynchronize(h->copy_stream[0]));       // device->host copies of the host-buffer entry points
     return SNK_OK;
 }
 int64_t snk_num_envs(snk_handle h) { return h ? h->n : 0; }
@@ -1219,6 +1243,7 @@ int snk_rollout_fused(snk_handle h, const uint8_t *act_TxN, int64_t T, int is_ab
     memset(&a, 0, sizeof(a));
     a.s = h->s; a.food = h->food; a.act = act_TxN; a.reward = reward; a.done = done; a.obs = obs; a.mask = mask;
     a.ep_return = ep_return; a.ep_score = ep_score; a.n = h->n; a.steps = (int)T; a.is_abs = is_abs;
+    a.prof = g_rollout_prof;
     a.auto_reset = (h->flags & SNK_AUTO_RESET) ? 1 : 0;
     const int fmt = obs ? obs_fmt : SNK_OBS_NONE;
     // small batches: the warp-specialised kernel, WS_EPB envs per CTA (4,096 envs -> 512 CTAs over the 148 SMs)
@@ -1271,6 +1296,14 @@ int snk_step_fused_host(snk_handle h, const float *q, float eps, const float *u,
                         float *reward, uint8_t *done, void *obs, int obs_fmt, uint8_t *mask, float *ep_return,
                         int32_t *ep_score) {
     return step_fused_host_impl(h, nullptr, q, eps, u, ridx, act_idx, reward, done, obs, obs_fmt, mask, ep_return, ep_score);
+}
+
+// The device staging buffers of the host-buffer entry points are read by copies on copy_stream[0] that the handle's own
+// stream does NOT wait for (so that later work on it — e.g. the minibatch gather — overlaps those copies): whoever is about
+// to overwrite the staging buffers first orders itself behind the last such copy.
+static int staging_guard(snk_handle h) {
+    SNK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_done, 0));
+    return SNK_OK;
 }
 
 // device staging buffer of the host getters (grown on demand)
@@ -1509,6 +1542,7 @@ static int step_fused_host_impl(snk_handle h, snk_replay_s *r, const float *q, f
     if (ep_return) { SNK_CUDA(ensure(&h->d_ep_return, 4 * n)); }
     if (ep_score) { SNK_CUDA(ensure(&h->d_ep_score, 4 * n)); }
     if (opb) { int rc = ensure_obs_staging(h, opb * n); if (rc != SNK_OK) return rc; }
+    { int rc = staging_guard(h); if (rc != SNK_OK) return rc; }
     cudaStream_t st = h->stream, down = h->copy_stream[0], up = h->copy_stream[1];
     StepArgs a;
     base_args(h, a);
@@ -1554,9 +1588,8 @@ static int step_fused_host_impl(snk_handle h, snk_replay_s *r, const float *q, f
     if (q && act_idx) SNK_CUDA(cudaMemcpyAsync(act_idx, h->d_act, n, cudaMemcpyDeviceToHost, down));
     h->step_counter++;
     if (r != nullptr) r->total += h->n;
-    // make the handle's stream wait for the copies, so snk_sync() covers the whole call
+    // snk_sync() waits for these copies; the handle's stream itself does not (see staging_guard)
     SNK_CUDA(cudaEventRecord(h->ev_done, down));
-    SNK_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
     return SNK_OK;
 }
 
@@ -1577,6 +1610,7 @@ static int to_host(snk_handle h, void *dst_host, const void *src_dev, size_t byt
 
 int snk_state_host(snk_handle h, void *obs_host, int obs_fmt) {
     SNK_CHECK_HANDLE(h);
+    { int rc0 = staging_guard(h); if (rc0 != SNK_OK) return rc0; }
     SNK_REQUIRE(obs_host != nullptr, "null out");
     const size_t opb = obs_bytes_per_env(obs_fmt);
     if (opb == 0) return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
@@ -1588,6 +1622,7 @@ int snk_state_host(snk_handle h, void *obs_host, int obs_fmt) {
 
 int snk_losing_mask_host(snk_handle h, uint8_t *mask_3xN_host) {
     SNK_CHECK_HANDLE(h);
+    { int rc0 = staging_guard(h); if (rc0 != SNK_OK) return rc0; }
     SNK_REQUIRE(mask_3xN_host != nullptr, "null out");
     SNK_CUDA(ensure(&h->d_mask, 3 * (size_t)h->n));
     int rc = snk_losing_mask(h, h->d_mask);
@@ -1597,6 +1632,7 @@ int snk_losing_mask_host(snk_handle h, uint8_t *mask_3xN_host) {
 
 int snk_available_actions_host(snk_handle h, uint8_t *dirs_3xN_host) {
     SNK_CHECK_HANDLE(h);
+    { int rc0 = staging_guard(h); if (rc0 != SNK_OK) return rc0; }
     SNK_REQUIRE(dirs_3xN_host != nullptr, "null out");
     SNK_CUDA(ensure(&h->d_mask, 3 * (size_t)h->n));
     int rc = snk_available_actions(h, h->d_mask);
@@ -1606,6 +1642,7 @@ int snk_available_actions_host(snk_handle h, uint8_t *dirs_3xN_host) {
 
 static int scalars_host(snk_handle h, int which, void *out_host, size_t elem) {
     SNK_CHECK_HANDLE(h);
+    { int rc0 = staging_guard(h); if (rc0 != SNK_OK) return rc0; }
     SNK_REQUIRE(out_host != nullptr, "null out");
     SNK_CUDA(ensure(&h->d_ep_score, 4 * (size_t)h->n));          // 4 bytes per env covers the u8 and the i32 scalars
     int rc = scalars(h, which, h->d_ep_score);
