@@ -62,8 +62,8 @@ constexpr size_t P_W4 = P_BIAS + 112 * 4;                    // [64][1600] bf16,
 constexpr size_t P_B4 = P_W4 + 64 * 1600 * 2, P_W5 = P_B4 + 64 * 4, P_B5 = P_W5 + 3 * 64 * 4;
 constexpr size_t P_W3B = P_B5 + 16;                          // bf16 conv3 weights as 36 stacked-tap M operands of 4 KB
 // Float32-faithful mode: fp16 (lo, hi) pairs of the same layouts
-constexpr size_t P_S_W2 = P_W3B + 36 * 4096;                 // [part (lo, hi)][k2][k1][chunk][o][8] fp16
-constexpr size_t P_S_W3 = P_S_W2 + 2 * 9 * 1024;             // 72 blocks of 4 KB: 36 lo blocks, then 36 hi blocks
+constexpr size_t P_S_W2 = P_W3B + 36 * 4096;                 // [k2][k1][chunk][n = (hi | lo) x 32 channels][8] fp16
+constexpr size_t P_S_W3 = P_S_W2 + 2 * 9 * 1024;             // 72 blocks (k2, k1, m) of 4 KB: 128 rows = (hi | lo) x 64 channels
 constexpr size_t P_S_W4 = P_S_W3 + 72 * 4096;                // [64][3200] fp16: columns [0,1600) = lo, [1600,3200) = hi
 constexpr size_t P_END = P_S_W4 + 64 * 3200 * 2;
 
@@ -259,23 +259,31 @@ __device__ __forceinline__ void conv1_pixmajor(const ConvArgs &a, long long s0, 
 // 8 real samples per iteration occupy the 16 slots: slot s = fp16(x), slot s + 8 = fp16(2^11 (x - fp16(x))) of sample s's
 // activations x.  Both halves run through the same MMAs as two independent "virtual samples" (every layer is linear up to
 // its epilogue); the epilogue adds the two accumulators (real = acc[s] + 2^-11 acc[s+8]), applies bias and relu in FP32
-// and splits the result again for the next layer.  Each weight is two fp16 numbers as well (w = hi + lo, lo unscaled:
-// it shares the accumulator with hi): every MMA of the bf16 engines is issued twice, with the lo weights first.  Both
-// halves of the conv3 weights (2 x 147 KB) cannot stay in tensor memory, so they stream through a ring of 4 KB blocks
-// (cp.async.bulk + mbarrier), 72 blocks per iteration; the six 80-column conv3 accumulators fill 480 of the 512 TMEM
-// columns and conv2 (16 buffers x 32 columns) time-shares them:  conv2 -> barrier -> conv3 (+ next conv1 on the CUDA
-// cores) -> conv3 epilogue -> barrier.
+// and splits the result again for the next layer.  Each weight is two fp16 numbers as well (w = hi + lo, lo unscaled);
+// the two halves sit side by side in ONE operand, so that they cost one MMA instead of two and land in separate
+// accumulators (the small lo products are added to the large hi sums in FP32 registers, not by the tensor core's
+// truncating accumulator):
+//   conv2: B (N operand) = [W2 hi (32 channels) | W2 lo (32 channels)], N = 64: 9 MMAs of 128x64x16 per tile; the epilogue
+//          adds accumulator columns j and j + 32;
+//   conv3: A (M operand) = [W3 hi (64 channels) ; W3 lo (64 channels)] of ONE kernel tap, 128 rows; tile y (80 TMEM columns)
+//          = output row y: 72 MMAs (6 x 6 taps x 2 channel halves) of 128x80x16 over input rows y .. y+5; the epilogue adds
+//          TMEM lanes l and l + 64 (through shared memory: they belong to different warps).
+// Both halves of the conv3 weights (2 x 147 KB) cannot stay in tensor memory, so they stream through a ring of 4 KB blocks
+// (cp.async.bulk + mbarrier), 72 blocks per iteration, each used by all five tiles; the five 80-column conv3 accumulators
+// fill 400 of the 512 TMEM columns and conv2 (8 buffers x 64 columns) time-shares them:  conv2 -> barrier -> conv3 (+ next
+// conv1 on the CUDA cores) -> conv3 epilogue -> barrier.  Measured (tools/phase_probe.py): the kernel is bound by the tensor
+// pipe's operand fetch (6.5 KB of shared memory per conv3 MMA).
 // Error budget against Float64 (tests/test_qnet_gpu.py): operands carry 22 bits (2^-22 relative each), products of fp16
 // numbers are exact in FP32, the accumulator adds with truncation (measured in round 1: ~3e-8 relative per MMA step;
-// 18 / 72 / 100 steps of the large terms per layer).  |activation| must stay below 65504 (fp16 range); the kernel
-// raises a flag otherwise (snk_qnet_overflow_host).
+// 9 / 72 / 25 steps per layer).  |activation| must stay below 65504 (fp16 range); the kernel raises a flag otherwise
+// (snk_qnet_overflow_host).
 namespace split {
 #define SPLIT_STAMP(k) do { if (a.timing != nullptr && blockIdx.x == 0 && it_local >= 0 && it_local < 16 && lane == 0) a.timing[it_local * 8 + (k)] = clock64(); } while (0)
 constexpr int S = e16::S, SR = 8;             // 16 slots = 8 real samples x (hi, lo)
 constexpr int A1_PLANE = e16::A1_PLANE, A2_PLANE = e16::A2_PLANE, TILES2 = e16::TILES2;
 constexpr int NSLOT = 8;                      // ring of 4 KB conv3 weight blocks
-constexpr int NBLK = 72;                      // (part, j, k1, m) blocks per iteration: 36 lo, then 36 hi
-constexpr int NACC = 16;                      // conv2 accumulator buffers (all 512 columns)
+constexpr int NBLK = 72;                      // (k2, k1, m) weight blocks per iteration, each 128 rows = [hi | lo] x 64 channels
+constexpr int NACC = 8;                       // conv2 accumulator buffers of 64 columns (all 512 columns)
 constexpr int OFF_A1 = 0;
 constexpr int OFF_A2 = OFF_A1 + 2 * A1_PLANE;
 constexpr int OFF_W2 = OFF_A2 + 4 * A2_PLANE;
@@ -287,8 +295,8 @@ static_assert(SMEM <= 232448, "split engine shared memory over the 227 KB limit"
 static_assert(5 * 40 * 64 * 4 <= 4 * A2_PLANE, "epilogue scratch must fit in the conv3 input planes");
 static_assert(NBLK % NSLOT == 0 && NSLOT % 2 == 0, "the issuer waits for ring slots in aligned pairs");
 constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;      // 2^11: keeps the low halves in fp16's normal range
-// B-descriptor offset (16-byte units) of weight block be = (j*6 + k1)*2 + m for tile 0: ((2j)*10 + k1)*S + 2m*(A2_PLANE/16)
-__constant__ uint32_t c_boff[36] = {0, 3200, 16, 3216, 32, 3232, 48, 3248, 64, 3264, 80, 3280, 320, 3520, 336, 3536, 352, 3552, 368, 3568, 384, 3584, 400, 3600, 640, 3840, 656, 3856, 672, 3872, 688, 3888, 704, 3904, 720, 3920};
+// B-descriptor offset (16-byte units) of weight block be = (k2*6 + k1)*2 + m for tile 0 (output row 0): (k2*10 + k1)*S + 2m*(A2_PLANE/16)
+__constant__ uint32_t c_boff[NBLK] = {0, 3200, 16, 3216, 32, 3232, 48, 3248, 64, 3264, 80, 3280, 160, 3360, 176, 3376, 192, 3392, 208, 3408, 224, 3424, 240, 3440, 320, 3520, 336, 3536, 352, 3552, 368, 3568, 384, 3584, 400, 3600, 480, 3680, 496, 3696, 512, 3712, 528, 3728, 544, 3744, 560, 3760, 640, 3840, 656, 3856, 672, 3872, 688, 3888, 704, 3904, 720, 3920, 800, 4000, 816, 4016, 832, 4032, 848, 4048, 864, 4064, 880, 4080};
 
 // x >= 0 (after relu) -> the fp16 bits of its high half, or of 2^11 x its low half
 __device__ __forceinline__ unsigned short split_half(float r, bool want_lo) {
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
 
     const uint64_t dA1 = desc_nosw(smem_u32(A1), A1_PLANE, 128);             // conv2 A: 8-slot core matrices, contiguous
     const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PLANE, 128);             // conv3 B (N operand): likewise
-    const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 512, 128);       // + 576 (16-byte units): the hi half
+    const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 1024, 128);      // conv2 B: 64 rows ([hi | lo] x 32 channels), 2 KB per tap
     const uint64_t dW3 = desc_nosw(smem_u32(smem + OFF_W3), 2048, 128);      // conv3 A: 128 stacked rows, K chunks 2 KB apart
 
     uint32_t acc_it = 0, w3_it = 0, c3_it = 0;
@@ -418,7 +426,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
             }
         }
 
-        // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][slot]; lo weights, then hi weights =================
+        // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][slot]; N = [hi | lo] weight halves =================
         if (!real) {
         } else if (warp < NISSUE) {
             tc_fence_after();
@@ -428,17 +436,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                 const int b = u % NACC;
                 mbar_wait(&acc_empty[b], ((u / NACC) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem + b * 32;
+                const uint32_t d = tmem + b * 64;
                 const uint64_t at = dA1 + (uint64_t)(t * 128);
                 if (elect_one()) {
 #pragma unroll
-                    for (int part = 0; part < 2; part++)
+                    for (int k2 = 0; k2 < 3; k2++)
 #pragma unroll
-                        for (int k2 = 0; k2 < 3; k2++)
-#pragma unroll
-                            for (int k1 = 0; k1 < 3; k1++)
-                                umma_bf16(d, at + (uint64_t)((k2 * 12 + k1) * S), dW2 + (uint64_t)(part * 576 + (k2 * 3 + k1) * 64),
-                                          idesc_f16(128, 32), (part | k2 | k1) ? 1u : 0u);
+                        for (int k1 = 0; k1 < 3; k1++)
+                            umma_bf16(d, at + (uint64_t)((k2 * 12 + k1) * S), dW2 + (uint64_t)((k2 * 3 + k1) * 128),
+                                      idesc_f16(128, 64), (k2 | k1) ? 1u : 0u);
                     umma_commit(&acc_full[b]);
                 }
                 __syncwarp();
@@ -452,35 +458,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                 const int b = u % NACC;
                 mbar_wait(&acc_full[b], (u / NACC) & 1);
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + b * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + b * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[b]);
                 const int P = t * 128 + q * 32 + lane;                      // row = [pixel][slot]; slot = lane & 15
                 const int pix = P / S, y = pix / 12, x = pix - 12 * y;
+                const bool valid = x < 10 && y < 10;                        // other rows are discarded garbage
+                uint8_t *dst = A2 + ((y * 10 + x) * S + (lane & 15)) * 16;  // [r][x][slot]
+                const uint32_t src = tmem + ((uint32_t)(q * 32) << 16) + b * 64;
                 // lanes l and l ^ 8 hold the two halves of one sample: both form the same FP32 sum, each keeps its own half
-                uint32_t w[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float r[2];
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const float mine = __uint_as_float(v[j + e]);
-                        const float other = __shfl_xor_sync(0xffffffffu, mine, 8);
-                        const float hi = is_lo ? other : mine, lo = is_lo ? mine : other;
-                        r[e] = fmaxf(fmaf(lo, LO_UNSCALE, hi) + bias[16 + j + e], 0.f);
+                for (int hh = 0; hh < 2; hh++) {                            // output channels 16 hh .. 16 hh + 15
+                    uint32_t vh[16], vl[16];
+                    tmem_ld16(src + hh * 16, vh);                           // hi-weight products
+                    tmem_ld16(src + 32 + hh * 16, vl);                      // lo-weight products
+                    tmem_ld_wait();
+                    if (hh == 1) {                                          // accumulator drained
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[b]);
                     }
-                    if (x < 10 && y < 10) amax = fmaxf(amax, fmaxf(r[0], r[1]));     // other rows are discarded garbage
-                    w[j >> 1] = (uint32_t)split_half(r[0], is_lo) | ((uint32_t)split_half(r[1], is_lo) << 16);
-                }
-                if (x < 10 && y < 10) {
-                    uint8_t *dst = A2 + ((y * 10 + x) * S + (lane & 15)) * 16;  // [r][x][slot]
+                    uint32_t w[8];
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; c8++)
-                        *reinterpret_cast<uint4 *>(dst + c8 * A2_PLANE) = make_uint4(w[c8 * 4], w[c8 * 4 + 1], w[c8 * 4 + 2], w[c8 * 4 + 3]);
+                    for (int j = 0; j < 16; j += 2) {
+                        float r[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const float mine = __uint_as_float(vh[j + e]) + __uint_as_float(vl[j + e]);
+                            const float other = __shfl_xor_sync(0xffffffffu, mine, 8);
+                            const float hi = is_lo ? other : mine, lo = is_lo ? mine : other;
+                            r[e] = fmaxf(fmaf(lo, LO_UNSCALE, hi) + bias[16 + hh * 16 + j + e], 0.f);
+                        }
+                        if (valid) amax = fmaxf(amax, fmaxf(r[0], r[1]));
+                        w[j >> 1] = (uint32_t)split_half(r[0], is_lo) | ((uint32_t)split_half(r[1], is_lo) << 16);
+                    }
+                    if (valid) {
+                        *reinterpret_cast<uint4 *>(dst + (2 * hh) * A2_PLANE) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4 *>(dst + (2 * hh + 1) * A2_PLANE) = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
                 }
             }
         }
@@ -491,21 +503,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
         __syncthreads();
         if (real && warp == 4) SPLIT_STAMP(2);
 
-        // ================= conv3: 32 -> 64, 6x6, valid; weights are the M operand, 36 lo blocks then 36 hi blocks =================
+        // ================= conv3: 32 -> 64, 6x6, valid; M = [hi ; lo] weight halves of one tap, tile y = output row y =================
         if (warp < NISSUE) {
             if (real) {
                 // The whole issuer warp runs this loop with warp-uniform values and one elected lane issues: descriptors
                 // then live in uniform registers.  The B-descriptor offset of a block comes from a constant table; blocks
-                // are waited for in pairs.
+                // are waited for in pairs.  Issuer 0 owns output rows 0, 2, 4, issuer 1 rows 1, 3.
                 tc_fence_after();
-                const uint64_t bbase = dA2 + (uint64_t)(uwarp * 10 * S);    // issuer w owns tiles t = w, w + 2, w + 4
+                const uint64_t bbase = dA2 + (uint64_t)(uwarp * 10 * S);
                 const uint32_t dbase = tmem + uwarp * 80;
+                const int my_tiles = uwarp == 0 ? 3 : 2;
 #pragma unroll 2
                 for (int bi = 0; bi < NBLK; bi += 2) {
                     const uint32_t b0 = (w3_it + bi) % NSLOT, b1 = b0 + 1;  // w3_it and bi are even
                     const uint32_t par = ((w3_it + bi) / NSLOT) & 1;       // both blocks share the ring pass
-                    const int be = bi >= 36 ? bi - 36 : bi;
-                    const uint64_t o0 = bbase + c_boff[be], o1 = bbase + c_boff[be + 1];
+                    const uint64_t o0 = bbase + c_boff[bi], o1 = bbase + c_boff[bi + 1];
                     const uint64_t w0 = dW3 + (uint64_t)(b0 * 256), w1 = w0 + 256;
                     mbar_wait(&w3_full[b0], par);
                     mbar_wait(&w3_full[b1], par);
@@ -513,8 +525,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                     if (elect_one()) {
 #pragma unroll
                         for (int i = 0; i < 3; i++) {
-                            umma_bf16(dbase + i * 160, w0, o0 + (uint64_t)(i * 20 * S), idesc_f16(128, 80), bi ? 1u : 0u);
-                            umma_bf16(dbase + i * 160, w1, o1 + (uint64_t)(i * 20 * S), idesc_f16(128, 80), 1u);
+                            if (i < my_tiles) {
+                                umma_bf16(dbase + i * 160, w0, o0 + (uint64_t)(i * 20 * S), idesc_f16(128, 80), bi ? 1u : 0u);
+                                umma_bf16(dbase + i * 160, w1, o1 + (uint64_t)(i * 20 * S), idesc_f16(128, 80), 1u);
+                            }
                         }
                         umma_commit(&w3_empty[b0]);
                         umma_commit(&w3_empty[b1]);
@@ -546,45 +560,47 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                 tc_fence_after();
                 if (warp == 4) SPLIT_STAMP(3);
                 float *scratch = reinterpret_cast<float *>(A2);             // [y][column = x*8 + sample][oc]: conv3 no longer reads A2
-                // out[y] = lower lanes of tile y + upper lanes of tile y + 1.  Warp quarter q owns lanes 32q..32q+31, i.e.
-                // output channels (q & 1)*32 + lane of the lower (q < 2) or upper (q >= 2) half.  For even y the upper half
-                // is parked in shared memory and the lower-lane warps finish the row; for odd y the other way round.  Each
-                // half is first reduced over its two slots: column x*16 + s holds the high-half slot of sample s, + 8 the low one.
+                // Tile y = output row y.  Warp quarter q owns TMEM lanes 32q..32q+31: output channels (q & 1)*32 + lane of the
+                // hi-weight half (q < 2) or of the lo-weight half (q >= 2) of the same outputs.  The lo-half warps reduce their
+                // part over its two slots (column x*16 + s = high-half slot of sample s, + 8 the low one) and park it in shared
+                // memory; the hi-half warps add it to theirs, bias, relu, split, store.  Group g takes rows g and g + 3.
                 const int oc = (q & 1) * 32 + lane;
-                const uint32_t my = tmem + ((uint32_t)(q * 32) << 16) + (q >= 2 ? 80 : 0);   // + y*80: my half of output row y
-                for (int y = grp; y < 5; y += NGRP) {
-                    if (((y & 1) == 0) != (q >= 2)) continue;              // this half is parked for even y by q >= 2, for odd y by q < 2
+                const uint32_t my = tmem + ((uint32_t)(q * 32) << 16);       // + y*80: my lanes of output row y
+                if (q >= 2) {
+                    for (int y = grp; y < 5; y += NGRP) {
 #pragma unroll 1
-                    for (int h = 0; h < 5; h++) {
-                        uint32_t v[16];
-                        tmem_ld16(my + y * 80 + h * 16, v);
-                        tmem_ld_wait();
+                        for (int h = 0; h < 5; h++) {
+                            uint32_t v[16];
+                            tmem_ld16(my + y * 80 + h * 16, v);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            scratch[(y * 40 + h * 8 + i) * 64 + oc] = fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i]));
+                            for (int i = 0; i < 8; i++)
+                                scratch[(y * 40 + h * 8 + i) * 64 + oc] = fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i]));
+                        }
                     }
                 }
                 asm volatile("bar.sync 1, 384;" ::: "memory");
-                const float bo = bias[48 + oc];
-                const int live = (int)(a.n - s0 < SR ? a.n - s0 : SR);
-                for (int y = grp; y < 5; y += NGRP) {
-                    if (((y & 1) == 0) == (q >= 2)) continue;
+                if (q < 2) {
+                    const float bo = bias[48 + oc];
+                    const int live = (int)(a.n - s0 < SR ? a.n - s0 : SR);
+                    for (int y = grp; y < 5; y += NGRP) {
 #pragma unroll 1
-                    for (int h = 0; h < 5; h++) {                            // h = output column x
-                        uint32_t v[16];
-                        tmem_ld16(my + y * 80 + h * 16, v);
-                        float other[8];                                      // all loads first: the stores below may alias as far
+                        for (int h = 0; h < 5; h++) {                        // h = output column x
+                            uint32_t v[16];
+                            tmem_ld16(my + y * 80 + h * 16, v);
+                            float other[8];                                  // all loads first: the stores below may alias as far
 #pragma unroll                                                               // as the compiler knows, and would serialise them
-                        for (int i = 0; i < 8; i++) other[i] = scratch[(y * 40 + h * 8 + i) * 64 + oc];
-                        tmem_ld_wait();
-                        unsigned short *dst = reinterpret_cast<unsigned short *>(a.out3) + 2 * s0 * 1600 + (y * 5 + h) * 64 + oc;
+                            for (int i = 0; i < 8; i++) other[i] = scratch[(y * 40 + h * 8 + i) * 64 + oc];
+                            tmem_ld_wait();
+                            unsigned short *dst = reinterpret_cast<unsigned short *>(a.out3) + 2 * s0 * 1600 + (y * 5 + h) * 64 + oc;
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {                        // i = sample
-                            const float r = fmaxf(fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i])) + other[i] + bo, 0.f);
-                            if (i < live) {
-                                amax = fmaxf(amax, r);
-                                dst[(2 * i) * 1600] = split_half(r, false);
-                                dst[(2 * i + 1) * 1600] = split_half(r, true);
+                            for (int i = 0; i < 8; i++) {                    // i = sample
+                                const float r = fmaxf(fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i])) + other[i] + bo, 0.f);
+                                if (i < live) {
+                                    amax = fmaxf(amax, r);
+                                    dst[(2 * i) * 1600] = split_half(r, false);
+                                    dst[(2 * i + 1) * 1600] = split_half(r, true);
+                                }
                             }
                         }
                     }
@@ -1104,7 +1120,9 @@ static void pack_params(const float *th, std::vector<uint8_t> &blob) {
                 for (int o = 0; o < 32; o++) {
                     const size_t i = (((k2 * 3 + k1) * 2 + c / 8) * 32 + o) * 8 + c % 8;
                     bf(P_W2)[i] = f2bf(w2(k1, k2, c, o));
-                    for (int part = 0; part < 2; part++) bf(P_S_W2)[(size_t)part * 4608 + i] = f2h_part(w2(k1, k2, c, o), part);
+                    // split mode: [k2][k1][chunk (2)][n = 32 half + o (64)][8], half 0 = hi, 1 = lo
+                    for (int half = 0; half < 2; half++)
+                        bf(P_S_W2)[(((k2 * 3 + k1) * 2 + c / 8) * 64 + half * 32 + o) * 8 + c % 8] = f2h_part(w2(k1, k2, c, o), 1 - half);
                 }
     // W3: 36 blocks (j, k1, m) of 128 stacked rows x 16 channels, canonical K-major core matrices:
     // row R = 64 h + o carries kernel row k2 = 2 j + h; [K chunk (2)][row group (16)][row (8)][8 channels]
@@ -1116,8 +1134,15 @@ static void pack_params(const float *th, std::vector<uint8_t> &blob) {
                         const size_t i = (size_t)((j * 6 + k1) * 2 + m) * 2048 + (((kk / 8) * 16 + R / 8) * 8 + R % 8) * 8 + kk % 8;
                         const float w = w3(k1, 2 * j + R / 64, 16 * m + kk, R % 64);
                         bf(P_W3B)[i] = f2bf(w);
-                        for (int part = 0; part < 2; part++) bf(P_S_W3)[(size_t)part * 36 * 2048 + i] = f2h_part(w, part);
                     }
+    // split mode: 72 blocks (k2, k1, m) of 128 rows x 16 channels: row R = 64 half + o, half 0 = hi, 1 = lo; same core-matrix order
+    for (int k2 = 0; k2 < 6; k2++)
+        for (int k1 = 0; k1 < 6; k1++)
+            for (int m = 0; m < 2; m++)
+                for (int R = 0; R < 128; R++)
+                    for (int kk = 0; kk < 16; kk++)
+                        bf(P_S_W3)[(size_t)((k2 * 6 + k1) * 2 + m) * 2048 + (((kk / 8) * 16 + R / 8) * 8 + R % 8) * 8 + kk % 8] =
+                            f2h_part(w3(k1, k2, 16 * m + kk, R % 64), 1 - R / 64);
     float *bias = reinterpret_cast<float *>(blob.data() + P_BIAS);
     memcpy(bias, b1, 64); memcpy(bias + 16, b2, 128); memcpy(bias + 48, b3, 256);
     // W4 (64,1600) column-major, Flux flatten index kF = x + 5 y + 25 c  ->  [n][k' = (y*5 + x)*64 + c]
