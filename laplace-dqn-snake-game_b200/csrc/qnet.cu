@@ -294,10 +294,28 @@ constexpr int SMEM = OFF_BAR + 512 + 128;
 static_assert(SMEM <= 232448, "split engine shared memory over the 227 KB limit");
 static_assert(5 * 40 * 64 * 4 <= 4 * A2_PLANE, "epilogue scratch must fit in the conv3 input planes");
 static_assert(NBLK % NSLOT == 0 && NSLOT % 2 == 0, "the issuer waits for ring slots in aligned pairs");
+#ifndef SPLIT_C3_ISSUERS
+#define SPLIT_C3_ISSUERS 1   /* warps issuing the conv3 MMAs */
+#endif
+#ifndef SPLIT_NOCONV1
+#define SPLIT_NOCONV1 0  /* timing experiment: skip conv1 (results are garbage) */
+#endif
+#ifndef SPLIT_NOLOAD
+#define SPLIT_NOLOAD 0   /* timing experiment: skip the conv3 weight loads (results are garbage) */
+#endif
 constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;      // 2^11: keeps the low halves in fp16's normal range
 // B-descriptor offset (16-byte units) of weight block be = (k2*6 + k1)*2 + m for tile 0 (output row 0): (k2*10 + k1)*S + 2m*(A2_PLANE/16)
 __constant__ uint32_t c_boff[NBLK] = {0, 3200, 16, 3216, 32, 3232, 48, 3248, 64, 3264, 80, 3280, 160, 3360, 176, 3376, 192, 3392, 208, 3408, 224, 3424, 240, 3440, 320, 3520, 336, 3536, 352, 3552, 368, 3568, 384, 3584, 400, 3600, 480, 3680, 496, 3696, 512, 3712, 528, 3728, 544, 3744, 560, 3760, 640, 3840, 656, 3856, 672, 3872, 688, 3888, 704, 3904, 720, 3920, 800, 4000, 816, 4016, 832, 4032, 848, 4048, 864, 4064, 880, 4080};
 
+// two values >= 0 (after relu) -> {fp16 bits of r0, r1} of their high halves, or of 2^11 x their low halves; packed
+// conversions (cvt.rn.f16x2.f32): 9 instructions per pair
+__device__ __forceinline__ uint32_t split_pair(float r0, float r1, bool want_lo) {
+    const __half2 h = __floats2half2_rn(r0, r1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((r0 - hf.x) * LO_SCALE, (r1 - hf.y) * LO_SCALE);
+    const __half2 o = want_lo ? l : h;
+    return *reinterpret_cast<const uint32_t *>(&o);
+}
 // x >= 0 (after relu) -> the fp16 bits of its high half, or of 2^11 x its low half
 __device__ __forceinline__ unsigned short split_half(float r, bool want_lo) {
     const __half h = __float2half_rn(r);
@@ -389,8 +407,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
     for (int i = tid; i < 112; i += THREADS) reinterpret_cast<float *>(smem + OFF_BIAS)[i] = reinterpret_cast<const float *>(a.params + P_BIAS)[i];
     if (tid == 0) {
         for (int i = 0; i < NACC; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
-        for (int i = 0; i < NSLOT; i++) { mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], NISSUE); }
-        mbar_init(c3_full, NISSUE);
+        for (int i = 0; i < NSLOT; i++) { mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], SPLIT_C3_ISSUERS); }
+        mbar_init(c3_full, SPLIT_C3_ISSUERS);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -421,6 +439,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                 const uint32_t u = w3_it + bi;
                 const int b = u % NSLOT;
                 mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
+                if (SPLIT_NOLOAD) { mbar_arrive(&w3_full[b]); continue; }
                 mbar_expect_tx(&w3_full[b], 4096);
                 bulk_load(smem + OFF_W3 + b * 4096, a.params + P_S_W3 + (size_t)bi * 4096, 4096, &w3_full[b]);
             }
@@ -452,6 +471,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
         } else if (warp >= 4) {
             const int grp = (warp - 4) >> 2, q = warp & 3;
             const bool is_lo = (lane & 8) != 0;                             // this lane's row is a low-half slot
+            const float my_scale = is_lo ? LO_UNSCALE : 1.0f;
             for (int t = 0; t < TILES2; t++) {
                 const uint32_t u = acc_it + t;
                 if ((int)(u % NGRP) != grp) continue;
@@ -481,13 +501,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                         float r[2];
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
-                            const float mine = __uint_as_float(vh[j + e]) + __uint_as_float(vl[j + e]);
-                            const float other = __shfl_xor_sync(0xffffffffu, mine, 8);
-                            const float hi = is_lo ? other : mine, lo = is_lo ? mine : other;
-                            r[e] = fmaxf(fmaf(lo, LO_UNSCALE, hi) + bias[16 + hh * 16 + j + e], 0.f);
+                            // each lane scales its own part (2^-11 is exact), the sum of the two parts is the same number in both
+                            const float mine = (__uint_as_float(vh[j + e]) + __uint_as_float(vl[j + e])) * my_scale;
+                            r[e] = fmaxf(mine + __shfl_xor_sync(0xffffffffu, mine, 8) + bias[16 + hh * 16 + j + e], 0.f);
                         }
                         if (valid) amax = fmaxf(amax, fmaxf(r[0], r[1]));
-                        w[j >> 1] = (uint32_t)split_half(r[0], is_lo) | ((uint32_t)split_half(r[1], is_lo) << 16);
+                        w[j >> 1] = split_pair(r[0], r[1], is_lo);
                     }
                     if (valid) {
                         *reinterpret_cast<uint4 *>(dst + (2 * hh) * A2_PLANE) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -505,14 +524,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
 
         // ================= conv3: 32 -> 64, 6x6, valid; M = [hi ; lo] weight halves of one tap, tile y = output row y =================
         if (warp < NISSUE) {
-            if (real) {
+            if (real && (SPLIT_C3_ISSUERS == 2 || warp == 0)) {
                 // The whole issuer warp runs this loop with warp-uniform values and one elected lane issues: descriptors
                 // then live in uniform registers.  The B-descriptor offset of a block comes from a constant table; blocks
-                // are waited for in pairs.  Issuer 0 owns output rows 0, 2, 4, issuer 1 rows 1, 3.
+                // are waited for in pairs.  With two issuers, issuer 0 owns output rows 0, 2, 4 and issuer 1 rows 1, 3.
                 tc_fence_after();
-                const uint64_t bbase = dA2 + (uint64_t)(uwarp * 10 * S);
-                const uint32_t dbase = tmem + uwarp * 80;
-                const int my_tiles = uwarp == 0 ? 3 : 2;
+                const int first = SPLIT_C3_ISSUERS == 2 ? uwarp : 0, stride = SPLIT_C3_ISSUERS;
+                const uint64_t bbase = dA2 + (uint64_t)(first * 10 * S);
+                const uint32_t dbase = tmem + first * 80;
+                const int my_tiles = (5 - first + stride - 1) / stride;
 #pragma unroll 2
                 for (int bi = 0; bi < NBLK; bi += 2) {
                     const uint32_t b0 = (w3_it + bi) % NSLOT, b1 = b0 + 1;  // w3_it and bi are even
@@ -524,10 +544,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
-                        for (int i = 0; i < 3; i++) {
+                        for (int i = 0; i < 5; i++) {
                             if (i < my_tiles) {
-                                umma_bf16(dbase + i * 160, w0, o0 + (uint64_t)(i * 20 * S), idesc_f16(128, 80), bi ? 1u : 0u);
-                                umma_bf16(dbase + i * 160, w1, o1 + (uint64_t)(i * 20 * S), idesc_f16(128, 80), 1u);
+                                umma_bf16(dbase + i * stride * 80, w0, o0 + (uint64_t)(i * stride * 10 * S), idesc_f16(128, 80), bi ? 1u : 0u);
+                                umma_bf16(dbase + i * stride * 80, w1, o1 + (uint64_t)(i * stride * 10 * S), idesc_f16(128, 80), 1u);
                             }
                         }
                         umma_commit(&w3_empty[b0]);
@@ -544,6 +564,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                     const uint32_t u = w3_it + bi;
                     const int b = u % NSLOT;
                     mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
+                    if (SPLIT_NOLOAD) { mbar_arrive(&w3_full[b]); continue; }
                     mbar_expect_tx(&w3_full[b], 4096);
                     bulk_load(smem + OFF_W3 + b * 4096, a.params + P_S_W3 + (size_t)bi * 4096, 4096, &w3_full[b]);
                 }
@@ -551,7 +572,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
             // next iteration's conv1 on the CUDA cores, by warps of the two schedulers without an MMA issuer
             if ((warp & 3) >= 2 && warp != 2 && it + gridDim.x < n_iter) {
                 const int w7 = warp == 3 ? 0 : 2 * ((warp - 4) >> 2) + (warp & 1) + 1;      // 3,6,7,10,11,14,15 -> 0..6
-                conv1_f32_split(a, (it + gridDim.x) * SR, A1, w7 * 32 + lane, 224, amax);
+                if (!SPLIT_NOCONV1) conv1_f32_split(a, (it + gridDim.x) * SR, A1, w7 * 32 + lane, 224, amax);
                 if (real && warp == 15) SPLIT_STAMP(6);
             }
             if (real && warp >= 4) {
@@ -566,41 +587,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                 // memory; the hi-half warps add it to theirs, bias, relu, split, store.  Group g takes rows g and g + 3.
                 const int oc = (q & 1) * 32 + lane;
                 const uint32_t my = tmem + ((uint32_t)(q * 32) << 16);       // + y*80: my lanes of output row y
-                if (q >= 2) {
-                    for (int y = grp; y < 5; y += NGRP) {
+                // even rows: the lo-half warps park, the hi-half warps finish; odd rows the other way round (all twelve warps work
+                // in both phases)
+                for (int y = grp; y < 5; y += NGRP) {
+                    if (((y & 1) == 0) != (q >= 2)) continue;
 #pragma unroll 1
-                        for (int h = 0; h < 5; h++) {
-                            uint32_t v[16];
-                            tmem_ld16(my + y * 80 + h * 16, v);
-                            tmem_ld_wait();
+                    for (int h = 0; h < 5; h++) {
+                        uint32_t v[16];
+                        tmem_ld16(my + y * 80 + h * 16, v);
+                        tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 8; i++)
-                                scratch[(y * 40 + h * 8 + i) * 64 + oc] = fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i]));
-                        }
+                        for (int i = 0; i < 8; i++)
+                            scratch[(y * 40 + h * 8 + i) * 64 + oc] = fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i]));
                     }
                 }
                 asm volatile("bar.sync 1, 384;" ::: "memory");
-                if (q < 2) {
-                    const float bo = bias[48 + oc];
-                    const int live = (int)(a.n - s0 < SR ? a.n - s0 : SR);
-                    for (int y = grp; y < 5; y += NGRP) {
+                const float bo = bias[48 + oc];
+                const int live = (int)(a.n - s0 < SR ? a.n - s0 : SR);
+                for (int y = grp; y < 5; y += NGRP) {
+                    if (((y & 1) == 0) == (q >= 2)) continue;
 #pragma unroll 1
-                        for (int h = 0; h < 5; h++) {                        // h = output column x
-                            uint32_t v[16];
-                            tmem_ld16(my + y * 80 + h * 16, v);
-                            float other[8];                                  // all loads first: the stores below may alias as far
+                    for (int h = 0; h < 5; h++) {                            // h = output column x
+                        uint32_t v[16];
+                        tmem_ld16(my + y * 80 + h * 16, v);
+                        float other[8];                                      // all loads first: the stores below may alias as far
 #pragma unroll                                                               // as the compiler knows, and would serialise them
-                            for (int i = 0; i < 8; i++) other[i] = scratch[(y * 40 + h * 8 + i) * 64 + oc];
-                            tmem_ld_wait();
-                            unsigned short *dst = reinterpret_cast<unsigned short *>(a.out3) + 2 * s0 * 1600 + (y * 5 + h) * 64 + oc;
+                        for (int i = 0; i < 8; i++) other[i] = scratch[(y * 40 + h * 8 + i) * 64 + oc];
+                        tmem_ld_wait();
+                        unsigned short *dst = reinterpret_cast<unsigned short *>(a.out3) + 2 * s0 * 1600 + (y * 5 + h) * 64 + oc;
 #pragma unroll
-                            for (int i = 0; i < 8; i++) {                    // i = sample
-                                const float r = fmaxf(fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i])) + other[i] + bo, 0.f);
-                                if (i < live) {
-                                    amax = fmaxf(amax, r);
-                                    dst[(2 * i) * 1600] = split_half(r, false);
-                                    dst[(2 * i + 1) * 1600] = split_half(r, true);
-                                }
+                        for (int i = 0; i < 8; i += 2) {                     // i = sample
+                            const float r0 = fmaxf(fmaf(__uint_as_float(v[i + 8]), LO_UNSCALE, __uint_as_float(v[i])) + other[i] + bo, 0.f);
+                            const float r1 = fmaxf(fmaf(__uint_as_float(v[i + 9]), LO_UNSCALE, __uint_as_float(v[i + 1])) + other[i + 1] + bo, 0.f);
+                            const uint32_t ph = split_pair(r0, r1, false), pl = split_pair(r0, r1, true);
+                            if (i < live) {
+                                amax = fmaxf(amax, r0);
+                                dst[(2 * i) * 1600] = (unsigned short)ph;
+                                dst[(2 * i + 1) * 1600] = (unsigned short)pl;
+                            }
+                            if (i + 1 < live) {
+                                amax = fmaxf(amax, r1);
+                                dst[(2 * i + 2) * 1600] = (unsigned short)(ph >> 16);
+                                dst[(2 * i + 3) * 1600] = (unsigned short)(pl >> 16);
                             }
                         }
                     }
