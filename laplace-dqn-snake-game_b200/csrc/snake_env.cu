@@ -275,25 +275,57 @@ template <bool STREAM, typename T>
 __device__ __forceinline__ void obs_store(T *p, const T &v) {
     if (STREAM) __stcs(p, v); else SNK_OBS_STORE(p, v);
 }
+// unit q (0..49) of env e -> its byte in the shared-memory planes = index of the output tables
+__device__ __forceinline__ uint32_t unit_index(const uint32_t *s_planes, int j) {
+    const int e = (int)(((unsigned)j * 5243u) >> 18);     // j / 50 for j < 2^15
+    const int qq = j - e * 50;
+    const int f = qq >= 25;
+    return reinterpret_cast<const uint8_t *>(s_planes)[e * (PLANE_WORDS * 4) + f * 32 + (qq - 25 * f)];
+}
 template <int OBS, int NT = TPB, int UNROLL = PHASE_B_UNROLL, bool STREAM = false>
 __device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_local, const uint32_t *s_planes,
                                            const ObsTables &tb, int tid) {
-    if (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I8 || OBS == SNK_OBS_PACKED2) {
-        // unit = 4 consecutive cells = one nibble of each plane; 50 units per env
+    if (OBS == SNK_OBS_F32) {
+        // unit = 4 consecutive cells = one nibble of each plane; 50 units per env; one 16-byte store per unit
         const int total = n_local * 50;
         float4 *o32 = reinterpret_cast<float4 *>(obs) + env0 * 50;
-        uint32_t *o8 = reinterpret_cast<uint32_t *>(obs) + env0 * 50;
-        uint8_t *op = reinterpret_cast<uint8_t *>(obs) + env0 * 50;
 #pragma unroll UNROLL
-        for (int j = tid; j < total; j += NT) {
-            int e = (int)(((unsigned)j * 5243u) >> 18);     // j / 50 for j < 2^15
-            int qq = j - e * 50;
-            int f = qq >= 25;
-            int q = qq - 25 * f;
-            const uint32_t idx = reinterpret_cast<const uint8_t *>(s_planes)[e * (PLANE_WORDS * 4) + f * 32 + q];
-            if (OBS == SNK_OBS_F32) obs_store<STREAM>(o32 + j, tb.f32[idx]);
-            else if (OBS == SNK_OBS_I8) obs_store<STREAM>(o8 + j, reinterpret_cast<const uint32_t *>(tb.f32)[idx]);
-            else op[j] = reinterpret_cast<const uint8_t *>(tb.f32)[idx];
+        for (int j = tid; j < total; j += NT) obs_store<STREAM>(o32 + j, tb.f32[unit_index(s_planes, j)]);
+    } else if (OBS == SNK_OBS_I8 || OBS == SNK_OBS_PACKED2) {
+        // the small formats are bound by instruction issue, not by HBM: one thread gathers 16 output bytes (4 units as int8,
+        // 16 units as 2-bit codes) and stores them as one uint4 — the CTA's output region is one contiguous byte range
+        constexpr int UPV = OBS == SNK_OBS_I8 ? 4 : 16;            // units per 16-byte vector
+        constexpr int BPE = OBS == SNK_OBS_I8 ? 200 : 50;          // output bytes per env
+        uint8_t *base = reinterpret_cast<uint8_t *>(obs) + env0 * BPE;
+        const int total = n_local * 50;
+        int done_units = 0;
+        if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+            const int nvec = total / UPV;
+            uint4 *o = reinterpret_cast<uint4 *>(base);
+#pragma unroll 2
+            for (int v = tid; v < nvec; v += NT) {
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (OBS == SNK_OBS_I8) {
+                        w[k] = reinterpret_cast<const uint32_t *>(tb.f32)[unit_index(s_planes, v * 4 + k)];
+                    } else {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            x |= (uint32_t)reinterpret_cast<const uint8_t *>(tb.f32)[unit_index(s_planes, v * 16 + k * 4 + b)] << (8 * b);
+                        w[k] = x;
+                    }
+                }
+                obs_store<STREAM>(o + v, make_uint4(w[0], w[1], w[2], w[3]));
+            }
+            done_units = nvec * UPV;
+        }
+        // remainder (or a region that is not 16-byte aligned): one unit per store
+        for (int j = done_units + tid; j < total; j += NT) {
+            const uint32_t idx = unit_index(s_planes, j);
+            if (OBS == SNK_OBS_I8) reinterpret_cast<uint32_t *>(base)[j] = reinterpret_cast<const uint32_t *>(tb.f32)[idx];
+            else base[j] = reinterpret_cast<const uint8_t *>(tb.f32)[idx];
         }
     } else if (OBS == SNK_OBS_I64) {
         // unit = 2 consecutive cells (16 bytes); 100 units per env
