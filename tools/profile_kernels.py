@@ -18,6 +18,7 @@ import __graft_entry__ as g
 
 S = g.load_package()
 dev = torch.device("cuda", 0)
+REPS = 1 if os.environ.get("PROFILE_ONCE") else 2          # under ncu one launch of each is enough (it replays the kernel itself)
 E = 1 << 20
 env = S.SnakeGame(E, auto_reset=True)
 q = torch.rand(E, 3, device=dev) * 2 - 1
@@ -25,7 +26,7 @@ u = torch.rand(E, device=dev)
 r = torch.randint(0, 3, (E,), device=dev, dtype=torch.uint8)
 for fmt in ("f32", "i8", "packed2", None):
     out = env.alloc_outputs(obs=fmt, mask=True, act=True)
-    for _ in range(2):
+    for _ in range(REPS):
         env.step_fused(q=q, eps=0.05, u=u, ridx=r, out=out)
     del out
 torch.cuda.synchronize()
@@ -34,7 +35,8 @@ env.close()
 env2 = S.SnakeGame(4096, auto_reset=True)
 acts = torch.randint(0, 3, (200, 4096), device=dev, dtype=torch.uint8)
 ro = env2.rollout(acts, obs="f32", mask=True)
-env2.rollout(acts, out=ro)
+if REPS > 1:
+    env2.rollout(acts, out=ro)
 torch.cuda.synchronize()
 
 n = 65536
@@ -45,7 +47,7 @@ for t in range(10):
 layers = S.qnet.glorot_layers(0)
 nets = {p: S.qnet.QNet(layers, dev, p) for p in ("f32", "bf16")}
 for p in ("f32", "bf16"):
-    for _ in range(2):
+    for _ in range(REPS):
         nets[p](o3["obs"])
 torch.cuda.synchronize()
 
@@ -54,18 +56,18 @@ st = o3["obs"][:B].contiguous()
 ac = torch.randint(0, 3, (B,), device=dev, dtype=torch.uint8)
 y = torch.randn(B, device=dev, dtype=torch.float64)
 plan_g = S.GramPlan(B, S.qnet.N_PARAMS, dev)
-for _ in range(2):
+for _ in range(REPS):
     nets["f32"].sample_grads(st, ac, y, planes=plan_g.planes(), want_loss=False)
 torch.cuda.synchronize()
 
 K, P = 1000, 181395
 A = torch.randn(K, P, device=dev, dtype=torch.float32).double()
-for _ in range(2):
+for _ in range(REPS):
     S.center_columns(A)
 plan = S.GramPlan(K, P, dev)
 A32 = A.float()
 G = torch.empty(K, K, dtype=torch.float32, device=dev)
-for _ in range(2):
+for _ in range(REPS):
     plan.pack(A)
     plan.pack(A32)
     plan.gram(3, 0, out=G)
