@@ -8,7 +8,7 @@
 // mean.  The reference itself never forms per-sample gradients (Zygote returns their mean); the oracle is a Float64
 // torch.func evaluation of the same expression (tests/test_sample_grads_gpu.py) — parity unpinned by the reference.
 //
-// One CTA per sample, all activations and back-propagated signals of the sample in shared memory, plain FP32 FMAs: per
+// One CTA (10 warps) per sample, all activations and back-propagated signals of the sample in shared memory, plain FP32 FMAs: per
 // sample the contractions are 25..2304 deep — CUDA-core work; the kernel is bound by FP32 issue (14.6 MFLOP per sample) and
 // by the 725 KB (two bf16 planes) it writes per sample.  The row goes STRAIGHT into the bf16 hi / 2 lo planes the Gram
 // kernel consumes (hi = bf16(v), lo2 = bf16(2 (v - hi)): the same split as k_gram_pack), optionally also as Float32.
@@ -21,7 +21,7 @@
 namespace snk {
 namespace qgrad {
 
-constexpr int NT = 256, NW = NT / 32;
+constexpr int NT = 320, NW = NT / 32;      // 10 warps: the conv3 backward-data pass has 32 x 10 row tasks
 // Flux.destructure offsets
 constexpr int O_W1 = 0, O_B1 = 288, O_W2 = 304, O_B2 = 4912, O_W3 = 4944, O_B3 = 78672, O_W4 = 78736, O_B4 = 181136,
               O_W5 = 181200, O_B5 = 181392, NP = 181395;
@@ -34,8 +34,9 @@ constexpr int S_HID = S_A3 + 1600;             // [64]          relu(dense1)
 constexpr int S_GH = S_HID + 64;               // [64]          d loss / d (dense1 pre-activation)
 constexpr int S_Q = S_GH + 64;                 // [4]           q-values, [3] = d loss / d q[a]
 constexpr int S_RED = S_Q + 4;                 // [256]         reduction scratch
-constexpr int S_G3 = S_RED + 256;              // [64][15][15]  d loss / d (conv3 pre-activation), zero padded by 5
-constexpr int S_G2 = S_G3 + 64 * 225;          // [32][12][12]  d loss / d (conv2 pre-activation), zero padded by 1
+constexpr int S_G3 = S_RED + 256;              // [64][5][5]    d loss / d (conv3 pre-activation)
+constexpr int S_PART = S_G3 + 1600;            // [256][25]     conv3 forward: partial sums of the four channel quarters
+constexpr int S_G2 = S_PART + 256 * 25;        // [32][12][12]  d loss / d (conv2 pre-activation), zero padded by 1
 constexpr int S_G1 = S_G2 + 32 * 144;          // [16][10][10]  d loss / d (conv1 pre-activation)
 constexpr int S_END = S_G1 + 1600;
 constexpr int SMEM_BYTES = S_END * 4;
@@ -226,10 +227,85 @@ __device__ __forceinline__ void bias_grad(const float *gp, int g_off, const Row 
     }
 }
 
-__global__ void __launch_bounds__(NT) k_sample_grads(const GradArgs a) {
+// conv3 forward, register-tiled: a3(x, y, o) = relu(b3[o] + sum_{c,a2,a1} W3[a1 + 6 (a2 + 6 (c + 32 o))] * a2in[c][y+5-a2][x+5-a1]).
+// Thread = (output channel o, quarter of the input channels): all 25 outputs of the channel in registers; per (c, a2) the thread
+// streams 6 consecutive weights of ITS channel (contiguous in memory over a1, a2, c) and the five input rows y+5-a2 are
+// warp-uniform shared-memory reads (the lanes of a warp are 32 output channels): 150 FMAs per 50 broadcast loads + 6 weights.
+// The four quarter sums are added through shared memory.
+__device__ __forceinline__ void conv3_forward_tiled(const float *__restrict__ W3, const float *__restrict__ b3, const float *a2s,
+                                                    float *part, float *a3s, int tid) {
+    if (tid < 256) {
+        const int o = tid & 63, cq = tid >> 6;
+        float acc[25];
+#pragma unroll
+        for (int i = 0; i < 25; i++) acc[i] = 0.f;
+        const float *w = W3 + 36 * (8 * cq + 32 * o);
+        for (int c = 0; c < 8; c++) {
+            const float *in = a2s + (8 * cq + c) * 100;
+#pragma unroll
+            for (int a2 = 0; a2 < 6; a2++) {
+                const float2 w01 = __ldg(reinterpret_cast<const float2 *>(w + 36 * c + 6 * a2));
+                const float2 w23 = __ldg(reinterpret_cast<const float2 *>(w + 36 * c + 6 * a2 + 2));
+                const float2 w45 = __ldg(reinterpret_cast<const float2 *>(w + 36 * c + 6 * a2 + 4));
+                const float wv[6] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
+#pragma unroll
+                for (int y = 0; y < 5; y++) {
+                    float row[10];
+#pragma unroll
+                    for (int i = 0; i < 10; i++) row[i] = in[(y + 5 - a2) * 10 + i];
+#pragma unroll
+                    for (int a1 = 0; a1 < 6; a1++)
+#pragma unroll
+                        for (int x = 0; x < 5; x++) acc[y * 5 + x] = fmaf(wv[a1], row[x + 5 - a1], acc[y * 5 + x]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 25; i++) part[i * 256 + tid] = acc[i];        // [position][quarter][o]: conflict-free
+    }
+    __syncthreads();
+    for (int k = tid; k < 1600; k += NT) {
+        const int o = k / 25, i = k - 25 * o;
+        const float *p = part + i * 256 + o;
+        a3s[k] = fmaxf(p[0] + p[64] + p[128] + p[192] + __ldg(b3 + o), 0.f);
+    }
+}
+
+// conv3 backward-data without the zero padding: d loss / d a2(u, v, c) = sum_o sum_{y, x} W3[x+5-u, y+5-v, c, o] g3(x, y, o), only
+// over the taps that exist (0 <= y+5-v <= 5; x+5-u is always a tap).  Thread = (input channel c, input row v): the ten u of the
+// row in registers; per (o, y) five broadcast reads of a g3 row and six consecutive weights give 30 FMAs.  Masked by relu'(a2)
+// and stored into the padded conv2-gradient plane.
+__device__ __forceinline__ void conv3_backward_data_tiled(const float *__restrict__ W3, const float *g3, const float *a2s, float *g2p, int tid) {
+    const int c = tid & 31, v = tid >> 5;                     // NT = 320: v = 0..9 = the warp index
+    float acc[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) acc[i] = 0.f;
+    const int y_lo = v - 5 > 0 ? v - 5 : 0, y_hi = v < 4 ? v : 4;
+    for (int o = 0; o < 64; o++) {
+        const float *w = W3 + 36 * (c + 32 * o);
+        for (int y = y_lo; y <= y_hi; y++) {
+            const int a2 = y + 5 - v;
+            const float2 w01 = __ldg(reinterpret_cast<const float2 *>(w + 6 * a2));
+            const float2 w23 = __ldg(reinterpret_cast<const float2 *>(w + 6 * a2 + 2));
+            const float2 w45 = __ldg(reinterpret_cast<const float2 *>(w + 6 * a2 + 4));
+            const float wv[6] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y};
+            const float *gr = g3 + o * 25 + y * 5;
+#pragma unroll
+            for (int x = 0; x < 5; x++) {
+                const float gv = gr[x];
+#pragma unroll
+                for (int a1 = 0; a1 < 6; a1++) acc[x + 5 - a1] = fmaf(wv[a1], gv, acc[x + 5 - a1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 10; u++) g2p[c * 144 + (v + 1) * 12 + (u + 1)] = a2s[c * 100 + v * 10 + u] > 0.f ? acc[u] : 0.f;
+}
+
+__global__ void __launch_bounds__(NT, 2) k_sample_grads(const GradArgs a) {
     extern __shared__ float sm[];
     float *xin = sm + S_XIN, *a1p = sm + S_A1, *a2s = sm + S_A2, *a3s = sm + S_A3, *hid = sm + S_HID, *gh = sm + S_GH;
-    float *qv = sm + S_Q, *red = sm + S_RED, *g3p = sm + S_G3, *g2p = sm + S_G2, *g1s = sm + S_G1;
+    float *qv = sm + S_Q, *red = sm + S_RED, *g3 = sm + S_G3, *part = sm + S_PART, *g2p = sm + S_G2, *g1s = sm + S_G1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float *th = a.theta;
     for (int i = tid; i < S_END; i += NT) sm[i] = 0.f;            // the zero borders of the padded arrays stay zero
@@ -249,13 +325,15 @@ __global__ void __launch_bounds__(NT) k_sample_grads(const GradArgs a) {
         __syncthreads();
         conv_forward<3, 16, 32, 10, 12, 144, 4>(th + O_W2, th + O_B2, a1p, a2s, 10, 100, 0, warp, lane);
         __syncthreads();
-        conv_forward<6, 32, 64, 5, 10, 100, 1>(th + O_W3, th + O_B3, a2s, a3s, 5, 25, 0, warp, lane);
+        conv3_forward_tiled(th + O_W3, th + O_B3, a2s, part, a3s, tid);
         __syncthreads();
         {   // Dense(1600, 64, relu): thread = (n, quarter of k)
-            const int n = tid & 63, part = tid >> 6;
-            float acc = 0.f;
-            for (int k = part * 400; k < part * 400 + 400; k++) acc = fmaf(__ldg(th + O_W4 + n + 64 * k), a3s[k], acc);
-            red[tid] = acc;
+            if (tid < 256) {
+                const int n = tid & 63, kq = tid >> 6;
+                float acc = 0.f;
+                for (int k = kq * 400; k < kq * 400 + 400; k++) acc = fmaf(__ldg(th + O_W4 + n + 64 * k), a3s[k], acc);
+                red[tid] = acc;
+            }
             __syncthreads();
             if (tid < 64) hid[tid] = fmaxf(red[tid] + red[tid + 64] + red[tid + 128] + red[tid + 192] + __ldg(th + O_B4 + tid), 0.f);
             __syncthreads();
@@ -314,13 +392,12 @@ __global__ void __launch_bounds__(NT) k_sample_grads(const GradArgs a) {
                 acc = fmaf(w.x, gh[4 * j], acc); acc = fmaf(w.y, gh[4 * j + 1], acc);
                 acc = fmaf(w.z, gh[4 * j + 2], acc); acc = fmaf(w.w, gh[4 * j + 3], acc);
             }
-            const int o = k / 25, p = k - 25 * o, y = p / 5, x = p - 5 * y;
-            g3p[o * 225 + (y + 5) * 15 + (x + 5)] = a3s[k] > 0.f ? acc : 0.f;
+            g3[k] = a3s[k] > 0.f ? acc : 0.f;                 // k = o*25 + y*5 + x
         }
         __syncthreads();
-        bias_grad<64, 5, 15, 225>(g3p, 5 * 15 + 5, row, O_B3, warp, lane);
-        conv_backward_weights<6, 32, 64, 5, 10, 100, 15, 225, 2>(g3p, 5 * 15 + 5, a2s, row, O_W3, tid);
-        conv_backward_data<6, 32, 64, 10, 15, 225, 4>(th + O_W3, g3p, a2s, 10, 100, 0, g2p, 12, 144, 13, warp, lane);
+        bias_grad<64, 5, 5, 25>(g3, 0, row, O_B3, warp, lane);
+        conv_backward_weights<6, 32, 64, 5, 10, 100, 5, 25, 1>(g3, 0, a2s, row, O_W3, tid);
+        conv3_backward_data_tiled(th + O_W3, g3, a2s, g2p, tid);
         __syncthreads();
         bias_grad<32, 10, 12, 144>(g2p, 13, row, O_B2, warp, lane);
         conv_backward_weights<3, 16, 32, 10, 12, 144, 12, 144, 1>(g2p, 13, a1p, row, O_W2, tid);
@@ -337,7 +414,7 @@ int launch_sample_grads(const float *theta_dev, const float *states, const uint8
     a.theta = theta_dev; a.states = states; a.actions = actions; a.targets = targets; a.B = B;
     a.hi = (__nv_bfloat16 *)hi; a.lo2 = (__nv_bfloat16 *)lo2; a.pitch = pitch; a.J = J; a.ldJ = ldJ; a.loss = loss;
     SNK_CUDA(cudaFuncSetAttribute(k_sample_grads, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    const long long max_grid = 2ll * sms;                    // 2 CTAs of 111 KB per SM
+    const long long max_grid = 2ll * sms;                    // 2 CTAs of 88 KB (and <= 102 registers x 320 threads) per SM
     const int grid = (int)(B < max_grid ? B : max_grid);
     k_sample_grads<<<grid, NT, SMEM_BYTES, st>>>(a);
     SNK_CUDA(cudaGetLastError());

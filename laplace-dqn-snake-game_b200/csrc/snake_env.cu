@@ -286,47 +286,69 @@ template <int OBS, int NT = TPB, int UNROLL = PHASE_B_UNROLL, bool STREAM = fals
 __device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_local, const uint32_t *s_planes,
                                            const ObsTables &tb, int tid) {
     if (OBS == SNK_OBS_F32) {
-        // unit = 4 consecutive cells = one nibble of each plane; 50 units per env; one 16-byte store per unit
-        const int total = n_local * 50;
+        // unit = 4 consecutive cells = one nibble of each plane; 50 units per env; one 16-byte store per unit.  Thread t < GE*50
+        // owns unit t % 50 of env t / 50 of every group of GE envs: the division happens once, the loop only adds constants,
+        // and a warp's stores stay contiguous (the group's GE*50 units are consecutive in memory).
+        constexpr int GE = NT / 50;                                // envs per pass of the CTA (5 at 256 threads)
         float4 *o32 = reinterpret_cast<float4 *>(obs) + env0 * 50;
+        if (tid < GE * 50) {
+            const int e0 = tid / 50, qq = tid - 50 * e0;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(s_planes) + e0 * (PLANE_WORDS * 4) + (qq >= 25 ? 7 : 0) + qq;
 #pragma unroll UNROLL
-        for (int j = tid; j < total; j += NT) obs_store<STREAM>(o32 + j, tb.f32[unit_index(s_planes, j)]);
-    } else if (OBS == SNK_OBS_I8 || OBS == SNK_OBS_PACKED2) {
-        // the small formats are bound by instruction issue, not by HBM: one thread gathers 16 output bytes (4 units as int8,
-        // 16 units as 2-bit codes) and stores them as one uint4 — the CTA's output region is one contiguous byte range
-        constexpr int UPV = OBS == SNK_OBS_I8 ? 4 : 16;            // units per 16-byte vector
-        constexpr int BPE = OBS == SNK_OBS_I8 ? 200 : 50;          // output bytes per env
-        uint8_t *base = reinterpret_cast<uint8_t *>(obs) + env0 * BPE;
+            for (int e = e0; e < n_local; e += GE, src += GE * (PLANE_WORDS * 4)) obs_store<STREAM>(o32 + e * 50 + qq, tb.f32[*src]);
+        }
+    } else if (OBS == SNK_OBS_I8) {
+        // int8 observations are bound by instruction issue, not by HBM: one thread gathers 4 units = 16 output bytes and stores
+        // one uint4.  Two envs are 25 such vectors; thread t < GP*25 owns vector t % 25 of env pair t / 25 of every group of
+        // GP pairs, with its four byte offsets computed once.
+        constexpr int GP = NT / 25;                                // env pairs per pass (10 at 256 threads)
+        uint8_t *base = reinterpret_cast<uint8_t *>(obs) + env0 * 200;
+        const int n_pairs = n_local >> 1;
+        if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+            if (tid < GP * 25) {
+                const int p0 = tid / 25, w = tid - 25 * p0;
+                int off[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int uu = 4 * w + k, e2 = uu >= 50, qq = uu - 50 * e2;
+                    off[k] = e2 * (PLANE_WORDS * 4) + (qq >= 25 ? 7 : 0) + qq;
+                }
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(s_planes) + p0 * (2 * PLANE_WORDS * 4);
+                const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tb.f32);
+                uint4 *o = reinterpret_cast<uint4 *>(base);
+#pragma unroll 2
+                for (int p = p0; p < n_pairs; p += GP, src += GP * (2 * PLANE_WORDS * 4))
+                    obs_store<STREAM>(o + p * 25 + w, make_uint4(t32[src[off[0]]], t32[src[off[1]]], t32[src[off[2]]], t32[src[off[3]]]));
+            }
+        }
+        // an odd last env, or a region that is not 16-byte aligned: one unit per store
+        const int done_units = (reinterpret_cast<uintptr_t>(base) & 15u) == 0 ? n_pairs * 100 : 0;
+        for (int j = done_units + tid; j < n_local * 50; j += NT)
+            reinterpret_cast<uint32_t *>(base)[j] = reinterpret_cast<const uint32_t *>(tb.f32)[unit_index(s_planes, j)];
+    } else if (OBS == SNK_OBS_PACKED2) {
+        // 2-bit codes: 16 units per 16-byte vector; the CTA's output region is one contiguous byte range
+        uint8_t *base = reinterpret_cast<uint8_t *>(obs) + env0 * 50;
         const int total = n_local * 50;
         int done_units = 0;
         if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
-            const int nvec = total / UPV;
+            const int nvec = total / 16;
             uint4 *o = reinterpret_cast<uint4 *>(base);
 #pragma unroll 2
             for (int v = tid; v < nvec; v += NT) {
                 uint32_t w[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    if (OBS == SNK_OBS_I8) {
-                        w[k] = reinterpret_cast<const uint32_t *>(tb.f32)[unit_index(s_planes, v * 4 + k)];
-                    } else {
-                        uint32_t x = 0;
+                    uint32_t x = 0;
 #pragma unroll
-                        for (int b = 0; b < 4; b++)
-                            x |= (uint32_t)reinterpret_cast<const uint8_t *>(tb.f32)[unit_index(s_planes, v * 16 + k * 4 + b)] << (8 * b);
-                        w[k] = x;
-                    }
+                    for (int b = 0; b < 4; b++)
+                        x |= (uint32_t)reinterpret_cast<const uint8_t *>(tb.f32)[unit_index(s_planes, v * 16 + k * 4 + b)] << (8 * b);
+                    w[k] = x;
                 }
                 obs_store<STREAM>(o + v, make_uint4(w[0], w[1], w[2], w[3]));
             }
-            done_units = nvec * UPV;
+            done_units = nvec * 16;
         }
-        // remainder (or a region that is not 16-byte aligned): one unit per store
-        for (int j = done_units + tid; j < total; j += NT) {
-            const uint32_t idx = unit_index(s_planes, j);
-            if (OBS == SNK_OBS_I8) reinterpret_cast<uint32_t *>(base)[j] = reinterpret_cast<const uint32_t *>(tb.f32)[idx];
-            else base[j] = reinterpret_cast<const uint8_t *>(tb.f32)[idx];
-        }
+        for (int j = done_units + tid; j < total; j += NT) base[j] = reinterpret_cast<const uint8_t *>(tb.f32)[unit_index(s_planes, j)];
     } else if (OBS == SNK_OBS_I64) {
         // unit = 2 consecutive cells (16 bytes); 100 units per env
         const int total = n_local * 100;
