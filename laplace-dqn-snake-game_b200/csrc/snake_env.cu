@@ -291,7 +291,11 @@ __device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_loca
         // and a warp's stores stay contiguous (the group's GE*50 units are consecutive in memory).
         constexpr int GE = NT / 50;                                // envs per pass of the CTA (5 at 256 threads)
         float4 *o32 = reinterpret_cast<float4 *>(obs) + env0 * 50;
-        if (tid < GE * 50) {
+        if (NT % 50 > 10) {                                        // thread counts that would idle too many lanes (the 96 expander threads
+            const int total = n_local * 50;                        // of the small-batch rollout kernel): one unit per thread and pass
+#pragma unroll UNROLL
+            for (int j = tid; j < total; j += NT) obs_store<STREAM>(o32 + j, tb.f32[unit_index(s_planes, j)]);
+        } else if (tid < GE * 50) {
             const int e0 = tid / 50, qq = tid - 50 * e0;
             const uint8_t *src = reinterpret_cast<const uint8_t *>(s_planes) + e0 * (PLANE_WORDS * 4) + (qq >= 25 ? 7 : 0) + qq;
 #pragma unroll UNROLL
@@ -303,7 +307,7 @@ __device__ __forceinline__ void expand_obs(void *obs, long long env0, int n_loca
         // GP pairs, with its four byte offsets computed once.
         constexpr int GP = NT / 25;                                // env pairs per pass (10 at 256 threads)
         uint8_t *base = reinterpret_cast<uint8_t *>(obs) + env0 * 200;
-        const int n_pairs = n_local >> 1;
+        const int n_pairs = (NT % 25 > 10) ? 0 : n_local >> 1;   // (see above; then everything goes through the per-unit loop below)
         if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
             if (tid < GP * 25) {
                 const int p0 = tid / 25, w = tid - 25 * p0;
@@ -498,8 +502,10 @@ __device__ __forceinline__ float env_advance(Env &e, int &aidx, int is_abs, u64 
     return reward;
 }
 
+// The Float32 / Int64 observation formats are HBM-bound at 3 CTAs per SM; the small formats are bound by instruction issue and
+// latency: capping them at 64 registers buys a fourth CTA per SM (no spills).
 template <int OBS, bool SELECT, bool SINK>
-__global__ void __launch_bounds__(TPB, SNK_MINB) k_step(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(TPB, (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I64) ? SNK_MINB : 4) k_step(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) uint32_t s_planes[TPB * PLANE_WORDS];
     __shared__ ObsTables s_tb;
     __shared__ uint8_t s_food_bit[MAX_FOOD];
