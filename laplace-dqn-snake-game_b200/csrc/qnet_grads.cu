@@ -271,6 +271,45 @@ __device__ __forceinline__ void conv3_forward_tiled(const float *__restrict__ W3
     }
 }
 
+// conv3 weight gradient, register-tiled: d loss / d W3[a1 + 6 (a2 + 6 (c + 32 o))] = sum_{y,x} g3(x, y, o) a2in[c][y+5-a2][x+5-a1].
+// Thread = (input channel c, kernel row a2) holds the five input rows y+5-a2 (50 values) in registers for all 64 output
+// channels; per o the 25 gradient values are warp-uniform shared-memory reads: 150 FMAs per 25 loads.  The six a1 of a task are
+// consecutive in theta: 12 bytes per plane and o, consecutive tasks are consecutive in memory.
+__device__ __forceinline__ void conv3_weight_grad_tiled(const float *g3, const float *a2s, const Row &row, int tid) {
+    if (tid >= 192) return;
+    const int c = tid / 6, a2 = tid - 6 * c;
+    float in[5][10];
+#pragma unroll
+    for (int y = 0; y < 5; y++)
+#pragma unroll
+        for (int i = 0; i < 10; i++) in[y][i] = a2s[c * 100 + (y + 5 - a2) * 10 + i];
+    for (int o = 0; o < 64; o++) {
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int y = 0; y < 5; y++)
+#pragma unroll
+            for (int x = 0; x < 5; x++) {
+                const float gv = g3[o * 25 + y * 5 + x];
+#pragma unroll
+                for (int a1 = 0; a1 < 6; a1++) acc[a1] = fmaf(gv, in[y][x + 5 - a1], acc[a1]);
+            }
+        const int idx = O_W3 + 6 * a2 + 36 * (c + 32 * o);            // even: 4-byte aligned in the bf16 planes
+        if (row.hi != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                uint32_t lo;
+                const uint32_t hi = split2(acc[2 * j], acc[2 * j + 1], lo);
+                *reinterpret_cast<uint32_t *>(row.hi + idx + 2 * j) = hi;
+                *reinterpret_cast<uint32_t *>(row.lo + idx + 2 * j) = lo;
+            }
+        }
+        if (row.J != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) row.J[idx + j] = acc[j];
+        }
+    }
+}
+
 // conv3 backward-data without the zero padding: d loss / d a2(u, v, c) = sum_o sum_{y, x} W3[x+5-u, y+5-v, c, o] g3(x, y, o), only
 // over the taps that exist (0 <= y+5-v <= 5; x+5-u is always a tap).  Thread = (input channel c, input row v): the ten u of the
 // row in registers; per (o, y) five broadcast reads of a g3 row and six consecutive weights give 30 FMAs.  Masked by relu'(a2)
@@ -396,7 +435,7 @@ __global__ void __launch_bounds__(NT, 2) k_sample_grads(const GradArgs a) {
         }
         __syncthreads();
         bias_grad<64, 5, 5, 25>(g3, 0, row, O_B3, warp, lane);
-        conv_backward_weights<6, 32, 64, 5, 10, 100, 5, 25, 1>(g3, 0, a2s, row, O_W3, tid);
+        conv3_weight_grad_tiled(g3, a2s, row, tid);
         conv3_backward_data_tiled(th + O_W3, g3, a2s, g2p, tid);
         __syncthreads();
         bias_grad<32, 10, 12, 144>(g2p, 13, row, O_B2, warp, lane);
