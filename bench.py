@@ -608,6 +608,8 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
     err = float(((got - want).abs() / scale)[offdiag].max().item())
     errs = [None] * world
     dist.all_gather_object(errs, err)
+    fingerprints = [None] * world                                # the ranks hold DIFFERENT transitions: norm of each rank's first J row
+    dist.all_gather_object(fingerprints, float(Jsub[0].double().norm().item()))
     n_checked = int(offdiag.sum().item())
     Gring = G.clone()
     dg.close()
@@ -646,7 +648,7 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
             "roofline": {"bound": "tensor", "achieved": mma, "peak": peak, "unit": "TFLOP/s", "frac": mma / peak,
                          "frac_algorithmic": mma / 2 / peak, "traffic": None,
                          "note": "per GPU, Gram phase only; peak = sustained bf16 (a %.0f ms region); executed MMA FLOP = 2 x algorithmic (hi/lo split)" % ms},
-            "verify_per_rank": {"entries_per_rank": n_checked, "max_err_over_sqrt_GiiGjj": errs,
+            "verify_per_rank": {"entries_per_rank": n_checked, "max_err_over_sqrt_GiiGjj": errs, "first_checked_row_norm_per_rank": fingerprints,
                                 "how": "128 random local rows x rows 0..7 of every rank (off-diagonal), Float64 dot products of FP32 J rows"},
             "nccl_allgather_baseline_ms": sorted(times_ag)[len(times_ag) // 2], "nccl_allgather_same_bits_rank0": same,
             "exchange": "snk_gram_shard_run: cudaMemcpyAsync from peer-mapped (cudaIpc) memory on a copy stream under the MMA main loop; "
