@@ -568,7 +568,7 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
     ro = S.rollout.Rollout(env, q_net, t_net, ring, epsilon=0.3)
     g = torch.Generator(device=dev)
     g.manual_seed(100 + rank)
-    for _ in range(8):                                           # 131,072 transitions through a 50,000-slot ring
+    for _ in range(30):                                          # 491,520 transitions through a 50,000-slot ring (mid-game boards)
         ro.step(u=torch.rand(n_env, device=dev, generator=g), ridx=torch.randint(0, 3, (n_env,), device=dev, generator=g, dtype=torch.uint8))
     batch = ring.stack_exp(ring.sample_indices(R))               # sample(rpb) + stack_exp, R distinct transitions
     y = S.masked_target(t_net(batch["next_states"]), batch["mask"], batch["rewards"], batch["dones"])

@@ -297,6 +297,9 @@ static_assert(NBLK % NSLOT == 0 && NSLOT % 2 == 0, "the issuer waits for ring sl
 #ifndef SPLIT_C3_ISSUERS
 #define SPLIT_C3_ISSUERS 1   /* warps issuing the conv3 MMAs */
 #endif
+#ifndef SPLIT_RELEASE
+#define SPLIT_RELEASE 2      /* ring slots released by one commit; measured conv3 phase: 1 -> 27.2 k cycles, 2 -> 25.7 k, 4 -> 26.5 k (ring stalls) */
+#endif
 #ifndef SPLIT_NOCONV1
 #define SPLIT_NOCONV1 0  /* timing experiment: skip conv1 (results are garbage) */
 #endif
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
             for (int bi = 0; bi < NSLOT; bi++) {
                 const uint32_t u = w3_it + bi;
                 const int b = u % NSLOT;
-                mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
+                if ((b % SPLIT_RELEASE) == 0) mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);     // one release per SPLIT_RELEASE slots
                 if (SPLIT_NOLOAD) { mbar_arrive(&w3_full[b]); continue; }
                 mbar_expect_tx(&w3_full[b], 4096);
                 bulk_load(smem + OFF_W3 + b * 4096, a.params + P_S_W3 + (size_t)bi * 4096, 4096, &w3_full[b]);
@@ -550,8 +553,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                                 umma_bf16(dbase + i * stride * 80, w1, o1 + (uint64_t)(i * stride * 10 * S), idesc_f16(128, 80), 1u);
                             }
                         }
-                        umma_commit(&w3_empty[b0]);
-                        umma_commit(&w3_empty[b1]);
+                        // one tcgen05.commit per SPLIT_RELEASE slots (each costs the MMA stream ~40 cycles): it tracks all
+                        // earlier MMAs, i.e. every slot of the group
+                        if ((b1 + 1) % SPLIT_RELEASE == 0) umma_commit(&w3_empty[b1 + 1 - SPLIT_RELEASE]);
                     }
                     __syncwarp();
                 }
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                 for (int bi = NSLOT; bi < NBLK; bi++) {
                     const uint32_t u = w3_it + bi;
                     const int b = u % NSLOT;
-                    mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
+                    if ((b % SPLIT_RELEASE) == 0) mbar_wait(&w3_empty[b], ((u / NSLOT) & 1) ^ 1);
                     if (SPLIT_NOLOAD) { mbar_arrive(&w3_full[b]); continue; }
                     mbar_expect_tx(&w3_full[b], 4096);
                     bulk_load(smem + OFF_W3 + b * 4096, a.params + P_S_W3 + (size_t)bi * 4096, 4096, &w3_full[b]);
