@@ -64,8 +64,8 @@ constexpr size_t P_W3B = P_B5 + 16;                          // bf16 conv3 weigh
 // Float32-faithful mode: fp16 (lo, hi) pairs of the same layouts
 constexpr size_t P_S_W2 = P_W3B + 36 * 4096;                 // [k2][k1][chunk][n = (hi | lo) x 32 channels][8] fp16
 constexpr size_t P_S_W3 = P_S_W2 + 2 * 9 * 1024;             // 72 blocks (k2, k1, m) of 4 KB: 128 rows = (hi | lo) x 64 channels
-constexpr size_t P_S_W4 = P_S_W3 + 72 * 4096;                // [64][3200] fp16: columns [0,1600) = lo, [1600,3200) = hi
-constexpr size_t P_END = P_S_W4 + 64 * 3200 * 2;
+constexpr size_t P_S_W4 = P_S_W3 + 72 * 4096;                // [128][1600] fp16: rows [0,64) = hi, [64,128) = lo (one N = 128 operand)
+constexpr size_t P_END = P_S_W4 + 128 * 1600 * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -981,14 +981,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_qnet_convs17(const __grid_const
 }  // namespace e17
 
 // ---- kernel B: Dense(1600,64,relu) + Dense(64,3) ---------------------------------------------------------
-// SPLIT = false: X = out3 [N][1600] bf16, W4' [64][1600] bf16.
-// SPLIT = true (Float32-faithful): X = out3 [2N][1600] fp16 (row 2s = hi, row 2s+1 = 2^11 lo of sample s), W4' [64][3200]
-// fp16 (lo | hi): 50 k-blocks, the 25 lo-weight blocks first; lanes l and l ^ 1 of the epilogue hold the two halves of one
-// sample and add their accumulators.  A 128-row tile then covers 64 samples.
+// SPLIT = false: X = out3 [N][1600] bf16, W4' [64][1600] bf16, N = 64 accumulator columns.
+// SPLIT = true (Float32-faithful): X = out3 [2N][1600] fp16 (row 2s = hi, row 2s+1 = 2^11 lo of sample s), W4' [128][1600]
+// fp16 (rows 0..63 = hi, 64..127 = lo halves of the weights: ONE N = 128 operand, so X is read once); the epilogue adds
+// accumulator columns j and j + 64 (weight halves) and lanes l and l ^ 1 (activation halves).  A 128-row tile covers 64 samples.
 constexpr int HB_M = 128, HB_K = 64, HB_STAGES = 6;
-constexpr int HB_STAGE_BYTES = HB_M * 128 + 64 * 128;      // A tile 16 KB + W4 tile 8 KB (SWIZZLE_128B rows of 64 16-bit elements)
-constexpr int HB_SMEM = HB_STAGES * HB_STAGE_BYTES + 1024 + 256 + 64 * 4 + 3 * 64 * 4 + 16;
 constexpr int HB_THREADS = 192;
+template <bool SPLIT>
+struct HeadCfg {
+    static constexpr int N = SPLIT ? 128 : 64;                           // accumulator columns per tile
+    static constexpr int STAGE_BYTES = HB_M * 128 + N * 128;             // A tile 16 KB + W4 tile (SWIZZLE_128B rows of 64 16-bit elements)
+    static constexpr int SMEM = HB_STAGES * STAGE_BYTES + 1024 + 256 + 64 * 4 + 3 * 64 * 4 + 16;
+};
 
 struct HeadArgs {
     const uint8_t *params;
@@ -1002,20 +1006,20 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_constant__ CUtensorMap map_x,   // out3, box 128 x 64
-                                                             const __grid_constant__ CUtensorMap map_w,   // W4', box 64 x 64
+                                                             const __grid_constant__ CUtensorMap map_w,   // W4', box N x 64
                                                              const HeadArgs a) {
+    using C = HeadCfg<SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = (uint64_t *)(smem + HB_STAGES * HB_STAGE_BYTES);
+    uint64_t *bars = (uint64_t *)(smem + HB_STAGES * C::STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + HB_STAGES, *acc_full = bars + 2 * HB_STAGES, *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
     float *s_b4 = (float *)(tmem_slot + 4), *s_w5 = s_b4 + 64, *s_b5 = s_w5 + 192;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_rows = SPLIT ? 2 * a.n : a.n;
     const long long n_tiles = (n_rows + HB_M - 1) / HB_M;
-    constexpr int KB1 = 1600 / HB_K;            // 25 k-blocks per weight half
-    constexpr int KB = SPLIT ? 2 * KB1 : KB1;
-    constexpr uint32_t IDESC = SPLIT ? idesc_f16(128, 64) : idesc_bf16(128, 64);
+    constexpr int KB = 1600 / HB_K;             // 25 k-blocks
+    constexpr uint32_t IDESC = SPLIT ? idesc_f16(128, 128) : idesc_bf16(128, 64);
 
     for (int i = tid; i < 64; i += HB_THREADS) s_b4[i] = reinterpret_cast<const float *>(a.params + P_B4)[i];
     for (int i = tid; i < 192; i += HB_THREADS) s_w5[i] = reinterpret_cast<const float *>(a.params + P_W5)[i];
@@ -1025,7 +1029,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
         for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * C::N);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1038,9 +1042,9 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
             for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x)
                 for (int kb = 0; kb < KB; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t *st = smem + stage * HB_STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], HB_STAGE_BYTES);
-                    tma_load_2d(&map_x, &full[stage], st, (kb % KB1) * HB_K, (int)((n_tiles - 1 - t) * HB_M));   // newest rows first, see below
+                    uint8_t *st = smem + stage * C::STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    tma_load_2d(&map_x, &full[stage], st, kb * HB_K, (int)((n_tiles - 1 - t) * HB_M));   // newest rows first, see below
                     tma_load_2d(&map_w, &full[stage], st + HB_M * 128, kb * HB_K, 0);
                     if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -1055,10 +1059,10 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
                 for (int kb = 0; kb < KB; kb++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem + stage * HB_STAGE_BYTES);
+                    const uint32_t base = smem_u32(smem + stage * C::STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < HB_K / 16; k++)
-                        umma_bf16(tmem + acc * 64, desc_sw128(base) + (uint64_t)(2 * k), desc_sw128(base + HB_M * 128) + (uint64_t)(2 * k),
+                        umma_bf16(tmem + acc * C::N, desc_sw128(base) + (uint64_t)(2 * k), desc_sw128(base + HB_M * 128) + (uint64_t)(2 * k),
                                   IDESC, (kb | k) ? 1u : 0u);
                     umma_commit(&empty[stage]);
                     if (++stage == HB_STAGES) { stage = 0; phase ^= 1; }
@@ -1077,17 +1081,18 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
             float q0 = s_b5[0], q1 = s_b5[1], q2 = s_b5[2];
 #pragma unroll
             for (int h = 0; h < 4; h++) {
-                uint32_t v[16];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * 64 + h * 16, v);
+                uint32_t v[16], vl[16];
+                const uint32_t src = tmem + ((uint32_t)(q * 32) << 16) + acc * C::N + h * 16;
+                tmem_ld16(src, v);
+                if (SPLIT) tmem_ld16(src + 64, vl);                                   // the lo-weight half of the same outputs
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const int c = h * 16 + j;
                     float x = __uint_as_float(v[j]);
                     if (SPLIT) {                                                      // even lane: high-half row, odd lane: low-half row
-                        const float other = __shfl_xor_sync(0xffffffffu, x, 1);
-                        const float hi = (lane & 1) ? other : x, lo = (lane & 1) ? x : other;
-                        x = fmaf(lo, 1.0f / 2048.0f, hi);
+                        x = (x + __uint_as_float(vl[j])) * ((lane & 1) ? 1.0f / 2048.0f : 1.0f);
+                        x += __shfl_xor_sync(0xffffffffu, x, 1);
                     }
                     const float hv = fmaxf(x + s_b4[c], 0.f);                        // Dense(1600,64,relu)
                     q0 = fmaf(s_w5[c * 3 + 0], hv, q0);                              // Dense(64,3); W5 stored (3,64) column-major
@@ -1110,7 +1115,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) k_qnet_head(const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem, 128);
+        tmem_dealloc(tmem, 2 * C::N);
     }
 }
 
@@ -1185,7 +1190,7 @@ static void pack_params(const float *th, std::vector<uint8_t> &blob) {
                     const float w = W4[n + 64 * (x + 5 * y + 25 * c)];
                     const size_t k = (size_t)(y * 5 + x) * 64 + c;
                     bf(P_W4)[(size_t)n * 1600 + k] = f2bf(w);
-                    for (int part = 0; part < 2; part++) bf(P_S_W4)[(size_t)n * 3200 + part * 1600 + k] = f2h_part(w, part);
+                    for (int half = 0; half < 2; half++) bf(P_S_W4)[(size_t)(half * 64 + n) * 1600 + k] = f2h_part(w, 1 - half);
                 }
     memcpy(blob.data() + P_B4, b4, 256);
     memcpy(blob.data() + P_W5, W5, 768);          // (3,64) column-major: W5[a + 3 c]
@@ -1363,7 +1368,7 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
         split::k_qnet_convs_split<<<grid, THREADS, split::SMEM, st>>>(sa);
         SNK_CUDA(cudaGetLastError());
         if ((rc = make_map_16bit(&mx, true, q->out3, 2 * q->out3_cap, 1600, HB_M, HB_K)) != SNK_OK) return rc;
-        if ((rc = make_map_16bit(&mw, true, q->params + P_S_W4, 64, 3200, 64, HB_K)) != SNK_OK) return rc;
+        if ((rc = make_map_16bit(&mw, true, q->params + P_S_W4, 128, 1600, 128, HB_K)) != SNK_OK) return rc;
     } else {
         ConvArgs ca;
         ca.obs = obs_f32; ca.n = N; ca.params = q->params; ca.out3 = (__nv_bfloat16 *)q->out3; ca.timing = q->timing;
@@ -1382,11 +1387,11 @@ int snk_qnet_forward(snk_qnet q, const float *obs_f32, int64_t N, float *q_out_3
     const long long n_tiles = ((f32 ? 2 * N : N) + HB_M - 1) / HB_M;
     grid = (int)(n_tiles < q->sms ? n_tiles : q->sms);
     if (f32) {
-        SNK_CUDA(cudaFuncSetAttribute(k_qnet_head<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM));
-        k_qnet_head<true><<<grid, HB_THREADS, HB_SMEM, st>>>(mx, mw, ha);
+        SNK_CUDA(cudaFuncSetAttribute(k_qnet_head<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg<true>::SMEM));
+        k_qnet_head<true><<<grid, HB_THREADS, HeadCfg<true>::SMEM, st>>>(mx, mw, ha);
     } else {
-        SNK_CUDA(cudaFuncSetAttribute(k_qnet_head<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM));
-        k_qnet_head<false><<<grid, HB_THREADS, HB_SMEM, st>>>(mx, mw, ha);
+        SNK_CUDA(cudaFuncSetAttribute(k_qnet_head<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg<false>::SMEM));
+        k_qnet_head<false><<<grid, HB_THREADS, HeadCfg<false>::SMEM, st>>>(mx, mw, ha);
     }
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
