@@ -280,12 +280,19 @@ __device__ __forceinline__ void conv1_pixmajor(const ConvArgs &a, long long s0, 
 namespace split {
 #define SPLIT_STAMP(k) do { if (a.timing != nullptr && blockIdx.x == 0 && it_local >= 0 && it_local < 16 && lane == 0) a.timing[it_local * 8 + (k)] = clock64(); } while (0)
 constexpr int S = e16::S, SR = 8;             // 16 slots = 8 real samples x (hi, lo)
-constexpr int A1_PLANE = e16::A1_PLANE, A2_PLANE = e16::A2_PLANE, TILES2 = e16::TILES2;
+constexpr int A2_PLANE = e16::A2_PLANE;
+// conv2's input A1: rows = [pixel of the padded 12x12 grid][8 real samples] (NOT slots): the two fp16 halves of an activation sit
+// along K — four planes of 8 channels: hi 0..7, hi 8..15, lo 0..7, lo 8..15 (lo UNSCALED here: both halves add into one
+// accumulator; below 2^-14 it is an fp16 subnormal, 3e-8 absolute, far inside the error budget) — so a conv2 row is a real
+// sample: half the rows of the slot layout and no cross-lane combine in the epilogue.
+constexpr int A1_PLANE = PIX12 * SR * 16;     // 18,432 bytes per 8-channel plane
+constexpr int TILES2 = 8;                     // real outputs are pixels p < 120: 960 rows = 7.5 tiles
+static_assert(4 * A1_PLANE == 2 * e16::A1_PLANE, "A1 keeps its size");
 constexpr int NSLOT = 8;                      // ring of 4 KB conv3 weight blocks
 constexpr int NBLK = 72;                      // (k2, k1, m) weight blocks per iteration, each 128 rows = [hi | lo] x 64 channels
 constexpr int NACC = 8;                       // conv2 accumulator buffers of 64 columns (all 512 columns)
 constexpr int OFF_A1 = 0;
-constexpr int OFF_A2 = OFF_A1 + 2 * A1_PLANE;
+constexpr int OFF_A2 = OFF_A1 + 4 * A1_PLANE;
 constexpr int OFF_W2 = OFF_A2 + 4 * A2_PLANE;
 constexpr int OFF_W3 = OFF_W2 + 2 * 9 * 1024;
 constexpr int OFF_BIAS = OFF_W3 + NSLOT * 4096;
@@ -319,6 +326,15 @@ __device__ __forceinline__ uint32_t split_pair(float r0, float r1, bool want_lo)
     const __half2 o = want_lo ? l : h;
     return *reinterpret_cast<const uint32_t *>(&o);
 }
+// both halves of a pair at once; SCALED: lo = 2^11 (r - hi) (slot layout), else lo = r - hi
+template <bool SCALED>
+__device__ __forceinline__ void split_pair2(float r0, float r1, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(r0, r1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = SCALED ? __floats2half2_rn((r0 - hf.x) * LO_SCALE, (r1 - hf.y) * LO_SCALE) : __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 // x >= 0 (after relu) -> the fp16 bits of its high half, or of 2^11 x its low half
 __device__ __forceinline__ unsigned short split_half(float r, bool want_lo) {
     const __half h = __float2half_rn(r);
@@ -329,7 +345,7 @@ __device__ __forceinline__ unsigned short split_half(float r, bool want_lo) {
 // conv1 (2 -> 16 channels, 3x3, pad 1, relu) of the 8 real samples starting at s0 in plain FP32 on the CUDA cores, one
 // thread per (sample, image row y, half row) as in e16::conv1_pixmajor, the 16 output channels in two passes of 8 (one
 // 16-byte unit of a chunk plane each) to stay inside the register budget.  A quarter warp = 8 samples of one half row, so
-// its 16-byte stores form conflict-free 128-byte wavefronts.  Writes both halves of conv2's operand plane A1.
+// its 16-byte stores form conflict-free 128-byte wavefronts.  Writes the hi and the (unscaled) lo planes of conv2's operand A1.
 __device__ __forceinline__ void conv1_f32_split(const SplitArgs &a, long long s0, uint8_t *A1, int t, int nt, float &amax) {
 #pragma unroll 1
     for (int item = t; item < SR * 20; item += nt) {
@@ -354,7 +370,7 @@ __device__ __forceinline__ void conv1_f32_split(const SplitArgs &a, long long s0
                 }
             }
         }
-        uint8_t *dst = A1 + (((y + 1) * 12 + (x0 + 1)) * S + s) * 16;
+        uint8_t *dst = A1 + (((y + 1) * 12 + (x0 + 1)) * SR + s) * 16;
 #pragma unroll
         for (int o8 = 0; o8 < 2; o8++) {
             float acc[5][8];
@@ -381,12 +397,11 @@ __device__ __forceinline__ void conv1_f32_split(const SplitArgs &a, long long s0
                 for (int j = 0; j < 4; j++) {
                     const float r0 = fmaxf(acc[px][2 * j], 0.f), r1 = fmaxf(acc[px][2 * j + 1], 0.f);
                     amax = fmaxf(amax, fmaxf(r0, r1));
-                    wh[j] = (uint32_t)split_half(r0, false) | ((uint32_t)split_half(r1, false) << 16);
-                    wl[j] = (uint32_t)split_half(r0, true) | ((uint32_t)split_half(r1, true) << 16);
+                    split_pair2<false>(r0, r1, wh[j], wl[j]);
                 }
-                uint8_t *d = dst + px * S * 16 + o8 * A1_PLANE;
-                *reinterpret_cast<uint4 *>(d) = make_uint4(wh[0], wh[1], wh[2], wh[3]);               // slot s: high halves
-                *reinterpret_cast<uint4 *>(d + SR * 16) = make_uint4(wl[0], wl[1], wl[2], wl[3]);     // slot s + 8: low halves
+                uint8_t *d = dst + px * SR * 16 + o8 * A1_PLANE;
+                *reinterpret_cast<uint4 *>(d) = make_uint4(wh[0], wh[1], wh[2], wh[3]);                      // plane o8: high halves
+                *reinterpret_cast<uint4 *>(d + 2 * A1_PLANE) = make_uint4(wl[0], wl[1], wl[2], wl[3]);       // plane 2 + o8: low halves
             }
         }
     }
@@ -423,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const uint64_t dA1 = desc_nosw(smem_u32(A1), A1_PLANE, 128);             // conv2 A: 8-slot core matrices, contiguous
+    const uint64_t dA1 = desc_nosw(smem_u32(A1), A1_PLANE, 128);             // conv2 A: 8-sample core matrices; + 2 planes = the lo half
     const uint64_t dA2 = desc_nosw(smem_u32(A2), A2_PLANE, 128);             // conv3 B (N operand): likewise
     const uint64_t dW2 = desc_nosw(smem_u32(smem + OFF_W2), 1024, 128);      // conv2 B: 64 rows ([hi | lo] x 32 channels), 2 KB per tap
     const uint64_t dW3 = desc_nosw(smem_u32(smem + OFF_W3), 2048, 128);      // conv3 A: 128 stacked rows, K chunks 2 KB apart
@@ -448,7 +463,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
             }
         }
 
-        // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][slot]; N = [hi | lo] weight halves =================
+        // ================= conv2: 16 -> 32, 3x3, pad 1; rows = [pixel][sample]; K = [hi ; lo] activation halves, N = [hi | lo] weight halves =================
         if (!real) {
         } else if (warp < NISSUE) {
             tc_fence_after();
@@ -462,31 +477,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                 const uint64_t at = dA1 + (uint64_t)(t * 128);
                 if (elect_one()) {
 #pragma unroll
-                    for (int k2 = 0; k2 < 3; k2++)
+                    for (int half = 1; half >= 0; half--)                   // the low activation halves first (small terms first)
 #pragma unroll
-                        for (int k1 = 0; k1 < 3; k1++)
-                            umma_bf16(d, at + (uint64_t)((k2 * 12 + k1) * S), dW2 + (uint64_t)((k2 * 3 + k1) * 128),
-                                      idesc_f16(128, 64), (k2 | k1) ? 1u : 0u);
+                        for (int k2 = 0; k2 < 3; k2++)
+#pragma unroll
+                            for (int k1 = 0; k1 < 3; k1++)
+                                umma_bf16(d, at + (uint64_t)(half * 2 * (A1_PLANE / 16) + (k2 * 12 + k1) * SR),
+                                          dW2 + (uint64_t)((k2 * 3 + k1) * 128), idesc_f16(128, 64), (half == 1 && (k2 | k1) == 0) ? 0u : 1u);
                     umma_commit(&acc_full[b]);
                 }
                 __syncwarp();
             }
         } else if (warp >= 4) {
             const int grp = (warp - 4) >> 2, q = warp & 3;
-            const bool is_lo = (lane & 8) != 0;                             // this lane's row is a low-half slot
-            const float my_scale = is_lo ? LO_UNSCALE : 1.0f;
             for (int t = 0; t < TILES2; t++) {
                 const uint32_t u = acc_it + t;
                 if ((int)(u % NGRP) != grp) continue;
                 const int b = u % NACC;
                 mbar_wait(&acc_full[b], (u / NACC) & 1);
                 tc_fence_after();
-                const int P = t * 128 + q * 32 + lane;                      // row = [pixel][slot]; slot = lane & 15
-                const int pix = P / S, y = pix / 12, x = pix - 12 * y;
+                const int P = t * 128 + q * 32 + lane;                      // row = [pixel][sample]
+                const int pix = P / SR, y = pix / 12, x = pix - 12 * y;
                 const bool valid = x < 10 && y < 10;                        // other rows are discarded garbage
-                uint8_t *dst = A2 + ((y * 10 + x) * S + (lane & 15)) * 16;  // [r][x][slot]
+                uint8_t *dst = A2 + ((y * 10 + x) * S + (lane & 7)) * 16;   // [r][x][slot]: slot s = hi, slot s + 8 = 2^11 lo
                 const uint32_t src = tmem + ((uint32_t)(q * 32) << 16) + b * 64;
-                // lanes l and l ^ 8 hold the two halves of one sample: both form the same FP32 sum, each keeps its own half
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {                            // output channels 16 hh .. 16 hh + 15
                     uint32_t vh[16], vl[16];
@@ -498,22 +512,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[b]);
                     }
-                    uint32_t w[8];
+                    uint32_t wh[8], wl[8];
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
-                        float r[2];
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            // each lane scales its own part (2^-11 is exact), the sum of the two parts is the same number in both
-                            const float mine = (__uint_as_float(vh[j + e]) + __uint_as_float(vl[j + e])) * my_scale;
-                            r[e] = fmaxf(mine + __shfl_xor_sync(0xffffffffu, mine, 8) + bias[16 + hh * 16 + j + e], 0.f);
-                        }
-                        if (valid) amax = fmaxf(amax, fmaxf(r[0], r[1]));
-                        w[j >> 1] = split_pair(r[0], r[1], is_lo);
+                        const float r0 = fmaxf(__uint_as_float(vh[j]) + __uint_as_float(vl[j]) + bias[16 + hh * 16 + j], 0.f);
+                        const float r1 = fmaxf(__uint_as_float(vh[j + 1]) + __uint_as_float(vl[j + 1]) + bias[16 + hh * 16 + j + 1], 0.f);
+                        if (valid) amax = fmaxf(amax, fmaxf(r0, r1));
+                        split_pair2<true>(r0, r1, wh[j >> 1], wl[j >> 1]);
                     }
                     if (valid) {
-                        *reinterpret_cast<uint4 *>(dst + (2 * hh) * A2_PLANE) = make_uint4(w[0], w[1], w[2], w[3]);
-                        *reinterpret_cast<uint4 *>(dst + (2 * hh + 1) * A2_PLANE) = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+                        for (int c8 = 0; c8 < 2; c8++) {
+                            uint8_t *d8 = dst + (2 * hh + c8) * A2_PLANE;
+                            *reinterpret_cast<uint4 *>(d8) = make_uint4(wh[4 * c8], wh[4 * c8 + 1], wh[4 * c8 + 2], wh[4 * c8 + 3]);
+                            *reinterpret_cast<uint4 *>(d8 + SR * 16) = make_uint4(wl[4 * c8], wl[4 * c8 + 1], wl[4 * c8 + 2], wl[4 * c8 + 3]);
+                        }
                     }
                 }
             }
