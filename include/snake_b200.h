@@ -23,7 +23,9 @@
  *     asynchronously — call snk_sync() before reading an output or reusing an input buffer.
  *     The per-call getters whose names end in `_host` (snk_state_host, snk_losing_mask_host, ...)
  *     return when the data has arrived;
- *   - every call runs on its handle's device and restores the caller's current device;
+ *   - every call runs on its handle's device and restores the caller's current device; the stateless
+ *     entry points (snk_masked_target, snk_center_columns, snk_gram*, ...) run on the device that
+ *     owns their workspace / output pointer;
  *   - one handle per host thread; there is no hidden global state besides the
  *     thread-local error string and the tile-engine switch snk_gram_config;
  *   - there is no CPU fallback: without a CUDA device snk_create fails.

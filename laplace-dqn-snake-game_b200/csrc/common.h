@@ -42,4 +42,15 @@ struct DeviceGuard {
     DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
 
+// The stateless entry points (Gram, centring, masked target, ...) take device pointers only: they run on the device that owns
+// their first output / workspace pointer, whatever the caller's current device is.
+inline int device_of(const void *p) {
+    cudaPointerAttributes a;
+    if (p != nullptr && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+    cudaGetLastError();
+    int cur = 0;
+    cudaGetDevice(&cur);
+    return cur;
+}
+
 }  // namespace snk

@@ -712,6 +712,7 @@ int snk_gram_planes_layout(int64_t rows, int64_t P, size_t *plane_bytes, int64_t
 }
 
 int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, void *hi, void *lo2, void *cuda_stream) {
+    DeviceGuard guard__(device_of(hi));
     SNK_REQUIRE(A != nullptr && hi != nullptr && lo2 != nullptr && rows > 0 && P > 0, "bad argument");
     SNK_REQUIRE(a_dtype == SNK_DTYPE_F64 || a_dtype == SNK_DTYPE_F32, "a_dtype must be SNK_DTYPE_F64 or SNK_DTYPE_F32");
     const long long Ppad = pitch_of(P);
@@ -746,6 +747,7 @@ int snk_gram_block_scratch_bytes(int64_t rows_a, int64_t rows_b, int64_t P, int 
 
 int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, const void *b_lo2, int64_t rows_b, int64_t P,
                    int terms, int block_k, int splits, void *scratch, float *Y, int64_t ldY, void *cuda_stream) {
+    DeviceGuard guard__(device_of(scratch));
     SNK_REQUIRE(a_hi && b_hi && scratch && Y && rows_a > 0 && rows_b > 0 && P > 0, "bad argument");
     SNK_REQUIRE(terms == 1 || (terms == 3 && b_lo2 != nullptr), "terms must be 1 (bf16) or 3 (hi/lo split, needs b_lo2)");
     if (block_k == 0) block_k = 64;
@@ -765,6 +767,7 @@ int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, const voi
 
 int snk_gram_symmetrize_block(const float *Y, int64_t ldY, const float *YT, int64_t ldYT, int64_t rows_a, int64_t rows_b,
                               float *G, int64_t ldG, void *cuda_stream) {
+    DeviceGuard guard__(device_of(G));
     SNK_REQUIRE(Y && YT && G && rows_a > 0 && rows_b > 0, "bad argument");
     dim3 rb(32, 8), rg((unsigned)((rows_b + 31) / 32), (unsigned)((rows_a + 31) / 32));
     k_gram_finish<<<rg, rb, 0, (cudaStream_t)cuda_stream>>>(Y, 1, 0, ldY, YT, 1, 0, ldYT, (int)rows_a, (int)rows_b, G, ldG);
@@ -790,6 +793,7 @@ int snk_gram_pack(const void *A, int a_dtype, int64_t P, int64_t K, void *worksp
 }
 
 int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k, int splits, float *G, void *cuda_stream) {
+    DeviceGuard guard__(device_of(workspace));
     SNK_REQUIRE(workspace != nullptr && G != nullptr && K > 0 && P > 0, "bad argument");
     SNK_REQUIRE(terms == 1 || terms == 3, "terms must be 1 (bf16) or 3 (bf16 hi/lo split)");
     if (block_k == 0) block_k = 64;

@@ -176,6 +176,7 @@ using namespace snk;
 
 extern "C" int snk_laplace_sample_weights(const double *mean, const double *var, const double *D, int64_t P, int64_t K,
                                           const double *z1, const double *z2, double *w, void *cuda_stream) {
+    snk::DeviceGuard guard__(snk::device_of(w));
     SNK_REQUIRE(mean && var && D && z1 && z2 && w, "null argument");
     SNK_REQUIRE(P > 0 && K > 1, "need P > 0 and K > 1");
     static const bool carve = [] {
@@ -189,6 +190,7 @@ extern "C" int snk_laplace_sample_weights(const double *mean, const double *var,
 }
 
 extern "C" int snk_d_store_snapshot(double *D, int64_t P, int64_t K, int64_t position, const float *theta, void *cuda_stream) {
+    snk::DeviceGuard guard__(snk::device_of(D));
     SNK_REQUIRE(D != nullptr && theta != nullptr, "null argument");
     SNK_REQUIRE(P > 0 && position >= 0 && position < K, "position must be in 0..K-1 (0-based column)");
     k_store_snapshot<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(D, P, position, theta);
@@ -197,6 +199,7 @@ extern "C" int snk_d_store_snapshot(double *D, int64_t P, int64_t K, int64_t pos
 }
 
 extern "C" int snk_center_columns(double *D, int64_t P, int64_t K, double *mean, double *var, void *cuda_stream) {
+    snk::DeviceGuard guard__(snk::device_of(D));
     SNK_REQUIRE(D != nullptr, "null D");
     SNK_REQUIRE(P > 0 && K > 0, "P and K must be positive");
     unsigned grid = (unsigned)((P + CENTER_TPB - 1) / CENTER_TPB);

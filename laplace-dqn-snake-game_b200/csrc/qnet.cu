@@ -559,13 +559,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                     mbar_wait(&w3_full[b1], par);
                     tc_fence_after();
                     if (elect_one()) {
+                        // one weight block against all tiles, then the next: consecutive MMAs share their A operand
 #pragma unroll
-                        for (int i = 0; i < 5; i++) {
-                            if (i < my_tiles) {
-                                umma_bf16(dbase + i * stride * 80, w0, o0 + (uint64_t)(i * stride * 10 * S), idesc_f16(128, 80), bi ? 1u : 0u);
-                                umma_bf16(dbase + i * stride * 80, w1, o1 + (uint64_t)(i * stride * 10 * S), idesc_f16(128, 80), 1u);
-                            }
-                        }
+                        for (int i = 0; i < 5; i++)
+                            if (i < my_tiles) umma_bf16(dbase + i * stride * 80, w0, o0 + (uint64_t)(i * stride * 10 * S), idesc_f16(128, 80), bi ? 1u : 0u);
+#pragma unroll
+                        for (int i = 0; i < 5; i++)
+                            if (i < my_tiles) umma_bf16(dbase + i * stride * 80, w1, o1 + (uint64_t)(i * stride * 10 * S), idesc_f16(128, 80), 1u);
                         // one tcgen05.commit per SPLIT_RELEASE slots (each costs the MMA stream ~40 cycles): it tracks all
                         // earlier MMAs, i.e. every slot of the group
                         if ((b1 + 1) % SPLIT_RELEASE == 0) umma_commit(&w3_empty[b1 + 1 - SPLIT_RELEASE]);

@@ -1427,6 +1427,7 @@ int snk_select_action(snk_handle h, const float *q_3xN, float eps, const float *
 
 int snk_masked_target(const float *q_next_3xB, const uint8_t *mask_3xB, const float *r, const uint8_t *done, double gamma,
                       float fill, double *y_f64, float *y_f32, int64_t B, void *cuda_stream) {
+    DeviceGuard guard__(device_of(q_next_3xB));
     SNK_REQUIRE(q_next_3xB && mask_3xB && r && done, "null input");
     SNK_REQUIRE(y_f64 || y_f32, "no output requested");
     SNK_REQUIRE(B >= 0, "negative batch");
