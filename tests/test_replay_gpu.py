@@ -92,3 +92,37 @@ def test_transition_chain_state_is_previous_next_state():
         assert torch.equal(s[t + 1][live], ns[t][live])
         assert torch.equal(s[t + 1][~live][:, 0], s[t + 1][~live][:, 1])      # fresh game: (init, init)
     assert torch.equal(s[:, :, 1], ns[:, :, 0])                                # shared middle board
+
+
+def test_host_buffer_store_path_equals_device_path():
+    """snk_step_fused_store_host (pinned host buffers, 2-bit packed observations, chunked + pipelined copies: the call bench.py's
+    e2e leg times) against snk_step_fused_store on device buffers: same outputs, same ring contents, several steps in a row
+    without a sync in between two calls (the staging buffers are guarded by the copy-done event)."""
+    S = pkg()
+    n, cap, steps = 200_000, 50_000, 6          # several chunks per step, more envs per step than ring slots
+    env_d, env_h = S.SnakeGame(n, auto_reset=True), S.SnakeGame(n, auto_reset=True)
+    rb_d, rb_h = S.ReplayBuffer(capacity=cap), S.ReplayBuffer(capacity=cap)
+    out = env_d.alloc_outputs(obs="packed2", mask=True, act=True)
+    host = {"obs_fmt": "packed2", "q": S.pinned_empty((n, 3), torch.float32), "u": S.pinned_empty((n,), torch.float32),
+            "ridx": S.pinned_empty((n,), torch.uint8), "act_idx": S.pinned_empty((n,), torch.uint8),
+            "reward": S.pinned_empty((n,), torch.float32), "done": S.pinned_empty((n,), torch.uint8),
+            "obs": S.pinned_empty((n, 50), torch.uint8), "mask": S.pinned_empty((n, 3), torch.uint8)}
+    g = torch.Generator().manual_seed(11)
+    for t in range(steps):
+        env_h.sync()                                   # the host inputs are about to be overwritten
+        host["q"].copy_(torch.rand(n, 3, generator=g) * 2 - 1)
+        host["u"].copy_(torch.rand(n, generator=g))
+        host["ridx"].copy_(torch.randint(0, 3, (n,), generator=g, dtype=torch.uint8))
+        env_d.step_fused(q=host["q"].cuda(), eps=0.2, u=host["u"].cuda(), ridx=host["ridx"].cuda(), out=out, replay=rb_d)
+        env_h.step_fused_host(host, q=True, eps=0.2, replay=rb_h)
+        if t % 2 == 1:                                 # every other step: enqueue the next call's getters right behind it
+            assert torch.equal(env_h.score_host(), env_d.score.cpu())
+        env_h.sync()
+        for k in ("act_idx", "reward", "done", "obs", "mask"):
+            assert torch.equal(out[k].cpu(), host[k]), (k, t)
+        assert len(rb_h) == len(rb_d) and rb_h.position == rb_d.position
+    idx = torch.arange(cap, device="cuda")
+    a, b = rb_d.stack_exp(idx, ep_stats=True), rb_h.stack_exp(idx, ep_stats=True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert env_h.count_errors() == 0
