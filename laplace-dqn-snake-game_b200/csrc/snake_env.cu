@@ -1080,6 +1080,9 @@ static cudaError_t ensure(T **p, size_t bytes) {
     return cudaMalloc((void **)p, bytes);
 }
 
+#ifndef SNK_HOST_CHUNK_MB
+#define SNK_HOST_CHUNK_MB 8u
+#endif
 static long long *g_rollout_prof = nullptr;
 
 extern "C" {
@@ -1613,11 +1616,11 @@ static int step_fused_host_impl(snk_handle h, snk_replay_s *r, const float *q, f
     a.mask = mask ? h->d_mask : nullptr; a.ep_return = ep_return ? h->d_ep_return : nullptr;
     a.ep_score = ep_score ? h->d_ep_score : nullptr;
     if (r != nullptr) { a.sink = r->ring; a.sink_base = r->total; a.sink_cap = r->capacity; a.sink_n = h->n; }
-    // Chunking trades copy/kernel overlap against per-copy overhead (~8 us per cudaMemcpyAsync): about 16 MB of traffic per
-    // chunk, at most 16 chunks; only the observation is copied per chunk, the small per-env outputs go down once at the end.
+    // Chunking trades copy/kernel overlap (and the time before the first output copy can start) against per-copy overhead
+    // (~8 us per cudaMemcpyAsync): about SNK_HOST_CHUNK_MB of traffic per chunk, at most 16 chunks; only the observation is copied per chunk, the small per-env outputs go down once at the end.
     const long long align = TPB * 8;
     const size_t traffic = (opb + 26) * n;
-    int n_chunks = (int)((traffic + (16u << 20) - 1) / (16u << 20));
+    int n_chunks = (int)((traffic + (SNK_HOST_CHUNK_MB << 20) - 1) / (SNK_HOST_CHUNK_MB << 20));
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > 16) n_chunks = 16;
     const long long per = ((h->n + n_chunks - 1) / n_chunks + align - 1) / align * align;

@@ -22,6 +22,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["config"]["envs_per_bench_step"] == 32768 and len(d["config"]["differences_from_the_gpu_arm"]) == 3
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -32,9 +33,22 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    p = os.path.join(ROOT, "profiles", "r01_bench_n1.json")
+    for name in ("r01_bench_n1.json", "r02_bench_n1.json"):
+        _check_gpu_line(os.path.join(ROOT, "profiles", name), round2=name.startswith("r02"))
+
+
+def _check_gpu_line(p, round2):
     d = json.loads(open(p).read().strip().splitlines()[-1])
     assert BASE | {"roofline", "gpu_launches", "clocks"} <= set(d)
+    if round2:
+        assert d["clocks"]["samples"] >= 8 and d["clocks"]["sm_mhz"] is not None          # the sampler starts before the warm-up
+        assert "packed2" in d["e2e"]["obs_format"] and "full_f32_obs_variant" in d["e2e"]
+        c4 = d["config4_65536_envs"]
+        assert c4["native_f32"]["max_err_vs_float64_of_maxQ"] < 2e-5 < c4["native_bf16"]["max_err_vs_float64_of_maxQ"]
+        for t in ("terms3", "terms1"):
+            r = d["gram_5a"][t]["roofline"]
+            assert r["frac_algorithmic"] <= r["frac"] + 1e-9 and r["traffic"] is not None
+        assert d["cpu_baseline"]["sample"].startswith("32768 envs")
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["traffic"] is None or 0.5 < r["traffic"] / (876 * d["config"]["envs_per_gpu"]) < 1.5
