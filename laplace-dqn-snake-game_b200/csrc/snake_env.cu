@@ -1081,7 +1081,7 @@ static cudaError_t ensure(T **p, size_t bytes) {
 }
 
 #ifndef SNK_HOST_CHUNK_MB
-#define SNK_HOST_CHUNK_MB 8u
+#define SNK_HOST_CHUNK_MB 16u      // measured at 2^20 envs, packed observations: 8 MB chunks 1.49 ms per step, 16 MB 1.37, 32 MB 1.39, 64 MB 1.42
 #endif
 static long long *g_rollout_prof = nullptr;
 
