@@ -711,11 +711,18 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
     const long long env = env0 + (mine ? lane : 0);
     if (warp == 0) {
         env_load(e, a.s, env);
-        int a0 = a.steps > 0 ? a.act[env] : 0, a1 = a.steps > 1 ? a.act[a.n + env] : 0;
+        // loop invariants pinned in registers: re-reading a kernel parameter is a uniform constant load (LDCU, tens of cycles
+        // of latency in front of the compare that uses it) — on a chain where every cycle counts
+        int steps = a.steps, is_abs = a.is_abs, auto_reset = a.auto_reset;
+        const uint8_t *actp = a.act + env;
+        long long astride = a.n;
+        asm volatile("" : "+r"(steps), "+r"(is_abs), "+r"(auto_reset), "+l"(actp), "+l"(astride));
+        int a0 = steps > 0 ? actp[0] : 0, a1 = steps > 1 ? actp[astride] : 0;
+        const uint8_t *act2 = actp + 2 * astride;
         const bool prof = a.prof != nullptr && blockIdx.x == 0 && lane == 0;
         long long p_wait = 0, p_t0 = prof ? clock64() : 0;
-        for (int t = 0; t < a.steps; t++) {
-            const int a2 = t + 2 < a.steps ? a.act[(long long)(t + 2) * a.n + env] : 0;      // in flight during two steps
+        for (int t = 0; t < steps; t++, act2 += astride) {
+            const int a2 = t + 2 < steps ? *act2 : 0;                       // in flight during two steps
             const int b = t & 1;
             const long long w0 = prof ? clock64() : 0;
             if (t >= 2) nbar_sync(EMPTY + b, 128);           // the expanders have consumed slot b (step t-2)
@@ -723,7 +730,7 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
             int aidx = a0;
             float reward = 0.0f;
             uint32_t m3;
-            if (!e.dn) reward = env_advance<false>(e, aidx, a.is_abs, list_mask, s_food_bit, m3);   // virtual_step is the expanders' job
+            if (!e.dn) reward = env_advance<false>(e, aidx, is_abs, list_mask, s_food_bit, m3);   // virtual_step is the expanders' job
             if (mine) {
                 Handoff h;
                 h.occ = e.occ; h.pocc = e.pocc; h.cons = e.cons;
@@ -733,7 +740,7 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
                 h.reward = reward; h.ret = e.ret; h.score = e.len - 2; h.pad = 0;
                 s_hand[b][lane] = h;
             }
-            if (e.dn && a.auto_reset) env_reset(e);
+            if (e.dn && auto_reset) env_reset(e);
             __syncwarp();
             nbar_arrive(FULL + b, 128);
             a0 = a1; a1 = a2;
