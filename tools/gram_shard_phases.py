@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Phase timing of the sharded Gram with 2 virtual ranks on one GPU (same kernels as the multi-GPU run)."""
-import ctypes as C
+"""Phase timing of the row-sharded Gram with 2 virtual ranks on one GPU (same kernels as the multi-GPU run): pack, the two block
+Grams of a rank (against its own planes and against the peer's), the symmetrise pass — through the snk_gram_shard_* phase calls."""
 import os
 import sys
 
@@ -16,13 +16,7 @@ R, P = 6250, 181395
 dev = torch.device("cuda", 0)
 A = torch.randn(2 * R, P, device=dev, dtype=torch.float32)
 peers = GS.LocalPeers(2 * R, P, 2, dev)
-L = S.lib()
-for s in peers.shards:
-    s.pack(A[s.col0[s.rank]:s.col0[s.rank] + s.rows].contiguous())
-torch.cuda.synchronize()
-sh = peers.shards[0]
-other = peers.shards[1]
-st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+rows = [A[s.col0[s.rank]:s.col0[s.rank] + s.rows].contiguous() for s in peers.shards]
 
 
 def timed(fn, n=3):
@@ -35,17 +29,15 @@ def timed(fn, n=3):
     return e0.elapsed_time(e1) / n
 
 
-def block(bplanes, col):
-    S._check(L.snk_gram_block(sh.planes.ptr, sh.rows, C.c_void_p(bplanes), C.c_void_p(bplanes + sh.plane_bytes), R, P, 3, 0, 0,
-                              sh.scratch.ptr, C.c_void_p(sh.Y.ptr.value + 4 * col), sh.K, st))
-
-
-print("block vs own planes   ms", timed(lambda: block(sh.planes.ptr.value, 0)))
-print("block vs other planes ms", timed(lambda: block(other.planes.ptr.value, R)))
-S._check(L.snk_copy_async(sh.stage[1].ptr, other.planes.ptr, 2 * sh.plane_bytes, st)); torch.cuda.synchronize()
-print("block vs staged copy  ms", timed(lambda: block(sh.stage[1].ptr.value, R)))
-print("copy of one peer's planes (local) ms", timed(lambda: S._check(L.snk_copy_async(sh.stage[1].ptr, other.planes.ptr, 2 * sh.plane_bytes, st))))
-print("pack ms", timed(lambda: sh.pack(A[:R].contiguous())))
+sh = peers.shards[0]
+print("pack (6,250 x 181,395 fp32 -> bf16 planes)  ms", timed(lambda: sh.pack(rows[0])))
+peers.shards[1].pack(rows[1])
+torch.cuda.synchronize()
+print("ring of rank 0 (2 block Grams + staged copy)  ms", timed(lambda: sh.ring(3)))
+peers.shards[1].ring(3)
+torch.cuda.synchronize()
+print("symmetrise of rank 0 (peer-read transpose)    ms", timed(lambda: sh.symmetrize(3)))
 for cg in (1, 2):
-    L.snk_gram_config(cg)
-    print("cta_group", cg, "block ms", timed(lambda: block(sh.planes.ptr.value, 0)))
+    S.lib().snk_gram_config(cg)
+    print("cta_group", cg, ": ring of rank 0 ms", timed(lambda: sh.ring(3)))
+peers.free()
