@@ -12,7 +12,6 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ.setdefault("SNK_QNET_ENGINE", "17")
 import __graft_entry__ as graft  # noqa: E402
 
 S = graft.load_package()
