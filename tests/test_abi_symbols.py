@@ -105,3 +105,30 @@ def test_product_sources_never_touch_the_oracle():
                 if re.search(r"(from|import)\s+oracle|oracle_lib|libsnake_oracle|oracle/", txt):
                     offenders.append(os.path.join(base, f))
     assert not offenders, offenders
+
+
+def test_ctypes_binding_matches_the_header(built):
+    """every prototype the Python binding declares has the header's parameter count and compatible ctypes (the Julia wrapper is
+    checked the same way in test_julia_wrapper_static.py)"""
+    from tests.test_julia_wrapper_static import c_declarations
+    decls, handles = c_declarations()
+    L = built.lib()
+    table = {"int": {C.c_int}, "int32_t": {C.c_int, C.c_int32}, "int64_t": {C.c_int64, C.c_longlong}, "uint32_t": {C.c_uint32, C.c_uint},
+             "uint64_t": {C.c_uint64, C.c_ulonglong}, "float": {C.c_float}, "double": {C.c_double}, "size_t": {C.c_size_t}}
+    problems, checked = [], 0
+    for name, params in decls.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue                                     # bound ad hoc by a tool (debug hooks)
+        checked += 1
+        if len(fn.argtypes) != len(params):
+            problems.append("%s: %d ctypes arguments for %d C parameters" % (name, len(fn.argtypes), len(params)))
+            continue
+        for k, (cp, at) in enumerate(zip(params, fn.argtypes)):
+            c = cp.replace("const ", "").strip()
+            base = c.rsplit(" ", 1)[0].strip() if " " in c else c
+            is_ptr = "*" in c or base in handles
+            ok = (at is C.c_void_p or at is C.c_char_p or hasattr(at, "contents")) if is_ptr else at in table.get(base, set())
+            if not ok:
+                problems.append("%s: argument %d is `%s` in C but %s in the binding" % (name, k + 1, cp, at))
+    assert checked >= 60 and not problems, "\n".join(problems)
