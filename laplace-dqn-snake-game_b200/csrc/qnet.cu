@@ -93,6 +93,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {     
         }
     }
 }
+// the same for a wait that is known to be long (an epilogue warp waiting for a whole MMA phase): back off between polls so
+// that a dozen polling warps do not compete with the tensor core's operand fetch for the shared-memory pipeline
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(128);
+        if (clock64() - t0 > 4000000000ll) {
+            printf("snk qnet: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -306,6 +319,9 @@ static_assert(NBLK % NSLOT == 0 && NSLOT % 2 == 0, "the issuer waits for ring sl
 #endif
 #ifndef SPLIT_RELEASE
 #define SPLIT_RELEASE 2      /* ring slots released by one commit; measured conv3 phase: 1 -> 27.2 k cycles, 2 -> 25.7 k, 4 -> 26.5 k (ring stalls) */
+#endif
+#ifndef SPLIT_EXP
+#define SPLIT_EXP 0          /* timing experiments (garbage results): 1 = every conv3 MMA reads the same A block, 2 = the same B offset */
 #endif
 #ifndef SPLIT_NOCONV1
 #define SPLIT_NOCONV1 0  /* timing experiment: skip conv1 (results are garbage) */
@@ -553,8 +569,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
                 for (int bi = 0; bi < NBLK; bi += 2) {
                     const uint32_t b0 = (w3_it + bi) % NSLOT, b1 = b0 + 1;  // w3_it and bi are even
                     const uint32_t par = ((w3_it + bi) / NSLOT) & 1;       // both blocks share the ring pass
-                    const uint64_t o0 = bbase + c_boff[bi], o1 = bbase + c_boff[bi + 1];
-                    const uint64_t w0 = dW3 + (uint64_t)(b0 * 256), w1 = w0 + 256;
+                    const uint64_t o0 = bbase + (SPLIT_EXP & 2 ? 0 : c_boff[bi]), o1 = bbase + (SPLIT_EXP & 2 ? 0 : c_boff[bi + 1]);   // SPLIT_EXP: timing experiments
+                    const uint64_t w0 = dW3 + (uint64_t)((SPLIT_EXP & 1 ? 0 : b0) * 256), w1 = w0 + (SPLIT_EXP & 1 ? 0 : 256);
                     mbar_wait(&w3_full[b0], par);
                     mbar_wait(&w3_full[b1], par);
                     tc_fence_after();
@@ -594,7 +610,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_qnet_convs_split(const __grid_co
             }
             if (real && warp >= 4) {
                 const int grp = (warp - 4) >> 2, q = warp & 3;
-                mbar_wait(c3_full, c3_it & 1);
+                mbar_wait_relaxed(c3_full, c3_it & 1);
                 tc_fence_after();
                 if (warp == 4) SPLIT_STAMP(3);
                 float *scratch = reinterpret_cast<float *>(A2);             // [y][column = x*8 + sample][oc]: conv3 no longer reads A2
