@@ -393,7 +393,7 @@ def run_ours(args):
     # ---- BASELINE config 5a: Gram of the deviation matrix (K=1000 snapshots x P=181,395 weights), tcgen05
     gram = None
     if rank == 0 and not args.skip_gram:
-        gram = bench_gram(S, dev)
+        gram = bench_gram(S, dev, cpu_too=(world == 1 and not args.skip_cpu))
 
     # ---- BASELINE config 5b shape: row-sharded Gram across the ranks (6,250 rows of J per GPU, P = 181,395)
     gram_sh = None
@@ -657,7 +657,7 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
             "timed": "per-sample gradients into the planes + one snk_gram_shard_run per rank; buffers and IPC mappings set up once"}
 
 
-def bench_gram(S, dev, K=1000, P=181395, iters=10):
+def bench_gram(S, dev, K=1000, P=181395, iters=10, cpu_too=False):
     """G = A A^T for A = D^T (K x P), synthetic N(0,1) snapshots cast through Float32 (the reference stores
     Float64.(theta::Float32)); L2 flushed between timed iterations; accuracy against torch Float64."""
     import torch
@@ -713,6 +713,16 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10):
     Ab = A.to(torch.bfloat16)
     ms = timed(lambda: torch.matmul(Ab, Ab.T))
     out["cublas_bf16_same_shape_ms"] = ms
+    if cpu_too:
+        # the reference-sized Gram in Float64 on the host cores (what LinearAlgebra/OpenBLAS does for the
+        # reference's svd(D) path); one run, ~2-10 s
+        Ah = A.cpu()
+        t0 = time.perf_counter()
+        Gh = Ah @ Ah.T
+        dt = time.perf_counter() - t0
+        out["cpu_fp64_baseline"] = {"ms": 1e3 * dt, "gflops": 2.0 * K * K * P / dt / 1e9, "cores": torch.get_num_threads(),
+                                    "kind": "library (torch CPU matmul, Float64)",
+                                    "rel_fro_err_of_gpu_split_vs_this": float(((plan.gram(3, 0).cpu().double() - Gh).norm() / Gh.norm()).item())}
     return out
 
 
