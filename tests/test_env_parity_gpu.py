@@ -577,6 +577,46 @@ def test_random_food_lists_differential(seed):
     assert np.array_equal(env.error_flags.cpu().numpy().astype(np.uint32), sc["error"])
 
 
+def test_multi_step_rollout_with_short_food_lists_reports_the_same_errors():
+    """R9 inside the multi-step kernel: with a 4-entry food list the real and the VIRTUAL eats (virtual_step runs sample_food!
+    on its copies, utils.jl:122-124) run out of candidates; in the warp-specialised kernel the virtual steps are evaluated by the
+    expander warps and their error bits travel back to the env state.  Actions come from a food-seeking policy run on the oracle."""
+    S = pkg()
+    rng = np.random.default_rng(4)
+    n, T = 600, 120
+    food = [(4, 4), (6, 6), (3, 7), (8, 8)]
+    ora = O.OracleBatch(n, food_rc=food, auto_reset=True)
+    acts = np.zeros((T, n), np.uint8)
+    refs = []
+    for t in range(T):
+        m, av = ora.losing_mask()
+        sc = ora.scalars()
+        head, foodrc = sc["head_rc"].astype(int), sc["food_rc"].astype(int)
+        best, best_score = np.zeros(n, np.int64), np.full(n, 1e9)
+        for k in range(3):
+            d = av[:, k].astype(int)
+            dr = np.where(d == 0, -1, np.where(d == 1, 1, 0))
+            dc = np.where(d == 2, -1, np.where(d == 3, 1, 0))
+            score = np.abs(head[:, 0] + dr - foodrc[:, 0]) + np.abs(head[:, 1] + dc - foodrc[:, 1]) + 1000.0 * m[:, k] + rng.random(n) * 0.5
+            take = score < best_score
+            best[take], best_score[take] = k, score[take]
+        acts[t] = best
+        refs.append(ora.step(acts[t], obs=("i8",)))
+    want_err = ora.scalars()["error"]
+    assert (want_err != 0).any()                                    # the scenario really exhausts the list
+    for n_run in (n, 40000):                                        # small-batch (warp-specialised) and large-batch kernels
+        rep = -(-n_run // n)
+        a = np.tile(acts, (1, rep))[:, :n_run].copy()
+        env = S.SnakeGame(n_run, auto_reset=True, food_list=food)
+        out = env.rollout(torch.from_numpy(a).cuda(), obs="i8", mask=True, ep_stats=True)
+        for t in (0, T // 2, T - 1):
+            assert np.array_equal(out["mask"][t, :n].cpu().numpy(), refs[t]["mask"]), t
+            assert np.array_equal(out["obs"][t, :n].cpu().numpy().reshape(n, 200), refs[t]["obs_i8"]), t
+            assert np.array_equal(out["ep_score"][t, :n].cpu().numpy(), refs[t]["ep_score"]), t
+        assert np.array_equal(env.error_flags.cpu().numpy()[:n].astype(np.uint32), want_err)
+        env.close()
+
+
 def test_multi_step_rollout_absolute_dirs_no_auto_reset():
     """rollout kernel with absolute directions (reverse moves lose) and frozen lost envs."""
     S = pkg()
