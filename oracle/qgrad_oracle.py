@@ -51,6 +51,6 @@ def per_sample_grads(layers, states, actions, targets):
         loss = 0.5 * d * d if abs(float(d.detach())) < 1.0 else d.abs() - 0.5     # Flux.huber_loss: quadratic strictly inside delta
         g = torch.autograd.grad(loss, leaves)
         rows.append(torch.cat([_colmajor(t) for t in g]).numpy())
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         qs.append(q.detach().numpy())
     return np.stack(rows), np.array(losses), np.stack(qs)
