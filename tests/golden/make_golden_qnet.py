@@ -40,7 +40,7 @@ def layers_for(S):
 
 def states(boards):
     """(B,2,10,10) in torch layout [n][frame][col][row] = Julia (10,10,2,B) column-major"""
-    return np.stack([np.stack([boards[t - 1].T, boards[t].T]) for t in FRAMES]).astype(np.float64)
+    return np.ascontiguousarray(np.stack([np.stack([boards[t - 1].T, boards[t].T]) for t in FRAMES]).astype(np.float64))
 
 
 def compute(S):
