@@ -55,6 +55,7 @@ mutable struct BatchedSnakeGame
         g = new(h[], n, zeros(Float32, 10, 10, 2, n), zeros(Float32, n), zeros(UInt8, n), ones(UInt8, 3, n),
                 zeros(UInt8, n))
         finalizer(x -> ccall((:snk_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), g)
+        virtual_step(g)            # both mirrors come from the library, also for the constructor state
         assemble_state!(g)
         return g
     end
