@@ -513,10 +513,10 @@ def bench_config4(S, dev, local, n=65536, steps=20):
         if name.startswith("native"):
             mma_x = 4.0 if name == "native_f32" else 1.0        # the split issues every MMA for (hi, lo) x (hi, lo)
             out[name]["roofline"] = {
-                "bound": "tensor", "achieved": tflops * mma_x, "peak": peak, "unit": "TFLOP/s", "frac": tflops * mma_x / peak,
-                "frac_algorithmic": tflops / peak, "traffic": None,
-                "note": "achieved = executed MMA FLOP (useful x %.0f) / time of snk_qnet_forward; frac_algorithmic = useful FLOP "
-                        "(4,870,784 per sample) / time / peak; ncu tensor-pipe %% in profiles/r02_ncu_qnet_*.csv" % mma_x}
+                "bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
+                "achieved_executed": tflops * mma_x, "frac_executed": tflops * mma_x / peak, "traffic": None,
+                "note": "achieved = useful FLOP (4,870,784 per sample, SURVEY 8a row Q) / time of snk_qnet_forward; executed = the MMAs issued "
+                        "(useful x %.0f); ncu tensor-pipe %% in profiles/r02_ncu_qnet_*.csv" % mma_x}
     out["like_for_like"] = "native_f32 (the reference network is Float32; bf16 and TF32 give different greedy actions)"
     out["replay_len"] = len(rb)
     env.close()
@@ -550,11 +550,19 @@ def ncu_traffic_bytes():
     return ncu_csv_traffic("ncu_k_step_full", "k_step")[0]
 
 
+def gram_block_flops(S, rows_a, rows_b, P, terms, symmetric):
+    """what the tensor pipe executes for one block (the library's own tile plan: computed tiles, padded, x products)"""
+    import ctypes as C
+    v = C.c_double(0)
+    S._check(S.lib().snk_gram_block_flops(int(rows_a), int(rows_b), int(P), int(terms), 1 if symmetric else 0, C.byref(v)))
+    return v.value
+
+
 def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181395, iters=3):
     """BASELINE config 5b: the Gram of per-sample gradients of the DQN loss over the replay buffer, row-sharded.
     Every rank fills its own device replay ring by acting with the Float32-faithful Q-net, draws R transitions, and
       timed: snk_qnet_sample_grads (rows of J straight into this rank's bf16 planes) + snk_gram_shard_run (planes ring over
-             NVLink peer memory under the tcgen05 main loop, device-side barriers, peer-read symmetrise) -> G[rows_rank, :].
+             NVLink peer memory under the tcgen05 main loop, device-side barriers, peer-read mirror) -> G[rows_rank, :].
     Verified on EVERY rank against Float64 dot products of Float32 J rows (>= 1000 off-diagonal entries), and against the
     NCCL all-gather + all-to-all form of the same Gram (bit-identical)."""
     import torch
@@ -613,7 +621,7 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
     n_checked = int(offdiag.sum().item())
     Gring = G.clone()
     dg.close()
-    # ---- baseline: the same block Grams behind library collectives (NCCL all-gather of the planes, all-to-all of Y^T blocks)
+    # ---- baseline: the same block Grams behind library collectives (NCCL all-gather of the planes, all-to-all of the blocks to mirror)
     J = q_net.sample_grads(batch["states"], batch["actions"], y, want_J=True, want_loss=False)["J"]
     ag = GS.AllGatherGram([R] * world, P, dev)
     times_ag = []
@@ -637,22 +645,33 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
     ms_prod = sorted(t_prod)[len(t_prod) // 2]
     Kt = R * world
     useful = 2.0 * Kt * Kt * P
-    mma = 2 * useful / world / ((ms - ms_prod) * 1e-3) / 1e12
+    executed = 0.0                                               # what the busiest rank's tensor pipe executes: its blocks' computed tiles x 3 products
+    for r in range(world):
+        tot = 0.0
+        for i, (_, a0, a1, b0, b1) in enumerate(GS.ring_schedule([R] * world, r)):
+            if a1 > a0 and b1 > b0:
+                tot += gram_block_flops(S, a1 - a0, b1 - b0, P, 3, i == 0)
+        executed = max(executed, tot)
+    gram_s = (ms - ms_prod) * 1e-3
+    mma = executed / gram_s / 1e12
+    alg = useful / world / gram_s / 1e12
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1421.8)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1421.8
     return {"workload": "config5b: Gram of per-sample DQN-loss gradients J (%d transitions per GPU out of each rank's 50,000-slot replay ring "
                         "x %d parameters), row-sharded over %d GPUs, hi/lo bf16 split" % (R, P, world),
             "data": "real J: rollout with the Float32-faithful Q-net (Glorot-init synthetic weights) -> replay ring -> sample -> "
                     "masked max-Q targets -> per-sample gradients",
             "K_total": Kt, "ms": ms, "producer_ms": ms_prod, "gram_ms": ms - ms_prod,
-            "useful_tflops_total": useful / ((ms - ms_prod) * 1e-3) / 1e12, "mma_tflops_per_gpu": mma,
-            "roofline": {"bound": "tensor", "achieved": mma, "peak": peak, "unit": "TFLOP/s", "frac": mma / peak,
-                         "frac_algorithmic": mma / 2 / peak, "traffic": None,
-                         "note": "per GPU, Gram phase only; peak = sustained bf16 (a %.0f ms region); executed MMA FLOP = 2 x algorithmic (hi/lo split)" % ms},
+            "useful_tflops_total": useful / gram_s / 1e12, "mma_tflops_per_gpu": mma,
+            "roofline": {"bound": "tensor", "achieved": alg, "peak": peak, "unit": "TFLOP/s", "frac": alg / peak,
+                         "achieved_executed": mma, "frac_executed": mma / peak, "executed_over_algorithmic": executed / (useful / world), "traffic": None,
+                         "note": "per GPU, Gram phase only; peak = sustained bf16 (a %.0f ms region); achieved = SURVEY 8(d)'s 2 K^2 P / GPUs / time; "
+                                 "executed = the tiles the busiest rank computes (own block: upper-triangle tiles; half the ring) x 3 products of the "
+                                 "hi/lo split, padding included" % ms},
             "verify_per_rank": {"entries_per_rank": n_checked, "max_err_over_sqrt_GiiGjj": errs, "first_checked_row_norm_per_rank": fingerprints,
                                 "how": "128 random local rows x rows 0..7 of every rank (off-diagonal), Float64 dot products of FP32 J rows"},
             "nccl_allgather_baseline_ms": sorted(times_ag)[len(times_ag) // 2], "nccl_allgather_same_bits_rank0": same,
             "exchange": "snk_gram_shard_run: cudaMemcpyAsync from peer-mapped (cudaIpc) memory on a copy stream under the MMA main loop; "
-                        "device-side barriers over peer memory; transpose exchange by peer loads inside the symmetrise kernel; "
+                        "device-side barriers over peer memory; transpose exchange by peer loads inside the mirror kernel; "
                         "torch.distributed only carries the IPC handles at set-up",
             "timed": "per-sample gradients into the planes + one snk_gram_shard_run per rank; buffers and IPC mappings set up once"}
 
@@ -698,18 +717,19 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10, cpu_too=False):
     for terms in (3, 1):
         ms = timed(lambda: plan.gram(terms, 0, out=G))
         err = float((G.double() - ref).norm() / ref.norm())
-        mma = (2 if terms == 3 else 1) * 2.0 * K * K * P / (ms * 1e-3) / 1e12
+        mma = gram_block_flops(S, K, K, P, terms, True) / (ms * 1e-3) / 1e12
         useful = 2.0 * K * K * P / (ms * 1e-3) / 1e12
         traffic, src = ncu_csv_traffic("ncu_gram_5a_terms%d_full" % terms, "k_gram")
         out["terms%d" % terms] = {"ms": ms, "useful_tflops": useful, "mma_tflops": mma,
                                   "frac_of_measured_bf16_peak": mma / peak, "rel_fro_err_vs_fp64": err,
-                                  "roofline": {"bound": "tensor", "achieved": mma, "peak": peak, "unit": "TFLOP/s",
-                                               "frac": mma / peak, "frac_algorithmic": useful / peak, "traffic": traffic,
+                                  "roofline": {"bound": "tensor", "achieved": useful, "peak": peak, "unit": "TFLOP/s",
+                                               "frac": useful / peak, "achieved_executed": mma, "frac_executed": mma / peak, "traffic": traffic,
                                                "algorithmic_bytes": (2 if terms == 3 else 1) * 2.0 * K * ((P + 63) // 64 * 64),
                                                "traffic_source": src,
-                                               "note": "achieved = executed MMA FLOP (the hi/lo split runs 2 products per k-step); frac_algorithmic = "
-                                                       "SURVEY 8(d)'s 2 K^2 P / time / peak; time covers the tile kernel + the split-K/symmetrise pass; "
-                                                       "traffic = ncu dram bytes of the tile kernel actually run, algorithmic_bytes = the bf16 planes read once"}}
+                                               "note": "achieved = SURVEY 8(d)'s 2 K^2 P / time; executed = the tiles actually computed (upper-triangle tiles of the "
+                                                       "padded problem) x products per k-step (3 for the hi/lo split); time covers the tile kernel + the "
+                                                       "split-K/mirror pass; traffic = ncu dram bytes of the tile kernel actually run, algorithmic_bytes = the "
+                                                       "bf16 planes read once"}}
     Ab = A.to(torch.bfloat16)
     ms = timed(lambda: torch.matmul(Ab, Ab.T))
     out["cublas_bf16_same_shape_ms"] = ms

@@ -253,12 +253,12 @@ SNK_API int snk_qnet_overflow_host(snk_qnet q, int *flag);
  * Row i of J = d huber(q_net(s_i)[a_i], y_i) / d theta, theta in Flux.destructure order (181,395 columns) — the per-sample
  * term of the batch loss, without its 1/B.  BASELINE config 5b takes the Gram of these rows over the replay buffer.
  * states (10,10,2,B) f32 and actions (B) u8 0-based as snk_replay_gather returns them, targets (B) Float64 as
- * snk_masked_target returns them.  Outputs (each optional): the bf16 planes hi / lo2 = 2 (v - hi) with a row pitch of
+ * snk_masked_target returns them.  Outputs (each optional): the bf16 planes hi / lo = bf16(v - hi) with a row pitch of
  * pitch_elems (exactly what snk_gram_block / snk_gram_shard_run(A_rows = NULL) consume: snk_gram_shard_planes,
  * snk_gram_planes_layout), J_f32 (B x ldJ) Float32, loss (B) Float32.  Computed in FP32 from the Float32 weights whatever
  * the handle's forward precision is. */
 SNK_API int snk_qnet_sample_grads(snk_qnet q, const float *states, const uint8_t *actions, const double *targets, int64_t B,
-                                  void *hi, void *lo2, int64_t pitch_elems, float *J_f32, int64_t ldJ, float *loss,
+                                  void *hi, void *lo, int64_t pitch_elems, float *J_f32, int64_t ldJ, float *loss,
                                   void *cuda_stream);
 /* profiling aid (SNK_QNET_BF16): device buffer of 512 int64 that receives clock64 stamps of the conv phases of CTA 0 on every
  * later forward (64 slots for each of its first 8 iterations, tools/qnet_phases17.py); NULL switches it off */
@@ -280,10 +280,11 @@ SNK_API int snk_d_store_snapshot(double *D, int64_t P, int64_t K, int64_t positi
 /* ---- Gram of the deviation matrix  plot_traj.jl:10-16 (svd(D), S.^2/(K-1) = eig(D'D)/(K-1)) ------------
  * G = A A^T with A = D^T: A is K x P row-major (row k = snapshot k) — byte-identical to Julia's P x K
  * column-major deviation_matrix.  G is K x K Float32 row-major (symmetric).
- *   snk_gram_pack  splits A (Float64 or Float32) into bf16 hi and 2*lo planes inside the workspace;
+ *   snk_gram_pack  splits A (Float64 or Float32) into bf16 hi and lo planes inside the workspace;
  *   snk_gram       runs the tcgen05 kernel (TMA loads, TMEM accumulators) + the deterministic split-K
  *                  reduction.  terms = 1: hi hi^T (bf16 inputs, ~3 digits); terms = 3: hi hi^T + hi lo^T + lo hi^T
- *                  (~2^-17 relative per product), computed as Y = hi hi^T + hi (2 lo)^T, G = (Y + Y^T)/2.
+ *                  (~2^-17 relative per product), all three into one accumulator.  Only the tiles that meet the upper
+ *                  triangle are computed; the reduction mirrors them, so G is exactly symmetric.
  *   block_k: 32 or 64 (0 = default); splits: split-K factor (0 = fill the SMs); the same `splits` must be
  *   given to snk_gram_workspace_bytes. */
 #define SNK_DTYPE_F32 1
@@ -296,28 +297,34 @@ SNK_API int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int
                      void *cuda_stream);
 
 /* ---- block-wise pieces, for the row-sharded multi-GPU Gram (rank g owns rows_g of A) -----------
- * planes: bf16 [rows][pitch] arrays hi and 2*lo (snk_gram_planes_layout gives bytes per plane and the pitch).
- * snk_gram_block:  Y (rows_a x rows_b, ld ldY) = hi_a hi_b^T [+ hi_a (2 lo_b)^T]; b planes may be a local copy of a
- *                  peer's planes.  scratch: snk_gram_block_scratch_bytes.
- * snk_gram_symmetrize_block: G_block = (Y + YT^T)/2 where YT is the (rows_b x rows_a) block the OTHER rank
+ * planes: bf16 [rows][pitch] arrays hi and lo (snk_gram_planes_layout gives bytes per plane and the pitch).
+ * snk_gram_block:  Y (rows_a x rows_b, ld ldY) = hi_a hi_b^T [+ hi_a lo_b^T + lo_a hi_b^T]: a finished block of G; the b
+ *                  planes may be a local copy of a peer's planes.  symmetric != 0 (same planes on both sides): only the
+ *                  tiles meeting the upper triangle are computed, the rest is mirrored.  scratch:
+ *                  snk_gram_block_scratch_bytes.  snk_gram_block_flops: what the tensor pipe executes for such a block
+ *                  (computed tiles, padded, x products) — the numerator of an MMA-rate figure.
+ * snk_gram_transpose_block: G_block (rows_a x rows_b) = YT^T where YT is the (rows_b x rows_a) block ANOTHER rank
  *                  computed; YT may be a peer-memory pointer (the kernel reads it with plain loads over NVLink). */
 SNK_API int snk_gram_planes_layout(int64_t rows, int64_t P, size_t *plane_bytes, int64_t *pitch_elems);
-SNK_API int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, void *hi, void *lo2, void *cuda_stream);
+SNK_API int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, void *hi, void *lo, void *cuda_stream);
 SNK_API int snk_gram_block_scratch_bytes(int64_t rows_a, int64_t rows_b, int64_t P, int splits, size_t *bytes);
-SNK_API int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, const void *b_lo2, int64_t rows_b, int64_t P,
-                           int terms, int block_k, int splits, void *scratch, float *Y, int64_t ldY, void *cuda_stream);
-SNK_API int snk_gram_symmetrize_block(const float *Y, int64_t ldY, const float *YT, int64_t ldYT, int64_t rows_a,
-                                      int64_t rows_b, float *G, int64_t ldG, void *cuda_stream);
+SNK_API int snk_gram_block(const void *a_hi, const void *a_lo, int64_t rows_a, const void *b_hi, const void *b_lo, int64_t rows_b,
+                           int64_t P, int terms, int symmetric, int block_k, int splits, void *scratch, float *Y, int64_t ldY,
+                           void *cuda_stream);
+SNK_API int snk_gram_block_flops(int64_t rows_a, int64_t rows_b, int64_t P, int terms, int symmetric, double *executed);
+SNK_API int snk_gram_transpose_block(const float *YT, int64_t ldYT, int64_t rows_a, int64_t rows_b, float *G, int64_t ldG,
+                                     void *cuda_stream);
 /* ---- the row-sharded Gram as ONE call per rank (one process per GPU; SURVEY 8b `snk_gram(..., comm)`, BASELINE config 5b)
  * rows_all[world]: rows of A owned by every rank; this rank owns rows_all[rank] rows x P.  Set-up, once:
  *   create -> export_host (192 bytes) -> [the host language moves the 192 bytes of every rank to every rank: MPI,
  *   Distributed.jl, torch.distributed, a file ...] -> connect_host(all handles, world x 192 bytes, own entry ignored).
  * snk_gram_shard_run(g, A_rows, ...) then enqueues the whole Gram on `cuda_stream`: pack -> planes ring over NVLink peer
- * memory under the tcgen05 main loop -> (Y + Y^T)/2 with the transposed blocks read from the peers' memory; the phases are
- * separated by a device-side barrier over peer memory (no host synchronisation, no communicator).  Every rank must call
+ * memory under the tcgen05 main loop (G is symmetric: a rank multiplies its rows against its own and the next world/2
+ * ranks' rows only) -> the other blocks are read, transposed, out of the memory of the peers that computed them; the phases
+ * are separated by a device-side barrier over peer memory (no host synchronisation, no communicator).  Every rank must call
  * it the same number of times.  G_rows: (rows x K_total) Float32, leading dimension ldG >= K_total.  A_rows == NULL: the
  * planes (snk_gram_shard_planes) were already written by a producer (snk_qnet_sample_grads).
- * pack / ring / symmetrize / barrier are the phases on their own; connect_local wires shards of ONE process together
+ * pack / ring / mirror / barrier are the phases on their own; connect_local wires shards of ONE process together
  * (virtual ranks on one GPU, used by the tests) — there the caller orders the phases itself. */
 #define SNK_GRAM_SHARD_HANDLE_BYTES 192
 typedef struct snk_gram_shard_s *snk_gram_shard;
@@ -331,9 +338,15 @@ SNK_API int snk_gram_shard_run(snk_gram_shard g, const void *A_rows, int a_dtype
                                int64_t ldG, void *cuda_stream);
 SNK_API int snk_gram_shard_pack(snk_gram_shard g, const void *A_rows, int a_dtype, void *cuda_stream);
 SNK_API int snk_gram_shard_ring(snk_gram_shard g, int terms, int block_k, void *cuda_stream);
-SNK_API int snk_gram_shard_symmetrize(snk_gram_shard g, int terms, float *G_rows, int64_t ldG, void *cuda_stream);
+SNK_API int snk_gram_shard_mirror(snk_gram_shard g, float *G_rows, int64_t ldG, void *cuda_stream);
+/* which blocks rank `rank` of `world` computes in the ring (the rest are mirrored): for step i = 0 .. *steps-1 the peer is
+ * (rank + i) % world; a0/a1[i] = the range of its OWN rows it multiplies, b0/b1[i] = the range of the peer's rows (the last
+ * step of an even world is shared: the lower rank takes the first rows of its own block against all of the peer's, the
+ * higher rank all of its own against the remaining rows of the peer's).  Arrays of world/2 + 1 entries.  Pure arithmetic. */
+SNK_API int snk_gram_shard_schedule(const int64_t *rows_all, int world, int rank, int *steps, int64_t *a0, int64_t *a1, int64_t *b0,
+                                    int64_t *b1);
 SNK_API int snk_gram_shard_barrier(snk_gram_shard g, void *cuda_stream);
-SNK_API int snk_gram_shard_planes(snk_gram_shard g, void **hi, void **lo2, int64_t *pitch_elems);
+SNK_API int snk_gram_shard_planes(snk_gram_shard g, void **hi, void **lo, int64_t *pitch_elems);
 /* SNK_ERR_TIMEOUT if a barrier gave up waiting for a peer (synchronises) */
 SNK_API int snk_gram_shard_status_host(snk_gram_shard g, int *timed_out);
 

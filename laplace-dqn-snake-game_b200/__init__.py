@@ -93,14 +93,16 @@ def lib():
         "snk_gram_planes_layout": [i64, i64, C.POINTER(C.c_size_t), C.POINTER(i64)],
         "snk_gram_pack_planes": [vp, i32, i64, i64, vp, vp, vp],
         "snk_gram_block_scratch_bytes": [i64, i64, i64, i32, C.POINTER(C.c_size_t)],
-        "snk_gram_block": [vp, i64, vp, vp, i64, i64, i32, i32, i32, vp, vp, i64, vp],
-        "snk_gram_symmetrize_block": [vp, i64, vp, i64, i64, i64, vp, i64, vp],
+        "snk_gram_block": [vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, i32, vp, vp, i64, vp],
+        "snk_gram_block_flops": [i64, i64, i64, i32, i32, C.POINTER(C.c_double)],
+        "snk_gram_transpose_block": [vp, i64, i64, i64, vp, i64, vp],
         "snk_gram_shard_create": [C.POINTER(vp), vp, i32, i32, i64, i32, i32], "snk_gram_shard_destroy": [vp],
         "snk_gram_shard_export_host": [vp, vp], "snk_gram_shard_connect_host": [vp, vp],
         "snk_gram_shard_connect_local": [vp, vp],
         "snk_gram_shard_run": [vp, vp, i32, i32, i32, vp, i64, vp],
         "snk_gram_shard_pack": [vp, vp, i32, vp], "snk_gram_shard_ring": [vp, i32, i32, vp],
-        "snk_gram_shard_symmetrize": [vp, i32, vp, i64, vp], "snk_gram_shard_barrier": [vp, vp],
+        "snk_gram_shard_mirror": [vp, vp, i64, vp], "snk_gram_shard_barrier": [vp, vp],
+        "snk_gram_shard_schedule": [vp, i32, i32, C.POINTER(i32), vp, vp, vp, vp],
         "snk_gram_shard_planes": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)],
         "snk_gram_shard_status_host": [vp, C.POINTER(i32)],
         "snk_ipc_alloc": [C.POINTER(vp), C.c_size_t], "snk_ipc_free": [vp],
@@ -451,7 +453,7 @@ class GramPlan:
         return self
 
     def planes(self):
-        """(hi pointer, lo2 pointer, pitch in elements) of the bf16 planes inside the workspace: a producer
+        """(hi pointer, lo pointer, pitch in elements) of the bf16 planes inside the workspace: a producer
         (QNet.sample_grads) can write them instead of pack()"""
         pb, pitch = C.c_size_t(0), C.c_int64(0)
         _check(lib().snk_gram_planes_layout(self.K, self.P, C.byref(pb), C.byref(pitch)))

@@ -9,21 +9,21 @@
 // Precision: tcgen05 has no FP64 kind.  A is split a = hi + lo (+ eps), hi = bf16(a), lo = bf16(a - hi)
 // (|eps| <= 2^-18 |a|), and
 //      a b ~= hi_a hi_b + hi_a lo_b + lo_a hi_b            (the dropped lo_a lo_b is <= 2^-18 |a b|)
-// Because G is symmetric the two cross terms are transposes of each other, so the kernel computes only
-//      Y = hi hi^T + hi (2 lo)^T          (2 MMAs per k-step instead of 3; 2 lo is exact in bf16)
-// with FP32 accumulation in TMEM, and the reduction pass forms  G = (Y + Y^T) / 2.
-// terms = 1 skips the second MMA (plain bf16 inputs, G = Y).
+// All three products of a k-step go into ONE TMEM accumulator (FP32), so a tile comes out finished.  Because G is
+// symmetric only the tiles that meet the upper triangle are computed (3 products each = 1.5 per output tile on
+// average; round 1 computed Y = hi hi^T + hi (2 lo)^T on every tile and G = (Y + Y^T)/2: 2 per tile); the reduction
+// pass mirrors them into the lower triangle, so G is exactly symmetric.  terms = 1 issues only hi hi^T (plain bf16).
 //
 // Kernel: persistent, warp-specialised (canonical sm_100 shape):
 //   warp 0   TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B / 64B boxes) -> smem ring, mbarrier expect_tx
 //   warp 1   MMA issuer     one thread issues tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, D in TMEM;
 //                           tcgen05.commit releases smem stages and publishes the accumulator
-//   warps 2-9 accumulate    every CHUNK_K contraction elements: tcgen05.ld 32x32b.x32 -> += FP32 registers
+//   warps 2-9 accumulate    every CHUNK_K contraction elements (<= 48 MMA steps): tcgen05.ld 32x32b.x32 -> += FP32 registers
 //                           (bounds the tensor core's truncating accumulation chain); at the end of the work
 //                           item the registers go to the partial tile in the workspace
 // Two TMEM accumulator stages (2 x 256 columns): the tensor core fills one while the other is drained.
 // Work item = (128 x 256 output tile, split of the contraction); partial tiles are reduced (deterministically)
-// by k_gram_finish, which also symmetrises.
+// by k_gram_finish, which also mirrors the upper triangle of a symmetric problem.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string.h>
@@ -41,17 +41,20 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;    // 2 accumulator stages x BN fp32 columns
 // The tensor core adds into its FP32 accumulator with truncation: a long chain of positive products (the
 // diagonal of a Gram) drifts low by ~5e-8 per MMA step.  So the TMEM accumulator only ever holds CHUNK_K
-// contraction elements (32 MMA steps per operand pair); the 8 accumulate warps drain it (tcgen05.ld) and add
-// it, round-to-nearest, into FP32 registers while the tensor core fills the other TMEM stage.
-constexpr int CHUNK_K = 512;
+// contraction elements (32 MMA steps for plain bf16, 16 k-slices x 3 products = 48 for the split); the 8 accumulate
+// warps drain it (tcgen05.ld) and add it, round-to-nearest, into FP32 registers while the tensor core fills the other
+// TMEM stage.
+template <int TERMS> constexpr int chunk_k() { return TERMS > 1 ? 256 : 512; }
 
 template <int BK, int TERMS>
 struct Cfg {
     static constexpr int ROW_BYTES = BK * 2;                                   // 64 (SW64) or 128 (SW128)
     static constexpr int A_BYTES = BM * ROW_BYTES;
     static constexpr int B_BYTES = BN * ROW_BYTES;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (TERMS > 1 ? 2 : 1);
+    static constexpr int PLANES = TERMS > 1 ? 2 : 1;                            // stage = [A hi | A lo | B hi | B lo]
+    static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int CH = chunk_k<TERMS>() / BK;                            // k-blocks per TMEM accumulation chunk
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr uint64_t LAYOUT = (BK == 64) ? 2ull /*SWIZZLE_128B*/ : 4ull /*SWIZZLE_64B*/;
     static constexpr uint64_t SBO = (8 * ROW_BYTES) >> 4;                      // 8-row swizzle atom pitch
@@ -163,20 +166,46 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
     tn = panel * PANEL + within - tm * width;
 }
 
+// Symmetric problems (A side == B side) only need the tiles that meet the upper triangle j >= i: row tm (bm rows high)
+// starts at column tile (tm*bm)/BN.  Same column panels, restricted to those tiles; the decode walks panels and rows
+// (a few hundred iterations at most, once per work item of millions of cycles).  Shared by device and host.
+__host__ __device__ inline int sym_tile_coords(int tile, int tiles_m, int tiles_n, int bm, int &tm, int &tn) {
+    int seen = 0;
+    for (int p0 = 0; p0 < tiles_n; p0 += PANEL) {
+        const int p1 = (p0 + PANEL < tiles_n) ? p0 + PANEL : tiles_n;
+        for (int r = 0; r < tiles_m; r++) {
+            const int first = (r * bm) / BN, f = first > p0 ? first : p0;
+            if (f >= p1) break;                       // rows further down start right of this panel
+            const int cnt = p1 - f;
+            if (tile >= 0 && tile < seen + cnt) { tm = r; tn = f + (tile - seen); return seen; }
+            seen += cnt;
+        }
+    }
+    return seen;                                      // tile < 0: the number of tiles
+}
+
 struct GramArgs {
     float *partials;        // [splits][Mt][Nt] fp32, Mt = tiles_m*BM, Nt = tiles_n*BN
     int tiles_m, tiles_n, splits;
+    int n_tiles;            // tiles_m*tiles_n, or the upper-triangle count when sym
+    int sym;
     int kblocks;            // ceil(P / BK)
     int kb_per_split;
     long long ld_part;      // Nt
     long long split_stride; // Mt*Nt
 };
 
+__device__ __forceinline__ void work_coords(const GramArgs &g, int tile, int bm, int &tm, int &tn) {
+    if (g.sym) sym_tile_coords(tile, g.tiles_m, g.tiles_n, bm, tm, tn);
+    else tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
+}
+
 template <int BK, int TERMS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
-       const __grid_constant__ CUtensorMap map_b_hi,   // hi, box BN rows x BK
-       const __grid_constant__ CUtensorMap map_b_lo,   // 2*lo, box BN rows x BK
+k_gram(const __grid_constant__ CUtensorMap map_a_hi,   // A side hi, box BM rows x BK
+       const __grid_constant__ CUtensorMap map_a_lo,   // A side lo
+       const __grid_constant__ CUtensorMap map_b_hi,   // B side hi, box BN rows x BK
+       const __grid_constant__ CUtensorMap map_b_lo,   // B side lo
        const GramArgs g) {
     using C = Cfg<BK, TERMS>;
     extern __shared__ uint8_t smem_raw[];
@@ -186,12 +215,13 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
     uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_work = g.tiles_m * g.tiles_n * g.splits;
+    const int n_tiles = g.n_tiles;
+    const int n_work = n_tiles * g.splits;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_a_hi);
         tma_prefetch_desc(&map_b_hi);
-        if (TERMS > 1) tma_prefetch_desc(&map_b_lo);
+        if (TERMS > 1) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
         for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NUM_EPI_WARPS); }
         fence_barrier_init();
@@ -208,19 +238,21 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
             int stage = 0;
             uint32_t phase = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int n_tiles = g.tiles_m * g.tiles_n;
                 const int split = w / n_tiles, tile = w % n_tiles;      // split-major: concurrent CTAs share a k-range
                 int tm, tn;
-                tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
+                work_coords(g, tile, BM, tm, tn);
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * C::STAGE_BYTES;
                     mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-                    tma_load_2d(&map_a, &full[stage], st, kb * BK, tm * BM);
-                    tma_load_2d(&map_b_hi, &full[stage], st + C::A_BYTES, kb * BK, tn * BN);
-                    if (TERMS > 1) tma_load_2d(&map_b_lo, &full[stage], st + C::A_BYTES + C::B_BYTES, kb * BK, tn * BN);
+                    tma_load_2d(&map_a_hi, &full[stage], st, kb * BK, tm * BM);
+                    tma_load_2d(&map_b_hi, &full[stage], st + C::PLANES * C::A_BYTES, kb * BK, tn * BN);
+                    if (TERMS > 1) {
+                        tma_load_2d(&map_a_lo, &full[stage], st + C::A_BYTES, kb * BK, tm * BM);
+                        tma_load_2d(&map_b_lo, &full[stage], st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, tn * BN);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -228,11 +260,11 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
-            constexpr int CH = CHUNK_K / BK;                          // k-blocks per TMEM accumulation chunk
+            constexpr int CH = C::CH;                                 // k-blocks per TMEM accumulation chunk
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int split = w / (g.tiles_m * g.tiles_n);
+                const int split = w / n_tiles;
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
                 for (int kb = kb0; kb < kb1; kb++) {
@@ -245,14 +277,18 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
                     mbar_wait(&full[stage], phase);                   // TMA bytes have landed
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint64_t a_desc = make_desc<BK, TERMS>(a_addr);
-                    const uint64_t bh_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES);
-                    const uint64_t bl_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES + C::B_BYTES);
+                    const uint64_t ah_desc = make_desc<BK, TERMS>(a_addr);
+                    const uint64_t al_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES);
+                    const uint64_t bh_desc = make_desc<BK, TERMS>(a_addr + C::PLANES * C::A_BYTES);
+                    const uint64_t bl_desc = make_desc<BK, TERMS>(a_addr + 2 * C::A_BYTES + C::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B along K inside the swizzled row
-                        umma_bf16(d_tmem, a_desc + adv, bh_desc + adv, IDESC, (in_chunk > 0 || k > 0) ? 1u : 0u);
-                        if (TERMS > 1) umma_bf16(d_tmem, a_desc + adv, bl_desc + adv, IDESC, 1u);
+                        umma_bf16(d_tmem, ah_desc + adv, bh_desc + adv, IDESC, (in_chunk > 0 || k > 0) ? 1u : 0u);
+                        if (TERMS > 1) {
+                            umma_bf16(d_tmem, ah_desc + adv, bl_desc + adv, IDESC, 1u);
+                            umma_bf16(d_tmem, al_desc + adv, bh_desc + adv, IDESC, 1u);
+                        }
                     }
                     umma_commit(&empty[stage]);                       // frees the smem stage when the MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -265,16 +301,15 @@ k_gram(const __grid_constant__ CUtensorMap map_a,      // hi, box BM rows x BK
         }
     } else {
         // ================= accumulate warps: TMEM chunk -> += registers; then -> partial tile =================
-        constexpr int CH = CHUNK_K / BK;
+        constexpr int CH = C::CH;
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                             // which 128 columns of the 256-wide tile
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int n_tiles = g.tiles_m * g.tiles_n;
             const int split = w / n_tiles, tile = w % n_tiles;
             int tm, tn;
-                tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
+            work_coords(g, tile, BM, tm, tn);
             const int kb0 = split * g.kb_per_split;
             const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
             const int n_chunks = (kb1 - kb0 + CH - 1) / CH;
@@ -361,16 +396,19 @@ struct Cfg2 {
     static constexpr int ROW_BYTES = BK * 2;
     static constexpr int A_BYTES = BM * ROW_BYTES;            // 128 rows per CTA
     static constexpr int B_BYTES = (BN / 2) * ROW_BYTES;      // half of the 256 B rows per CTA
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (TERMS > 1 ? 2 : 1);
+    static constexpr int PLANES = TERMS > 1 ? 2 : 1;
+    static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int CH = chunk_k<TERMS>() / BK;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
 template <int BK, int TERMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box 128 rows x BK
+k_gram2(const __grid_constant__ CUtensorMap map_a_hi,   // hi of the A side, box 128 rows x BK
+        const __grid_constant__ CUtensorMap map_a_lo,   // lo of the A side
         const __grid_constant__ CUtensorMap map_b_hi,   // hi of the B side, box 128 rows x BK
-        const __grid_constant__ CUtensorMap map_b_lo,   // 2*lo of the B side, box 128 rows x BK
+        const __grid_constant__ CUtensorMap map_b_lo,   // lo of the B side
         const GramArgs g) {
     using C = Cfg2<BK, TERMS>;
     extern __shared__ uint8_t smem_raw[];
@@ -382,13 +420,13 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int n_tiles = g.tiles_m * g.tiles_n;
+    const int n_tiles = g.n_tiles;
     const int n_work = n_tiles * g.splits;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_a_hi);
         tma_prefetch_desc(&map_b_hi);
-        if (TERMS > 1) tma_prefetch_desc(&map_b_lo);
+        if (TERMS > 1) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
         for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * NUM_EPI_WARPS); }
         fence_barrier_init();
@@ -407,17 +445,20 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
             for (int w = cluster_id; w < n_work; w += n_clusters) {
                 const int split = w / n_tiles, tile = w % n_tiles;
                 int tm, tn;
-                tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
+                work_coords(g, tile, BM2, tm, tn);
                 const int kb0 = split * g.kb_per_split;
                 const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
+                const int row_a = tm * BM2 + (int)rank * BM, row_b = tn * BN + (int)rank * (BN / 2);
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *st = smem + stage * C::STAGE_BYTES;
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);      // both CTAs' bytes land here
-                    tma_load_2d_pair(&map_a, &full[stage], st, kb * BK, tm * BM2 + (int)rank * BM);
-                    tma_load_2d_pair(&map_b_hi, &full[stage], st + C::A_BYTES, kb * BK, tn * BN + (int)rank * (BN / 2));
-                    if (TERMS > 1)
-                        tma_load_2d_pair(&map_b_lo, &full[stage], st + C::A_BYTES + C::B_BYTES, kb * BK, tn * BN + (int)rank * (BN / 2));
+                    tma_load_2d_pair(&map_a_hi, &full[stage], st, kb * BK, row_a);
+                    tma_load_2d_pair(&map_b_hi, &full[stage], st + C::PLANES * C::A_BYTES, kb * BK, row_b);
+                    if (TERMS > 1) {
+                        tma_load_2d_pair(&map_a_lo, &full[stage], st + C::A_BYTES, kb * BK, row_a);
+                        tma_load_2d_pair(&map_b_lo, &full[stage], st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -425,7 +466,7 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
     } else if (warp == 1) {
         // ================= MMA issuer: one thread of the leader CTA =================
         if (lane == 0 && rank == 0) {
-            constexpr int CH = CHUNK_K / BK;
+            constexpr int CH = C::CH;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int w = cluster_id; w < n_work; w += n_clusters) {
@@ -442,14 +483,18 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint64_t a_desc = make_desc<BK, TERMS>(a_addr);
-                    const uint64_t bh_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES);
-                    const uint64_t bl_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES + C::B_BYTES);
+                    const uint64_t ah_desc = make_desc<BK, TERMS>(a_addr);
+                    const uint64_t al_desc = make_desc<BK, TERMS>(a_addr + C::A_BYTES);
+                    const uint64_t bh_desc = make_desc<BK, TERMS>(a_addr + C::PLANES * C::A_BYTES);
+                    const uint64_t bl_desc = make_desc<BK, TERMS>(a_addr + 2 * C::A_BYTES + C::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-                        umma2_bf16(d_tmem, a_desc + adv, bh_desc + adv, IDESC2, (in_chunk > 0 || k > 0) ? 1u : 0u);
-                        if (TERMS > 1) umma2_bf16(d_tmem, a_desc + adv, bl_desc + adv, IDESC2, 1u);
+                        umma2_bf16(d_tmem, ah_desc + adv, bh_desc + adv, IDESC2, (in_chunk > 0 || k > 0) ? 1u : 0u);
+                        if (TERMS > 1) {
+                            umma2_bf16(d_tmem, ah_desc + adv, bl_desc + adv, IDESC2, 1u);
+                            umma2_bf16(d_tmem, al_desc + adv, bh_desc + adv, IDESC2, 1u);
+                        }
                     }
                     umma2_commit_mc(&empty[stage]);                   // frees the stage in both CTAs
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -462,7 +507,7 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
         }
     } else {
         // ================= accumulate warps (both CTAs): own 128 rows of the 256 x 256 tile =================
-        constexpr int CH = CHUNK_K / BK;
+        constexpr int CH = C::CH;
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         int acc = 0;
@@ -470,7 +515,7 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
         for (int w = cluster_id; w < n_work; w += n_clusters) {
             const int split = w / n_tiles, tile = w % n_tiles;
             int tm, tn;
-                tile_coords(tile, g.tiles_m, g.tiles_n, tm, tn);
+            work_coords(g, tile, BM2, tm, tn);
             const int kb0 = split * g.kb_per_split;
             const int kb1 = min(kb0 + g.kb_per_split, g.kblocks);
             const int n_chunks = (kb1 - kb0 + CH - 1) / CH;
@@ -510,12 +555,12 @@ k_gram2(const __grid_constant__ CUtensorMap map_a,      // hi of the A side, box
     }
 }
 
-// D (P x K column-major, i.e. row k of A contiguous) -> hi[k][p], lo2[k][p] bf16 with row pitch Ppad.
+// D (P x K column-major, i.e. row k of A contiguous) -> hi[k][p], lo[k][p] bf16 with row pitch Ppad.
 // One thread packs 8 consecutive elements: eight coalesced scalar loads (rows of odd length start unaligned), one
 // 16-byte store per plane.  HBM-bound: reads the source once, writes 4 bytes per element.
 template <typename T>
 __global__ void k_gram_pack(const T *__restrict__ A, long long P, long long K, long long Ppad,
-                            __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo2) {
+                            __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
     const long long k = blockIdx.y;
     const T *row = A + k * P;
     for (long long p8 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; p8 < Ppad; p8 += (long long)gridDim.x * blockDim.x * 8) {
@@ -528,23 +573,23 @@ __global__ void k_gram_pack(const T *__restrict__ A, long long P, long long K, l
             __nv_bfloat16 hh[2], ll[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                // 2*lo: exact scaling, folds the 1/2 of (Y + Y^T)/2.  For fp32 input the remainder a - hi is exact in fp32,
-                // so the fp32 path gives the same bits as the fp64 one without the emulated double->bf16 conversions.
+                // For fp32 input the remainder a - hi is exact in fp32, so the fp32 path gives the same bits as the fp64
+                // one without the emulated double->bf16 conversions.
                 if constexpr (sizeof(T) == 4) {
                     const float v = (float)a[2 * j + e];
                     hh[e] = __float2bfloat16_rn(v);
-                    ll[e] = __float2bfloat16_rn(2.0f * (v - __bfloat162float(hh[e])));
+                    ll[e] = __float2bfloat16_rn(v - __bfloat162float(hh[e]));
                 } else {
                     const double v = (double)a[2 * j + e];
                     hh[e] = __double2bfloat16(v);
-                    ll[e] = __double2bfloat16(2.0 * (v - (double)__bfloat162float(hh[e])));
+                    ll[e] = __double2bfloat16(v - (double)__bfloat162float(hh[e]));
                 }
             }
             h[j] = (uint32_t)__bfloat16_as_ushort(hh[0]) | ((uint32_t)__bfloat16_as_ushort(hh[1]) << 16);
             l[j] = (uint32_t)__bfloat16_as_ushort(ll[0]) | ((uint32_t)__bfloat16_as_ushort(ll[1]) << 16);
         }
         *reinterpret_cast<uint4 *>(hi + k * Ppad + p8) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4 *>(lo2 + k * Ppad + p8) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4 *>(lo + k * Ppad + p8) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -585,7 +630,7 @@ static int make_map(CUtensorMap *m, const void *base, long long rows, long long 
 
 struct Plan {
     long long rows_a, rows_b, P, Ppad, Mt, Nt;
-    int tiles_m, tiles_n, splits, kblocks, kb_per_split, bk, pair;
+    int tiles_m, tiles_n, n_tiles, sym, splits, kblocks, kb_per_split, bk, pair;
     size_t scratch_bytes;
 };
 
@@ -593,7 +638,7 @@ static int g_cta_group = 2;      // 2 = CTA-pair kernel (k_gram2), 1 = single-CT
 
 static long long pitch_of(long long P) { return (P + 63) / 64 * 64; }
 
-static void make_plan(long long rows_a, long long rows_b, long long P, int bk, int splits_req, Plan *pl, int terms = 3) {
+static void make_plan(long long rows_a, long long rows_b, long long P, int bk, int splits_req, Plan *pl, int terms, int sym) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -610,8 +655,21 @@ static void make_plan(long long rows_a, long long rows_b, long long P, int bk, i
     pl->Mt = (long long)pl->tiles_m * bm;
     pl->Nt = (long long)pl->tiles_n * BN;
     pl->kblocks = (int)((P + bk - 1) / bk);
-    int tiles = pl->tiles_m * pl->tiles_n;
-    int splits = splits_req > 0 ? splits_req : (tiles >= units ? 1 : (2 * units) / tiles);   // ~2 work items per CTA: the second's main loop hides the first's epilogue (measured best at K=1000: 9 splits)
+    int tm_ = 0, tn_ = 0;
+    pl->sym = sym;
+    pl->n_tiles = sym ? sym_tile_coords(-1, pl->tiles_m, pl->tiles_n, bm, tm_, tn_) : pl->tiles_m * pl->tiles_n;
+    int tiles = pl->n_tiles;
+    // split-K fills the machine when there are fewer tiles than CTAs (or pairs): one round of work items, or two when that
+    // wastes noticeably fewer slots (measured at K=1000, 10 upper-triangle tiles on 74 pairs: 7 splits 0.441 ms, 14 splits 0.452)
+    int splits = splits_req;
+    if (splits <= 0) {
+        splits = 1;
+        if (tiles < units) {
+            const int s1 = units / tiles, s2 = (2 * units) / tiles;
+            const double e1 = (double)tiles * s1 / units, e2 = (double)tiles * s2 / (2.0 * units);
+            splits = e2 > e1 + 0.03 ? s2 : s1;
+        }
+    }
     if (splits > pl->kblocks) splits = pl->kblocks;
     if (splits > 64) splits = 64;
     pl->kb_per_split = (pl->kblocks + splits - 1) / splits;
@@ -620,73 +678,88 @@ static void make_plan(long long rows_a, long long rows_b, long long P, int bk, i
 }
 
 template <int BK, int TERMS>
-static int launch(const Plan &pl, const void *a_hi, const void *b_hi, const void *b_lo, float *scratch, cudaStream_t st) {
+static int launch(const Plan &pl, const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo, float *scratch,
+                  cudaStream_t st) {
     using C = Cfg<BK, TERMS>;
-    CUtensorMap ma, mbh, mbl;
+    if (TERMS == 1) { a_lo = a_hi; b_lo = b_hi; }               // the lo maps are never dereferenced then
+    const int box_b = pl.pair ? BN / 2 : BN;                     // the pair stages half a B tile per CTA
+    CUtensorMap mah, mal, mbh, mbl;
     int rc;
-    if ((rc = make_map(&ma, a_hi, pl.rows_a, pl.P, pl.Ppad, BM, BK)) != SNK_OK) return rc;
-    if ((rc = make_map(&mbh, b_hi, pl.rows_b, pl.P, pl.Ppad, BN, BK)) != SNK_OK) return rc;
-    if ((rc = make_map(&mbl, TERMS > 1 ? b_lo : b_hi, pl.rows_b, pl.P, pl.Ppad, BN, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&mah, a_hi, pl.rows_a, pl.P, pl.Ppad, BM, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&mal, a_lo, pl.rows_a, pl.P, pl.Ppad, BM, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&mbh, b_hi, pl.rows_b, pl.P, pl.Ppad, box_b, BK)) != SNK_OK) return rc;
+    if ((rc = make_map(&mbl, b_lo, pl.rows_b, pl.P, pl.Ppad, box_b, BK)) != SNK_OK) return rc;
     GramArgs g;
     g.partials = scratch;
-    g.tiles_m = pl.tiles_m; g.tiles_n = pl.tiles_n; g.splits = pl.splits; g.kblocks = pl.kblocks;
-    g.kb_per_split = pl.kb_per_split; g.ld_part = pl.Nt; g.split_stride = pl.Mt * pl.Nt;
+    g.tiles_m = pl.tiles_m; g.tiles_n = pl.tiles_n; g.n_tiles = pl.n_tiles; g.sym = pl.sym; g.splits = pl.splits;
+    g.kblocks = pl.kblocks; g.kb_per_split = pl.kb_per_split; g.ld_part = pl.Nt; g.split_stride = pl.Mt * pl.Nt;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int n_work = pl.tiles_m * pl.tiles_n * pl.splits;
+    int n_work = pl.n_tiles * pl.splits;
     if (pl.pair) {
         using C2 = Cfg2<BK, TERMS>;
-        CUtensorMap mb2h, mb2l;                                  // B side in 128-row boxes (each CTA stages half a tile)
-        if ((rc = make_map(&mb2h, b_hi, pl.rows_b, pl.P, pl.Ppad, BN / 2, BK)) != SNK_OK) return rc;
-        if ((rc = make_map(&mb2l, TERMS > 1 ? b_lo : b_hi, pl.rows_b, pl.P, pl.Ppad, BN / 2, BK)) != SNK_OK) return rc;
         int pairs = sms / 2;
         int grid2 = 2 * (n_work < pairs ? n_work : pairs);
         SNK_CUDA(cudaFuncSetAttribute(k_gram2<BK, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
-        k_gram2<BK, TERMS><<<grid2, NUM_THREADS, C2::SMEM_BYTES, st>>>(ma, mb2h, mb2l, g);
+        k_gram2<BK, TERMS><<<grid2, NUM_THREADS, C2::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, g);
         SNK_CUDA(cudaGetLastError());
         return SNK_OK;
     }
     int grid = n_work < sms ? n_work : sms;
     SNK_CUDA(cudaFuncSetAttribute(k_gram<BK, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    k_gram<BK, TERMS><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mbh, mbl, g);
+    k_gram<BK, TERMS><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, g);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }
 
-static int run_block(const Plan &pl, int terms, const void *a_hi, const void *b_hi, const void *b_lo, float *scratch,
-                     cudaStream_t st) {
-    if (pl.bk == 64) return terms == 1 ? launch<64, 1>(pl, a_hi, b_hi, b_lo, scratch, st) : launch<64, 3>(pl, a_hi, b_hi, b_lo, scratch, st);
-    return terms == 1 ? launch<32, 1>(pl, a_hi, b_hi, b_lo, scratch, st) : launch<32, 3>(pl, a_hi, b_hi, b_lo, scratch, st);
+static int run_block(const Plan &pl, int terms, const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo,
+                     float *scratch, cudaStream_t st) {
+    if (pl.bk == 64)
+        return terms == 1 ? launch<64, 1>(pl, a_hi, a_lo, b_hi, b_lo, scratch, st) : launch<64, 3>(pl, a_hi, a_lo, b_hi, b_lo, scratch, st);
+    return terms == 1 ? launch<32, 1>(pl, a_hi, a_lo, b_hi, b_lo, scratch, st) : launch<32, 3>(pl, a_hi, a_lo, b_hi, b_lo, scratch, st);
 }
 
-// out[i][j] = sum_s part[s][i][j], or 0.5 * (that + sum_s yt[s][j][i]) when a transposed source is given: the hi/lo
-// split computes Y = hi hi^T + hi (2 lo)^T and G = (Y + Y^T)/2.  yt is row-major with leading dimension ld_yt and may be
-// the same partial buffer (single GPU) or a block in a PEER's memory (row-sharded Gram: plain loads over NVLink).
-// The partials are summed in split order: deterministic.
-__global__ void k_gram_finish(const float *__restrict__ part, int splits, long long split_stride, long long ld_part,
-                              const float *__restrict__ yt, int yt_splits, long long yt_split_stride, long long ld_yt,
-                              int rows_a, int rows_b, float *__restrict__ out, long long ld_out) {
+// out[i][j] = sum_s part[s][i][j], the partials summed in split order (deterministic).  sym: only the tiles meeting the upper
+// triangle hold data; out[i][j] for j >= i comes from the partials and out[j][i] is the same value — G is exactly symmetric.
+__global__ void k_gram_finish(const float *__restrict__ part, int splits, long long split_stride, long long ld_part, int rows_a,
+                              int rows_b, float *__restrict__ out, long long ld_out, int sym) {
     __shared__ float tile[32][33];
     const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
-    if (yt != nullptr) {
-        for (int r = ty; r < 32; r += 8) {                 // coalesced read of yt[bj + r][bi + tx]
-            int i = bj + r, j = bi + tx;
-            float acc = 0.f;
-            if (i < rows_b && j < rows_a)
-                for (int s = 0; s < yt_splits; s++) acc += yt[s * yt_split_stride + (long long)i * ld_yt + j];
-            tile[r][tx] = acc;
-        }
-        __syncthreads();
-    }
+    if (sym && bj < bi) return;
     for (int r = ty; r < 32; r += 8) {
-        int i = bi + r, j = bj + tx;
+        const int i = bi + r, j = bj + tx;
+        float acc = 0.f;
         if (i < rows_a && j < rows_b) {
-            float acc = 0.f;
             for (int s = 0; s < splits; s++) acc += part[s * split_stride + (long long)i * ld_part + j];
-            out[(long long)i * ld_out + j] = (yt != nullptr) ? 0.5f * (acc + tile[tx][r]) : acc;
+            if (!sym || j >= i) out[(long long)i * ld_out + j] = acc;
         }
+        tile[r][tx] = acc;
+    }
+    if (!sym) return;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                     // the mirror image, written row-wise: out[bj + r][bi + tx]
+        const int i = bi + tx, j = bj + r;
+        if (i < rows_a && j < rows_b && j > i) out[(long long)j * ld_out + i] = tile[tx][r];
+    }
+}
+
+// out[i][j] = src[j][i]  (out rows_a x rows_b, src rows_b x rows_a).  src may live in a PEER's memory (row-sharded Gram:
+// the blocks this rank did not compute are the transposes of blocks its peers did) — plain coalesced loads over NVLink.
+__global__ void k_transpose_block(const float *__restrict__ src, long long ld_src, int rows_a, int rows_b, float *__restrict__ out,
+                                  long long ld_out) {
+    __shared__ float tile[32][33];
+    const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 32; r += 8) {
+        const int j = bj + r, i = bi + tx;
+        tile[r][tx] = (j < rows_b && i < rows_a) ? src[(long long)j * ld_src + i] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi + r, j = bj + tx;
+        if (i < rows_a && j < rows_b) out[(long long)i * ld_out + j] = tile[tx][r];
     }
 }
 
@@ -711,18 +784,18 @@ int snk_gram_planes_layout(int64_t rows, int64_t P, size_t *plane_bytes, int64_t
     return SNK_OK;
 }
 
-int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, void *hi, void *lo2, void *cuda_stream) {
+int snk_gram_pack_planes(const void *A, int a_dtype, int64_t P, int64_t rows, void *hi, void *lo, void *cuda_stream) {
     DeviceGuard guard__(device_of(hi));
-    SNK_REQUIRE(A != nullptr && hi != nullptr && lo2 != nullptr && rows > 0 && P > 0, "bad argument");
+    SNK_REQUIRE(A != nullptr && hi != nullptr && lo != nullptr && rows > 0 && P > 0, "bad argument");
     SNK_REQUIRE(a_dtype == SNK_DTYPE_F64 || a_dtype == SNK_DTYPE_F32, "a_dtype must be SNK_DTYPE_F64 or SNK_DTYPE_F32");
     const long long Ppad = pitch_of(P);
     dim3 grid((unsigned)((Ppad / 8 + 255) / 256 < 96 ? (Ppad / 8 + 255) / 256 : 96), (unsigned)rows);
     if (a_dtype == SNK_DTYPE_F64)
         k_gram_pack<double><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const double *)A, P, rows, Ppad, (__nv_bfloat16 *)hi,
-                                                                         (__nv_bfloat16 *)lo2);
+                                                                         (__nv_bfloat16 *)lo);
     else
         k_gram_pack<float><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const float *)A, P, rows, Ppad, (__nv_bfloat16 *)hi,
-                                                                        (__nv_bfloat16 *)lo2);
+                                                                        (__nv_bfloat16 *)lo);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }
@@ -733,49 +806,60 @@ int snk_gram_block_scratch_bytes(int64_t rows_a, int64_t rows_b, int64_t P, int 
     const int saved = g_cta_group;
     for (int cg = 1; cg <= 2; cg++)
         for (int bk = 32; bk <= 64; bk += 32) {
-            for (int terms = 1; terms <= 3; terms += 2) {
-                Plan p;
-                g_cta_group = cg;
-                make_plan(rows_a, rows_b, P, bk, splits, &p, terms);
-                if (p.scratch_bytes > best) best = p.scratch_bytes;
-            }
+            for (int terms = 1; terms <= 3; terms += 2)
+                for (int sym = 0; sym <= (rows_a == rows_b ? 1 : 0); sym++) {
+                    Plan p;
+                    g_cta_group = cg;
+                    make_plan(rows_a, rows_b, P, bk, splits, &p, terms, sym);
+                    if (p.scratch_bytes > best) best = p.scratch_bytes;
+                }
         }
     g_cta_group = saved;
     *bytes = best;
     return SNK_OK;
 }
 
-int snk_gram_block(const void *a_hi, int64_t rows_a, const void *b_hi, const void *b_lo2, int64_t rows_b, int64_t P,
-                   int terms, int block_k, int splits, void *scratch, float *Y, int64_t ldY, void *cuda_stream) {
+int snk_gram_block(const void *a_hi, const void *a_lo, int64_t rows_a, const void *b_hi, const void *b_lo, int64_t rows_b, int64_t P,
+                   int terms, int symmetric, int block_k, int splits, void *scratch, float *Y, int64_t ldY, void *cuda_stream) {
     DeviceGuard guard__(device_of(scratch));
     SNK_REQUIRE(a_hi && b_hi && scratch && Y && rows_a > 0 && rows_b > 0 && P > 0, "bad argument");
-    SNK_REQUIRE(terms == 1 || (terms == 3 && b_lo2 != nullptr), "terms must be 1 (bf16) or 3 (hi/lo split, needs b_lo2)");
+    SNK_REQUIRE(terms == 1 || (terms == 3 && a_lo != nullptr && b_lo != nullptr), "terms must be 1 (bf16) or 3 (hi/lo split, needs both lo planes)");
+    SNK_REQUIRE(!symmetric || (a_hi == b_hi && rows_a == rows_b), "symmetric needs the same planes on both sides");
     if (block_k == 0) block_k = 64;
     SNK_REQUIRE(block_k == 32 || block_k == 64, "block_k must be 32 or 64");
     SNK_REQUIRE(ldY >= rows_b, "ldY too small");
     Plan pl;
-    make_plan(rows_a, rows_b, P, block_k, splits, &pl, terms);
+    make_plan(rows_a, rows_b, P, block_k, splits, &pl, terms, symmetric ? 1 : 0);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    int rc = run_block(pl, terms, a_hi, b_hi, b_lo2, (float *)scratch, st);
+    int rc = run_block(pl, terms, a_hi, a_lo, b_hi, b_lo, (float *)scratch, st);
     if (rc != SNK_OK) return rc;
     dim3 rb(32, 8), rg((unsigned)((rows_b + 31) / 32), (unsigned)((rows_a + 31) / 32));
-    k_gram_finish<<<rg, rb, 0, st>>>((const float *)scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, nullptr, 0, 0, 0, (int)rows_a,
-                                     (int)rows_b, Y, ldY);
+    k_gram_finish<<<rg, rb, 0, st>>>((const float *)scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, (int)rows_a, (int)rows_b, Y, ldY,
+                                     pl.sym);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }
 
-int snk_gram_symmetrize_block(const float *Y, int64_t ldY, const float *YT, int64_t ldYT, int64_t rows_a, int64_t rows_b,
-                              float *G, int64_t ldG, void *cuda_stream) {
+int snk_gram_block_flops(int64_t rows_a, int64_t rows_b, int64_t P, int terms, int symmetric, double *executed) {
+    SNK_REQUIRE(executed != nullptr && rows_a > 0 && rows_b > 0 && P > 0 && (terms == 1 || terms == 3), "bad argument");
+    SNK_REQUIRE(!symmetric || rows_a == rows_b, "symmetric needs a square block");
+    Plan pl;
+    make_plan(rows_a, rows_b, P, 64, 1, &pl, terms, symmetric ? 1 : 0);
+    // what the tensor pipe executes: every computed tile, padded, times the products per k-step
+    *executed = 2.0 * (pl.pair ? BM2 : BM) * BN * (double)pl.Ppad * pl.n_tiles * (terms == 3 ? 3 : 1);
+    return SNK_OK;
+}
+
+int snk_gram_transpose_block(const float *YT, int64_t ldYT, int64_t rows_a, int64_t rows_b, float *G, int64_t ldG, void *cuda_stream) {
     DeviceGuard guard__(device_of(G));
-    SNK_REQUIRE(Y && YT && G && rows_a > 0 && rows_b > 0, "bad argument");
+    SNK_REQUIRE(YT && G && rows_a > 0 && rows_b > 0 && ldYT >= rows_a && ldG >= rows_b, "bad argument");
     dim3 rb(32, 8), rg((unsigned)((rows_b + 31) / 32), (unsigned)((rows_a + 31) / 32));
-    k_gram_finish<<<rg, rb, 0, (cudaStream_t)cuda_stream>>>(Y, 1, 0, ldY, YT, 1, 0, ldYT, (int)rows_a, (int)rows_b, G, ldG);
+    k_transpose_block<<<rg, rb, 0, (cudaStream_t)cuda_stream>>>(YT, ldYT, (int)rows_a, (int)rows_b, G, ldG);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }
 
-// ---- single-GPU convenience: workspace = [hi | lo2 | scratch] ---------------------------------------
+// ---- single-GPU convenience: workspace = [hi | lo | scratch] ---------------------------------------
 int snk_gram_workspace_bytes(int64_t K, int64_t P, int splits, size_t *bytes) {
     SNK_REQUIRE(bytes != nullptr && K > 0 && P > 0 && splits >= 0, "bad argument");
     size_t plane = 0, scratch = 0;
@@ -803,14 +887,13 @@ int snk_gram(const void *workspace, int64_t P, int64_t K, int terms, int block_k
     const uint8_t *ws = (const uint8_t *)workspace;
     float *scratch = (float *)(ws + 2 * plane);
     Plan pl;
-    make_plan(K, K, P, block_k, splits, &pl, terms);
+    make_plan(K, K, P, block_k, splits, &pl, terms, 1);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    int rc = run_block(pl, terms, ws, ws, ws + plane, scratch, st);
+    int rc = run_block(pl, terms, ws, ws + plane, ws, ws + plane, scratch, st);
     if (rc != SNK_OK) return rc;
-    // G = sum of the split partials; for the hi/lo split also G = (Y + Y^T)/2, Y^T read from the same partials
+    // G = sum of the split partials of the upper-triangle tiles, mirrored into the lower triangle
     dim3 rb(32, 8), rg((unsigned)((K + 31) / 32), (unsigned)((K + 31) / 32));
-    k_gram_finish<<<rg, rb, 0, st>>>(scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, terms > 1 ? scratch : nullptr, pl.splits,
-                                     pl.Mt * pl.Nt, pl.Nt, (int)K, (int)K, G, K);
+    k_gram_finish<<<rg, rb, 0, st>>>(scratch, pl.splits, pl.Mt * pl.Nt, pl.Nt, (int)K, (int)K, G, K, 1);
     SNK_CUDA(cudaGetLastError());
     return SNK_OK;
 }

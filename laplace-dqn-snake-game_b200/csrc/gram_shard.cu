@@ -2,14 +2,17 @@
 // snk_gram_shard per rank (= per process, one GPU each), ONE call per rank and Gram (snk_gram_shard_run).
 //
 // Rank g owns rows_g of A (K_total x P).  G[rows_g, :] needs every other rank's rows — the one real exchange on the path:
-//   1. pack: my rows -> bf16 planes (hi, 2 lo) in cudaIpc-exportable memory (or written there directly by a producer,
+//   1. pack: my rows -> bf16 planes (hi, lo) in cudaIpc-exportable memory (or written there directly by a producer,
 //      snk_qnet_sample_grads);
 //   2. planes ring: at step i my rows are multiplied against the planes of rank (g+i) % R while the planes of rank
 //      (g+i+1) % R are copied from that peer's memory over NVLink into the other half of a double buffer on a copy
 //      stream — the all-gather never exists as a separate phase, it hides under the tcgen05 main loop;
-//         Y[rows_g, rows_p] = hi_g hi_p^T + hi_g (2 lo_p)^T
-//   3. G = (Y + Y^T)/2: the symmetrise kernel reads the transposed block Y[rows_p, rows_g] straight out of rank p's
-//      memory (peer loads over NVLink) — the transpose all-to-all is fused into that kernel.
+//         Y[rows_g, rows_p] = hi_g hi_p^T + hi_g lo_p^T + lo_g hi_p^T        (a finished block of G)
+//      G is symmetric, so the ring stops half way: i = 0 (my own block, upper-triangle tiles only) .. R/2; the step
+//      R/2 of an even R is shared between the two ranks of the pair (snk_gram_shard_schedule);
+//   3. mirror: the blocks I did not compute are the transposes of blocks my peers did — the transpose kernel reads
+//      Y[rows_p, rows_g] straight out of rank p's memory (peer loads over NVLink), the transpose all-to-all is fused
+//      into that kernel.
 // The three phases are separated by a DEVICE-side barrier over peer memory (k_peer_barrier: every rank stores its epoch
 // into a slot of every peer's flag array and spins on its own array), so a run is a pure stream of kernels and copies:
 // no host synchronisation, no communicator.  The host language only has to move 192 bytes of IPC handles per rank once
@@ -53,6 +56,25 @@ __global__ void k_peer_barrier(PeerFlags peers, unsigned long long *mine, int wo
     __threadfence_system();
 }
 
+// the ring schedule of one rank (see snk_gram_shard_schedule in the header)
+struct Step { long long a0, a1, b0, b1; };
+// where the two ranks of a pair divide the lower rank's rows.  Rounding to the 256-row tile would not shorten the longer side
+// (6,250 rows: 13 x 25 tiles against 25 x 13 either way), so the split is simply even.
+static long long split_point(long long rows) { return rows / 2; }
+static int schedule(const long long *rows_all, int world, int rank, Step *out) {
+    const int steps = world / 2 + 1;
+    for (int i = 0; i < steps; i++) {
+        const int p = (rank + i) % world;
+        Step s = {0, rows_all[rank], 0, rows_all[p]};
+        if (i > 0 && world % 2 == 0 && i == world / 2) {
+            if (rank < p) s.a1 = split_point(rows_all[rank]);
+            else s.b0 = split_point(rows_all[p]);
+        }
+        out[i] = s;
+    }
+    return steps;
+}
+
 }  // namespace gram_shard
 }  // namespace snk
 
@@ -64,7 +86,7 @@ struct snk_gram_shard_s {
     long long P, rows, K, max_rows, pitch;
     size_t plane_bytes;
     std::vector<long long> rows_all, col0;
-    uint8_t *planes;                 // [hi | lo2] of my rows (exported)
+    uint8_t *planes;                 // [hi | lo] of my rows (exported)
     uint8_t *stage[2];               // peers' planes, double buffered
     float *Y;                        // my row block of Y: rows x K (exported)
     void *scratch;
@@ -112,8 +134,17 @@ int snk_gram_shard_create(snk_gram_shard *out, const int64_t *rows_all, int worl
     int64_t pitch = 0;
     snk_gram_planes_layout(mx, P, &g->plane_bytes, &pitch);
     g->pitch = pitch;
-    size_t sb = 0;
-    snk_gram_block_scratch_bytes(g->rows, mx, P, splits, &sb);
+    size_t sb = 0;                                   // the largest split-K scratch any block of my schedule needs
+    {
+        Step sch[MAX_WORLD];
+        const int steps = schedule(g->rows_all.data(), world, rank, sch);
+        for (int i = 0; i < steps; i++) {
+            size_t need = 0;
+            if (sch[i].a1 > sch[i].a0 && sch[i].b1 > sch[i].b0)
+                snk_gram_block_scratch_bytes(sch[i].a1 - sch[i].a0, sch[i].b1 - sch[i].b0, P, splits, &need);
+            if (need > sb) sb = need;
+        }
+    }
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes < 256 ? 256 : bytes); };
     A((void **)&g->planes, 2 * g->plane_bytes);
@@ -188,10 +219,10 @@ int snk_gram_shard_connect_local(snk_gram_shard g, const snk_gram_shard *peers) 
     return SNK_OK;
 }
 
-int snk_gram_shard_planes(snk_gram_shard g, void **hi, void **lo2, int64_t *pitch_elems) {
+int snk_gram_shard_planes(snk_gram_shard g, void **hi, void **lo, int64_t *pitch_elems) {
     SNK_REQUIRE(g != nullptr, "null shard");
     if (hi) *hi = g->planes;
-    if (lo2) *lo2 = g->planes + g->plane_bytes;
+    if (lo) *lo = g->planes + g->plane_bytes;
     if (pitch_elems) *pitch_elems = g->pitch;
     return SNK_OK;
 }
@@ -211,22 +242,43 @@ int snk_gram_shard_barrier(snk_gram_shard g, void *cuda_stream) {
     return SNK_OK;
 }
 
+int snk_gram_shard_schedule(const int64_t *rows_all, int world, int rank, int *steps, int64_t *a0, int64_t *a1, int64_t *b0,
+                            int64_t *b1) {
+    SNK_REQUIRE(rows_all && steps && a0 && a1 && b0 && b1, "null argument");
+    SNK_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world, "bad argument");
+    long long rows[MAX_WORLD];
+    for (int r = 0; r < world; r++) rows[r] = rows_all[r];
+    Step st[MAX_WORLD];
+    *steps = schedule(rows, world, rank, st);
+    for (int i = 0; i < *steps; i++) { a0[i] = st[i].a0; a1[i] = st[i].a1; b0[i] = st[i].b0; b1[i] = st[i].b1; }
+    return SNK_OK;
+}
+
 int snk_gram_shard_ring(snk_gram_shard g, int terms, int block_k, void *cuda_stream) {
     SNK_REQUIRE(g != nullptr && g->connected, "shard not connected");
+    SNK_REQUIRE(terms == 1 || terms == 3, "terms must be 1 (bf16) or 3 (bf16 hi/lo split)");
     DeviceGuard guard(g->device);
     cudaStream_t st = (cudaStream_t)cuda_stream, cs = g->copy;
     const int W = g->world;
+    Step sch[MAX_WORLD];
+    const int steps = schedule(g->rows_all.data(), W, g->rank, sch);
+    const size_t row_bytes = (size_t)g->pitch * 2;
     SNK_CUDA(cudaEventRecord(g->ev_go, st));                      // the peers' planes are ready when the stream gets here
     SNK_CUDA(cudaStreamWaitEvent(cs, g->ev_go, 0));
-    for (int i = 0; i < W; i++) {
+    for (int i = 0; i < steps; i++) {
         const int p = (g->rank + i) % W;
-        if (i + 1 < W) {                                          // prefetch the NEXT peer's planes while this step computes
+        if (i + 1 < steps) {                                      // prefetch the NEXT peer's planes while this step computes
             const int nxt = (g->rank + i + 1) % W;
+            const Step &n = sch[i + 1];
             if (i >= 1) SNK_CUDA(cudaStreamWaitEvent(cs, g->ev_used[i - 1], 0));   // that buffer was the B operand of step i-1
             uint8_t *dst = g->stage[(i + 1) % 2];
-            const size_t used = (size_t)g->rows_all[nxt] * g->pitch * 2;
-            SNK_CUDA(cudaMemcpyAsync(dst, g->peer_planes[nxt], used, cudaMemcpyDefault, cs));
-            SNK_CUDA(cudaMemcpyAsync(dst + g->plane_bytes, g->peer_planes[nxt] + g->plane_bytes, used, cudaMemcpyDefault, cs));
+            const size_t off = (size_t)n.b0 * row_bytes, used = (size_t)(n.b1 - n.b0) * row_bytes;   // only the rows this step reads
+            if (used > 0) {
+                SNK_CUDA(cudaMemcpyAsync(dst + off, g->peer_planes[nxt] + off, used, cudaMemcpyDefault, cs));
+                if (terms > 1)
+                    SNK_CUDA(cudaMemcpyAsync(dst + g->plane_bytes + off, g->peer_planes[nxt] + g->plane_bytes + off, used,
+                                             cudaMemcpyDefault, cs));
+            }
             SNK_CUDA(cudaEventRecord(g->ev_copied[i + 1], cs));
         }
         const uint8_t *b_hi = g->planes;
@@ -234,27 +286,42 @@ int snk_gram_shard_ring(snk_gram_shard g, int terms, int block_k, void *cuda_str
             SNK_CUDA(cudaStreamWaitEvent(st, g->ev_copied[i], 0));
             b_hi = g->stage[i % 2];
         }
-        int rc = snk_gram_block(g->planes, g->rows, b_hi, b_hi + g->plane_bytes, g->rows_all[p], g->P, terms, block_k, g->splits,
-                                g->scratch, g->Y + g->col0[p], g->K, cuda_stream);
-        if (rc != SNK_OK) return rc;
+        const Step &s = sch[i];
+        if (s.a1 > s.a0 && s.b1 > s.b0) {
+            const uint8_t *a_hi = g->planes + (size_t)s.a0 * row_bytes;
+            const uint8_t *bb = b_hi + (size_t)s.b0 * row_bytes;
+            int rc = snk_gram_block(a_hi, a_hi + g->plane_bytes, s.a1 - s.a0, bb, bb + g->plane_bytes, s.b1 - s.b0, g->P, terms,
+                                    i == 0 ? 1 : 0, block_k, g->splits, g->scratch,
+                                    g->Y + (size_t)s.a0 * g->K + g->col0[p] + s.b0, g->K, cuda_stream);
+            if (rc != SNK_OK) return rc;
+        }
         SNK_CUDA(cudaEventRecord(g->ev_used[i], st));
     }
     return SNK_OK;
 }
 
-int snk_gram_shard_symmetrize(snk_gram_shard g, int terms, float *G_rows, int64_t ldG, void *cuda_stream) {
+int snk_gram_shard_mirror(snk_gram_shard g, float *G_rows, int64_t ldG, void *cuda_stream) {
     SNK_REQUIRE(g != nullptr && g->connected && G_rows != nullptr && ldG >= g->K, "bad argument");
     DeviceGuard guard(g->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (terms == 1) {
-        SNK_CUDA(cudaMemcpy2DAsync(G_rows, (size_t)ldG * 4, g->Y, (size_t)g->K * 4, (size_t)g->K * 4, (size_t)g->rows,
-                                   cudaMemcpyDeviceToDevice, st));
-        return SNK_OK;
+    const int W = g->world;
+    Step mine[MAX_WORLD], theirs[MAX_WORLD];
+    const int steps = schedule(g->rows_all.data(), W, g->rank, mine);
+    for (int i = 0; i < steps; i++) {                             // the blocks I computed: out of my Y
+        const int p = (g->rank + i) % W;
+        const Step &s = mine[i];
+        if (s.a1 == s.a0 || s.b1 == s.b0) continue;
+        SNK_CUDA(cudaMemcpy2DAsync(G_rows + (size_t)s.a0 * ldG + g->col0[p] + s.b0, (size_t)ldG * 4,
+                                   g->Y + (size_t)s.a0 * g->K + g->col0[p] + s.b0, (size_t)g->K * 4, (size_t)(s.b1 - s.b0) * 4,
+                                   (size_t)(s.a1 - s.a0), cudaMemcpyDeviceToDevice, st));
     }
-    for (int p = 0; p < g->world; p++) {
-        // rank p's block (rows_p x rows_g) of ITS Y, leading dimension K, read through the peer mapping
-        int rc = snk_gram_symmetrize_block(g->Y + g->col0[p], g->K, g->peer_Y[p] + g->col0[g->rank], g->K, g->rows, g->rows_all[p],
-                                           G_rows + g->col0[p], ldG, cuda_stream);
+    for (int i = 1; i < steps; i++) {                             // the blocks rank q = g - i computed against my rows: transposed
+        const int q = (g->rank - i + W) % W;
+        schedule(g->rows_all.data(), W, q, theirs);
+        const Step &s = theirs[i];                                // q's rows [a0,a1) x my rows [b0,b1), in q's Y
+        if (s.a1 == s.a0 || s.b1 == s.b0) continue;
+        int rc = snk_gram_transpose_block(g->peer_Y[q] + (size_t)s.a0 * g->K + g->col0[g->rank] + s.b0, g->K, s.b1 - s.b0, s.a1 - s.a0,
+                                          G_rows + (size_t)s.b0 * ldG + g->col0[q] + s.a0, ldG, cuda_stream);
         if (rc != SNK_OK) return rc;
     }
     return SNK_OK;
@@ -268,8 +335,8 @@ int snk_gram_shard_run(snk_gram_shard g, const void *A_rows, int a_dtype, int te
     if (A_rows != nullptr && (rc = snk_gram_shard_pack(g, A_rows, a_dtype, cuda_stream)) != SNK_OK) return rc;   // NULL: planes already written
     if ((rc = snk_gram_shard_barrier(g, cuda_stream)) != SNK_OK) return rc;      // every rank's planes are packed
     if ((rc = snk_gram_shard_ring(g, terms, block_k, cuda_stream)) != SNK_OK) return rc;
-    if ((rc = snk_gram_shard_barrier(g, cuda_stream)) != SNK_OK) return rc;      // every rank's Y row block is complete
-    if ((rc = snk_gram_shard_symmetrize(g, terms, G_rows, ldG, cuda_stream)) != SNK_OK) return rc;
+    if ((rc = snk_gram_shard_barrier(g, cuda_stream)) != SNK_OK) return rc;      // every rank's blocks of Y are complete
+    if ((rc = snk_gram_shard_mirror(g, G_rows, ldG, cuda_stream)) != SNK_OK) return rc;
     return snk_gram_shard_barrier(g, cuda_stream);                                // nobody still reads my Y / planes
 }
 

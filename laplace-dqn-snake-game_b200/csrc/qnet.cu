@@ -45,7 +45,7 @@
 namespace snk {
 namespace qgrad {       // qnet_grads.cu
 int launch_sample_grads(const float *theta_dev, const float *states, const uint8_t *actions, const double *targets, long long B,
-                        void *hi, void *lo2, long long pitch, float *J, long long ldJ, float *loss, int sms, cudaStream_t st);
+                        void *hi, void *lo, long long pitch, float *J, long long ldJ, float *loss, int sms, cudaStream_t st);
 }
 namespace qnet {
 
@@ -1334,16 +1334,16 @@ int snk_qnet_destroy(snk_qnet q) {
 
 // per-sample gradients of huber(q_net(s_i)[a_i], y_i) (utils.jl:452-466), always from the Float32 weights: csrc/qnet_grads.cu
 int snk_qnet_sample_grads(snk_qnet q, const float *states, const uint8_t *actions, const double *targets, int64_t B, void *hi,
-                          void *lo2, int64_t pitch_elems, float *J_f32, int64_t ldJ, float *loss, void *cuda_stream) {
+                          void *lo, int64_t pitch_elems, float *J_f32, int64_t ldJ, float *loss, void *cuda_stream) {
     SNK_REQUIRE(q != nullptr && states != nullptr && actions != nullptr && targets != nullptr && B >= 0, "bad argument");
-    SNK_REQUIRE((hi == nullptr) == (lo2 == nullptr), "hi and lo2 planes come together");
+    SNK_REQUIRE((hi == nullptr) == (lo == nullptr), "hi and lo planes come together");
     SNK_REQUIRE(hi != nullptr || J_f32 != nullptr || loss != nullptr, "no output requested");
-    SNK_REQUIRE(hi == nullptr || (pitch_elems >= 181395 && pitch_elems % 8 == 0 && (((uintptr_t)hi | (uintptr_t)lo2) & 15u) == 0),
+    SNK_REQUIRE(hi == nullptr || (pitch_elems >= 181395 && pitch_elems % 8 == 0 && (((uintptr_t)hi | (uintptr_t)lo) & 15u) == 0),
                 "planes need a pitch >= 181395 that is a multiple of 8 elements and 16-byte aligned bases");
     SNK_REQUIRE(J_f32 == nullptr || ldJ >= 181395, "ldJ too small");
     if (B == 0) return SNK_OK;
     DeviceGuard guard(q->device);
-    return qgrad::launch_sample_grads(q->theta, states, actions, targets, B, hi, lo2, pitch_elems, J_f32, ldJ, loss, q->sms,
+    return qgrad::launch_sample_grads(q->theta, states, actions, targets, B, hi, lo, pitch_elems, J_f32, ldJ, loss, q->sms,
                                       (cudaStream_t)cuda_stream);
 }
 

@@ -11,7 +11,7 @@
 // One CTA (10 warps) per sample, all activations and back-propagated signals of the sample in shared memory, plain FP32 FMAs: per
 // sample the contractions are 25..2304 deep — CUDA-core work; the kernel is bound by FP32 issue (14.6 MFLOP per sample) and
 // by the 725 KB (two bf16 planes) it writes per sample.  The row goes STRAIGHT into the bf16 hi / 2 lo planes the Gram
-// kernel consumes (hi = bf16(v), lo2 = bf16(2 (v - hi)): the same split as k_gram_pack), optionally also as Float32.
+// kernel consumes (hi = bf16(v), lo = bf16(v - hi): the same split as k_gram_pack), optionally also as Float32.
 // Weights are read from global memory (L2-resident, 726 KB) through warp-uniform loads: a warp owns an output channel (or
 // a pair), its lanes the output positions.
 #include <cuda_bf16.h>
@@ -47,7 +47,7 @@ struct GradArgs {
     const uint8_t *actions;      // (B) 0-based index into available_actions
     const double *targets;       // (B) Float64 (what snk_masked_target returns)
     long long B;
-    __nv_bfloat16 *hi, *lo2;     // planes [B][pitch] or NULL
+    __nv_bfloat16 *hi, *lo;     // planes [B][pitch] or NULL
     long long pitch;
     float *J;                    // [B][ldJ] Float32 or NULL
     long long ldJ;
@@ -60,8 +60,8 @@ struct Row {
 };
 __device__ __forceinline__ uint32_t split2(float v0, float v1, uint32_t &lo) {
     const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(2.0f * (v0 - __bfloat162float(h0)));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(2.0f * (v1 - __bfloat162float(h1)));
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
     lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     return (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
 }
@@ -69,7 +69,7 @@ __device__ __forceinline__ void emit1(const Row &r, int idx, float v) {
     if (r.hi != nullptr) {
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         r.hi[idx] = h;
-        r.lo[idx] = __float2bfloat16_rn(2.0f * (v - __bfloat162float(h)));
+        r.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
     if (r.J != nullptr) r.J[idx] = v;
 }
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(NT, 2) k_sample_grads(const GradArgs a) {
         __syncthreads();
         Row row;
         row.hi = a.hi != nullptr ? a.hi + s * a.pitch : nullptr;
-        row.lo = a.lo2 != nullptr ? a.lo2 + s * a.pitch : nullptr;
+        row.lo = a.lo != nullptr ? a.lo + s * a.pitch : nullptr;
         row.J = a.J != nullptr ? a.J + s * a.ldJ : nullptr;
         // ---------------- forward (structs.jl:127-139) ----------------
         for (int i = tid; i < 200; i += NT) {
@@ -448,10 +448,10 @@ __global__ void __launch_bounds__(NT, 2) k_sample_grads(const GradArgs a) {
 }
 
 int launch_sample_grads(const float *theta_dev, const float *states, const uint8_t *actions, const double *targets, long long B,
-                        void *hi, void *lo2, long long pitch, float *J, long long ldJ, float *loss, int sms, cudaStream_t st) {
+                        void *hi, void *lo, long long pitch, float *J, long long ldJ, float *loss, int sms, cudaStream_t st) {
     GradArgs a;
     a.theta = theta_dev; a.states = states; a.actions = actions; a.targets = targets; a.B = B;
-    a.hi = (__nv_bfloat16 *)hi; a.lo2 = (__nv_bfloat16 *)lo2; a.pitch = pitch; a.J = J; a.ldJ = ldJ; a.loss = loss;
+    a.hi = (__nv_bfloat16 *)hi; a.lo = (__nv_bfloat16 *)lo; a.pitch = pitch; a.J = J; a.ldJ = ldJ; a.loss = loss;
     SNK_CUDA(cudaFuncSetAttribute(k_sample_grads, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const long long max_grid = 2ll * sms;                    // 2 CTAs of 88 KB (and <= 102 registers x 320 threads) per SM
     const int grid = (int)(B < max_grid ? B : max_grid);

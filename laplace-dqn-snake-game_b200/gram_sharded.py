@@ -3,15 +3,17 @@
 Rank g owns rows_g of A (K_total x P).  G[rows_g, :] needs every other rank's rows, so this is the one
 place on the path with a real exchange step:
 
-  1. every rank packs its rows into bf16 planes (hi, 2*lo) in IPC-exportable device memory;
+  1. every rank packs its rows into bf16 planes (hi, lo) in IPC-exportable device memory;
   2. planes ring: at step i rank g multiplies its rows against the planes of rank (g+i) % R.  While the
      tensor cores work on step i, the planes of rank (g+i+1) % R are copied from that peer's memory over
      NVLink into the other half of a double buffer (cudaMemcpyAsync on a peer-mapped pointer, own copy
      stream) — the all-gather is never materialised as a separate phase;
-        Y[rows_g, rows_p] = hi_g hi_p^T + hi_g (2 lo_p)^T
-  3. the hi/lo cross terms are transposes of each other, so G = (Y + Y^T)/2: the symmetrise kernel reads
-     the transposed block Y[rows_p, rows_g] straight out of rank p's memory (peer loads over NVLink) —
-     the transpose "all-to-all" is fused into that kernel.
+        Y[rows_g, rows_p] = hi_g hi_p^T + hi_g lo_p^T + lo_g hi_p^T       (a finished block of G)
+     G is symmetric, so the ring stops half way (i = 0 .. R/2, the own block on its upper-triangle tiles only,
+     the step R/2 of an even R shared by the two ranks of the pair: `ring_schedule`);
+  3. the blocks a rank did not compute are transposes of blocks its peers did: the transpose kernel reads
+     Y[rows_p, rows_g] straight out of rank p's memory (peer loads over NVLink) — the transpose
+     "all-to-all" is fused into that kernel.
 
 The orchestration lives in the C library (csrc/gram_shard.cu: snk_gram_shard_*, one call per rank and Gram, device-side
 barriers over peer memory); this module is the thin Python caller.  torch.distributed only carries the 192-byte IPC
@@ -27,9 +29,17 @@ from . import _check, _ptr, lib, DTYPE_F32, DTYPE_F64
 from .shard import shard_range
 
 
-def ring_schedule(rank, world):
-    """Peers in the order rank multiplies against them: itself first, then around the ring."""
-    return [(rank + i) % world for i in range(world)]
+def ring_schedule(rows_all, rank):
+    """The blocks rank `rank` computes, in ring order (snk_gram_shard_schedule — the library's own arithmetic, no GPU):
+    a list of (peer, a0, a1, b0, b1): its own rows [a0, a1) against rows [b0, b1) of `peer`.  Every other block of its row
+    slab is the transpose of a block in a peer's list."""
+    world = len(rows_all)
+    n = world // 2 + 1
+    arr = (C.c_int64 * world)(*[int(r) for r in rows_all])
+    steps = C.c_int(0)
+    a0, a1, b0, b1 = [(C.c_int64 * n)() for _ in range(4)]
+    _check(lib().snk_gram_shard_schedule(arr, world, int(rank), C.byref(steps), a0, a1, b0, b1))
+    return [((rank + i) % world, a0[i], a1[i], b0[i], b1[i]) for i in range(steps.value)]
 
 
 HANDLE_BYTES = 192            # SNK_GRAM_SHARD_HANDLE_BYTES
@@ -65,7 +75,7 @@ class GramShard:
         _check(lib().snk_gram_shard_connect_host(self._g, (C.c_uint8 * len(blob)).from_buffer_copy(blob)))
 
     def planes(self):
-        """(hi pointer, lo2 pointer, pitch in elements) of this rank's bf16 planes, for a producer that writes them directly"""
+        """(hi pointer, lo pointer, pitch in elements) of this rank's bf16 planes, for a producer that writes them directly"""
         hi, lo, pitch = C.c_void_p(), C.c_void_p(), C.c_int64()
         _check(lib().snk_gram_shard_planes(self._g, C.byref(hi), C.byref(lo), C.byref(pitch)))
         return hi.value, lo.value, pitch.value
@@ -91,8 +101,8 @@ class GramShard:
     def ring(self, terms=3, block_k=0):
         _check(lib().snk_gram_shard_ring(self._g, int(terms), int(block_k), self._stream()))
 
-    def symmetrize(self, terms=3):
-        _check(lib().snk_gram_shard_symmetrize(self._g, int(terms), _ptr(self.G), self.K, self._stream()))
+    def mirror(self):
+        _check(lib().snk_gram_shard_mirror(self._g, _ptr(self.G), self.K, self._stream()))
         return self.G
 
     def check(self):
@@ -124,7 +134,7 @@ class LocalPeers:
         for s in self.shards:
             s.ring(terms, block_k)
         torch.cuda.synchronize()
-        out = [s.symmetrize(terms) for s in self.shards]
+        out = [s.mirror() for s in self.shards]
         torch.cuda.synchronize()
         return torch.cat(out, 0)
 
@@ -161,9 +171,9 @@ class DistributedGram:
 class AllGatherGram:
     """The same row-sharded Gram through library collectives — the baseline the planes ring is measured against
     (BASELINE config 5b names "NCCL all-gather"): NCCL all-gather of every rank's packed planes (materialised:
-    world x 2 planes per GPU), the block Grams against the gathered planes, an NCCL all-to-all of the transposed Y
-    blocks, and the local symmetrise kernel.  Same kernels, same result bits as DistributedGram; the exchange is
-    a separate phase here instead of running under the MMA main loop."""
+    world x 2 planes per GPU), the same blocks of the same schedule against the gathered planes, an NCCL all-to-all of
+    the computed blocks to the ranks that need their transposes, and a local transpose.  Same kernels, same result
+    bits as DistributedGram; the exchange is a separate phase here instead of running under the MMA main loop."""
 
     def __init__(self, rows_all, P, device, splits=0, group=None):
         self.group = group
@@ -175,12 +185,16 @@ class AllGatherGram:
         max_rows = max(self.rows_all)
         pb, pitch = C.c_size_t(0), C.c_int64(0)
         _check(lib().snk_gram_planes_layout(max_rows, self.P, C.byref(pb), C.byref(pitch)))
-        self.plane_bytes = pb.value
-        sb = C.c_size_t(0)
-        _check(lib().snk_gram_block_scratch_bytes(self.rows, max_rows, self.P, splits, C.byref(sb)))
+        self.plane_bytes, self.pitch = pb.value, pitch.value
+        self.sched = [ring_schedule(self.rows_all, r) for r in range(self.world)]
+        need = 256
+        for (_, a0, a1, b0, b1) in self.sched[self.rank]:
+            if a1 > a0 and b1 > b0:
+                sb = C.c_size_t(0)
+                _check(lib().snk_gram_block_scratch_bytes(a1 - a0, b1 - b0, self.P, splits, C.byref(sb)))
+                need = max(need, sb.value)
         self.all_planes = torch.empty(self.world, 2 * self.plane_bytes, dtype=torch.uint8, device=self.device)
-        self.scratch = torch.empty(max(sb.value, 256), dtype=torch.uint8, device=self.device)
-        self.Y = torch.empty(self.rows, self.K, dtype=torch.float32, device=self.device)
+        self.scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         self.G = torch.empty(self.rows, self.K, dtype=torch.float32, device=self.device)
 
     def run(self, A_rows, terms=3, block_k=0):
@@ -188,32 +202,45 @@ class AllGatherGram:
         assert tuple(A_rows.shape) == (self.rows, self.P)
         dt = {torch.float64: DTYPE_F64, torch.float32: DTYPE_F32}[A_rows.dtype]
         mine = self.all_planes[self.rank]
+        row_bytes = 2 * self.pitch
         with torch.cuda.device(self.device):
             st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _check(L.snk_gram_pack_planes(_ptr(A_rows, device=self.device), dt, self.P, self.rows, C.c_void_p(mine.data_ptr()),
                                           C.c_void_p(mine.data_ptr() + self.plane_bytes), st))
             dist.all_gather_into_tensor(self.all_planes.view(-1), mine, group=self.group)
-            for p in ring_schedule(self.rank, self.world):
-                b_hi = self.all_planes[p].data_ptr()
-                _check(L.snk_gram_block(C.c_void_p(mine.data_ptr()), self.rows, C.c_void_p(b_hi), C.c_void_p(b_hi + self.plane_bytes),
-                                        self.rows_all[p], self.P, terms, block_k, self.splits, C.c_void_p(self.scratch.data_ptr()),
-                                        C.c_void_p(self.Y.data_ptr() + 4 * self.col0[p]), self.K, st))
-            if terms == 1:
-                self.G.copy_(self.Y)
-                return self.G
-            send = [self.Y[:, self.col0[p]:self.col0[p] + self.rows_all[p]].contiguous() for p in range(self.world)]
-            recv = [torch.empty(self.rows_all[p], self.rows, dtype=torch.float32, device=self.device) for p in range(self.world)]
-            dist.all_to_all(recv, send, group=self.group)
-            for p in range(self.world):
-                _check(L.snk_gram_symmetrize_block(C.c_void_p(self.Y.data_ptr() + 4 * self.col0[p]), self.K,
-                                                   C.c_void_p(recv[p].data_ptr()), self.rows, self.rows, self.rows_all[p],
-                                                   C.c_void_p(self.G.data_ptr() + 4 * self.col0[p]), self.K, st))
+            send = [torch.empty(0, dtype=torch.float32, device=self.device) for _ in range(self.world)]
+            for i, (p, a0, a1, b0, b1) in enumerate(self.sched[self.rank]):
+                if a1 == a0 or b1 == b0:
+                    continue
+                a_hi = mine.data_ptr() + a0 * row_bytes
+                b_hi = self.all_planes[p].data_ptr() + b0 * row_bytes
+                blk = self.G[a0:a1, self.col0[p] + b0:self.col0[p] + b1]
+                _check(L.snk_gram_block(C.c_void_p(a_hi), C.c_void_p(a_hi + self.plane_bytes), a1 - a0, C.c_void_p(b_hi),
+                                        C.c_void_p(b_hi + self.plane_bytes), b1 - b0, self.P, terms, 1 if i == 0 else 0, block_k,
+                                        self.splits, C.c_void_p(self.scratch.data_ptr()), C.c_void_p(blk.data_ptr()), self.K, st))
+                if i > 0:
+                    send[p] = blk.contiguous()
+            # what rank q = rank - i computed against my rows comes back as its (a1-a0) x (b1-b0) block
+            recv = [torch.empty(0, dtype=torch.float32, device=self.device) for _ in range(self.world)]
+            for i in range(1, len(self.sched[self.rank])):
+                q = (self.rank - i) % self.world
+                _, a0, a1, b0, b1 = self.sched[q][i]
+                recv[q] = torch.empty((a1 - a0) * (b1 - b0), dtype=torch.float32, device=self.device)
+            dist.all_to_all(recv, [t.reshape(-1) for t in send], group=self.group)
+            for i in range(1, len(self.sched[self.rank])):
+                q = (self.rank - i) % self.world
+                _, a0, a1, b0, b1 = self.sched[q][i]
+                if a1 == a0 or b1 == b0:
+                    continue
+                dst = self.G[b0:b1, self.col0[q] + a0:self.col0[q] + a1]
+                _check(L.snk_gram_transpose_block(C.c_void_p(recv[q].data_ptr()), b1 - b0, b1 - b0, a1 - a0,
+                                                  C.c_void_p(dst.data_ptr()), self.K, st))
         return self.G
 
     def close(self):
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
-        self.all_planes = self.scratch = self.Y = self.G = None
+        self.all_planes = self.scratch = self.G = None
 
 
 def gram_distributed(A_rows, rows_all, terms=3, block_k=0, splits=0, group=None):

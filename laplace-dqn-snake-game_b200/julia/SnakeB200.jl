@@ -275,11 +275,11 @@ end
 """Per-sample gradients of `Flux.huber_loss(q_net(s)[a], y)` (utils.jl:452-466), rows in Flux.destructure order, written as
 the bf16 planes a Gram consumes (`planes(::GramShard)`) and / or as Float32 rows; device pointers."""
 sample_grads!(q::DeviceQNet, d_states::Ptr{Float32}, d_actions::Ptr{UInt8}, d_targets::Ptr{Float64}, B::Integer,
-              d_hi::Ptr{Cvoid}, d_lo2::Ptr{Cvoid}, pitch::Integer, d_J::Ptr{Float32}, ldJ::Integer, d_loss::Ptr{Float32}) =
+              d_hi::Ptr{Cvoid}, d_lo::Ptr{Cvoid}, pitch::Integer, d_J::Ptr{Float32}, ldJ::Integer, d_loss::Ptr{Float32}) =
     check(ccall((:snk_qnet_sample_grads, lib), Cint,
                 (Ptr{Cvoid}, Ptr{Float32}, Ptr{UInt8}, Ptr{Float64}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float32}, Int64,
                  Ptr{Float32}, Ptr{Cvoid}),
-                q.handle, d_states, d_actions, d_targets, B, d_hi, d_lo2, pitch, d_J, ldJ, d_loss, C_NULL))
+                q.handle, d_states, d_actions, d_targets, B, d_hi, d_lo, pitch, d_J, ldJ, d_loss, C_NULL))
 
 # ---- Laplace deviation matrix (compute_D.jl, plot_traj.jl, la_utils.jl) ----------------------------------------
 """deviation_matrix[:, position] = Float64.(theta) (compute_D.jl:67-71); position is 1-based like Julia's."""
@@ -398,7 +398,7 @@ dtype 2, Float32: dtype 1) or C_NULL when the planes were filled by `sample_grad
 run!(g::GramShard, d_A::Ptr{Cvoid}, dtype::Integer, d_G::Ptr{Float32}; terms::Integer = 3) =
     check(ccall((:snk_gram_shard_run, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float32}, Int64, Ptr{Cvoid}),
                 g.handle, d_A, dtype, terms, 0, d_G, g.K, C_NULL))
-"""(hi, lo2, pitch): the bf16 planes of this rank's rows, for a producer that writes them directly"""
+"""(hi, lo, pitch): the bf16 planes of this rank's rows, for a producer that writes them directly"""
 function planes(g::GramShard)
     hi = Ref{Ptr{Cvoid}}(C_NULL); lo = Ref{Ptr{Cvoid}}(C_NULL); pitch = Ref{Int64}(0)
     check(ccall((:snk_gram_shard_planes, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}, Ref{Int64}), g.handle, hi, lo, pitch))

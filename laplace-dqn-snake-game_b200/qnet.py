@@ -103,7 +103,7 @@ class QNet:
     def sample_grads(self, states, actions, targets, planes=None, want_J=False, want_loss=True):
         """Per-sample gradients of huber(q_net(s_i)[a_i], y_i) (utils.jl:452-466), FP32, Flux.destructure order.
         states (B,2,10,10) f32, actions (B) u8 (0-based), targets (B) f64 — as ReplayBuffer.stack_exp / masked_target give.
-        planes: (hi_ptr, lo2_ptr, pitch) of bf16 Gram planes to fill (GramShard.planes(), GramPlan.planes()) or None.
+        planes: (hi_ptr, lo_ptr, pitch) of bf16 Gram planes to fill (GramShard.planes(), GramPlan.planes()) or None.
         Returns dict(J (B, 181395) f32 if want_J, loss (B) f32 if want_loss)."""
         from . import _check, _ptr, lib
         B = states.shape[0]

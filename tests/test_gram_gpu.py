@@ -29,10 +29,31 @@ def test_gram_matches_fp64_oracle(K, P, block_k):
     # bf16 hi/lo split: inputs good to 2^-17, products to ~2^-16, fp32 accumulation over P terms
     assert np.max(np.abs(G3 - ref) / scale) < 2e-5, np.max(np.abs(G3 - ref) / scale)
     assert _rel_fro(G3, ref) < 1e-5
-    assert np.array_equal(G3, G3.T)                                         # symmetrised exactly
+    assert np.array_equal(G3, G3.T) and np.array_equal(G1, G1.T)           # upper triangle mirrored: exactly symmetric
     # plain bf16 inputs: 2^-9 per operand
     assert np.max(np.abs(G1 - ref) / scale) < 8e-3
     assert _rel_fro(G1, ref) < 4e-3
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("K,P", [(2500, 515), (1000, 2048), (130, 300)])
+def test_both_tile_engines_and_multi_panel_triangles(cta_group, K, P):
+    """the single-CTA (128 x 256 tiles) and the CTA-pair (256 x 256) engine on upper-triangle tile lists that span more than
+    one column panel (K = 2500: 10 tile columns)"""
+    S = pkg()
+    rng = np.random.default_rng(K + cta_group)
+    A = rng.normal(0, 1, (K, P))
+    ref = GO.gram(A)
+    dA = torch.from_numpy(A).cuda()
+    S.lib().snk_gram_config(cta_group)
+    try:
+        plan = S.GramPlan(K, P, dA.device).pack(dA)
+        G3 = plan.gram(terms=3).cpu().numpy()
+        G1 = plan.gram(terms=1).cpu().numpy()
+    finally:
+        S.lib().snk_gram_config(2)
+    assert _rel_fro(G3, ref) < 1e-5 and _rel_fro(G1, ref) < 4e-3
+    assert np.array_equal(G3, G3.T)
 
 
 def test_gram_of_centred_snapshots_spectrum():
@@ -66,9 +87,10 @@ def test_gram_float32_input_and_explicit_splits():
         assert _rel_fro(G, ref) < 1e-5, splits
 
 
-@pytest.mark.parametrize("world,K,P,terms", [(2, 512, 3000, 3), (3, 700, 5003, 3), (4, 1000, 2048, 1), (8, 1000, 9999, 3)])
+@pytest.mark.parametrize("world,K,P,terms", [(2, 512, 3000, 3), (3, 700, 5003, 3), (4, 1000, 2048, 1), (8, 1000, 9999, 3), (2, 2500, 1031, 3),
+                                             (5, 33, 700, 3), (6, 1800, 515, 3)])
 def test_row_sharded_gram_with_virtual_ranks(world, K, P, terms):
-    """The multi-GPU algorithm (planes ring -> block Grams -> transposed-peer symmetrise) with R virtual ranks
+    """The multi-GPU algorithm (half planes ring -> block Grams -> transposed-peer mirror) with R virtual ranks
     in one process on one GPU: same kernels and pointer arithmetic, local 'peer' memory."""
     S = pkg()
     from snake_b200 import gram_sharded as GS
@@ -83,10 +105,11 @@ def test_row_sharded_gram_with_virtual_ranks(world, K, P, terms):
     assert _rel_fro(G, ref) < tol
     single = S.gram(torch.from_numpy(A).cuda(), terms=terms).cpu().numpy()
     assert _rel_fro(G, single.astype(np.float64)) < 2e-6       # same arithmetic up to split-K summation order
+    assert np.array_equal(G, G.T)                              # every block below the ring's half is a copy of its mirror image
 
 
 def test_sharded_run_with_device_barriers_two_virtual_ranks_on_two_streams():
-    """snk_gram_shard_run — pack, planes ring, symmetrise separated by the device-side peer barrier — for two virtual ranks of
+    """snk_gram_shard_run — pack, planes ring, mirror separated by the device-side peer barrier — for two virtual ranks of
     one process, each on its own stream: rank 0's barrier kernel spins until rank 1's stream reaches its barrier.  Run twice
     (the barrier epochs keep counting)."""
     S = pkg()

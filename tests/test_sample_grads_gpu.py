@@ -59,14 +59,14 @@ def test_rows_match_float64_autograd(B, seed):
     assert norm.min() > 0
     assert (np.linalg.norm(J - want, axis=1) / norm).max() < 2e-5
     assert (np.abs(J - want).max(1) / np.abs(want).max(1)).max() < 2e-5
-    # the planes the Gram consumes: hi + lo2/2 == the FP32 row to 2^-16 per element, padding columns zero
+    # the planes the Gram consumes: hi + lo == the FP32 row to 2^-16 per element, padding columns zero
     hi_p, lo_p, pitch = plan.planes()
     nb = B * pitch
     hi = plan.ws[:nb * 2].view(torch.bfloat16).view(B, pitch).float().cpu().numpy().astype(np.float64)
     lo = plan.ws[lo_p - hi_p:lo_p - hi_p + nb * 2].view(torch.bfloat16).view(B, pitch).float().cpu().numpy().astype(np.float64)
     P = S.qnet.N_PARAMS
     assert np.all(hi[:, P:] == 0) and np.all(lo[:, P:] == 0)
-    rec = hi[:, :P] + 0.5 * lo[:, :P]
+    rec = hi[:, :P] + lo[:, :P]
     assert np.all(np.abs(rec - J) <= 2.0 ** -16 * np.abs(J) + 1e-30)
     # Gram of the per-sample gradients straight from the planes (no pack pass) vs Float64
     G = plan.gram(terms=3).cpu().numpy().astype(np.float64)

@@ -66,7 +66,7 @@ def test_shard_range_properties():
 
 
 def _gram_worker(rank, world, port, K, P, q):
-    """The sharded-Gram schedule (ring order, column offsets, transposed-peer symmetrise) under gloo, with
+    """The sharded-Gram schedule (half ring, column offsets, the shared last step, transposed-peer mirror) under gloo, with
     numpy standing in for the device kernels: planes are exchanged with all_gather, block products follow
     ring_schedule, and the result must be the full Gram's row block."""
     import numpy as np
@@ -81,24 +81,59 @@ def _gram_worker(rank, world, port, K, P, q):
     col0 = [sum(rows_all[:r]) for r in range(world)]
     mine = A[col0[rank]:col0[rank] + rows_all[rank]]
     hi = mine.astype(np.float32).astype(np.float64)            # stand-in split: hi + lo == mine
-    lo2 = 2 * (mine - hi)
+    lo = mine - hi
     planes = [None] * world
-    dist.all_gather_object(planes, (hi, lo2))
-    Y = np.zeros((rows_all[rank], K))
-    order = ring_schedule(rank, world)
-    assert order[0] == rank and sorted(order) == list(range(world))
-    for p in order:
+    dist.all_gather_object(planes, (hi, lo))
+    Y = np.full((rows_all[rank], K), np.nan)
+    sched = ring_schedule(rows_all, rank)
+    assert sched[0][0] == rank and len(sched) == world // 2 + 1
+    for p, a0, a1, b0, b1 in sched:
         ph, pl = planes[p]
-        Y[:, col0[p]:col0[p] + rows_all[p]] = hi @ ph.T + hi @ pl.T
+        Y[a0:a1, col0[p] + b0:col0[p] + b1] = hi[a0:a1] @ ph[b0:b1].T + hi[a0:a1] @ pl[b0:b1].T + lo[a0:a1] @ ph[b0:b1].T
     Ys = [None] * world
     dist.all_gather_object(Ys, Y)
-    G = np.zeros_like(Y)
-    for p in range(world):
-        yt = Ys[p][:, col0[rank]:col0[rank] + rows_all[rank]]
-        G[:, col0[p]:col0[p] + rows_all[p]] = 0.5 * (Y[:, col0[p]:col0[p] + rows_all[p]] + yt.T)
+    G = Y.copy()
+    for i in range(1, len(sched)):
+        src = (rank - i) % world                               # rank src computed (its rows a0:a1) x (my rows b0:b1) at ITS step i
+        _, a0, a1, b0, b1 = ring_schedule(rows_all, src)[i]
+        assert np.isnan(G[b0:b1, col0[src] + a0:col0[src] + a1]).all()          # nobody computes a block twice
+        G[b0:b1, col0[src] + a0:col0[src] + a1] = Ys[src][a0:a1, col0[rank] + b0:col0[rank] + b1].T
+    assert not np.isnan(G).any()
     ref = (A @ A.T)[col0[rank]:col0[rank] + rows_all[rank]]
     q.put((rank, float(np.abs(G - ref).max() / np.abs(ref).max())))
     dist.destroy_process_group()
+
+
+def test_ring_schedule_covers_every_block_exactly_once():
+    """pure arithmetic (snk_gram_shard_schedule needs no GPU): for every world size the computed blocks and their mirror images
+    tile the K x K matrix exactly once, and the shared last step of an even world splits the lower rank's rows"""
+    import numpy as np
+    pkg()
+    from snake_b200.gram_sharded import ring_schedule
+    for world, rows_all in [(1, [5]), (2, [3, 4]), (2, [1250, 1250]), (3, [7, 7, 6]), (4, [300, 300, 299, 299]), (5, [2] * 5),
+                            (8, [6250] * 8), (8, [1] * 8), (16, [40] * 16)]:
+        K = sum(rows_all)
+        col0 = [sum(rows_all[:r]) for r in range(world)]
+        cover = np.zeros((K, K), dtype=np.int32) if K <= 5000 else None
+        work = []
+        for g in range(world):
+            sched = ring_schedule(rows_all, g)
+            assert len(sched) == world // 2 + 1 and sched[0] == (g, 0, rows_all[g], 0, rows_all[g])
+            w = 0
+            for i, (p, a0, a1, b0, b1) in enumerate(sched):
+                assert p == (g + i) % world and 0 <= a0 <= a1 <= rows_all[g] and 0 <= b0 <= b1 <= rows_all[p]
+                w += (a1 - a0) * (b1 - b0) * (0.5 if i == 0 else 1.0)
+                if cover is not None:
+                    cover[col0[g] + a0:col0[g] + a1, col0[p] + b0:col0[p] + b1] += 1
+                    if i > 0:
+                        cover[col0[p] + b0:col0[p] + b1, col0[g] + a0:col0[g] + a1] += 1
+            work.append(w)
+        if cover is not None:
+            assert (cover == 1).all(), (world, rows_all)
+        if min(rows_all) >= 40:
+            assert max(work) / min(work) < 1.02, (world, work)          # the shared step keeps the ranks balanced
+    p8 = ring_schedule([6250] * 8, 1)
+    assert p8[4] == (5, 0, 3125, 0, 6250) and ring_schedule([6250] * 8, 5)[4] == (1, 0, 6250, 3125, 6250)
 
 
 def test_sharded_gram_schedule_two_ranks():

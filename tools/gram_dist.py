@@ -98,10 +98,9 @@ def main():
         useful = 2.0 * Kt * Kt * P
         print(json.dumps({"world": world, "terms": args.terms, "small_rel_fro_err": errs, "rows_per_rank": R, "K_total": Kt,
                           "P": P, "ms": ms, "useful_tflops_total": useful / (ms * 1e-3) / 1e12,
-                          "mma_tflops_per_gpu": useful * (2 if args.terms == 3 else 1) / world / (ms * 1e-3) / 1e12,
                           "diag_check": diag, "nccl_allgather_ms": sorted(times_ag)[len(times_ag) // 2],
                           "nccl_allgather_same_bits": same, "nccl_allgather_same_bits_5b_size_rank0": same_big,
-                          "note": "time = pack + barriers + planes ring over NVLink + block Grams + peer-read symmetrise (buffers/IPC set up once)"}))
+                          "note": "time = pack + barriers + planes ring over NVLink + block Grams + peer-read mirror (buffers/IPC set up once)"}))
     dist.destroy_process_group()
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Phase timing of the row-sharded Gram with 2 virtual ranks on one GPU (same kernels as the multi-GPU run): pack, the two block
-Grams of a rank (against its own planes and against the peer's), the symmetrise pass — through the snk_gram_shard_* phase calls."""
+Grams of a rank (against its own planes and against the peer's), the mirror pass — through the snk_gram_shard_* phase calls."""
 import os
 import sys
 
@@ -36,7 +36,7 @@ torch.cuda.synchronize()
 print("ring of rank 0 (2 block Grams + staged copy)  ms", timed(lambda: sh.ring(3)))
 peers.shards[1].ring(3)
 torch.cuda.synchronize()
-print("symmetrise of rank 0 (peer-read transpose)    ms", timed(lambda: sh.symmetrize(3)))
+print("mirror of rank 0 (copy + peer-read transpose)  ms", timed(lambda: sh.mirror()))
 for cg in (1, 2):
     S.lib().snk_gram_config(cg)
     print("cta_group", cg, ": ring of rank 0 ms", timed(lambda: sh.ring(3)))

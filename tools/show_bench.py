@@ -24,11 +24,11 @@ if g:
     print("gram5a pack %.3f ms (%.2f hbm) pack_f32 %.3f (%.2f) center %.3f (%.2f)" % (g["pack_ms"], g["pack_hbm_frac"], g["pack_f32_ms"], g["pack_f32_hbm_frac"], g["center_ms"], g["center_hbm_frac"]))
     for t in ("terms3", "terms1"):
         r = g[t]
-        print("  %s: %.3f ms, mma %.0f TF (%.2f), algorithmic %.2f, err %.2g, traffic %s" % (t, r["ms"], r["mma_tflops"], r["roofline"]["frac"], r["roofline"]["frac_algorithmic"], r["rel_fro_err_vs_fp64"], r["roofline"]["traffic"]))
+        print("  %s: %.3f ms, mma %.0f TF (%.2f), algorithmic %.2f, err %.2g, traffic %s" % (t, r["ms"], r["mma_tflops"], r["roofline"]["frac_executed"], r["roofline"]["frac"], r["rel_fro_err_vs_fp64"], r["roofline"]["traffic"]))
 gs = d.get("gram_5b_sharded")
 if gs:
     print("gram5b K=%d: total %.1f ms (producer %.1f, gram %.1f), mma/gpu %.0f TF (%.2f of sustained), nccl baseline %.1f ms, same bits %s, verify %s"
-          % (gs["K_total"], gs["ms"], gs["producer_ms"], gs["gram_ms"], gs["mma_tflops_per_gpu"], gs["roofline"]["frac"], gs["nccl_allgather_baseline_ms"],
+          % (gs["K_total"], gs["ms"], gs["producer_ms"], gs["gram_ms"], gs["mma_tflops_per_gpu"], gs["roofline"]["frac_executed"], gs["nccl_allgather_baseline_ms"],
              gs["nccl_allgather_same_bits_rank0"], gs["verify_per_rank"]["max_err_over_sqrt_GiiGjj"]))
 cb = d.get("cpu_baseline")
 if cb:
