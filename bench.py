@@ -654,7 +654,7 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
         executed = max(executed, tot)
     gram_s = (ms - ms_prod) * 1e-3
     mma = executed / gram_s / 1e12
-    alg = useful / world / gram_s / 1e12
+    alg = float(Kt) * (Kt + 1) * P / world / gram_s / 1e12       # a symmetric-half implementation reports M(M+1)P
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1421.8)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1421.8
     return {"workload": "config5b: Gram of per-sample DQN-loss gradients J (%d transitions per GPU out of each rank's 50,000-slot replay ring "
                         "x %d parameters), row-sharded over %d GPUs, hi/lo bf16 split" % (R, P, world),
@@ -664,7 +664,8 @@ def bench_gram_sharded(S, dev, rank, world, local, max_over_ranks, R=6250, P=181
             "useful_tflops_total": useful / gram_s / 1e12, "mma_tflops_per_gpu": mma,
             "roofline": {"bound": "tensor", "achieved": alg, "peak": peak, "unit": "TFLOP/s", "frac": alg / peak,
                          "achieved_executed": mma, "frac_executed": mma / peak, "executed_over_algorithmic": executed / (useful / world), "traffic": None,
-                         "note": "per GPU, Gram phase only; peak = sustained bf16 (a %.0f ms region); achieved = SURVEY 8(d)'s 2 K^2 P / GPUs / time; "
+                         "note": "per GPU, Gram phase only; peak = sustained bf16 (a %.0f ms region); achieved = SURVEY 8(d)'s count for a symmetric-half "
+                                 "implementation, K(K+1)P / GPUs / time (useful_tflops_total keeps the full-square 2 K^2 P of the earlier lines); "
                                  "executed = the tiles the busiest rank computes (own block: upper-triangle tiles; half the ring) x 3 products of the "
                                  "hi/lo split, padding included" % ms},
             "verify_per_rank": {"entries_per_rank": n_checked, "max_err_over_sqrt_GiiGjj": errs, "first_checked_row_norm_per_rank": fingerprints,
@@ -718,15 +719,17 @@ def bench_gram(S, dev, K=1000, P=181395, iters=10, cpu_too=False):
         ms = timed(lambda: plan.gram(terms, 0, out=G))
         err = float((G.double() - ref).norm() / ref.norm())
         mma = gram_block_flops(S, K, K, P, terms, True) / (ms * 1e-3) / 1e12
-        useful = 2.0 * K * K * P / (ms * 1e-3) / 1e12
+        useful = 2.0 * K * K * P / (ms * 1e-3) / 1e12            # full-square equivalent (what the earlier rounds' lines called useful)
+        alg = float(K) * (K + 1) * P / (ms * 1e-3) / 1e12        # a symmetric-half implementation reports K(K+1)P
         traffic, src = ncu_csv_traffic("ncu_gram_5a_terms%d_full" % terms, "k_gram")
         out["terms%d" % terms] = {"ms": ms, "useful_tflops": useful, "mma_tflops": mma,
                                   "frac_of_measured_bf16_peak": mma / peak, "rel_fro_err_vs_fp64": err,
-                                  "roofline": {"bound": "tensor", "achieved": useful, "peak": peak, "unit": "TFLOP/s",
-                                               "frac": useful / peak, "achieved_executed": mma, "frac_executed": mma / peak, "traffic": traffic,
+                                  "roofline": {"bound": "tensor", "achieved": alg, "peak": peak, "unit": "TFLOP/s",
+                                               "frac": alg / peak, "achieved_executed": mma, "frac_executed": mma / peak, "traffic": traffic,
                                                "algorithmic_bytes": (2 if terms == 3 else 1) * 2.0 * K * ((P + 63) // 64 * 64),
                                                "traffic_source": src,
-                                               "note": "achieved = SURVEY 8(d)'s 2 K^2 P / time; executed = the tiles actually computed (upper-triangle tiles of the "
+                                               "note": "achieved = SURVEY 8(d)'s count for a symmetric-half implementation, K(K+1)P / time (useful_tflops keeps the "
+                                                       "full-square 2 K^2 P); executed = the tiles actually computed (upper-triangle tiles of the "
                                                        "padded problem) x products per k-step (3 for the hi/lo split); time covers the tile kernel + the "
                                                        "split-K/mirror pass; traffic = ncu dram bytes of the tile kernel actually run, algorithmic_bytes = the "
                                                        "bf16 planes read once"}}
