@@ -132,3 +132,19 @@ def test_ctypes_binding_matches_the_header(built):
             if not ok:
                 problems.append("%s: argument %d is `%s` in C but %s in the binding" % (name, k + 1, cp, at))
     assert checked >= 60 and not problems, "\n".join(problems)
+
+
+def test_gram_tile_plan_arithmetic_without_a_gpu(built):
+    """snk_gram_block_flops is the library's own tile plan (no launch): a symmetric block computes only the tiles that meet the
+    upper triangle, 3 products per k-step for the hi/lo split, on the padded problem"""
+    L = built.lib()
+    v = C.c_double(0)
+    P, Ppad = 181395, 181440
+    tile = 2.0 * 256 * 256 * Ppad
+    assert L.snk_gram_block_flops(1000, 1000, P, 3, 1, C.byref(v)) == 0 and v.value == 10 * 3 * tile        # 4 x 4 tiles -> 10
+    assert L.snk_gram_block_flops(1000, 1000, P, 3, 0, C.byref(v)) == 0 and v.value == 16 * 3 * tile
+    assert L.snk_gram_block_flops(6250, 6250, P, 3, 1, C.byref(v)) == 0 and v.value == 325 * 3 * tile       # 25 x 25 -> 325
+    assert L.snk_gram_block_flops(3125, 6250, P, 3, 0, C.byref(v)) == 0 and v.value == 13 * 25 * 3 * tile
+    assert L.snk_gram_block_flops(6250, 6250, P, 1, 1, C.byref(v)) == 0 and v.value == 325 * tile
+    assert L.snk_gram_block_flops(10, 20, P, 3, 1, C.byref(v)) == -1                                         # symmetric needs a square block
+    assert L.snk_gram_block_flops(10, 10, P, 2, 0, C.byref(v)) == -1

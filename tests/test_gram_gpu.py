@@ -108,6 +108,24 @@ def test_row_sharded_gram_with_virtual_ranks(world, K, P, terms):
     assert np.array_equal(G, G.T)                              # every block below the ring's half is a copy of its mirror image
 
 
+def test_transpose_block_ragged_sizes_and_leading_dimensions():
+    """snk_gram_transpose_block (the mirror step of the sharded Gram): G (rows_a x rows_b, ld) = YT^T for sizes that are not
+    multiples of the 32 x 32 staging tile, inside larger buffers (the untouched surroundings stay untouched)"""
+    import ctypes as C
+    S = pkg()
+    L = S.lib()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for ra, rb in [(1, 1), (33, 65), (100, 7), (250, 313)]:
+        ldyt, ldg = ra + 5, rb + 11
+        YT = torch.randn(rb, ldyt, device="cuda", generator=g)
+        G = torch.full((ra + 2, ldg), -7.0, device="cuda")
+        S._check(L.snk_gram_transpose_block(C.c_void_p(YT.data_ptr()), ldyt, ra, rb, C.c_void_p(G.data_ptr()), ldg,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert torch.equal(G[:ra, :rb], YT[:, :ra].T)
+        assert bool((G[ra:] == -7.0).all()) and bool((G[:, rb:] == -7.0).all())
+
+
 def test_sharded_run_with_device_barriers_two_virtual_ranks_on_two_streams():
     """snk_gram_shard_run — pack, planes ring, mirror separated by the device-side peer barrier — for two virtual ranks of
     one process, each on its own stream: rank 0's barrier kernel spins until rank 1's stream reaches its barrier.  Run twice
