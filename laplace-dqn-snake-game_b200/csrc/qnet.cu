@@ -44,6 +44,8 @@
 
 namespace snk {
 namespace qgrad {       // qnet_grads.cu
+long long theta_ext_floats();
+void build_theta_ext(const float *theta_host, float *ext);     // theta + the two re-ordered copies of W3 the gradient kernel reads
 int launch_sample_grads(const float *theta_dev, const float *states, const uint8_t *actions, const double *targets, long long B,
                         void *hi, void *lo, long long pitch, float *J, long long ldJ, float *loss, int sms, cudaStream_t st);
 }
@@ -1268,7 +1270,7 @@ struct snk_qnet_s {
     int device;
     int precision;               // SNK_QNET_BF16 | SNK_QNET_F32
     uint8_t *params;
-    float *theta;                // Flux.destructure(q_net) as given, Float32 on the device (per-sample gradients)
+    float *theta;                // Flux.destructure(q_net) as given, Float32 on the device, followed by two re-ordered copies of W3 (per-sample gradients)
     void *out3;                  // conv3 activations: bf16 [cap][1600] or fp16 [2 cap][1600]
     long long out3_cap;          // in samples
     int *d_overflow;             // SNK_QNET_F32: an activation left the fp16 range
@@ -1306,8 +1308,10 @@ int snk_qnet_create(snk_qnet *out, const float *theta_host, int64_t n_params, in
     cudaDeviceGetAttribute(&q->sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = cudaMalloc((void **)&q->params, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(q->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&q->theta, (size_t)n_params * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(q->theta, theta_host, (size_t)n_params * 4, cudaMemcpyHostToDevice);
+    std::vector<float> ext((size_t)qgrad::theta_ext_floats());
+    qgrad::build_theta_ext(theta_host, ext.data());
+    if (e == cudaSuccess) e = cudaMalloc((void **)&q->theta, ext.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(q->theta, ext.data(), ext.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void **)&q->d_overflow, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(q->d_overflow, 0, sizeof(int));
     if (e != cudaSuccess) {
