@@ -1617,6 +1617,8 @@ static int step_fused_host_impl(snk_handle h, snk_replay_s *r, const float *q, f
     if (r != nullptr) { a.sink = r->ring; a.sink_base = r->total; a.sink_cap = r->capacity; a.sink_n = h->n; }
     // Chunking trades copy/kernel overlap (and the time before the first output copy can start) against per-copy overhead
     // (~8 us per cudaMemcpyAsync): about SNK_HOST_CHUNK_MB of traffic per chunk, at most 16 chunks; only the observation is copied per chunk, the small per-env outputs go down once at the end.
+    // (A first chunk of 1/8 size, so that the output copies start earlier, was A/B-measured on one box: 1.365 against 1.363 ms
+    // per step — the step is bound by the device->host transfer itself, 62 MB at ~47 GB/s with the uploads running beside it.)
     const long long align = TPB * 8;
     const size_t traffic = (opb + 26) * n;
     int n_chunks = (int)((traffic + (SNK_HOST_CHUNK_MB << 20) - 1) / (SNK_HOST_CHUNK_MB << 20));
