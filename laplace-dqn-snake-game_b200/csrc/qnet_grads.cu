@@ -10,7 +10,7 @@
 //
 // One CTA (10 warps) per sample, all activations and back-propagated signals of the sample in shared memory, plain FP32 FMAs: per
 // sample the contractions are 25..2304 deep — CUDA-core work; the kernel is bound by FP32 issue (14.6 MFLOP per sample) and
-// by the 725 KB (two bf16 planes) it writes per sample.  The row goes STRAIGHT into the bf16 hi / 2 lo planes the Gram
+// by the 725 KB (two bf16 planes) it writes per sample.  The row goes STRAIGHT into the bf16 hi / lo planes the Gram
 // kernel consumes (hi = bf16(v), lo = bf16(v - hi): the same split as k_gram_pack), optionally also as Float32.
 // Where the weights come from (measured: what bounded the first version was not FP32 issue but the load/store unit — a
 // warp-wide load whose lanes touch 32 different cache lines costs ~32 cycles, and one shared-memory load per FMA saturates
