@@ -305,9 +305,11 @@ def run_ours(args):
     def e2e_run(fmt, dtype, per_env, store):
         host["obs"] = S.pinned_empty((E, 2, 10, 10) if per_env == 200 else (E, per_env), dtype)
         host["obs_fmt"] = fmt
+        # SNK_OBS_BITS carries reward / done / mask / action inside its 24-byte record: no separate output arrays
+        h = {k: v for k, v in host.items() if k in ("q", "u", "ridx", "obs", "obs_fmt")} if fmt == "bits" else host
 
         def it():
-            env.step_fused_host(host, q=True, eps=eps, replay=ring if store else None)
+            env.step_fused_host(h, q=True, eps=eps, replay=ring if store else None)
             if store:                                             # sample(rpb) + stack_exp (utils.jl:442-443): 64 transitions as Float32;
                 idx = torch.randint(0, len(ring), (64,), generator=idx_rng, dtype=torch.int64)     # ordered behind the step's kernels,
                 ring.stack_exp_host(idx, out=batch_host)                                          # beside its device->host copies
@@ -325,12 +327,13 @@ def run_ours(args):
         barrier()
         return max_over_ranks(t0.elapsed_time(t1))
 
-    e2e_ms = e2e_run("packed2", torch.uint8, 50, True)
+    e2e_ms = e2e_run("bits", torch.uint8, 24, True)
     e2e_value = world * E * Ke / (e2e_ms * 1e-3)
     h2d = E * (12 + 4 + 1) + 64 * 8
-    d2h = E * (50 + 3 + 4 + 1 + 1) + 64 * 1613
-    e2e_f32_ms = e2e_i8_ms = None
+    d2h = E * 24 + 64 * 1613
+    e2e_f32_ms = e2e_i8_ms = e2e_p2_ms = None
     if not args.skip_variants:
+        e2e_p2_ms = e2e_run("packed2", torch.uint8, 50, True)
         e2e_f32_ms = e2e_run("f32", torch.float32, 200, False)
         e2e_i8_ms = e2e_run("i8", torch.int8, 200, False)
     del host["obs"]
@@ -431,15 +434,22 @@ def run_ours(args):
                          "bytes_per_env_step": BYTES_PER_STEP_CONFIG3, "kernel_ms": kern_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step": e2e_ms / Ke,
-                    "api": "snk_step_fused_store_host (pinned host buffers: q/u/ridx up; 2-bit packed next_state (50 B/env, lossless) + "
-                           "reward/done/mask/action down; every transition store!d into the device replay ring) + snk_sync + "
-                           "snk_replay_gather_host (stack_exp of 64 sampled transitions as Float32, utils.jl:343-383) per step",
-                    "obs_format": "packed2 (SNK_OBS_PACKED2); Float32 only for the 64 sampled transitions, as the reference casts (utils.jl:361-362)",
+                    "api": "snk_step_fused_store_host (pinned host buffers: q/u/ridx up; one 24-byte record per env down = next_state as "
+                           "two bit-boards + reward / done / next_is_suicidal / action, lossless; every transition store!d into the device "
+                           "replay ring) + snk_sync + snk_replay_gather_host (stack_exp of 64 sampled transitions as Float32, "
+                           "utils.jl:343-383) per step",
+                    "obs_format": "bits (SNK_OBS_BITS, include/snake_b200.h; decoded by unpack_bits, bit-identical to the int8 state: "
+                                  "tests/test_env_parity_gpu.py); Float32 only for the 64 sampled transitions, as the reference casts "
+                                  "(utils.jl:361-362)",
                     "host_affinity_rank0": affinity},
             "gpu_launches": K * world,
             "clocks": clocks,
             "warmup_extra_untimed_steps": extra,
         }
+        if e2e_p2_ms is not None:
+            line["e2e"]["packed2_obs_variant"] = {"value": world * E * Ke / (e2e_p2_ms * 1e-3), "d2h_bytes_per_step": E * 59 + 64 * 1613,
+                                                  "api": "the same call with 2-bit packed next_state (50 B/env) + separate reward / done / mask / "
+                                                         "action arrays (the headline form earlier in round 2)"}
         if e2e_f32_ms is not None:
             line["e2e"]["full_f32_obs_variant"] = {"value": world * E * Ke / (e2e_f32_ms * 1e-3), "d2h_bytes_per_step": E * 809,
                                                    "api": "snk_step_fused_host, Float32 next_state for every env (round-1 headline form)"}

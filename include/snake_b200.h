@@ -75,6 +75,17 @@ extern "C" {
 #define SNK_OBS_I8 2           /* same values as int8: 200 B/env */
 #define SNK_OBS_I64 3          /* game.state::Array{Int,4}, structs.jl:17: 1600 B/env */
 #define SNK_OBS_PACKED2 4      /* 2 bits/cell, 4 cells/byte (cell j of a byte in bits 2j..2j+1), codes 0,1,2 and 3 = wall: 50 B/env */
+/* SNK_OBS_BITS: 24 B/env, lossless — the two boards as bit-boards plus the step's scalars (little endian):
+ *   [0,8)   u64 snake bitmap of the OLDER board: bit (r-1) + 8 (c-1) <=> interior cell (r, c), 0-based, 1 <= r, c <= 8
+ *   [8,16)  u64 snake bitmap of the NEWER board (without the head cell below when that lies on a wall)
+ *   [16] food of the older board, [17] food of the newer board, [18] head of the newer board: cell (r, c) as r | c << 4,
+ *        0-based full-board coordinates; food byte 0 = no food on the board
+ *   [19] bits 0-2 next_is_suicidal of the three offered moves, bit 3 done, bits 4-5 the action taken (index or direction)
+ *   [20,24) Float32 reward
+ * board(r, c) = -1 on the wall ring, 1 where the bitmap (or, newer board, the head: update_board! overwrites the wall cell on
+ * a wall death, utils.jl:48-50) is set, 2 on the food cell unless the snake is there, else 0.  Accepted by snk_step*,
+ * snk_step_fused*, snk_state*, snk_patch_reset_obs (not by snk_rollout); the host mirrors decode it (unpack_bits). */
+#define SNK_OBS_BITS 5
 
 typedef struct snk_env *snk_handle;
 

@@ -18,13 +18,45 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNAKE_B200_LIB", os.path.join(_HERE, "libsnake_b200.so"))   # same override as julia/SnakeB200.jl
 
-OBS_NONE, OBS_F32, OBS_I8, OBS_I64, OBS_PACKED2 = 0, 1, 2, 3, 4
+OBS_NONE, OBS_F32, OBS_I8, OBS_I64, OBS_PACKED2, OBS_BITS = 0, 1, 2, 3, 4, 5
 AUTO_RESET = 1
 ENV_ERR_FOOD, ENV_ERR_ACTION = 1, 2
 _OBS = {
     "f32": (OBS_F32, torch.float32, 200), "i8": (OBS_I8, torch.int8, 200),
     "i64": (OBS_I64, torch.int64, 200), "packed2": (OBS_PACKED2, torch.uint8, 50),
+    "bits": (OBS_BITS, torch.uint8, 24),          # bit-boards + the step's scalars in one 24-byte record: unpack_bits()
 }
+
+
+def unpack_bits(rec):
+    """Decodes SNK_OBS_BITS records (include/snake_b200.h): rec (N, 24) uint8, CPU or CUDA ->
+    dict(state (N,2,10,10) int8 [= Julia (10,10,2,N): state[n, f, c, r]], reward (N,) f32, done (N,) u8, mask (N,3) u8 =
+    next_is_suicidal, action (N,) u8).  Lossless: state equals the 'i8' observation of the same step bit for bit."""
+    rec = rec.reshape(-1, 24)
+    n, dev = rec.shape[0], rec.device
+    shifts = torch.arange(8, device=dev, dtype=torch.uint8)
+    idx = torch.arange(n, device=dev)
+
+    def board(occ_bytes, food, head=None):
+        # bitmap bit (r-1) + 8 (c-1): byte j of the little-endian u64 is column c = j + 1, its bit i is row r = i + 1
+        b = torch.zeros(n, 10, 10, dtype=torch.int8, device=dev)              # [c][r]
+        b[:, 0, :] = -1
+        b[:, 9, :] = -1
+        b[:, :, 0] = -1
+        b[:, :, 9] = -1
+        b[:, 1:9, 1:9] = ((occ_bytes[:, :, None] >> shifts) & 1).to(torch.int8)
+        fr, fc = (food & 15).long(), (food >> 4).long()
+        cur = b[idx, fc, fr]
+        b[idx, fc, fr] = torch.where((food != 0) & (cur == 0), torch.full_like(cur, 2), cur)     # the snake hides the food
+        if head is not None:
+            b[idx, (head >> 4).long(), (head & 15).long()] = 1               # drawn last: overwrites the wall on a wall death
+        return b
+
+    state = torch.stack([board(rec[:, 0:8], rec[:, 16]), board(rec[:, 8:16], rec[:, 17], rec[:, 18])], dim=1)
+    flags = rec[:, 19]
+    return {"state": state, "reward": rec[:, 20:24].contiguous().view(torch.float32).reshape(n),
+            "done": (flags >> 3) & 1, "mask": torch.stack([(flags >> k) & 1 for k in range(3)], dim=1),
+            "action": (flags >> 4) & 3}
 
 # direction codes in the order of utils.jl:8
 U, D, L, R = 0, 1, 2, 3

@@ -496,6 +496,19 @@ __device__ __forceinline__ float env_advance(Env &e, int &aidx, int is_abs, u64 
 
 // The Float32 / Int64 observation formats are HBM-bound at 3 CTAs per SM; the small formats are bound by instruction issue and
 // latency: capping them at 64 registers buys a fourth CTA per SM (no spills).
+// SNK_OBS_BITS: the two boards in the library's own bit-board form plus the step's scalars, 24 bytes per env (see the
+// header).  Written by the env's own thread in phase A: no table expansion, no phase B.
+__device__ __forceinline__ void store_bits_record(void *obs, long long env, u64 pocc, int pfr, int pfc, u64 occ, int fr, int fc,
+                                                  int hr, int hc, uint32_t m3, bool done, int aidx, float reward) {
+    u64 *rec = reinterpret_cast<u64 *>(obs) + 3 * env;
+    const uint32_t cells = (uint32_t)(pfr | (pfc << 4)) | ((uint32_t)(fr | (fc << 4)) << 8) | ((uint32_t)(hr | (hc << 4)) << 16) |
+                           (((m3 & 7u) | ((uint32_t)done << 3) | (((uint32_t)aidx & 3u) << 4)) << 24);
+    rec[0] = pocc;
+    rec[1] = occ;
+    rec[2] = (u64)cells | ((u64)__float_as_uint(reward) << 32);
+}
+__host__ __device__ constexpr bool obs_expands(int fmt) { return fmt != SNK_OBS_NONE && fmt != SNK_OBS_BITS; }   // formats that go through phase B
+
 template <int OBS, bool SELECT, bool SINK>
 __global__ void __launch_bounds__(TPB, (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I64) ? SNK_MINB : 4) k_step(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) uint32_t s_planes[TPB * PLANE_WORDS];
@@ -509,7 +522,7 @@ __global__ void __launch_bounds__(TPB, (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I64
     const long long env = env0 + tid;
 
     if (tid < MAX_FOOD) s_food_bit[tid] = a.food.bit[tid];
-    if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid);
+    if (obs_expands(OBS)) fill_tables<OBS>(s_tb, tid);
     __syncthreads();
 
     if (tid < n_local) {
@@ -555,10 +568,12 @@ __global__ void __launch_bounds__(TPB, (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I64
         if (a.ep_return != nullptr) a.ep_return[env] = e.ret;
         if (a.ep_score != nullptr) a.ep_score[env] = e.len - 2;
 
-        if (OBS != SNK_OBS_NONE) {
+        if (obs_expands(OBS)) {
             board_planes(e.pocc, e.pfr, e.pfc, false, 0, 0, s_planes + tid * PLANE_WORDS);
             board_planes(e.occ, e.fr, e.fc, true, e.hr, e.hc, s_planes + tid * PLANE_WORDS + 8);
         }
+        if (OBS == SNK_OBS_BITS)
+            store_bits_record(a.obs, env, e.pocc, e.pfr, e.pfc, e.occ, e.fr, e.fc, e.hr, e.hc, m3, e.dn, aidx, reward);
 
         if (SINK) {
             // store!(rpb, exp) for envs in index order == ring slot (stored_so_far + env) mod capacity; when the
@@ -584,7 +599,7 @@ __global__ void __launch_bounds__(TPB, (OBS == SNK_OBS_F32 || OBS == SNK_OBS_I64
         env_store(e, a.s, env, chi_live || e.len >= CHI_FROM_LEN, e.cons != cons_loaded);
     }
 
-    if (OBS != SNK_OBS_NONE) {
+    if (obs_expands(OBS)) {
         __syncthreads();
         expand_obs<OBS>(a.obs, env0, n_local, s_planes, s_tb, tid);
     }
@@ -803,6 +818,16 @@ __global__ void __launch_bounds__(TPB) k_state(EnvState s, long long n, void *ob
     const int tid = threadIdx.x;
     const long long env0 = (long long)blockIdx.x * TPB;
     const int n_local = (n - env0) < TPB ? (int)(n - env0) : TPB;
+    if (OBS == SNK_OBS_BITS) {           // boards of the current state; no step has produced scalars: flags = done bit only
+        if (tid < n_local) {
+            const long long env = env0 + tid;
+            const u64 misc = s.misc[env];
+            store_bits_record(obs, env, s.pocc[env], (int)(misc >> M_PFR) & 15, (int)(misc >> M_PFC) & 15, s.occ[env],
+                              (int)(misc >> M_FR) & 15, (int)(misc >> M_FC) & 15, (int)(misc >> M_HR) & 15, (int)(misc >> M_HC) & 15,
+                              0u, ((misc >> M_DONE) & 1ull) != 0, 0, 0.0f);
+        }
+        return;
+    }
     fill_tables<OBS>(s_tb, tid);
     if (tid < n_local) {
         long long env = env0 + tid;
@@ -827,6 +852,15 @@ __global__ void __launch_bounds__(TPB) k_patch_reset(long long n, const uint8_t 
     __shared__ int s_cnt;
     const int tid = threadIdx.x;
     const long long env0 = (long long)blockIdx.x * TPB;
+    if (OBS == SNK_OBS_BITS) {           // the boards of the record become (init, init); its flags and reward stay the step's
+        if (env0 + tid < n && done[env0 + tid] != 0) {
+            u64 *rec = reinterpret_cast<u64 *>(obs) + 3 * (env0 + tid);
+            rec[0] = INIT_OCC;
+            rec[1] = INIT_OCC;
+            rec[2] = (rec[2] & ~0xFFFFFFull) | (u64)((3 | (4 << 4)) | ((3 | (4 << 4)) << 8) | ((7 | (1 << 4)) << 16));
+        }
+        return;
+    }
     fill_tables<OBS>(s_tb, tid);
     if (tid == 0) {
         s_cnt = 0;
@@ -1080,7 +1114,7 @@ static cudaError_t ensure(T **p, size_t bytes) {
 }
 
 #ifndef SNK_HOST_CHUNK_MB
-#define SNK_HOST_CHUNK_MB 16u      // measured at 2^20 envs, packed observations: 8 MB chunks 1.49 ms per step, 16 MB 1.37, 32 MB 1.39, 64 MB 1.42
+#define SNK_HOST_CHUNK_MB 16u      // measured at 2^20 envs: packed2 observations 8 MB chunks 1.49 ms per step, 16 MB 1.37, 32 MB 1.39, 64 MB 1.42; bit records 4 MB 0.90, 8 MB 0.82, 16 MB 0.753, 32 MB 0.756
 #endif
 static long long *g_rollout_prof = nullptr;
 
@@ -1243,6 +1277,7 @@ static int launch_step(snk_handle h, StepArgs &a, int obs_fmt, bool select, long
         case SNK_OBS_I8: SNK_LAUNCH(SNK_OBS_I8); break;
         case SNK_OBS_I64: SNK_LAUNCH(SNK_OBS_I64); break;
         case SNK_OBS_PACKED2: SNK_LAUNCH(SNK_OBS_PACKED2); break;
+        case SNK_OBS_BITS: SNK_LAUNCH(SNK_OBS_BITS); break;
         default: return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
     }
 #undef SNK_LAUNCH
@@ -1335,6 +1370,7 @@ static size_t obs_bytes_per_env(int fmt) {
         case SNK_OBS_I8: return 200;
         case SNK_OBS_I64: return 1600;
         case SNK_OBS_PACKED2: return 50;
+        case SNK_OBS_BITS: return 24;
         default: return 0;
     }
 }
@@ -1387,6 +1423,7 @@ int snk_state(snk_handle h, void *obs, int obs_fmt) {
         case SNK_OBS_I8: k_state<SNK_OBS_I8><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
         case SNK_OBS_I64: k_state<SNK_OBS_I64><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
         case SNK_OBS_PACKED2: k_state<SNK_OBS_PACKED2><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
+        case SNK_OBS_BITS: k_state<SNK_OBS_BITS><<<grid, TPB, 0, h->stream>>>(h->s, h->n, obs); break;
         default: return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
     }
     SNK_CUDA(cudaGetLastError());
@@ -1404,6 +1441,7 @@ int snk_patch_reset_obs(snk_handle h, const uint8_t *done, void *obs, int obs_fm
         case SNK_OBS_I8: k_patch_reset<SNK_OBS_I8><<<grid, TPB, 0, h->stream>>>(h->n, done, obs); break;
         case SNK_OBS_I64: k_patch_reset<SNK_OBS_I64><<<grid, TPB, 0, h->stream>>>(h->n, done, obs); break;
         case SNK_OBS_PACKED2: k_patch_reset<SNK_OBS_PACKED2><<<grid, TPB, 0, h->stream>>>(h->n, done, obs); break;
+        case SNK_OBS_BITS: k_patch_reset<SNK_OBS_BITS><<<grid, TPB, 0, h->stream>>>(h->n, done, obs); break;
         default: return fail(SNK_ERR_INVALID, "unknown obs_fmt %d", obs_fmt);
     }
     SNK_CUDA(cudaGetLastError());

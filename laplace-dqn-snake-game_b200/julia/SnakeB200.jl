@@ -12,7 +12,7 @@ module SnakeB200
 
 export BatchedSnakeGame, available_actions, step!, step_fused!, virtual_step, assemble_state!,
        epsilon_greedy, masked_target, center_columns!, reset!, set_food_list!, score, lost,
-       DeviceReplayBuffer, store_step!, store_step_host!, stack_exp, sample_indices, DeviceQNet, forward!, overflowed,
+       DeviceReplayBuffer, store_step!, store_step_host!, store_step_host_bits!, stack_exp, sample_indices, DeviceQNet, forward!, overflowed,
        sample_grads!, store_snapshot!, gram!, sample_model_weights!, empty_buffer!, patch_reset_obs!,
        GramShard, export_handle, connect!, run!, planes,
        step_device!, step_abs_device!, step_fused_device!, rollout_device!, state_device!, losing_mask_device!,
@@ -21,7 +21,7 @@ export BatchedSnakeGame, available_actions, step!, step_fused!, virtual_step, as
 
 const lib = get(ENV, "SNAKE_B200_LIB", joinpath(@__DIR__, "..", "libsnake_b200.so"))
 
-const OBS_F32, OBS_I8, OBS_I64, OBS_PACKED2 = Cint(1), Cint(2), Cint(3), Cint(4)
+const OBS_F32, OBS_I8, OBS_I64, OBS_PACKED2, OBS_BITS = Cint(1), Cint(2), Cint(3), Cint(4), Cint(5)
 const AUTO_RESET = UInt32(1)
 const QNET_BF16, QNET_F32 = Cint(0), Cint(1)
 # utils.jl:8 order
@@ -220,6 +220,54 @@ function store_step_host!(g::BatchedSnakeGame, r::DeviceReplayBuffer, q::Matrix{
                 g.next_is_suicidal, C_NULL, C_NULL))
     sync(g)
     return g
+end
+
+"""The same step with ONE 24-byte record per game coming down (`SNK_OBS_BITS`, include/snake_b200.h: the next state as two
+bit-boards, next_is_suicidal, lost, the action taken and the reward) — less than half the bytes of the packed form; `records` is
+(24, N) UInt8 and `unpack_bits(records)` turns it into the reference's arrays."""
+function store_step_host_bits!(g::BatchedSnakeGame, r::DeviceReplayBuffer, q::Matrix{Float32}, epsilon::Float32, records::Matrix{UInt8};
+                               u::Vector{Float32} = rand(Float32, g.n), ridx::Vector{UInt8} = rand(UInt8(0):UInt8(2), g.n))
+    size(q) == (3, g.n) && size(records) == (24, g.n) || throw(DimensionMismatch("q must be (3, N), records (24, N)"))
+    check(ccall((:snk_step_fused_store_host, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float32}, Cfloat, Ptr{Float32}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Float32}, Ptr{UInt8},
+                 Ptr{Cvoid}, Cint, Ptr{UInt8}, Ptr{Float32}, Ptr{Int32}),
+                g.handle, r.handle, q, epsilon, u, ridx, C_NULL, C_NULL, C_NULL, records, OBS_BITS, C_NULL, C_NULL, C_NULL))
+    sync(g)
+    return records
+end
+
+"""Decodes `SNK_OBS_BITS` records (24, N): (state::Array{Int,4} (10,10,2,N) as `game.state`, reward, lost, next_is_suicidal
+(3, N), action 1:3).  Pure Julia, no library call."""
+function unpack_bits(records::Matrix{UInt8})
+    N = size(records, 2)
+    state = zeros(Int, 10, 10, 2, N)
+    reward = Vector{Float32}(undef, N); lost = Vector{Bool}(undef, N)
+    suicidal = Matrix{Bool}(undef, 3, N); action = Vector{Int}(undef, N)
+    for n in 1:N
+        rec = @view records[:, n]
+        for f in 1:2
+            b = @view state[:, :, f, n]
+            b[1, :] .= -1; b[10, :] .= -1; b[:, 1] .= -1; b[:, 10] .= -1
+            for c in 1:8, r in 1:8                       # bit (r-1) + 8 (c-1) of the little-endian u64: byte c, bit r-1
+                (rec[8 * (f - 1) + c] >> (r - 1)) & 0x01 == 0x01 && (b[r + 1, c + 1] = 1)
+            end
+            food = rec[16 + f]
+            if food != 0x00
+                fr, fc = Int(food & 0x0f) + 1, Int(food >> 4) + 1
+                b[fr, fc] == 0 && (b[fr, fc] = 2)        # the snake hides the food
+            end
+        end
+        head = rec[19]
+        state[Int(head & 0x0f) + 1, Int(head >> 4) + 1, 2, n] = 1      # drawn last: overwrites the wall on a wall death
+        flags = rec[20]
+        for k in 1:3
+            suicidal[k, n] = (flags >> (k - 1)) & 0x01 == 0x01
+        end
+        lost[n] = (flags >> 3) & 0x01 == 0x01
+        action[n] = Int((flags >> 4) & 0x03) + 1
+        reward[n] = reinterpret(Float32, UInt32(rec[21]) | UInt32(rec[22]) << 8 | UInt32(rec[23]) << 16 | UInt32(rec[24]) << 24)
+    end
+    return state, reward, lost, suicidal, action
 end
 
 """`stack_exp(sample(rpb))` (utils.jl:343-383) into HOST arrays for the 0-based slots `idx`: (states, actions 1:3, rewards,

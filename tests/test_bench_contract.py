@@ -42,7 +42,7 @@ def _check_gpu_line(p, round2):
     assert BASE | {"roofline", "gpu_launches", "clocks"} <= set(d)
     if round2:
         assert d["clocks"]["samples"] >= 8 and d["clocks"]["sm_mhz"] is not None          # the sampler starts before the warm-up
-        assert "packed2" in d["e2e"]["obs_format"] and "full_f32_obs_variant" in d["e2e"]
+        assert ("bits" in d["e2e"]["obs_format"] or "packed2" in d["e2e"]["obs_format"]) and "full_f32_obs_variant" in d["e2e"]
         c4 = d["config4_65536_envs"]
         assert c4["native_f32"]["max_err_vs_float64_of_maxQ"] < 2e-5 < c4["native_bf16"]["max_err_vs_float64_of_maxQ"]
         for t in ("terms3", "terms1"):

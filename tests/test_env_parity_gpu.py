@@ -96,6 +96,42 @@ def test_obs_formats_and_ragged_sizes(fmt, n):
     assert np.array_equal(unpack2(st) if fmt == "packed2" else st, want)
 
 
+@pytest.mark.parametrize("n,select", [(1, False), (129, True), (5000, False), (70001, True)])
+def test_bits_records_decode_to_the_oracle_step(n, select):
+    """SNK_OBS_BITS (24-byte records: two bit-boards + the step's scalars, written in phase A without the table expansion) decoded
+    by unpack_bits == every output of the oracle's step — boards incl. wall deaths, food hidden under the snake, resets — for
+    given actions and for the fused epsilon-greedy selection; snk_state and snk_patch_reset_obs in the same format."""
+    S = pkg()
+    env = S.SnakeGame(n, auto_reset=True)
+    ora = O.OracleBatch(n, auto_reset=True)
+    out = env.alloc_outputs(obs="bits", mask=False)
+    out.pop("reward"), out.pop("done")                         # everything comes out of the record
+    assert tuple(out["obs"].shape) == (n, 24)
+    rng = np.random.default_rng(n)
+    steps = 400 if n <= 5000 else 60
+    for t in range(steps):
+        if select:
+            q = rng.normal(0, 1, (n, 3)).astype(np.float32)
+            u, ridx = rng.random(n, dtype=np.float32), rng.integers(0, 3, n).astype(np.uint8)
+            act = ora.select(q, 0.3, u, ridx)
+            env.step_fused(q=torch.from_numpy(q).cuda(), eps=0.3, u=torch.from_numpy(u).cuda(), ridx=torch.from_numpy(ridx).cuda(), out=out)
+        else:
+            act = synth_actions(n, t, seed=3)
+            env.step_fused(act_idx=torch.from_numpy(act).cuda(), out=out)
+        ref = ora.step(act, obs=("i8",))
+        d = S.unpack_bits(out["obs"])
+        assert np.array_equal(d["state"].cpu().numpy().reshape(n, 200), ref["obs_i8"]), t
+        assert np.array_equal(bits(d["reward"].cpu().numpy()), bits(ref["reward"])), t
+        assert np.array_equal(d["done"].cpu().numpy(), ref["done"]), t
+        assert np.array_equal(d["mask"].cpu().numpy(), ref["mask"]), t
+        assert np.array_equal(d["action"].cpu().numpy(), act), t
+        if t % 37 == 5:                                         # next acting state: the reset rows patched in place
+            env.patch_reset_obs(d["done"].contiguous(), out["obs"], "bits")
+            assert np.array_equal(S.unpack_bits(out["obs"])["state"].cpu().numpy().reshape(n, 200), ora.state("i8")), t
+            assert np.array_equal(S.unpack_bits(env.assemble_state("bits"))["state"].cpu().numpy().reshape(n, 200), ora.state("i8")), t
+    assert env.count_errors() == 0
+
+
 def test_plain_step_and_no_auto_reset():
     """step! without auto-reset: a lost env is frozen (reward 0, done 1, mask trues(3), terminal boards)."""
     S = pkg()

@@ -126,3 +126,34 @@ def test_host_buffer_store_path_equals_device_path():
     for k in a:
         assert torch.equal(a[k], b[k]), k
     assert env_h.count_errors() == 0
+
+
+def test_host_store_path_with_bit_records():
+    """the same host entry with SNK_OBS_BITS: ONE 24-byte record per env comes down (no separate reward / done / mask / action
+    arrays) — the format bench.py's e2e leg uses — and decodes to what the device path returns in the int8 format"""
+    S = pkg()
+    n, cap, steps = 150_001, 40_000, 5
+    env_d, env_h = S.SnakeGame(n, auto_reset=True), S.SnakeGame(n, auto_reset=True)
+    rb_d, rb_h = S.ReplayBuffer(capacity=cap), S.ReplayBuffer(capacity=cap)
+    out = env_d.alloc_outputs(obs="i8", mask=True, act=True)
+    host = {"obs_fmt": "bits", "q": S.pinned_empty((n, 3), torch.float32), "u": S.pinned_empty((n,), torch.float32),
+            "ridx": S.pinned_empty((n,), torch.uint8), "obs": S.pinned_empty((n, 24), torch.uint8)}
+    g = torch.Generator().manual_seed(5)
+    for t in range(steps):
+        env_h.sync()
+        host["q"].copy_(torch.rand(n, 3, generator=g) * 2 - 1)
+        host["u"].copy_(torch.rand(n, generator=g))
+        host["ridx"].copy_(torch.randint(0, 3, (n,), generator=g, dtype=torch.uint8))
+        env_d.step_fused(q=host["q"].cuda(), eps=0.2, u=host["u"].cuda(), ridx=host["ridx"].cuda(), out=out, replay=rb_d)
+        env_h.step_fused_host(host, q=True, eps=0.2, replay=rb_h)
+        env_h.sync()
+        d = S.unpack_bits(host["obs"])
+        assert torch.equal(d["state"], out["obs"].cpu()), t
+        assert torch.equal(d["reward"], out["reward"].cpu()) and torch.equal(d["done"], out["done"].cpu()), t
+        assert torch.equal(d["mask"], out["mask"].cpu()) and torch.equal(d["action"], out["act_idx"].cpu()), t
+    idx = torch.arange(cap, device="cuda")
+    a, b = rb_d.stack_exp(idx), rb_h.stack_exp(idx)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert env_h.count_errors() == 0
+
