@@ -270,7 +270,8 @@ def run_ours(args):
     # ---- the same fused step with the other observation formats (report all three byte counts)
     variants = {}
     if rank == 0 and not use_graph and not args.skip_variants:
-        for name, fmt, nbytes in (("int8_obs", "i8", BYTES_PER_STEP_CONFIG3 - 800 + 200), ("no_obs", None, BYTES_PER_STEP_CONFIG3 - 800)):
+        for name, fmt, nbytes in (("int8_obs", "i8", BYTES_PER_STEP_CONFIG3 - 800 + 200), ("bit_records", "bits", BYTES_PER_STEP_CONFIG3 - 800 + 24),
+                                  ("no_obs", None, BYTES_PER_STEP_CONFIG3 - 800)):
             out_v = env.alloc_outputs(obs=fmt, mask=True)
             Kv = min(K, 400)
             for i in range(5):
@@ -285,9 +286,10 @@ def run_ours(args):
             variants[name] = {"value": E / (ms_v * 1e-3), "unit": UNIT, "ms_per_step": ms_v, "bytes_per_env_step": nbytes,
                               "hbm_frac": E * nbytes / (ms_v * 1e-3) / 1e9 / peaks()[0]}
             del out_v
-        variants["note"] = ("single GPU, device-timed like `value`; int8 observations (the reference's game.state is an integer array) "
-                            "and no observation at all (reward / done / mask only): the smaller the output, the more the kernel is "
-                            "bound by its per-env arithmetic and latency instead of HBM")
+        variants["note"] = ("single GPU, device-timed like `value`; int8 observations (the reference's game.state is an integer array), "
+                            "24-byte bit records (SNK_OBS_BITS: the state as two bit-boards, no table expansion) and no observation at all "
+                            "(reward / done / mask only): the smaller the output, the more the kernel is bound by its per-env arithmetic "
+                            "and latency instead of HBM")
 
     # ---- e2e: one iteration of a host trainer's data path through the host-buffer C ABI, copies inside the timed region
     Ke = max(2, min(K, args.e2e_steps))

@@ -5,7 +5,7 @@
   ncu --set full --clock-control none --import-source on -k regex:'k_step|k_rollout|k_qnet|k_gram|k_sample_grads|k_center' \
       -o gpurun_out/r02_kernels python tools/profile_kernels.py
 
-Order of launches (the summaries under profiles/ refer to it): k_step F32+select x2, I8 x2, PACKED2 x2, NONE x2 at 2^20 envs;
+Order of launches (the summaries under profiles/ refer to it): k_step F32+select x2, I8 x2, PACKED2 x2, BITS x2, NONE x2 at 2^20 envs;
 k_rollout_ws (4,096 envs x 200 steps) x2; Q-net forward f32 x2 and bf16 x2 at 65,536 samples; k_sample_grads (1,024 samples)
 x2; centre + pack(f64) + pack(f32) + Gram terms 3 and 1 at K=1000 x2; one 6,250 x 6,250 block Gram (the config-5b shard block)."""
 import os
@@ -24,7 +24,7 @@ env = S.SnakeGame(E, auto_reset=True)
 q = torch.rand(E, 3, device=dev) * 2 - 1
 u = torch.rand(E, device=dev)
 r = torch.randint(0, 3, (E,), device=dev, dtype=torch.uint8)
-for fmt in ("f32", "i8", "packed2", None):
+for fmt in ("f32", "i8", "packed2", "bits", None):
     out = env.alloc_outputs(obs=fmt, mask=True, act=True)
     for _ in range(REPS):
         env.step_fused(q=q, eps=0.05, u=u, ridx=r, out=out)
