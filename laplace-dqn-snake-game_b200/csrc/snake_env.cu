@@ -679,12 +679,18 @@ __global__ void __launch_bounds__(RTPB) k_rollout(const __grid_constant__ Rollou
 }
 
 // ---- small batches: warp-specialised multi-step rollout -------------------------------------------------------------
-// At 4,096 envs (BASELINE config 2) a step moves 3.5 MB: the time per step is the serial instruction chain of ONE env-step,
-// not memory.  So the chain is cut to the bone and everything else runs beside it: warp 0 of a CTA (EPB envs, one per lane)
-// only advances the envs and drops a 32-byte record per env into a double-buffered hand-over slot; warps 1..3 turn the
-// records into the outputs — scalars, the two boards as unit bytes, the expanded observation — while warp 0 is already in
-// the next step.  Actions are prefetched two steps ahead.  Named barriers: FULL[b] (warp 0 arrives, expanders wait),
-// EMPTY[b] (expanders arrive, warp 0 waits two steps later), and one among the expanders.
+// At 4,096 envs (BASELINE config 2) a step moves 3.5 MB: the time per step is a serial instruction chain, not memory.  So
+// three chains run side by side in a CTA (EPB envs, one per lane): warp 0 only advances the envs (260 instructions per step)
+// and drops a 48-byte record per env into a double-buffered hand-over slot; warp 1 computes next_is_suicidal from the record
+// (three virtual steps: a chain as long as the step's) and writes the per-env scalars; warps 2.. turn the record into the two
+// boards as unit bytes and expand the observation — all while warp 0 is already in the next step.  Actions are prefetched two
+// steps ahead.  Named barriers: FULL[b] (warp 0 arrives, every consumer waits), EMPTY[b] (the consumers arrive once they
+// have read the record, warp 0 waits two steps later), and one among the expansion warps.
+// Measured (tools/rollout_probe.py, cycles per step of CTA 0): without an observation the step costs 1,010 cycles = warp
+// 0's chain (937) + hand-over; with Float32 observations 1,470 — no stage waits for another (each wait < 30 cycles), the SAME
+// 260 instructions of warp 0 take 1,300 cycles while the expansion warps stream their stores.  Expanding into shared memory
+// without storing, or storing without expanding, leaves warp 0 at 1,030; a bulk asynchronous copy of a staged region instead
+// of the stores makes it 1,660.
 struct __align__(16) Handoff {
     u64 occ, pocc, cons;
     uint32_t pk;             // hr hc fr fc pfr pfc (4 bits each) | done << 24
@@ -694,10 +700,18 @@ struct __align__(16) Handoff {
 };
 __device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+#ifndef SNK_WS_XW
+#define SNK_WS_XW 5              // expansion warps per CTA; measured at 4,096 envs, Float32 observations: 2 -> 1.13 us per step, 3 -> 1.02, 4 -> 0.90, 5 -> 0.87, 6 -> 0.97, 8 -> 0.98
+#endif
+constexpr int WS_XW = SNK_WS_XW;
+constexpr bool WS_STREAM = true;        // streaming (.cs) and plain stores measure the same here
+constexpr int WS_THREADS = 32 * (2 + WS_XW);   // warp 0 logic, warp 1 mask + scalars, warps 2.. boards + expansion
 
 template <int OBS, int EPB>
-__global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ RolloutArgs a) {
+__global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant__ RolloutArgs a) {
     static_assert(EPB <= 32, "one env per lane of the logic warp");
+    constexpr int NX = 32 * WS_XW;                           // expansion threads
+    constexpr int PER = OBS == SNK_OBS_F32 ? 800 : OBS == SNK_OBS_I8 ? 200 : OBS == SNK_OBS_I64 ? 1600 : OBS == SNK_OBS_PACKED2 ? 50 : 0;
     __shared__ Handoff s_hand[2][EPB];
     __shared__ __align__(16) uint32_t s_planes[EPB * PLANE_WORDS];
     __shared__ ObsTables s_tb;
@@ -709,9 +723,12 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
     const int n_local = rem < EPB ? (int)rem : EPB;
     if (tid < MAX_FOOD) s_food_bit[tid] = a.food.bit[tid];
     if (tid < EPB) s_err[tid] = 0;
-    if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid, 128);
+    if (OBS != SNK_OBS_NONE) fill_tables<OBS>(s_tb, tid, WS_THREADS);
     __syncthreads();
-    constexpr int FULL = 1, EMPTY = 3, XB = 5;              // barrier ids: FULL+b, EMPTY+b, expanders
+    // barrier ids: FULL+b (warp 0 arrives, every consumer waits), EMPTY+b (the consumers arrive once they have read slot b,
+    // warp 0 waits two steps later), XB among the expansion warps.  Consumers that have nothing to do for this format
+    // (expansion warps without an observation) still take part in FULL / EMPTY so that the counts stay WS_THREADS.
+    constexpr int FULL = 1, EMPTY = 3, XB = 5;
     const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
     Env e;
     const bool mine = warp == 0 && lane < n_local;
@@ -727,17 +744,18 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
         int a0 = steps > 0 ? actp[0] : 0, a1 = steps > 1 ? actp[astride] : 0;
         const uint8_t *act2 = actp + 2 * astride;
         const bool prof = a.prof != nullptr && blockIdx.x == 0 && lane == 0;
-        long long p_wait = 0, p_t0 = prof ? clock64() : 0;
+        long long p_wait = 0, p_work = 0, p_arr = 0, p_t0 = prof ? clock64() : 0;
         for (int t = 0; t < steps; t++, act2 += astride) {
             const int a2 = t + 2 < steps ? *act2 : 0;                       // in flight during two steps
             const int b = t & 1;
             const long long w0 = prof ? clock64() : 0;
-            if (t >= 2) nbar_sync(EMPTY + b, 128);           // the expanders have consumed slot b (step t-2)
-            if (prof) p_wait += clock64() - w0;
+            if (t >= 2) nbar_sync(EMPTY + b, WS_THREADS);    // every consumer has read slot b (step t-2)
+            const long long w1 = prof ? clock64() : 0;
+            if (prof) p_wait += w1 - w0;
             int aidx = a0;
             float reward = 0.0f;
             uint32_t m3;
-            if (!e.dn) reward = env_advance<false>(e, aidx, is_abs, list_mask, s_food_bit, m3);   // virtual_step is the expanders' job
+            if (!e.dn) reward = env_advance<false>(e, aidx, is_abs, list_mask, s_food_bit, m3);   // virtual_step is warp 1's job
             if (mine) {
                 Handoff h;
                 h.occ = e.occ; h.pocc = e.pocc; h.cons = e.cons;
@@ -749,59 +767,82 @@ __global__ void __launch_bounds__(128) k_rollout_ws(const __grid_constant__ Roll
             }
             if (e.dn && auto_reset) env_reset(e);
             __syncwarp();
-            nbar_arrive(FULL + b, 128);
+            const long long w2 = prof ? clock64() : 0;
+            nbar_arrive(FULL + b, WS_THREADS);
+            if (prof) { p_work += w2 - w1; p_arr += clock64() - w2; }
             a0 = a1; a1 = a2;
         }
-        if (prof) { a.prof[0] = clock64() - p_t0; a.prof[1] = p_wait; }
-    } else {
-        const int et = tid - 32;                             // 0..95
-        const bool prof = a.prof != nullptr && blockIdx.x == 0 && et == 0;
-        long long p_full = 0, p_role = 0, p_exp = 0;
-        const size_t obs_step = (size_t)a.n * (OBS == SNK_OBS_F32 ? 800 : OBS == SNK_OBS_I8 ? 200 : OBS == SNK_OBS_I64 ? 1600 : 50);
+        if (prof) { a.prof[0] = clock64() - p_t0; a.prof[1] = p_wait; a.prof[6] = p_work; a.prof[7] = p_arr; }
+    } else if (warp == 1) {
+        // ---- mask warp: next_is_suicidal (three virtual steps: as long a chain as the step itself) and the per-env scalars,
+        // beside the expansion of the same step, not in front of it
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && lane == 0;
+        long long p_full = 0, p_role = 0;
         for (int t = 0; t < a.steps; t++) {
             const int b = t & 1;
             long long c0 = prof ? clock64() : 0;
-            nbar_sync(FULL + b, 128);
+            nbar_sync(FULL + b, WS_THREADS);
             if (prof) { const long long c1 = clock64(); p_full += c1 - c0; c0 = c1; }
-            // threads 0..EPB-1: losing mask + scalars; threads 32..: the older board; threads 64..: the newer board
-            const int j = et & 31, role = et >> 5;
-            if (j < n_local) {
-                const Handoff h = s_hand[b][j];
+            Handoff h;
+            if (lane < n_local) h = s_hand[b][lane];
+            __syncwarp();
+            if (t + 2 < a.steps) nbar_arrive(EMPTY + b, WS_THREADS);       // the record is in registers
+            if (lane < n_local) {
                 const int hr = (int)h.pk & 15, hc = (int)(h.pk >> 4) & 15, fr = (int)(h.pk >> 8) & 15, fc = (int)(h.pk >> 12) & 15;
+                const int dn = (int)(h.pk >> 24) & 1;
+                uint32_t m3 = 7u;
+                if (!dn) {
+                    int err = 0;
+                    m3 = losing_mask3(h.occ, h.cons, hr, hc, (int)h.pk2 & 15, (int)(h.pk2 >> 4) & 15, fr, fc, (int)(h.pk2 >> 8) & 3,
+                                      (int)(h.pk2 >> 10) & 1023, list_mask, s_food_bit, err);
+                    if (err) s_err[lane] |= err;
+                }
+                const long long o = (long long)t * a.n + env0 + lane;
+                if (a.reward != nullptr) a.reward[o] = h.reward;
+                if (a.done != nullptr) a.done[o] = (uint8_t)dn;
+                if (a.mask != nullptr) {
+                    uint8_t *m = a.mask + 3 * o;
+                    m[0] = (uint8_t)(m3 & 1u); m[1] = (uint8_t)((m3 >> 1) & 1u); m[2] = (uint8_t)((m3 >> 2) & 1u);
+                }
+                if (a.ep_return != nullptr) a.ep_return[o] = h.ret;
+                if (a.ep_score != nullptr) a.ep_score[o] = h.score;
+            }
+            if (prof) p_role += clock64() - c0;
+        }
+        if (prof) { a.prof[2] = p_full; a.prof[3] = p_role; }
+    } else {
+        // ---- expansion warps: the two boards as unit bytes (threads 0..EPB-1 the older, 32..32+EPB-1 the newer), then the
+        // expanded observation by all of them
+        const int et = tid - 64;                             // 0..NX-1
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && et == 0;
+        long long p_exp = 0, p_xfull = 0;
+        const size_t obs_step = (size_t)a.n * PER;
+        for (int t = 0; t < a.steps; t++) {
+            const int b = t & 1;
+            long long c0 = prof ? clock64() : 0;
+            nbar_sync(FULL + b, WS_THREADS);
+            if (prof) { const long long c1 = clock64(); p_xfull += c1 - c0; c0 = c1; }
+            const int j = et & 31, role = et >> 5;
+            if (OBS != SNK_OBS_NONE && j < n_local && role < 2) {
+                const Handoff h = s_hand[b][j];
                 if (role == 0) {
-                    const int dn = (int)(h.pk >> 24) & 1;
-                    uint32_t m3 = 7u;
-                    if (!dn) {
-                        int err = 0;
-                        m3 = losing_mask3(h.occ, h.cons, hr, hc, (int)h.pk2 & 15, (int)(h.pk2 >> 4) & 15, fr, fc, (int)(h.pk2 >> 8) & 3,
-                                          (int)(h.pk2 >> 10) & 1023, list_mask, s_food_bit, err);
-                        if (err) s_err[j] |= err;
-                    }
-                    const long long o = (long long)t * a.n + env0 + j;
-                    if (a.reward != nullptr) a.reward[o] = h.reward;
-                    if (a.done != nullptr) a.done[o] = (uint8_t)dn;
-                    if (a.mask != nullptr) {
-                        uint8_t *m = a.mask + 3 * o;
-                        m[0] = (uint8_t)(m3 & 1u); m[1] = (uint8_t)((m3 >> 1) & 1u); m[2] = (uint8_t)((m3 >> 2) & 1u);
-                    }
-                    if (a.ep_return != nullptr) a.ep_return[o] = h.ret;
-                    if (a.ep_score != nullptr) a.ep_score[o] = h.score;
-                } else if (OBS != SNK_OBS_NONE && role == 1) {
                     board_planes(h.pocc, (int)(h.pk >> 16) & 15, (int)(h.pk >> 20) & 15, false, 0, 0, s_planes + j * PLANE_WORDS);
-                } else if (OBS != SNK_OBS_NONE) {
-                    board_planes(h.occ, fr, fc, true, hr, hc, s_planes + j * PLANE_WORDS + 8);
+                } else {
+                    board_planes(h.occ, (int)(h.pk >> 8) & 15, (int)(h.pk >> 12) & 15, true, (int)h.pk & 15, (int)(h.pk >> 4) & 15,
+                                 s_planes + j * PLANE_WORDS + 8);
                 }
             }
-            if (t + 2 < a.steps) nbar_arrive(EMPTY + b, 128);       // the record has been read: warp 0 may overwrite it at step t+2
+            if (t + 2 < a.steps) nbar_arrive(EMPTY + b, WS_THREADS);       // the record has been read: warp 0 may overwrite it at step t+2
             if (OBS != SNK_OBS_NONE) {
-                nbar_sync(XB, 96);
-                if (prof) { const long long c1 = clock64(); p_role += c1 - c0; c0 = c1; }
-                expand_obs<OBS, 96, 5, true>((uint8_t *)a.obs + (size_t)t * obs_step, env0, n_local, s_planes, s_tb, et);
-                nbar_sync(XB, 96);
+                // (Staging the CTA's contiguous region of the step in shared memory and sending it off as one bulk asynchronous
+                // copy was measured slower: 1.04 against 0.90 us per step with Float32 observations.)
+                nbar_sync(XB, NX);
+                expand_obs<OBS, NX, 5, WS_STREAM>((uint8_t *)a.obs + (size_t)t * obs_step, env0, n_local, s_planes, s_tb, et);
+                nbar_sync(XB, NX);
                 if (prof) p_exp += clock64() - c0;
             }
         }
-        if (prof) { a.prof[2] = p_full; a.prof[3] = p_role; a.prof[4] = p_exp; }
+        if (prof) { a.prof[4] = p_exp; a.prof[5] = p_xfull; }
     }
     __syncthreads();
     if (mine) {
@@ -1121,7 +1162,8 @@ static long long *g_rollout_prof = nullptr;
 extern "C" {
 
 // profiling aid: device buffer of 8 int64 receiving cycle counts of CTA 0 of the small-batch rollout kernel
-// ([0] logic warp total, [1] its wait for the expanders, [2] expander wait for the logic warp, [3] mask/boards, [4] expansion)
+// ([0] logic warp total, [1] its wait for the consumers, [2] mask warp: wait for the logic warp, [3] mask warp: mask + scalars,
+// [4] expansion warps: boards + expansion, [5] expansion warps: wait for the logic warp)
 int snk_debug_rollout_timing(long long *device_buf) {
     g_rollout_prof = device_buf;
     return SNK_OK;
@@ -1347,7 +1389,7 @@ int snk_rollout_fused(snk_handle h, const uint8_t *act_TxN, int64_t T, int is_ab
     const bool small = h->n <= 32 * 1024;
 #define SNK_RO(FMT)                                                                                       \
     do {                                                                                                  \
-        if (small) k_rollout_ws<FMT, WS_EPB><<<nblocks(h->n, WS_EPB), 128, 0, h->stream>>>(a);               \
+        if (small) k_rollout_ws<FMT, WS_EPB><<<nblocks(h->n, WS_EPB), WS_THREADS, 0, h->stream>>>(a);        \
         else k_rollout<FMT, RTPB><<<nblocks(h->n, RTPB), RTPB, 0, h->stream>>>(a);                        \
     } while (0)
     switch (fmt) {
