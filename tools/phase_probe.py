@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Cycle-level phase timings of two latency-bound kernels (CTA 0): the Float32-faithful Q-net conv kernel (clock64 stamps per
-iteration) and the warp-specialised small-batch rollout kernel (cycle sums of the logic warp and of expander thread 0)."""
+iteration) and the warp-specialised small-batch rollout kernel (cycle sums of the logic warp, the mask warp and expansion thread 0)."""
 import ctypes as C
 import os
 import sys
@@ -41,5 +41,6 @@ env2.rollout(acts, out=out)
 torch.cuda.synchronize()
 L.snk_debug_rollout_timing(None)
 p = pb.cpu().tolist()
-print("rollout_ws, CTA 0, cycles per step: logic total %.0f (waiting for expanders %.0f) | expander: waiting for logic %.0f, mask+boards %.0f, expansion %.0f"
-      % tuple(x / T for x in p[:5]))
+print("rollout_ws, CTA 0, cycles per step: logic warp total %.0f (waiting for the consumers %.0f, its own chain %.0f) | mask warp: waiting %.0f, "
+      "mask + scalars %.0f | expansion warps: waiting %.0f, boards + expansion %.0f   (per observation format: tools/rollout_probe.py)"
+      % tuple(p[k] / T for k in (0, 1, 6, 2, 3, 5, 4)))
