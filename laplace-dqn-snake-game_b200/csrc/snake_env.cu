@@ -686,11 +686,15 @@ __global__ void __launch_bounds__(RTPB) k_rollout(const __grid_constant__ Rollou
 // boards as unit bytes and expand the observation — all while warp 0 is already in the next step.  Actions are prefetched two
 // steps ahead.  Named barriers: FULL[b] (warp 0 arrives, every consumer waits), EMPTY[b] (the consumers arrive once they
 // have read the record, warp 0 waits two steps later), and one among the expansion warps.
-// Measured (tools/rollout_probe.py, cycles per step of CTA 0): without an observation the step costs 1,010 cycles = warp
-// 0's chain (937) + hand-over; with Float32 observations 1,470 — no stage waits for another (each wait < 30 cycles), the SAME
-// 260 instructions of warp 0 take 1,300 cycles while the expansion warps stream their stores.  Expanding into shared memory
-// without storing, or storing without expanding, leaves warp 0 at 1,030; a bulk asynchronous copy of a staged region instead
-// of the stores makes it 1,660.
+// Measured: without an observation a step costs 1,010 cycles = warp 0's chain (170 instructions) + hand-over; with Float32
+// observations 1,470.  ncu's warp-stall sampling per instruction (profiles/r02_ncu_rollout_ws_stalls.txt) shows why: warp 0
+// then spends a third of its time blocked at EMPTY — the pace is set by the consumers' chain FULL -> board conversion (190
+// instructions on one warp per board) -> barrier -> expansion -> barrier.  (The clock64 counters of tools/rollout_probe.py
+// cannot see that wait: after BAR.SYNC.DEFER_BLOCKING the clock read issues before the warp blocks, so it is booked as work.)
+// Tried on top and not kept, Float32 observations, us per step: the board conversion spread over 8 threads per env 1.03 (its
+// instructions land on the schedulers of warps 0 and 1); expansion warps only on the schedulers warps 0 and 1 do not use
+// (groups of four warps, the other two idle) 1.35; the CTA's region of a step staged in shared memory and sent off as one
+// bulk asynchronous copy 1.04; actions preloaded into shared memory 0.87 (no change); plain instead of streaming stores 0.87.
 struct __align__(16) Handoff {
     u64 occ, pocc, cons;
     uint32_t pk;             // hr hc fr fc pfr pfc (4 bits each) | done << 24
