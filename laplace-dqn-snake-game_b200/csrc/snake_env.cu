@@ -711,7 +711,9 @@ __global__ void __launch_bounds__(RTPB) k_rollout(const __grid_constant__ Rollou
 // Tried on top and not kept, Float32 observations, us per step: the board conversion spread over 8 threads per env 1.03 (its
 // instructions land on the schedulers of warps 0 and 1); expansion warps only on the schedulers warps 0 and 1 do not use
 // (groups of four warps, the other two idle) 1.35; the CTA's region of a step staged in shared memory and sent off as one
-// bulk asynchronous copy 1.04; actions preloaded into shared memory 0.87 (no change); plain instead of streaming stores 0.87.
+// bulk asynchronous copy 1.04; actions preloaded into shared memory 0.87 (no change); plain instead of streaming stores 0.87;
+// (after the shorter board conversion, 0.80) the per-env scalars written by the idle upper lanes of the first role warp
+// instead of the mask warp 0.87 — whatever lengthens the role warps' chain FULL -> boards -> barrier -> expansion costs.
 struct __align__(16) Handoff {
     u64 occ, pocc, cons;
     uint32_t pk;             // hr hc fr fc pfr pfc (4 bits each) | done << 24
