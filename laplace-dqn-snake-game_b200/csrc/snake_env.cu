@@ -728,12 +728,20 @@ __device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.a
 #endif
 constexpr int WS_XW = SNK_WS_XW;
 constexpr bool WS_STREAM = true;        // streaming (.cs) and plain stores measure the same here
-constexpr int WS_THREADS = 32 * (2 + WS_XW);   // warp 0 logic, warp 1 mask + scalars, warps 2.. boards + expansion
+// warp 0 logic, warp 1 mask + scalars, warps 2 .. 1+XW boards + expansion, warp 2+XW a second mask warp for the small observation
+// formats: the two take turns (even / odd steps).  Once the board conversion got shorter the single mask warp was the busiest chain
+// of the CTA (ncu: 88 % of its samples outside barriers, 206 instructions per step); each now has two steps' time for one step.
+constexpr int WS_THREADS = 32 * (3 + WS_XW);   // launched
+constexpr int WS_BAR = 32 * (2 + WS_XW);       // threads meeting at a FULL / EMPTY barrier: logic + ONE mask warp + expansion
 
 template <int OBS, int EPB>
 __global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant__ RolloutArgs a) {
     static_assert(EPB <= 32, "one env per lane of the logic warp");
     constexpr int NX = 32 * WS_XW;                           // expansion threads
+    // Measured, us per step at 4,096 envs with one / two mask warps: no observation 0.61 / 0.45, packed 0.65 / 0.57, int8 0.66 /
+    // 0.65, Float32 0.80 / 0.82 — with the large formats the expansion chain sets the pace and the extra warp only adds
+    // contention, so the second mask warp stays idle there (it waits at the final barrier).
+    constexpr bool TWO_MASK = OBS != SNK_OBS_F32 && OBS != SNK_OBS_I64;
     constexpr int PER = OBS == SNK_OBS_F32 ? 800 : OBS == SNK_OBS_I8 ? 200 : OBS == SNK_OBS_I64 ? 1600 : OBS == SNK_OBS_PACKED2 ? 50 : 0;
     __shared__ Handoff s_hand[2][EPB];
     __shared__ __align__(16) uint32_t s_planes[EPB * PLANE_WORDS];
@@ -750,7 +758,7 @@ __global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant
     __syncthreads();
     // barrier ids: FULL+b (warp 0 arrives, every consumer waits), EMPTY+b (the consumers arrive once they have read slot b,
     // warp 0 waits two steps later), XB among the expansion warps.  Consumers that have nothing to do for this format
-    // (expansion warps without an observation) still take part in FULL / EMPTY so that the counts stay WS_THREADS.
+    // (expansion warps without an observation) still take part in FULL / EMPTY so that the counts stay WS_BAR.
     constexpr int FULL = 1, EMPTY = 3, XB = 5;
     const u64 list_mask = a.food.n >= 64 ? ~0ull : ((1ull << a.food.n) - 1ull);
     Env e;
@@ -772,7 +780,7 @@ __global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant
             const int a2 = t + 2 < steps ? *act2 : 0;                       // in flight during two steps
             const int b = t & 1;
             const long long w0 = prof ? clock64() : 0;
-            if (t >= 2) nbar_sync(EMPTY + b, WS_THREADS);    // every consumer has read slot b (step t-2)
+            if (t >= 2) nbar_sync(EMPTY + b, WS_BAR);    // every consumer has read slot b (step t-2)
             const long long w1 = prof ? clock64() : 0;
             if (prof) p_wait += w1 - w0;
             int aidx = a0;
@@ -791,25 +799,25 @@ __global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant
             if (e.dn && auto_reset) env_reset(e);
             __syncwarp();
             const long long w2 = prof ? clock64() : 0;
-            nbar_arrive(FULL + b, WS_THREADS);
+            nbar_arrive(FULL + b, WS_BAR);
             if (prof) { p_work += w2 - w1; p_arr += clock64() - w2; }
             a0 = a1; a1 = a2;
         }
         if (prof) { a.prof[0] = clock64() - p_t0; a.prof[1] = p_wait; a.prof[6] = p_work; a.prof[7] = p_arr; }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (TWO_MASK && warp == 2 + WS_XW)) {
         // ---- mask warp: next_is_suicidal (three virtual steps: as long a chain as the step itself) and the per-env scalars,
         // beside the expansion of the same step, not in front of it
-        const bool prof = a.prof != nullptr && blockIdx.x == 0 && lane == 0;
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && lane == 0 && warp == 1;
         long long p_full = 0, p_role = 0;
-        for (int t = 0; t < a.steps; t++) {
+        for (int t = (TWO_MASK && warp != 1) ? 1 : 0; t < a.steps; t += TWO_MASK ? 2 : 1) {   // two mask warps: even / odd steps
             const int b = t & 1;
             long long c0 = prof ? clock64() : 0;
-            nbar_sync(FULL + b, WS_THREADS);
+            nbar_sync(FULL + b, WS_BAR);
             if (prof) { const long long c1 = clock64(); p_full += c1 - c0; c0 = c1; }
             Handoff h;
             if (lane < n_local) h = s_hand[b][lane];
             __syncwarp();
-            if (t + 2 < a.steps) nbar_arrive(EMPTY + b, WS_THREADS);       // the record is in registers
+            if (t + 2 < a.steps) nbar_arrive(EMPTY + b, WS_BAR);       // the record is in registers
             if (lane < n_local) {
                 const int hr = (int)h.pk & 15, hc = (int)(h.pk >> 4) & 15, fr = (int)(h.pk >> 8) & 15, fc = (int)(h.pk >> 12) & 15;
                 const int dn = (int)(h.pk >> 24) & 1;
@@ -818,7 +826,7 @@ __global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant
                     int err = 0;
                     m3 = losing_mask3(h.occ, h.cons, hr, hc, (int)h.pk2 & 15, (int)(h.pk2 >> 4) & 15, fr, fc, (int)(h.pk2 >> 8) & 3,
                                       (int)(h.pk2 >> 10) & 1023, list_mask, s_food_bit, err);
-                    if (err) s_err[lane] |= err;
+                    if (err) atomicOr(&s_err[lane], err);
                 }
                 const long long o = (long long)t * a.n + env0 + lane;
                 if (a.reward != nullptr) a.reward[o] = h.reward;
@@ -833,7 +841,7 @@ __global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant
             if (prof) p_role += clock64() - c0;
         }
         if (prof) { a.prof[2] = p_full; a.prof[3] = p_role; }
-    } else {
+    } else if (warp < 2 + WS_XW) {
         // ---- expansion warps: the two boards as unit bytes (threads 0..EPB-1 the older, 32..32+EPB-1 the newer), then the
         // expanded observation by all of them
         const int et = tid - 64;                             // 0..NX-1
@@ -843,7 +851,7 @@ __global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant
         for (int t = 0; t < a.steps; t++) {
             const int b = t & 1;
             long long c0 = prof ? clock64() : 0;
-            nbar_sync(FULL + b, WS_THREADS);
+            nbar_sync(FULL + b, WS_BAR);
             if (prof) { const long long c1 = clock64(); p_xfull += c1 - c0; c0 = c1; }
             const int j = et & 31, role = et >> 5;
             if (OBS != SNK_OBS_NONE && j < n_local && role < 2) {
@@ -855,7 +863,7 @@ __global__ void __launch_bounds__(WS_THREADS) k_rollout_ws(const __grid_constant
                                  s_planes + j * PLANE_WORDS + 8);
                 }
             }
-            if (t + 2 < a.steps) nbar_arrive(EMPTY + b, WS_THREADS);       // the record has been read: warp 0 may overwrite it at step t+2
+            if (t + 2 < a.steps) nbar_arrive(EMPTY + b, WS_BAR);       // the record has been read: warp 0 may overwrite it at step t+2
             if (OBS != SNK_OBS_NONE) {
                 // (Staging the CTA's contiguous region of the step in shared memory and sending it off as one bulk asynchronous
                 // copy was measured slower: 1.04 against 0.90 us per step with Float32 observations.)
